@@ -1,0 +1,351 @@
+#!/usr/bin/env python
+"""Headline benchmark: radiomic patches/sec (2-D 64x64, full feature set) on N B200s.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W]          # our CUDA engine
+  python bench.py --impl reference [...]                        # the CPU path, all host cores
+
+A step = one pass of the hot path (discretise -> 5 texture matrices -> 93 fp64 features)
+over one batch of synthetic lesion-like patches (SURVEY.md section 8 d).  N=1 runs
+BASELINE.json configs[1]: 100k 64x64 uint8 patches, full feature set.  With N>1 (torchrun) each
+rank holds its own 100k-patch shard (weak scaling) and the step ends with the path's only
+collective, the all-gather of the feature block.  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "radiomic patches/sec (2D 64x64, full feature set)"
+UNIT = "patches/s"
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--patches", type=int, default=100000, help="patches per GPU per step")
+    ap.add_argument("--size", type=int, default=64)
+    ap.add_argument("--bin-width", type=float, default=25.0)
+    ap.add_argument("--literal-force2d", action="store_true",
+                    help="pyradiomics' literal angle set for a 2-D array with force2D (1 angle) instead of in-plane (4)")
+    ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-alt", action="store_true", help="skip the secondary (binWidth 10 / literal) measurements")
+    return ap.parse_args()
+
+
+def settings_dict(args):
+    return {"label": 255, "binWidth": args.bin_width, "force2D": bool(args.literal_force2d)}
+
+
+def bytes_per_patch(H, W, F, pix=1):
+    # SURVEY.md section 8 d: pixels + uint8 mask + fp64 feature row
+    return H * W * pix + H * W + 8 * F
+
+
+# ----------------------------------------------------------------------------- CPU arm
+def _cpu_init():
+    os.environ["OMP_NUM_THREADS"] = "1"
+
+
+def _cpu_chunk(job):
+    imgs, masks, settings = job
+    from oracle import cmatrices, radiomics_oracle as orc
+
+    out = []
+    for b in range(len(imgs)):
+        out.append(list(orc.execute(imgs[b], masks[b], settings, matrix_backend=cmatrices).values()))
+    return np.asarray(out)
+
+
+class CpuArm:
+    """The reference's CPU path for this metric.  pyradiomics is not installable here (SURVEY.md
+    fact 2), so the engine timed is the oracle: C matrix builders + NumPy feature formulas, the
+    same split pyradiomics has (kind = "port"), fanned out over all host cores the way
+    RadiomicExtractor.py:60-65 fans records over a process pool."""
+
+    def __init__(self, settings, cores=None):
+        import multiprocessing as mp
+
+        from oracle import cmatrices
+
+        cmatrices.build()
+        self.settings = settings
+        self.cores = cores or os.cpu_count() or 1
+        self.pool = mp.get_context("fork").Pool(self.cores, initializer=_cpu_init)
+
+    def run(self, imgs, masks):
+        n = len(imgs)
+        per = max(1, min(16, n // (self.cores * 4) or 1))
+        jobs = [(imgs[s:s + per], masks[s:s + per], self.settings) for s in range(0, n, per)]
+        t0 = time.perf_counter()
+        res = self.pool.map(_cpu_chunk, jobs)
+        dt = time.perf_counter() - t0
+        return np.concatenate(res), dt
+
+    def calibrate(self, imgs, masks, target_s):
+        n0 = min(len(imgs), self.cores * 4)
+        _, dt = self.run(imgs[:n0], masks[:n0])
+        rate = n0 / dt
+        return int(max(self.cores * 4, min(len(imgs), rate * target_s)))
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from multimodal_isic_b200 import synth
+
+    st = settings_dict(args)
+    arm = CpuArm(st)
+    pool_n = 4096
+    imgs, masks = synth.make_patches(pool_n, args.size, seed=1234)
+    n = arm.calibrate(imgs, masks, args.cpu_seconds / max(1, args.steps + args.warmup) * 1.0)
+    n = max(arm.cores * 4, min(n, pool_n))
+    for _ in range(args.warmup):
+        arm.run(imgs[:n], masks[:n])
+    tot = 0.0
+    for _ in range(args.steps):
+        _, dt = arm.run(imgs[:n], masks[:n])
+        tot += dt
+    arm.close()
+    value = n * args.steps / tot
+    F = 93
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": workload_config(args, n, F),
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port",
+                         "sample": "%d of the workload's 64x64 patches per step, oracle (C matrices + NumPy features), "
+                                   "multiprocessing pool over %d cores" % (n, arm.cores)},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args, patches_per_step, F):
+    return {
+        "workload": "BASELINE.json configs[1]: full 2D feature set (firstorder/GLCM/GLDM/GLRLM/GLSZM/NGTDM, F=%d) on "
+                    "%dx%d uint8 synthetic lesion-like patches" % (F, args.size, args.size),
+        "patches_per_gpu_per_step": patches_per_step, "patch": [args.size, args.size], "features": F,
+        "binWidth": args.bin_width,
+        "angles": "literal force2D on 2-D input (1 angle, 2 neighbours)" if args.literal_force2d
+        else "in-plane (4 angles, 8 neighbours)",
+        "label": 255, "parallelism": "patch-sharded, one process per GPU, all-gather of the feature block",
+        "l2_policy": "inputs (%.0f MB per step) larger than the 126 MB L2" % (patches_per_step * args.size * args.size * 2 / 1e6),
+    }
+
+
+# ----------------------------------------------------------------------------- clocks
+class ClockSampler(threading.Thread):
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.stop_flag = threading.Event()
+        self.max_mhz = None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        while not self.stop_flag.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q,
+                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                self.samples.append(float(f[0]))
+                self.max_mhz = float(f[1])
+                for nme, v in zip(names, f[2:]):
+                    if v.lower().startswith("active"):
+                        self.reasons.add(nme)
+            except Exception:
+                pass
+            self.stop_flag.wait(0.1)
+
+    def summary(self):
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None, "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ----------------------------------------------------------------------------- GPU arm
+def gpu_arm(args):
+    import torch
+    import torch.distributed as dist
+
+    import multimodal_isic_b200 as pkg
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    st = settings_dict(args)
+    ex = pkg.RadiomicsExtractor({"setting": st}, device=local)
+    F = ex.engine.F
+    B, H = args.patches, args.size
+    # every rank owns a different shard of the (virtual) global patch list
+    imgs, masks = pkg.synth.make_patches_torch(B, H, seed=1234 + rank, device=dev)
+    out = torch.empty((B, F), dtype=torch.float64, device=dev)
+    status = torch.empty((B,), dtype=torch.int32, device=dev)
+    gathered = torch.empty((world * B, F), dtype=torch.float64, device=dev) if world > 1 else None
+
+    def step():
+        ex.engine.extract_device(imgs, masks, out, status)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        barrier()
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        barrier()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(3, args.warmup)):
+        step()
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    l0 = ex.engine.launches
+    ms = timed(step, args.steps)
+    launches = ex.engine.launches - l0
+    # kernel-only duration (same kernel, events directly around the launches on its stream)
+    kms = timed(lambda: ex.engine.extract_device(imgs, masks, out, status), args.steps) / args.steps
+    bad = int((status != 0).sum().item())
+
+    # ---- end to end through the public API with HOST buffers (pinned), copies in the timed region
+    h_img = imgs.cpu().pin_memory()
+    h_msk = masks.cpu().pin_memory()
+    h_out = torch.empty((B, F), dtype=torch.float64).pin_memory()
+    h_st = torch.empty((B,), dtype=torch.int32).pin_memory()
+
+    def e2e_step():
+        ex.pipeline.run(h_img, h_msk, h_out, h_st)
+        if world > 1:
+            dist.all_gather_into_tensor(gathered, out)  # same collective on the device-resident block
+
+    for _ in range(2):
+        e2e_step()
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        e2e_step()
+    barrier()
+    e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
+    if world > 1:
+        dist.all_reduce(e2e_s, op=dist.ReduceOp.MAX)
+    e2e_s = float(e2e_s.item())
+    if rank == 0:
+        sampler.stop_flag.set()
+        sampler.join(2)
+    same = bool(torch.equal(h_out, out.cpu()))
+
+    alt = {}
+    if not args.no_alt and world == 1:
+        for name, s2 in (("binWidth10_inplane", {"label": 255, "binWidth": 10.0, "force2D": False}),
+                         ("binWidth10_literal_force2D", {"label": 255, "binWidth": 10.0, "force2D": True})):
+            ex2 = pkg.RadiomicsExtractor({"setting": s2}, device=local)
+            o2 = torch.empty((B, ex2.engine.F), dtype=torch.float64, device=dev)
+            for _ in range(2):
+                ex2.engine.extract_device(imgs, masks, o2, status)
+            m2 = timed(lambda: ex2.engine.extract_device(imgs, masks, o2, status), 3) / 3
+            alt[name] = {"value": B / (m2 / 1e3), "unit": UNIT, "ms_per_step": m2}
+
+    cpu = None
+    if rank == 0 and not args.no_cpu_baseline and world == 1:
+        arm = CpuArm(st)
+        n_pool = min(B, 8192)
+        ci, cm = h_img[:n_pool].numpy(), h_msk[:n_pool].numpy()
+        n = arm.calibrate(ci, cm, args.cpu_seconds)
+        ref, dt = arm.run(ci[:n], cm[:n])
+        arm.close()
+        got = out[:n].cpu().numpy()
+        ok = bool(np.allclose(got, ref, rtol=1e-6, atol=1e-9, equal_nan=True))
+        cpu = {"value": n / dt, "unit": UNIT, "cores": arm.cores, "kind": "port",
+               "sample": "first %d patches of the workload, oracle (C matrices + NumPy features) on a %d-process pool; "
+                         "GPU rows match it within rtol 1e-6/atol 1e-9: %s" % (n, arm.cores, ok)}
+
+    if rank == 0:
+        peaks = {}
+        try:
+            with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as fh:
+                peaks = json.load(fh)
+        except Exception:
+            pass
+        peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
+        bpp = bytes_per_patch(H, H, F)
+        achieved = B * bpp / (kms / 1e3) / 1e9
+        traffic = None
+        try:
+            with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
+                traffic = json.load(fh).get("dram_bytes_per_launch")
+        except Exception:
+            pass
+        total = world * B * args.steps
+        line = {
+            "metric": METRIC, "value": total / (ms / 1e3), "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": max(3, args.warmup), "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": workload_config(args, B, F),
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                         "traffic": traffic, "kernel": "radb_extract_kernel<uint8>", "kernel_ms": kms,
+                         "bytes_per_patch": bpp, "peak_source": peak_src,
+                         "note": "algorithmic bytes = H*W px + H*W mask + 8*F; the matrix stages are shared-memory-"
+                                 "atomic / fp64 bound, not HBM bound (DESIGN.md)"},
+            "cpu_baseline": cpu,
+            "e2e": {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(world * B * H * H * 2),
+                    "d2h_bytes_per_step": int(world * B * (F * 8 + 4)), "matches_device_path": same},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+            "invalid_rows": bad,
+            "alt": alt,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        gpu_arm(args)
+
+
+if __name__ == "__main__":
+    main()

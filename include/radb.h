@@ -1,0 +1,121 @@
+/* radb -- C ABI of the B200-native radiomic feature engine (libradb_b200.so).
+ *
+ * This is the drop-in boundary for the radiomic-extraction hot path of rbuler/multimodal-isic.
+ * The reference has no FFI of its own on this path: it reaches its native code through the
+ * third-party pyradiomics package.  Each entry point below names the reference-side interface
+ * it stands in for (file:line under /root/reference) and the pyradiomics call behind it.
+ *
+ * Conventions: plain pointers and sizes only; `img`, `mask`, `out`, `status` and every debug
+ * buffer are DEVICE pointers owned by the caller; calls are asynchronous and ordered on the
+ * given CUDA stream (a `cudaStream_t` passed as void*); no allocation happens after
+ * radb_create.  Every function returns 0 on success and a negative code on misuse / CUDA
+ * errors (text via radb_last_error); nothing aborts.  A handle is not thread-safe: one handle
+ * per (thread, device).
+ */
+#ifndef RADB_H
+#define RADB_H
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct radb_handle radb_handle;
+
+/* feature classes, in the output order (params.yml:164-171 order without shape2D) */
+enum {
+    RADB_CLASS_FIRSTORDER = 1u << 0,
+    RADB_CLASS_GLCM = 1u << 1,
+    RADB_CLASS_GLDM = 1u << 2,
+    RADB_CLASS_GLRLM = 1u << 3,
+    RADB_CLASS_GLSZM = 1u << 4,
+    RADB_CLASS_NGTDM = 1u << 5,
+    RADB_CLASS_ALL = 0x3fu
+};
+
+/* pixel types of `img` */
+enum { RADB_DTYPE_U8 = 0, RADB_DTYPE_U16 = 1, RADB_DTYPE_F32 = 2 };
+
+/* per-patch status written to `status[b]`; rows with status != 0 are NaN.
+ * 1-3 are the ValueErrors pyradiomics' imageoperations.checkMask raises through
+ * RadiomicExtractor.py:38 (no try/except there: the reference aborts the run). */
+enum {
+    RADB_ST_OK = 0,
+    RADB_ST_LABEL_ABSENT = 1,   /* "Label (255) not present in mask" */
+    RADB_ST_SINGLE_VOXEL = 2,   /* "mask only contains 1 segmented voxel" */
+    RADB_ST_TOO_FEW_DIMS = 3,   /* ROI spans < minimumROIDimensions (2) axes */
+    RADB_ST_NG_OVERFLOW = 4     /* more gray levels than the handle was sized for */
+};
+
+/* error codes (function return values) */
+enum {
+    RADB_OK = 0,
+    RADB_E_INVALID = -1,      /* bad argument / unsupported setting */
+    RADB_E_CUDA = -2,         /* CUDA runtime error */
+    RADB_E_UNSUPPORTED = -3,  /* valid pyradiomics setting this build does not implement yet */
+    RADB_E_SMEM = -4          /* patch size x gray levels exceed 227 KB of shared memory */
+};
+
+/* Resolved extraction settings.  Stands in for the `setting:` section of the pyradiomics
+ * parameter file the reference loads at RadiomicExtractor.py:15 (params.yml:62-119) and that
+ * RadiomicsFeatureExtractor.execute forwards to every feature class. */
+typedef struct radb_settings {
+    double bin_width;          /* params.yml:96  binWidth (10); pyradiomics default 25 */
+    int32_t bin_count;         /* binCount; 0 = unused (fixed-width binning) */
+    int32_t label;             /* params.yml:93  label (255) */
+    int32_t n_angles;          /* unidirectional offsets resolved on the host from force2D /
+                                  force2Ddimension (params.yml:100): 1 (row-only, the literal
+                                  2-D + force2D case) or 4 (in-plane) */
+    int8_t angles[8][2];       /* (dy, dx) per unidirectional angle; the bidirectional set used
+                                  by GLSZM/GLDM/NGTDM is these plus their negations */
+    int32_t symmetrical_glcm;  /* params.yml:119 symmetricalGLCM (True) */
+    double gldm_alpha;         /* gldm_a (0) */
+    double voxel_array_shift;  /* voxelArrayShift (0) */
+    uint32_t class_mask;       /* RADB_CLASS_* bits: params.yml:164-171 featureClass */
+    int32_t max_ng;            /* shared-memory sizing bound on gray levels; 0 = derive from
+                                  dtype and bin_width */
+    int32_t device;            /* CUDA device ordinal */
+} radb_settings;
+
+/* RadiomicsExtractor.__init__ (RadiomicExtractor.py:14-15): build an extractor from settings. */
+int radb_create(const radb_settings* s, radb_handle** out);
+void radb_destroy(radb_handle* h);
+
+/* get_enabled_features (RadiomicExtractor.py:20-21) at feature granularity: number and names
+ * ("original_glcm_Contrast", ...) of the columns of one output row, in output order. */
+int radb_feature_count(const radb_handle* h);
+const char* radb_feature_name(const radb_handle* h, int i);
+
+/* Dynamic shared memory (bytes) one CTA needs for HxW patches of `dtype`; < 0 if it cannot fit. */
+int radb_smem_bytes(const radb_handle* h, int H, int W, int dtype);
+
+/* extractor.execute(image, mask, label=label) (RadiomicExtractor.py:38,42,45,48), batched:
+ * B (image, mask) pairs of H x W pixels -> out[B][F] float64 rows + status[B].
+ * img/mask strides are BYTES between consecutive patches.  Asynchronous on `cuda_stream`. */
+int radb_extract(radb_handle* h, const void* img, int dtype, const uint8_t* mask, int64_t B, int H, int W,
+                 int64_t img_stride_b, int64_t mask_stride_b, double* out, int32_t* status, void* cuda_stream);
+
+/* Same launch as radb_extract, additionally dumping the discretised image and the integer
+ * texture matrices the features were reduced from (what pyradiomics' cMatrices.calculate_*
+ * return) for bit-exact parity tests.  Any debug pointer may be NULL.  All buffers must be
+ * zero-filled by the caller.  Shapes (Ng = radb_max_ng(h), Na = n_angles, Nr = max(H, W)):
+ *   levels int32 [B][H][W]      glcm  int32 [B][Na][Ng][Ng]   glrlm int32 [B][Na][Ng][Nr]
+ *   glszm  int32 [B][Ng][H*W]   gldm  int32 [B][Ng][2*Na+1]   ngtdm_n int32 [B][Ng]
+ *   ngtdm_s float64 [B][Ng]     ng    int32 [B] (max gray level of each patch) */
+int radb_debug_matrices(radb_handle* h, const void* img, int dtype, const uint8_t* mask, int64_t B, int H,
+                        int W, int64_t img_stride_b, int64_t mask_stride_b, double* out, int32_t* status,
+                        int32_t* levels, int32_t* glcm, int32_t* glrlm, int32_t* glszm, int32_t* gldm,
+                        int32_t* ngtdm_n, double* ngtdm_s, int32_t* ng, void* cuda_stream);
+
+int radb_max_ng(const radb_handle* h);
+
+/* Number of kernel launches this handle has issued (bench.py's gpu_launches evidence). */
+int64_t radb_launch_count(const radb_handle* h);
+
+const char* radb_last_error(void);
+const char* radb_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RADB_H */

@@ -1,0 +1,131 @@
+// Host-side helpers shared by the C-ABI (radb_api.cu) and the emulation harness (tests/emu):
+// settings validation, feature-name table (SURVEY.md A.2 order), launch-parameter setup.
+#pragma once
+#include <math.h>
+#include <string>
+#include <vector>
+#include "../../include/radb.h"
+#include "radb_params.h"
+
+static_assert(sizeof(radb_settings) == 72, "radb_settings layout is part of the ABI (ctypes mirror in _abi.py)");
+
+namespace radb {
+
+struct ClassInfo {
+    unsigned bit;
+    const char* name;
+    std::vector<const char*> feats;
+};
+
+// A.2: alphabetical get<Name>FeatureValue order, deprecated features excluded.
+static inline const std::vector<ClassInfo>& classes()
+{
+    static const std::vector<ClassInfo> c = {
+        {RADB_CLASS_FIRSTORDER, "firstorder",
+         {"10Percentile", "90Percentile", "Energy", "Entropy", "InterquartileRange", "Kurtosis", "Maximum",
+          "MeanAbsoluteDeviation", "Mean", "Median", "Minimum", "Range", "RobustMeanAbsoluteDeviation",
+          "RootMeanSquared", "Skewness", "TotalEnergy", "Uniformity", "Variance"}},
+        {RADB_CLASS_GLCM, "glcm",
+         {"Autocorrelation", "ClusterProminence", "ClusterShade", "ClusterTendency", "Contrast", "Correlation",
+          "DifferenceAverage", "DifferenceEntropy", "DifferenceVariance", "Id", "Idm", "Idmn", "Idn", "Imc1",
+          "Imc2", "InverseVariance", "JointAverage", "JointEnergy", "JointEntropy", "MCC",
+          "MaximumProbability", "SumAverage", "SumEntropy", "SumSquares"}},
+        {RADB_CLASS_GLDM, "gldm",
+         {"DependenceEntropy", "DependenceNonUniformity", "DependenceNonUniformityNormalized",
+          "DependenceVariance", "GrayLevelNonUniformity", "GrayLevelVariance", "HighGrayLevelEmphasis",
+          "LargeDependenceEmphasis", "LargeDependenceHighGrayLevelEmphasis",
+          "LargeDependenceLowGrayLevelEmphasis", "LowGrayLevelEmphasis", "SmallDependenceEmphasis",
+          "SmallDependenceHighGrayLevelEmphasis", "SmallDependenceLowGrayLevelEmphasis"}},
+        {RADB_CLASS_GLRLM, "glrlm",
+         {"GrayLevelNonUniformity", "GrayLevelNonUniformityNormalized", "GrayLevelVariance",
+          "HighGrayLevelRunEmphasis", "LongRunEmphasis", "LongRunHighGrayLevelEmphasis",
+          "LongRunLowGrayLevelEmphasis", "LowGrayLevelRunEmphasis", "RunEntropy", "RunLengthNonUniformity",
+          "RunLengthNonUniformityNormalized", "RunPercentage", "RunVariance", "ShortRunEmphasis",
+          "ShortRunHighGrayLevelEmphasis", "ShortRunLowGrayLevelEmphasis"}},
+        {RADB_CLASS_GLSZM, "glszm",
+         {"GrayLevelNonUniformity", "GrayLevelNonUniformityNormalized", "GrayLevelVariance",
+          "HighGrayLevelZoneEmphasis", "LargeAreaEmphasis", "LargeAreaHighGrayLevelEmphasis",
+          "LargeAreaLowGrayLevelEmphasis", "LowGrayLevelZoneEmphasis", "SizeZoneNonUniformity",
+          "SizeZoneNonUniformityNormalized", "SmallAreaEmphasis", "SmallAreaHighGrayLevelEmphasis",
+          "SmallAreaLowGrayLevelEmphasis", "ZoneEntropy", "ZonePercentage", "ZoneVariance"}},
+        {RADB_CLASS_NGTDM, "ngtdm", {"Busyness", "Coarseness", "Complexity", "Contrast", "Strength"}},
+    };
+    return c;
+}
+
+struct Plan {
+    radb_settings s;
+    int max_ng;
+    int F;
+    int off[6];
+    std::vector<std::string> names;
+};
+
+// Validates settings; returns 0 or a RADB_E_* code with a message.
+static inline int make_plan(const radb_settings& s, Plan& pl, std::string& err)
+{
+    if (!(s.bin_width > 0) || !isfinite(s.bin_width)) { err = "bin_width must be > 0"; return RADB_E_INVALID; }
+    if (s.bin_count != 0) { err = "binCount binning is not implemented (fixed binWidth only)"; return RADB_E_UNSUPPORTED; }
+    if (s.n_angles < 1 || s.n_angles > RADB_MAX_ANGLES) { err = "n_angles must be 1..4 (distance-1 offsets in a plane)"; return RADB_E_INVALID; }
+    for (int a = 0; a < s.n_angles; a++) {
+        int dy = s.angles[a][0], dx = s.angles[a][1];
+        if (dy < -1 || dy > 1 || dx < -1 || dx > 1 || (dy == 0 && dx == 0)) {
+            err = "angle offsets must have infinity-norm 1 (distances other than [1] are not implemented)";
+            return RADB_E_UNSUPPORTED;
+        }
+        for (int b = 0; b < a; b++)
+            if ((s.angles[b][0] == dy && s.angles[b][1] == dx) || (s.angles[b][0] == -dy && s.angles[b][1] == -dx)) {
+                err = "duplicate angle";
+                return RADB_E_INVALID;
+            }
+    }
+    if ((s.class_mask & RADB_CLASS_ALL) == 0) { err = "no feature class enabled"; return RADB_E_INVALID; }
+    if (s.gldm_alpha < 0) { err = "gldm_alpha must be >= 0"; return RADB_E_INVALID; }
+    pl.s = s;
+    int ng = s.max_ng;
+    if (ng <= 0) ng = (int)floor(255.0 / s.bin_width) + 1;  // uint8 pixels: levels 1..floor(255/bw)+1
+    if (ng > 255) { err = "more than 255 gray levels (binWidth too small for the u8 level image)"; return RADB_E_UNSUPPORTED; }
+    pl.max_ng = ng;
+    pl.F = 0;
+    pl.names.clear();
+    int k = 0;
+    for (const auto& c : classes()) {
+        if (s.class_mask & c.bit) {
+            pl.off[k] = pl.F;
+            for (auto f : c.feats) pl.names.push_back(std::string("original_") + c.name + "_" + f);
+            pl.F += (int)c.feats.size();
+        } else
+            pl.off[k] = -1;
+        k++;
+    }
+    return 0;
+}
+
+static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParams& p, std::string& err)
+{
+    if (dtype != RADB_DTYPE_U8) { err = "only uint8 pixels are implemented in this build (u16/f32 pending)"; return RADB_E_UNSUPPORTED; }
+    if (H < 1 || W < 1 || (long long)H * W > 65535) { err = "patch must have 1..65535 pixels"; return RADB_E_INVALID; }
+    memset(&p, 0, sizeof(p));
+    p.H = H;
+    p.W = W;
+    p.label = pl.s.label;
+    p.n_angles = pl.s.n_angles;
+    for (int a = 0; a < pl.s.n_angles; a++) { p.ang_y[a] = pl.s.angles[a][0]; p.ang_x[a] = pl.s.angles[a][1]; }
+    p.symmetric = pl.s.symmetrical_glcm ? 1 : 0;
+    p.alpha = (int)floor(pl.s.gldm_alpha);
+    p.bin_width = pl.s.bin_width;
+    p.shift = pl.s.voxel_array_shift;
+    p.max_ng = pl.max_ng;
+    p.F = pl.F;
+    p.off_fo = pl.off[0];
+    p.off_glcm = pl.off[1];
+    p.off_gldm = pl.off[2];
+    p.off_glrlm = pl.off[3];
+    p.off_glszm = pl.off[4];
+    p.off_ngtdm = pl.off[5];
+    radb_layout(&p, 1);
+    if (p.smem_total > 227 * 1024) { err = "patch size x gray levels need more than 227 KB of shared memory"; return RADB_E_SMEM; }
+    return 0;
+}
+
+}  // namespace radb

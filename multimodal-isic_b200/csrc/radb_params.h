@@ -1,0 +1,99 @@
+// Launch parameters + shared-memory layout shared by the C-ABI host code (radb_api.cu),
+// the kernels (radb_kernels.cuh) and the CPU emulation harness under tests/emu.
+#pragma once
+#include <stdint.h>
+
+#define RADB_NT 128          // threads per CTA (4 warps); one CTA per patch
+#define RADB_MAX_ANGLES 4    // unidirectional offsets at distance 1 in a plane
+#define RADB_GLCM_NF 24
+#define RADB_GLRLM_NF 16
+#define RADB_FSC_STRIDE 40   // per-angle scratch: 24 GLCM + 16 GLRLM features
+
+enum { RADB_U8 = 0, RADB_U16 = 1, RADB_F32 = 2 };
+
+struct RadbParams {
+    const void* img;
+    const uint8_t* mask;
+    long long img_stride;   // bytes between patches
+    long long mask_stride;  // bytes between patches
+    double* out;            // [B][F]
+    int* status;            // [B]
+    long long B;
+    int H, W, WP, HW;
+    int label;
+    int n_angles;
+    int ang_y[RADB_MAX_ANGLES], ang_x[RADB_MAX_ANGLES];
+    int symmetric;
+    int alpha;
+    double bin_width;
+    double shift;
+    int max_ng;
+    int nr;        // GLRLM columns = max(H, W)
+    int s0;        // dense GLSZM columns (zone sizes 1..s0); larger zones go to the overflow list
+    int ovf_cap;
+    int F;
+    int off_fo, off_glcm, off_gldm, off_glrlm, off_glszm, off_ngtdm;  // output column of each class, -1 = off
+    int use_tma;
+    // shared-memory byte offsets
+    int o_stage, o_mask, o_mbar, o_zero, o_lev, o_zsize, o_hist, o_lut, o_lhist, o_glcm, o_px, o_py,
+        o_padd, o_psub, o_glrlm, o_pr, o_gldm, o_ngc, o_ngn, o_szm, o_ovf, o_mcc, o_idx, o_fsc, o_misc,
+        o_ngp, o_qv, o_pg, smem_total;
+    int mcc_stride;  // doubles per angle in the MCC workspace
+    // optional debug outputs (device pointers, may be null); dims use max_ng
+    int* dbg_levels;   // [B][H][W]
+    int* dbg_glcm;     // [B][Na][max_ng][max_ng]
+    int* dbg_glrlm;    // [B][Na][max_ng][nr]
+    int* dbg_glszm;    // [B][max_ng][HW]
+    int* dbg_gldm;     // [B][max_ng][2*Na+1]
+    int* dbg_ngn;      // [B][max_ng]
+    double* dbg_ngs;   // [B][max_ng]
+    int* dbg_ng;       // [B]
+};
+
+static inline int radb_align(int v, int a) { return (v + a - 1) / a * a; }
+
+// Fills WP/HW/nr/s0/ovf_cap and every o_* offset from H, W, max_ng, n_angles, pixel size.
+static inline void radb_layout(RadbParams* p, int pix_bytes)
+{
+    const int H = p->H, W = p->W, ng = p->max_ng, na = p->n_angles;
+    p->HW = H * W;
+    p->WP = radb_align(W + 2, 4);
+    p->nr = H > W ? H : W;
+    p->s0 = 16;
+    p->ovf_cap = p->HW / (p->s0 + 1) + 1;
+    int o = 0;
+    p->o_stage = o;                       // raw pixels (TMA destination); later CCL labels (u16[HW])
+    int stage_bytes = radb_align(p->HW * pix_bytes, 16);
+    p->o_mask = o + stage_bytes;          // raw mask (TMA destination)
+    int both = stage_bytes + radb_align(p->HW, 16);
+    int lab_bytes = radb_align(p->HW * 2, 16);
+    o += both > lab_bytes ? both : lab_bytes;
+    p->o_mbar = o; o += 16;
+    p->o_zero = o;                        // everything from here on is zeroed at CTA start
+    p->o_lev = o; o += radb_align((H + 2) * p->WP, 16);
+    p->o_zsize = o; o += radb_align(p->HW * 2, 16);
+    p->o_hist = o; o += 256 * 4;
+    p->o_lut = o; o += 256;
+    p->o_lhist = o; o += radb_align(ng * 4, 16);
+    p->o_glcm = o; o += radb_align(na * ng * ng * 4, 16);
+    p->o_px = o; o += radb_align(na * ng * 4, 16);
+    p->o_py = o; o += radb_align(na * ng * 4, 16);
+    p->o_padd = o; o += radb_align(na * 2 * ng * 4, 16);
+    p->o_psub = o; o += radb_align(na * ng * 4, 16);
+    p->o_glrlm = o; o += radb_align(na * ng * p->nr * 2, 16);
+    p->o_pr = o; o += radb_align(na * p->nr * 4, 16);
+    p->o_gldm = o; o += radb_align(ng * (2 * na + 1) * 4, 16);
+    p->o_ngc = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] voxel counts per neighbour count
+    p->o_ngn = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] sum |cnt*i - sum(neigh)|
+    p->o_szm = o; o += radb_align(ng * p->s0 * 4, 16);
+    p->o_ovf = o; o += radb_align(p->ovf_cap * 4, 16);
+    p->mcc_stride = ng * (ng + 1) / 2 + 4 * ng;
+    p->o_mcc = o; o += radb_align(na * p->mcc_stride * 8, 16);
+    p->o_idx = o; o += radb_align(na * ng, 16);
+    p->o_fsc = o; o += radb_align((na * RADB_FSC_STRIDE + 64) * 8, 16);
+    p->o_ngp = o; o += radb_align(2 * ng * 8, 16);
+    p->o_qv = o; o += 16 * 8;
+    p->o_pg = o; o += radb_align(ng * 4, 16);
+    p->o_misc = o; o += 32 * 4;
+    p->smem_total = o;
+}

@@ -1,0 +1,175 @@
+"""Thin host wrapper over the C-ABI (``include/radb.h``): one ``Engine`` = one ``radb_handle``
+on one device.  PyTorch is used for device/pinned buffers and streams only; every number is
+computed by the sm_100a kernels in ``csrc/``.  No CPU fallback."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+import torch
+
+from . import _abi
+
+
+class RadbError(RuntimeError):
+    pass
+
+
+class Engine:
+    def __init__(self, bin_width, label, angles, symmetrical_glcm=True, gldm_alpha=0.0, voxel_array_shift=0.0,
+                 classes=_abi.CLASS_ORDER, max_ng=0, device=0):
+        if not torch.cuda.is_available():
+            raise RadbError("radb: no CUDA device visible -- the radiomic engine has no CPU fallback")
+        self.lib = _abi.load_library()
+        self.device = int(device)
+        self.n_angles = len(angles)
+        self._settings = _abi.make_settings(bin_width, label, angles, symmetrical_glcm, gldm_alpha,
+                                            voxel_array_shift, classes, max_ng, device)
+        h = ctypes.c_void_p()
+        rc = self.lib.radb_create(ctypes.byref(self._settings), ctypes.byref(h))
+        if rc != 0:
+            raise RadbError("radb_create failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+        self._h = h
+        self.F = self.lib.radb_feature_count(self._h)
+        self.names = [self.lib.radb_feature_name(self._h, i).decode() for i in range(self.F)]
+        self.max_ng = self.lib.radb_max_ng(self._h)
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.radb_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    @property
+    def launches(self):
+        return int(self.lib.radb_launch_count(self._h))
+
+    def smem_bytes(self, H, W, dtype=_abi.DTYPE_U8):
+        return int(self.lib.radb_smem_bytes(self._h, H, W, dtype))
+
+    def _check(self, images, masks):
+        if images.dtype != torch.uint8:
+            raise NotImplementedError("only uint8 images are implemented (got %s)" % images.dtype)
+        if masks.dtype != torch.uint8:
+            raise TypeError("masks must be uint8")
+        if images.dim() != 3 or images.shape != masks.shape:
+            raise ValueError("images and masks must both be [B, H, W]")
+        if not (images.is_cuda and masks.is_cuda and images.device.index == self.device):
+            raise ValueError("images / masks must live on cuda:%d" % self.device)
+        if not (images.is_contiguous() and masks.is_contiguous()):
+            raise ValueError("images / masks must be contiguous")
+
+    def extract_device(self, images, masks, out=None, status=None, stream=None):
+        """Device tensors in, device tensors out; asynchronous on ``stream`` (default: current)."""
+        self._check(images, masks)
+        B, H, W = images.shape
+        dev = images.device
+        if out is None:
+            out = torch.empty((B, self.F), dtype=torch.float64, device=dev)
+        if status is None:
+            status = torch.empty((B,), dtype=torch.int32, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = self.lib.radb_extract(self._h, images.data_ptr(), _abi.DTYPE_U8, masks.data_ptr(), B, H, W, H * W,
+                                   H * W, out.data_ptr(), status.data_ptr(), st.cuda_stream)
+        if rc != 0:
+            raise RadbError("radb_extract failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+        return out, status
+
+    def debug_matrices(self, images, masks):
+        """Features plus the integer matrices (numpy, trimmed to shapes the oracle uses)."""
+        self._check(images, masks)
+        B, H, W = images.shape
+        dev = images.device
+        ng, na, nr = self.max_ng, self.n_angles, max(H, W)
+        z = lambda shape, dt=torch.int32: torch.zeros(shape, dtype=dt, device=dev)
+        out = z((B, self.F), torch.float64)
+        status = z((B,))
+        bufs = dict(levels=z((B, H, W)), glcm=z((B, na, ng, ng)), glrlm=z((B, na, ng, nr)),
+                    glszm=z((B, ng, H * W)), gldm=z((B, ng, 2 * na + 1)), ngtdm_n=z((B, ng)),
+                    ngtdm_s=z((B, ng), torch.float64), ng=z((B,)))
+        st = torch.cuda.current_stream(dev)
+        rc = self.lib.radb_debug_matrices(self._h, images.data_ptr(), _abi.DTYPE_U8, masks.data_ptr(), B, H, W,
+                                          H * W, H * W, out.data_ptr(), status.data_ptr(),
+                                          *[bufs[k].data_ptr() for k in ("levels", "glcm", "glrlm", "glszm", "gldm",
+                                                                          "ngtdm_n", "ngtdm_s", "ng")],
+                                          st.cuda_stream)
+        if rc != 0:
+            raise RadbError("radb_debug_matrices failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+        torch.cuda.synchronize(dev)
+        res = {k: v.cpu().numpy() for k, v in bufs.items()}
+        res["features"] = out.cpu().numpy()
+        res["status"] = status.cpu().numpy()
+        return res
+
+
+class HostPipeline:
+    """Host-buffer entry point: streams host (NumPy) patches through the engine in chunks with
+    double-buffered pinned staging so H2D copies, kernels and D2H copies overlap."""
+
+    def __init__(self, engine, chunk=16384):
+        self.engine = engine
+        self.chunk = int(chunk)
+        self._bufs = None
+        self._key = None
+
+    def _ensure(self, H, W):
+        key = (H, W)
+        if self._key == key:
+            return
+        dev = torch.device("cuda", self.engine.device)
+        n, F = self.chunk, self.engine.F
+        self._bufs = []
+        for _ in range(2):
+            self._bufs.append(dict(
+                h_img=torch.empty((n, H, W), dtype=torch.uint8).pin_memory(),
+                h_msk=torch.empty((n, H, W), dtype=torch.uint8).pin_memory(),
+                d_img=torch.empty((n, H, W), dtype=torch.uint8, device=dev),
+                d_msk=torch.empty((n, H, W), dtype=torch.uint8, device=dev),
+                d_out=torch.empty((n, F), dtype=torch.float64, device=dev),
+                d_st=torch.empty((n,), dtype=torch.int32, device=dev),
+                stream=torch.cuda.Stream(dev), done=torch.cuda.Event()))
+        self._key = key
+
+    def run(self, images, masks, out=None, status=None):
+        """``images``/``masks``: host arrays [B, H, W] uint8 (NumPy or CPU tensors; pinned tensors
+        skip the staging copy).  Returns host ``(features [B, F] float64, status [B] int32)``."""
+        images = torch.as_tensor(images)
+        masks = torch.as_tensor(masks)
+        if images.is_cuda:
+            raise ValueError("HostPipeline takes host buffers; use Engine.extract_device for device tensors")
+        B, H, W = images.shape
+        F = self.engine.F
+        self._ensure(H, W)
+        if out is None:
+            out = torch.empty((B, F), dtype=torch.float64).pin_memory()
+        if status is None:
+            status = torch.empty((B,), dtype=torch.int32).pin_memory()
+        pinned_in = images.is_pinned() and masks.is_pinned()
+        k = 0
+        for s in range(0, B, self.chunk):
+            n = min(self.chunk, B - s)
+            b = self._bufs[k % 2]
+            b["done"].synchronize()  # previous use of this slot has drained
+            with torch.cuda.stream(b["stream"]):
+                if pinned_in:
+                    b["d_img"][:n].copy_(images[s:s + n], non_blocking=True)
+                    b["d_msk"][:n].copy_(masks[s:s + n], non_blocking=True)
+                else:
+                    b["h_img"][:n].copy_(images[s:s + n])
+                    b["h_msk"][:n].copy_(masks[s:s + n])
+                    b["d_img"][:n].copy_(b["h_img"][:n], non_blocking=True)
+                    b["d_msk"][:n].copy_(b["h_msk"][:n], non_blocking=True)
+                self.engine.extract_device(b["d_img"][:n], b["d_msk"][:n], b["d_out"][:n], b["d_st"][:n],
+                                           stream=b["stream"])
+                out[s:s + n].copy_(b["d_out"][:n], non_blocking=True)
+                status[s:s + n].copy_(b["d_st"][:n], non_blocking=True)
+                b["done"].record(b["stream"])
+            k += 1
+        for b in self._bufs:
+            b["done"].synchronize()
+        return out, status

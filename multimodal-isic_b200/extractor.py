@@ -1,0 +1,157 @@
+"""Drop-in for ``/root/reference/RadiomicExtractor.py``: same class name, constructor argument
+and method names (including the ``parallell_extraction`` spelling), same per-record result
+(``{"grayscale","red","green","blue"}`` -> ordered mapping of pyradiomics feature names), so
+``/root/reference/extract_radiomics.py:48-71`` runs unchanged on top of it.  The arithmetic
+runs in the sm_100a CUDA engine (``csrc/``) through the C-ABI in ``include/radb.h``."""
+from __future__ import annotations
+
+import logging
+import time
+from collections import OrderedDict
+
+import numpy as np
+import torch
+
+from . import _abi
+from .engine import Engine, HostPipeline
+from .settings import Settings
+
+logger = logging.getLogger(__name__)
+
+CHANNELS = ("grayscale", "red", "green", "blue")
+
+
+def _status_error(code, label):
+    msg = _abi.STATUS_MESSAGES.get(int(code), "extraction failed (status %d)" % code)
+    if code == 1:
+        msg = msg % (label,)
+    elif code == 3:
+        msg = msg % (1, 2)
+    return ValueError(msg)
+
+
+class RadiomicsExtractor:
+    """``RadiomicsExtractor(param_file)`` -- mirrors ``RadiomicExtractor.py:12-94``.
+
+    ``param_file`` is the pyradiomics YAML path the reference passes (``'params.yml'``) or the
+    equivalent dict.  Extra keyword-only arguments are B200-side knobs: ``device`` (CUDA
+    ordinal), ``strict`` (raise instead of warn for enabled-but-unimplemented image types /
+    classes), ``chunk`` (patches per pipelined H2D chunk), ``max_ng``."""
+
+    def __init__(self, param_file, *, device=0, strict=False, chunk=16384, max_ng=0, **setting_overrides):
+        self.params = Settings(param_file, strict=strict, **setting_overrides)
+        self.device = int(device)
+        eng_classes, self._perm = self.params.engine_columns()
+        s = self.params.settings
+        self.engine = Engine(self.params.bin_width, self.params.label, self.params.angles(2),
+                             bool(s["symmetricalGLCM"]), float(s["gldm_a"]), float(s["voxelArrayShift"]),
+                             eng_classes, max_ng, self.device)
+        self.feature_names = self.params.feature_names()
+        self._perm_t = None
+        self._identity = self._perm == list(range(self.engine.F))
+        self.pipeline = HostPipeline(self.engine, chunk)
+
+    # ---- reference API -------------------------------------------------------------------
+    def get_enabled_image_types(self):  # RadiomicExtractor.py:17-18
+        return list(self.params.enabledImagetypes.keys())
+
+    def get_enabled_features(self):  # RadiomicExtractor.py:20-21
+        return list(self.params.enabledFeatures.keys())
+
+    @staticmethod
+    def _load_record(record):
+        """cv2 decode exactly as RadiomicExtractor.py:29-36 (host side)."""
+        import cv2
+
+        im = cv2.imread(record["image_path"], cv2.IMREAD_COLOR)
+        if im is None:
+            raise FileNotFoundError(record["image_path"])
+        gray = cv2.cvtColor(im, cv2.COLOR_BGR2GRAY)
+        sg = cv2.imread(record["segmentation_path"], cv2.IMREAD_GRAYSCALE)
+        if sg is None:
+            raise FileNotFoundError(record["segmentation_path"])
+        if im.shape[:2] != sg.shape[:2]:
+            sg = cv2.resize(sg, (im.shape[1], im.shape[0]), interpolation=cv2.INTER_NEAREST)
+        planes = np.stack([gray, im[:, :, 2], im[:, :, 1], im[:, :, 0]])  # gray, R, G, B
+        return np.ascontiguousarray(planes), np.ascontiguousarray(sg)
+
+    def extract_radiomics(self, list_of_dicts):  # RadiomicExtractor.py:23-55 (one record)
+        planes, sg = self._load_record(list_of_dicts)
+        masks = np.ascontiguousarray(np.broadcast_to(sg, planes.shape))
+        feats, status = self.extract_batch(planes, masks, strict=True)
+        return {ch: OrderedDict(zip(self.feature_names, feats[i].tolist())) for i, ch in enumerate(CHANNELS)}
+
+    def parallell_extraction(self, list_of_dicts, n_processes=None):  # RadiomicExtractor.py:58-71
+        """Order-preserving extraction of all records.  ``n_processes`` is accepted for
+        signature compatibility; the fan-out is over GPU CTAs, not host processes.  Records of
+        equal image size are batched into one launch."""
+        logger.info("Extraction mode: parallel")
+        t0 = time.time()
+        loaded = [self._load_record(r) for r in list_of_dicts]
+        results = [None] * len(loaded)
+        groups = {}
+        for i, (planes, _) in enumerate(loaded):
+            groups.setdefault(planes.shape[1:], []).append(i)
+        for shape, idxs in groups.items():
+            imgs = np.concatenate([loaded[i][0] for i in idxs])
+            msks = np.concatenate([np.broadcast_to(loaded[i][1], loaded[i][0].shape) for i in idxs])
+            feats, _ = self.extract_batch(imgs, np.ascontiguousarray(msks), strict=True)
+            for k, i in enumerate(idxs):
+                results[i] = {ch: OrderedDict(zip(self.feature_names, feats[4 * k + c].tolist()))
+                              for c, ch in enumerate(CHANNELS)}
+        h, m, s = self._convert_time(t0, time.time())
+        logger.info(f" Time taken: {h}h:{m}m:{s}s")
+        return results
+
+    def serial_extraction(self, list_of_dicts):  # RadiomicExtractor.py:74-85
+        logger.info("Extraction mode: serial")
+        t0 = time.time()
+        all_results = [self.extract_radiomics(r) for r in list_of_dicts]
+        h, m, s = self._convert_time(t0, time.time())
+        logger.info(f" Time taken: {h}h:{m}m:{s}s")
+        return all_results
+
+    def _convert_time(self, start_time, end_time):  # RadiomicExtractor.py:88-94
+        dt = end_time - start_time
+        return int(dt // 3600), int((dt % 3600) // 60), int(dt % 60)
+
+    # ---- batched entry points --------------------------------------------------------------
+    def _permute(self, out):
+        if self._identity:
+            return out
+        if self._perm_t is None or self._perm_t.device != out.device:
+            self._perm_t = torch.as_tensor(self._perm, device=out.device)
+        return out.index_select(1, self._perm_t)
+
+    def extract_batch(self, images, masks, strict=False):
+        """``images``/``masks`` ``[B, H, W]`` uint8.  CUDA tensors -> CUDA tensors
+        ``(features [B, F] float64, status [B] int32)``, asynchronous on the current stream;
+        host arrays -> NumPy arrays through the pinned, chunk-pipelined path.
+        ``strict=True`` raises the ValueError pyradiomics would raise for an invalid ROI
+        (the reference has no try/except, RadiomicExtractor.py:23-55); otherwise such rows are NaN."""
+        if isinstance(images, torch.Tensor) and images.is_cuda:
+            out, status = self.engine.extract_device(images, masks)
+            out = self._permute(out)
+            if strict:
+                bad = torch.nonzero(status)
+                if bad.numel():
+                    raise _status_error(int(status[bad[0, 0]]), self.params.label)
+            return out, status
+        out, status = self.pipeline.run(images, masks)
+        out = self._permute(out).numpy()
+        status = status.numpy()
+        if strict and status.any():
+            raise _status_error(int(status[np.nonzero(status)[0][0]]), self.params.label)
+        return out, status
+
+
+def features_to_dataframe(results, suffixes=("gs", "red", "green", "blue")):
+    """``extract_radiomics.py:54-71``: 4 per-channel frames concatenated on axis 1 with
+    ``_gs/_red/_green/_blue`` suffixes, as plain float64 columns."""
+    import pandas as pd
+
+    frames = [pd.DataFrame([item[ch] for item in results]) for ch in CHANNELS]
+    df = pd.concat(frames, axis=1)
+    n = len(df.columns) // 4
+    df.columns = [f"{col}_{sfx}" for col, sfx in zip(df.columns, sum(([s] * n for s in suffixes), []))]
+    return df.astype("float64")

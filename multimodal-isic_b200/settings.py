@@ -1,0 +1,169 @@
+"""Extraction settings: parse the pyradiomics parameter file the reference passes to
+``RadiomicsFeatureExtractor(param_file)`` (``/root/reference/RadiomicExtractor.py:15``,
+``/root/reference/params.yml``) or an equivalent dict, and resolve them into what the
+CUDA engine needs."""
+from __future__ import annotations
+
+import warnings
+from collections import OrderedDict
+
+import yaml
+
+from ._abi import CLASS_ORDER
+
+# pyradiomics defaults (featureextractor._getDefaultSettings / per-class kwargs.get defaults)
+DEFAULTS = OrderedDict(
+    minimumROIDimensions=2, minimumROISize=None, normalize=False, normalizeScale=1, removeOutliers=None,
+    resampledPixelSpacing=None, interpolator="sitkBSpline", preCrop=False, padDistance=5, distances=[1],
+    force2D=False, force2Ddimension=0, resegmentRange=None, label=1, additionalInfo=True,
+    binWidth=25, binCount=None, symmetricalGLCM=True, weightingNorm=None, gldm_a=0, voxelArrayShift=0,
+)
+
+FEATURE_NAMES = {
+    "firstorder": ["10Percentile", "90Percentile", "Energy", "Entropy", "InterquartileRange", "Kurtosis",
+                   "Maximum", "MeanAbsoluteDeviation", "Mean", "Median", "Minimum", "Range",
+                   "RobustMeanAbsoluteDeviation", "RootMeanSquared", "Skewness", "TotalEnergy", "Uniformity",
+                   "Variance"],
+    "glcm": ["Autocorrelation", "ClusterProminence", "ClusterShade", "ClusterTendency", "Contrast",
+             "Correlation", "DifferenceAverage", "DifferenceEntropy", "DifferenceVariance", "Id", "Idm", "Idmn",
+             "Idn", "Imc1", "Imc2", "InverseVariance", "JointAverage", "JointEnergy", "JointEntropy", "MCC",
+             "MaximumProbability", "SumAverage", "SumEntropy", "SumSquares"],
+    "gldm": ["DependenceEntropy", "DependenceNonUniformity", "DependenceNonUniformityNormalized",
+             "DependenceVariance", "GrayLevelNonUniformity", "GrayLevelVariance", "HighGrayLevelEmphasis",
+             "LargeDependenceEmphasis", "LargeDependenceHighGrayLevelEmphasis",
+             "LargeDependenceLowGrayLevelEmphasis", "LowGrayLevelEmphasis", "SmallDependenceEmphasis",
+             "SmallDependenceHighGrayLevelEmphasis", "SmallDependenceLowGrayLevelEmphasis"],
+    "glrlm": ["GrayLevelNonUniformity", "GrayLevelNonUniformityNormalized", "GrayLevelVariance",
+              "HighGrayLevelRunEmphasis", "LongRunEmphasis", "LongRunHighGrayLevelEmphasis",
+              "LongRunLowGrayLevelEmphasis", "LowGrayLevelRunEmphasis", "RunEntropy", "RunLengthNonUniformity",
+              "RunLengthNonUniformityNormalized", "RunPercentage", "RunVariance", "ShortRunEmphasis",
+              "ShortRunHighGrayLevelEmphasis", "ShortRunLowGrayLevelEmphasis"],
+    "glszm": ["GrayLevelNonUniformity", "GrayLevelNonUniformityNormalized", "GrayLevelVariance",
+              "HighGrayLevelZoneEmphasis", "LargeAreaEmphasis", "LargeAreaHighGrayLevelEmphasis",
+              "LargeAreaLowGrayLevelEmphasis", "LowGrayLevelZoneEmphasis", "SizeZoneNonUniformity",
+              "SizeZoneNonUniformityNormalized", "SmallAreaEmphasis", "SmallAreaHighGrayLevelEmphasis",
+              "SmallAreaLowGrayLevelEmphasis", "ZoneEntropy", "ZonePercentage", "ZoneVariance"],
+    "ngtdm": ["Busyness", "Coarseness", "Complexity", "Contrast", "Strength"],
+}
+SUPPORTED_CLASSES = set(CLASS_ORDER)
+SUPPORTED_IMAGE_TYPES = {"Original"}
+# settings whose non-default value would change results and that the engine does not implement
+_UNSUPPORTED_IF_SET = ("normalize", "removeOutliers", "resampledPixelSpacing", "resegmentRange", "weightingNorm",
+                       "binCount", "minimumROISize")
+
+
+def in_plane_angles(ndim=2, distances=(1,), force2D=False, force2Ddimension=0):
+    """pyradiomics ``cmatrices.c:build_angles`` for an ``ndim``-D array: the
+    unidirectional offsets, in the C generator's order.  For the reference's literal call --
+    a 2-D SimpleITK image (``RadiomicExtractor.py:31``) with ``force2D: True``
+    (``params.yml:100``, ``force2Ddimension`` 0) -- axis 0 is removed and a single along-row
+    offset remains; ``force2D: False`` on a 2-D image gives the 4 in-plane offsets."""
+    if list(distances) != [1]:
+        raise NotImplementedError("distances other than [1] are not implemented")
+    if ndim != 2:
+        raise NotImplementedError("only 2-D images (the reference's input) are implemented")
+    fd = force2Ddimension if force2D else -1
+    D, stride = 1, 3
+    n_all = 1
+    for d in range(ndim):
+        if d != fd:
+            n_all *= stride
+    n_all -= 1
+    out = []
+    for a_idx in range(n_all // 2):
+        a_off, ang = 1, []
+        for d in range(ndim):
+            if d == fd:
+                ang.append(0)
+            else:
+                ang.append(D - (a_idx // a_off) % stride)
+                a_off *= stride
+        out.append(tuple(ang))
+    return out
+
+
+class Settings:
+    """Resolved settings + enabled image types / feature classes (file order preserved)."""
+
+    def __init__(self, params=None, strict=False, **overrides):
+        if params is None:
+            params = {}
+        if isinstance(params, (str, bytes)) or hasattr(params, "__fspath__"):
+            with open(params) as fh:
+                params = yaml.safe_load(fh) or {}
+        if not isinstance(params, dict):
+            raise TypeError("param_file must be a path or a dict")
+        if not any(k in params for k in ("setting", "imageType", "featureClass")):
+            params = {"setting": dict(params)}  # a bare settings dict
+        self.settings = OrderedDict(DEFAULTS)
+        self.settings.update(params.get("setting") or {})
+        self.settings.update(overrides)
+        # pyradiomics: no imageType section -> Original only; no featureClass section -> all classes
+        image_types = params.get("imageType")
+        self.enabledImagetypes = OrderedDict((k, v or {}) for k, v in (image_types or {"Original": {}}).items())
+        feature_class = params.get("featureClass")
+        if feature_class is None:
+            feature_class = OrderedDict((c, []) for c in ("firstorder", "glcm", "gldm", "glrlm", "glszm", "ngtdm"))
+        self.enabledFeatures = OrderedDict((k, list(v) if v else []) for k, v in feature_class.items())
+        self.strict = strict
+        self._validate()
+
+    def _complain(self, msg):
+        if self.strict:
+            raise NotImplementedError(msg)
+        warnings.warn(msg, RuntimeWarning, stacklevel=4)
+
+    def _validate(self):
+        s = self.settings
+        for k in _UNSUPPORTED_IF_SET:
+            if s.get(k) not in (None, False):
+                raise NotImplementedError("setting %r=%r is not implemented by the B200 engine" % (k, s[k]))
+        if not float(s["binWidth"]) > 0:
+            raise ValueError("binWidth must be > 0")
+        skipped_types = [t for t in self.enabledImagetypes if t not in SUPPORTED_IMAGE_TYPES]
+        if skipped_types:
+            self._complain("image types %s are not implemented yet; only 'Original' features are computed"
+                           % skipped_types)
+        self.image_types = [t for t in self.enabledImagetypes if t in SUPPORTED_IMAGE_TYPES]
+        if not self.image_types:
+            raise NotImplementedError("no implemented image type is enabled (need 'Original')")
+        skipped_cls = [c for c in self.enabledFeatures if c not in SUPPORTED_CLASSES]
+        if skipped_cls:
+            self._complain("feature classes %s are not implemented yet and are skipped" % skipped_cls)
+        self.classes = [c for c in self.enabledFeatures if c in SUPPORTED_CLASSES]
+        if not self.classes:
+            raise ValueError("no implemented feature class is enabled")
+        for c in self.classes:
+            unknown = [f for f in self.enabledFeatures[c] if f not in FEATURE_NAMES[c]]
+            if unknown:
+                raise ValueError("unknown / deprecated features for class %s: %s" % (c, unknown))
+
+    # ---- resolved views
+    @property
+    def label(self):
+        return int(self.settings["label"])
+
+    @property
+    def bin_width(self):
+        return float(self.settings["binWidth"])
+
+    def angles(self, ndim=2):
+        s = self.settings
+        return in_plane_angles(ndim, s["distances"], bool(s["force2D"]), int(s["force2Ddimension"]))
+
+    def feature_names(self):
+        """Output keys in pyradiomics order: image type, then class (file order), then A.2 order."""
+        names = []
+        for c in self.classes:
+            sel = self.enabledFeatures[c]
+            for f in FEATURE_NAMES[c]:
+                if not sel or f in sel:
+                    names.append("original_%s_%s" % (c, f))
+        return names
+
+    def engine_columns(self):
+        """(engine class order, column permutation) mapping engine rows to ``feature_names()``."""
+        eng_classes = [c for c in CLASS_ORDER if c in self.classes]
+        eng_names = ["original_%s_%s" % (c, f) for c in eng_classes for f in FEATURE_NAMES[c]]
+        pos = {n: i for i, n in enumerate(eng_names)}
+        return eng_classes, [pos[n] for n in self.feature_names()]

@@ -1,0 +1,69 @@
+"""Patch-sharded multi-GPU driver (SURVEY.md section 8 e).  One process per GPU
+(``torch.distributed``); the patch list is split into contiguous cost-balanced shards, every
+rank runs the single-GPU engine on its shard, and the only collective is an all-gather of the
+``[rows, F]`` float64 feature block (NCCL over NVLink on GPUs; gloo in the CPU tests, where
+the per-rank compute is injected)."""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+
+def shard_bounds(costs, world):
+    """Contiguous shards with near-equal total cost.  ``costs``: per-patch cost estimate
+    (ROI pixel count or H*W).  Returns ``world + 1`` boundaries; deterministic on every rank."""
+    costs = np.asarray(costs, dtype=np.float64)
+    n = len(costs)
+    if n == 0:
+        return [0] * (world + 1)
+    cum = np.concatenate([[0.0], np.cumsum(np.maximum(costs, 1e-9))])
+    targets = cum[-1] * np.arange(1, world) / world
+    inner = np.searchsorted(cum, targets, side="left")
+    # pick the boundary (inner or inner-1) closest to the target
+    inner = np.where((inner > 0) & (np.abs(cum[np.maximum(inner - 1, 0)] - targets) < np.abs(cum[np.minimum(inner, n)] - targets)),
+                     inner - 1, inner)
+    b = [0] + [int(x) for x in np.clip(inner, 0, n)] + [n]
+    for i in range(1, len(b)):
+        b[i] = max(b[i], b[i - 1])
+    return b
+
+
+def all_gather_rows(local, rows_per_rank, group=None):
+    """All-gather of variable-length row blocks: pads to the longest shard, one
+    ``all_gather_into_tensor``, then trims.  ``local``: ``[rows_per_rank[rank], F]``."""
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    F = local.shape[1]
+    mx = int(max(rows_per_rank)) if len(rows_per_rank) else 0
+    pad = torch.zeros((mx, F), dtype=local.dtype, device=local.device)
+    pad[: local.shape[0]] = local
+    gathered = torch.empty((world * mx, F), dtype=local.dtype, device=local.device)
+    if world == 1:
+        gathered.copy_(pad)
+    elif local.is_cuda:
+        dist.all_gather_into_tensor(gathered, pad, group=group)
+    else:
+        parts = [torch.empty_like(pad) for _ in range(world)]
+        dist.all_gather(parts, pad, group=group)
+        gathered = torch.cat(parts)
+    assert rows_per_rank[rank] == local.shape[0]
+    return torch.cat([gathered[r * mx: r * mx + int(rows_per_rank[r])] for r in range(world)])
+
+
+def sharded_extract(extract_fn, n_patches, costs=None, group=None, F=None):
+    """Run ``extract_fn(lo, hi) -> (features [hi-lo, F], status [hi-lo])`` on this rank's shard and
+    all-gather to the full ``[n_patches, F]`` matrix (original order) on every rank."""
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    rank = dist.get_rank(group) if dist.is_initialized() else 0
+    if costs is None:
+        costs = np.ones(n_patches)
+    b = shard_bounds(costs, world)
+    lo, hi = b[rank], b[rank + 1]
+    feats, status = extract_fn(lo, hi)
+    if world == 1:
+        return feats, status, b
+    rows = [b[r + 1] - b[r] for r in range(world)]
+    full = all_gather_rows(feats, rows, group)
+    st = all_gather_rows(status.view(-1, 1).to(torch.int32), rows, group).view(-1)
+    return full, st, b

@@ -1,0 +1,62 @@
+// CPU emulation harness: runs the *device* code of multimodal-isic_b200/csrc/radb_kernels.cuh
+// thread-for-thread on host threads (tests/emu/cuda_emu.h).  TEST INFRASTRUCTURE ONLY -- used
+// by tests/ (marker: not gpu) to check kernel logic against the oracle without a GPU.
+// Not part of the product; the product library has no CPU path.
+#include "cuda_emu.h"
+#include <string.h>
+#include <string>
+#include "../../multimodal-isic_b200/csrc/radb_host.h"
+#include "../../multimodal-isic_b200/csrc/radb_kernels.cuh"
+
+static std::string g_err;
+
+extern "C" const char* radb_emu_last_error() { return g_err.c_str(); }
+
+extern "C" int radb_emu_feature_count(const radb_settings* s)
+{
+    radb::Plan pl;
+    if (radb::make_plan(*s, pl, g_err)) return -1;
+    return pl.F;
+}
+extern "C" int radb_emu_max_ng(const radb_settings* s)
+{
+    radb::Plan pl;
+    if (radb::make_plan(*s, pl, g_err)) return -1;
+    return pl.max_ng;
+}
+
+// Host-pointer twin of radb_debug_matrices.
+extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dtype, const uint8_t* mask, int64_t B,
+                                int H, int W, int64_t img_stride_b, int64_t mask_stride_b, double* out,
+                                int32_t* status, int32_t* levels, int32_t* glcm, int32_t* glrlm, int32_t* glszm,
+                                int32_t* gldm, int32_t* ngtdm_n, double* ngtdm_s, int32_t* ng)
+{
+    radb::Plan pl;
+    int rc = radb::make_plan(*s, pl, g_err);
+    if (rc) return rc;
+    RadbParams p;
+    rc = radb::fill_params(pl, H, W, dtype, p, g_err);
+    if (rc) return rc;
+    p.img = img;
+    p.mask = mask;
+    p.img_stride = img_stride_b;
+    p.mask_stride = mask_stride_b;
+    p.out = out;
+    p.status = status;
+    p.B = B;
+    p.dbg_levels = levels;
+    p.dbg_glcm = glcm;
+    p.dbg_glrlm = glrlm;
+    p.dbg_glszm = glszm;
+    p.dbg_gldm = gldm;
+    p.dbg_ngn = ngtdm_n;
+    p.dbg_ngs = ngtdm_s;
+    p.dbg_ng = ng;
+    std::vector<unsigned char> smem((size_t)p.smem_total + 64);
+    unsigned char* sm = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
+    emu::launch((unsigned)B, RADB_NT, [&]() {
+        // poison the shared memory like a fresh CTA would find it (stale data from the last CTA)
+        radb_cta<unsigned char>(p, (long long)blockIdx.x, sm);
+    });
+    return 0;
+}

@@ -1,0 +1,103 @@
+"""Runs the emulated kernel (tests/emu) and compares any engine result with the oracle.
+Shared by the CPU (emulation) and GPU parity tests so that both read the same way."""
+from __future__ import annotations
+
+import ctypes
+
+import numpy as np
+
+from multimodal_isic_b200 import _abi
+from oracle import cmatrices, radiomics_oracle as orc
+
+
+class EmuRunner:
+    def __init__(self, so_path):
+        self.lib = ctypes.CDLL(so_path)
+        vp, i32, i64 = ctypes.c_void_p, ctypes.c_int, ctypes.c_int64
+        self.lib.radb_emu_extract.argtypes = [vp, vp, i32, vp, i64, i32, i32, i64, i64] + [vp] * 10
+        self.lib.radb_emu_last_error.restype = ctypes.c_char_p
+
+    def run(self, imgs, masks, bin_width=10, label=255, angles=((0, 1),), symmetrical=True, alpha=0):
+        imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+        masks = np.ascontiguousarray(masks, dtype=np.uint8)
+        B, H, W = imgs.shape
+        s = _abi.make_settings(bin_width, label, angles, symmetrical, alpha)
+        F = self.lib.radb_emu_feature_count(ctypes.byref(s))
+        ng = self.lib.radb_emu_max_ng(ctypes.byref(s))
+        assert F > 0 and ng > 0, self.lib.radb_emu_last_error()
+        na, nr = len(angles), max(H, W)
+        r = dict(features=np.zeros((B, F)), status=np.zeros(B, np.int32), levels=np.zeros((B, H, W), np.int32),
+                 glcm=np.zeros((B, na, ng, ng), np.int32), glrlm=np.zeros((B, na, ng, nr), np.int32),
+                 glszm=np.zeros((B, ng, H * W), np.int32), gldm=np.zeros((B, ng, 2 * na + 1), np.int32),
+                 ngtdm_n=np.zeros((B, ng), np.int32), ngtdm_s=np.zeros((B, ng)), ng=np.zeros(B, np.int32))
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        rc = self.lib.radb_emu_extract(ctypes.byref(s), p(imgs), 0, p(masks), B, H, W, H * W, H * W,
+                                       *[p(r[k]) for k in ("features", "status", "levels", "glcm", "glrlm", "glszm",
+                                                           "gldm", "ngtdm_n", "ngtdm_s", "ng")])
+        assert rc == 0, self.lib.radb_emu_last_error()
+        return r
+
+
+RTOL, ATOL = 1e-6, 1e-9  # BASELINE.json north_star: every floating-point feature
+
+
+def compare_with_oracle(r, imgs, masks, settings, check_matrices=True):
+    """Bit-exact discretised image + integer matrices, features within rtol 1e-6 / atol 1e-9.
+    ``r``: dict from EmuRunner.run or Engine.debug_matrices.  Returns the number of valid patches."""
+    s = orc.resolve_settings(settings)
+    names = orc.feature_names()
+    nvalid = 0
+    for b in range(len(imgs)):
+        try:
+            m = orc.matrices(imgs[b], masks[b], s, matrix_backend=cmatrices)
+        except ValueError as e:
+            msg = str(e)
+            want = 1 if "not present" in msg else 2 if "1 segmented voxel" in msg else 3
+            assert r["status"][b] == want, (b, msg, r["status"][b])
+            assert np.isnan(r["features"][b]).all()
+            continue
+        nvalid += 1
+        assert r["status"][b] == 0, (b, r["status"][b])
+        Ng = m["Ng"]
+        if check_matrices:
+            assert r["ng"][b] == Ng
+            np.testing.assert_array_equal(r["levels"][b], m["levels"])
+            np.testing.assert_array_equal(r["glcm"][b][:, :Ng, :Ng].transpose(1, 2, 0), m["glcm"])
+            assert r["glcm"][b].sum() == m["glcm"].sum()
+            np.testing.assert_array_equal(r["glrlm"][b][:, :Ng, :].transpose(1, 2, 0), m["glrlm"])
+            Ns = m["glszm"].shape[1]
+            np.testing.assert_array_equal(r["glszm"][b][:Ng, :Ns], m["glszm"])
+            assert r["glszm"][b].sum() == m["glszm"].sum()
+            np.testing.assert_array_equal(r["gldm"][b][:Ng], m["gldm"])
+            np.testing.assert_array_equal(r["ngtdm_n"][b][:Ng], m["ngtdm_n"])
+            np.testing.assert_allclose(r["ngtdm_s"][b][:Ng], m["ngtdm_s"], rtol=1e-12, atol=1e-12)
+        f = orc.execute(imgs[b], masks[b], s, matrix_backend=cmatrices)
+        ref = np.array([f[k] for k in names])
+        got = r["features"][b]
+        bad = [(k, a, g) for k, a, g in zip(names, ref, got) if not np.isclose(g, a, rtol=RTOL, atol=ATOL, equal_nan=True)]
+        assert not bad, (b, bad[:5])
+    return nvalid
+
+
+def edge_case_batch(H=16, W=12, seed=3):
+    """Edge cases the reference's engine distinguishes: absent label, single voxel, 1-D ROI,
+    flat ROI, full-patch ROI, two-level checkerboard, ROI touching every border, sparse ROI."""
+    rng = np.random.default_rng(seed)
+    n = 9
+    imgs = rng.integers(0, 256, (n, H, W)).astype(np.uint8)
+    masks = np.zeros((n, H, W), np.uint8)
+    masks[0] = 0                                   # label absent
+    masks[1, H // 2, W // 2] = 255                 # single voxel
+    masks[2, 3, 2:W - 2] = 255                     # one row: too few dimensions
+    masks[3, 2:H - 2, 2:W - 2] = 255
+    imgs[3] = 130                                  # flat ROI (one gray level)
+    masks[4] = 255                                 # whole patch
+    yy, xx = np.mgrid[:H, :W]
+    imgs[5] = np.where((yy + xx) % 2 == 0, 40, 200)
+    masks[5, 1:H - 1, 1:W - 1] = 255               # checkerboard: lambda = -1 in the GLCM spectrum
+    masks[6] = 255
+    masks[6, 4:8, 3:7] = 0                         # hole + touches every border
+    masks[7] = np.where(rng.random((H, W)) < 0.15, 255, 0)  # sparse, many isolated voxels
+    masks[8, 0:2, 0:2] = 255                       # 2x2 ROI in a corner
+    masks[7, 0, 0] = 128                           # other labels are not ROI
+    return imgs, masks

@@ -1,0 +1,126 @@
+"""Host logic + the C-ABI library surface (no compute calls: no GPU needed)."""
+import ctypes
+import os
+import re
+import warnings
+
+import numpy as np
+import pytest
+import torch
+import yaml
+
+import multimodal_isic_b200 as pkg
+from multimodal_isic_b200 import _abi
+from oracle import radiomics_oracle as orc
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+REFERENCE_LIKE_PARAMS = """
+setting:
+  additionalInfo: False
+  label: 255
+  binWidth: 10
+  force2D: True
+  symmetricalGLCM: True
+imageType:
+  Original: {}
+  Wavelet: {}
+  LoG:
+    sigma: [1.0, 2.0, 3.0]
+featureClass:
+  firstorder: []
+  shape2D: []
+  glcm: []
+  gldm: []
+  glrlm: []
+  glszm: []
+  ngtdm: []
+"""
+
+
+def test_library_exports_every_declared_symbol(built):
+    built.build_cuda()
+    header = open(os.path.join(ROOT, "include", "radb.h")).read()
+    declared = set(re.findall(r"\b(radb_[a-z_]+)\s*\(", header))
+    assert declared == set(pkg.EXPORTED_SYMBOLS)
+    lib = ctypes.CDLL(pkg.LIB_PATH)
+    for sym in declared:
+        assert hasattr(lib, sym), sym
+    lib.radb_version.restype = ctypes.c_char_p
+    assert b"sm_100a" in lib.radb_version()
+
+
+def test_settings_struct_layout_matches_header():
+    # field order/types of radb_settings in include/radb.h <-> ctypes mirror
+    header = open(os.path.join(ROOT, "include", "radb.h")).read()
+    body = re.search(r"typedef struct radb_settings \{(.*?)\} radb_settings;", header, re.S).group(1)
+    body = re.sub(r"/\*.*?\*/", "", body, flags=re.S)
+    fields = re.findall(r"\b(?:double|int32_t|uint32_t|int8_t)\s+([a-z_]+)", body)
+    assert fields == [f[0] for f in _abi.RadbSettings._fields_]
+    assert ctypes.sizeof(_abi.RadbSettings) == 72  # static_assert in csrc/radb_host.h
+
+
+def test_no_cpu_fallback_without_gpu():
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    with pytest.raises(pkg.RadbError, match="no CPU fallback"):
+        pkg.RadiomicsExtractor({"setting": {"label": 255}})
+    with pytest.raises(RuntimeError, match="missing"):
+        _abi.load_library("/nonexistent/libradb_b200.so")
+
+
+def test_settings_reference_like_file(tmp_path):
+    f = tmp_path / "params.yml"
+    f.write_text(REFERENCE_LIKE_PARAMS)
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        s = pkg.Settings(str(f))
+    assert any("Wavelet" in str(x.message) for x in w) and any("shape2D" in str(x.message) for x in w)
+    assert s.label == 255 and s.bin_width == 10.0
+    assert s.angles() == orc.angles(2, force2D=True)[0] == [(0, 1)]          # literal force2D on 2-D input
+    assert list(s.enabledImagetypes) == ["Original", "Wavelet", "LoG"]
+    assert list(s.enabledFeatures) == ["firstorder", "shape2D", "glcm", "gldm", "glrlm", "glszm", "ngtdm"]
+    assert s.feature_names() == orc.feature_names()
+    with pytest.raises(NotImplementedError):
+        pkg.Settings(str(f), strict=True)
+
+
+def test_settings_class_order_and_feature_subset():
+    s = pkg.Settings({"setting": {"label": 1}, "featureClass": {"glcm": ["Contrast", "Idm"], "firstorder": None}})
+    assert s.feature_names()[:2] == ["original_glcm_Contrast", "original_glcm_Idm"]
+    eng_classes, perm = s.engine_columns()
+    assert eng_classes == ["firstorder", "glcm"]
+    eng = ["original_%s_%s" % (c, f) for c in eng_classes for f in pkg.FEATURE_NAMES[c]]
+    assert [eng[i] for i in perm] == s.feature_names()
+    assert pkg.Settings({"binWidth": 25, "force2D": False}).angles() == orc.angles(2)[0]
+    with pytest.raises(ValueError):
+        pkg.Settings({"featureClass": {"glcm": ["Homogeneity1"]}})
+    with pytest.raises(NotImplementedError):
+        pkg.Settings({"setting": {"binCount": 16}})
+
+
+def test_feature_name_tables_agree():
+    assert pkg.FEATURE_NAMES == {k: v for k, v in orc.FEATURE_NAMES.items()}
+
+
+def test_shard_bounds():
+    assert pkg.shard_bounds([1] * 8, 4) == [0, 2, 4, 6, 8]
+    b = pkg.shard_bounds([100, 1, 1, 1, 1, 100], 2)
+    assert b[0] == 0 and b[-1] == 6 and 1 <= b[1] <= 5
+    assert pkg.shard_bounds([], 3) == [0, 0, 0, 0]
+    rng = np.random.default_rng(0)
+    c = rng.uniform(1, 50, 1000)
+    b = pkg.shard_bounds(c, 8)
+    loads = [c[b[i]:b[i + 1]].sum() for i in range(8)]
+    assert max(loads) / (sum(loads) / 8) < 1.05
+
+
+def test_dataframe_contract():
+    # extract_radiomics.py:54-71 + reduce_dim.py:88,97-100
+    names = orc.feature_names()
+    rec = {ch: dict(zip(names, np.arange(len(names), dtype=float))) for ch in ("grayscale", "red", "green", "blue")}
+    df = pkg.features_to_dataframe([rec, rec, rec])
+    assert df.shape == (3, 4 * 93) and len(df.columns) % 4 == 0
+    assert df.columns[0] == names[0] + "_gs" and df.columns[93] == names[0] + "_red"
+    assert df.columns[-1] == names[-1] + "_blue"
+    assert all(str(t) == "float64" for t in df.dtypes)
