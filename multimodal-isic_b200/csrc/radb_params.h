@@ -37,7 +37,8 @@ struct RadbParams {
     // shared-memory byte offsets
     int o_stage, o_mask, o_mbar, o_zero, o_lev, o_zsize, o_hist, o_lut, o_lhist, o_glcm, o_px, o_py,
         o_padd, o_psub, o_glrlm, o_pr, o_gldm, o_ngc, o_ngn, o_szm, o_ovf, o_mcc, o_idx, o_fsc, o_misc,
-        o_ngp, o_qv, o_pg, smem_total;
+        o_ngp, o_qv, o_pg, o_ovf2, o_inv2, o_clog, smem_total;
+    int ninv;        // entries of the 1/k^2 table
     int mcc_stride;  // doubles per angle in the MCC workspace
     // optional debug outputs (device pointers, may be null); dims use max_ng
     int* dbg_levels;   // [B][H][W]
@@ -87,6 +88,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->o_ngn = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] sum |cnt*i - sum(neigh)|
     p->o_szm = o; o += radb_align(ng * p->s0 * 4, 16);
     p->o_ovf = o; o += radb_align(p->ovf_cap * 4, 16);
+    p->o_ovf2 = o; o += radb_align(p->ovf_cap * 4, 16);  // overflow zones sorted by key
     p->mcc_stride = ng * (ng + 1) / 2 + 4 * ng;
     p->o_mcc = o; o += radb_align(na * p->mcc_stride * 8, 16);
     p->o_idx = o; o += radb_align(na * ng, 16);
@@ -94,6 +96,10 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->o_ngp = o; o += radb_align(2 * ng * 8, 16);
     p->o_qv = o; o += 16 * 8;
     p->o_pg = o; o += radb_align(ng * 4, 16);
+    p->ninv = ng > p->nr ? ng : p->nr;
+    if (p->ninv < 16) p->ninv = 16;
+    p->o_inv2 = o; o += radb_align(p->ninv * 8, 16);
+    p->o_clog = o; o += 128 * 8;
     p->o_misc = o; o += 32 * 4;
     p->smem_total = o;
 }

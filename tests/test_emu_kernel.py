@@ -57,3 +57,26 @@ def test_emu_golden_fixture(emu):
     z = np.load(os.path.join(GOLD, "oracle_features_seed0.npz"))
     r = emu.run(z["images"][:2], z["masks"][:2], 10, 255, INPLANE)
     np.testing.assert_allclose(r["features"], z["inplane_bw10"][:2], rtol=1e-6, atol=1e-9)
+
+
+def test_emu_force2d_dimension1_column_only(emu):
+    # force2Ddimension=1 removes axis 1: the only offset is (1, 0); zones are column runs
+    imgs, masks = synth.make_patches(2, 24, 20, seed=3)
+    ang = orc.angles(2, force2D=True, force2Ddimension=1)[0]
+    assert ang == [(1, 0)]
+    r = emu.run(imgs, masks, 10, 255, ang)
+    s = dict(label=255, binWidth=10, force2D=True, force2Ddimension=1)
+    assert compare_with_oracle(r, imgs, masks, s) == 2
+
+
+def test_emu_bitwise_reproducible(emu):
+    # thread interleaving differs between runs; the output must not (integer atomics only,
+    # rank-sorted overflow list, fixed reduction trees)
+    H = W = 40
+    yy, xx = np.mgrid[:H, :W]
+    img = np.clip(100 + 40 * np.sin(xx / 9.0) + 30 * np.cos(yy / 7.0), 0, 255).astype(np.uint8)[None]
+    mask = np.full((1, H, W), 255, np.uint8)
+    a = emu.run(img, mask, 10, 255, INPLANE)["features"]
+    for _ in range(3):
+        b = emu.run(img, mask, 10, 255, INPLANE)["features"]
+        assert a.tobytes() == b.tobytes()

@@ -68,6 +68,14 @@ def test_ragged_sizes(gpu_pkg, hw):
     compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=False))
 
 
+def test_force2d_dimension1_column_only(gpu_pkg):
+    imgs, masks = gpu_pkg.synth.make_patches(6, 48, 40, seed=3)
+    ang = orc.angles(2, force2D=True, force2Ddimension=1)[0]
+    r = _dbg(_engine(gpu_pkg, 10, ang), imgs, masks)
+    s = dict(label=255, binWidth=10, force2D=True, force2Ddimension=1)
+    assert compare_with_oracle(r, imgs, masks, s) == 6
+
+
 def test_random_noise_many_levels(gpu_pkg):
     rng = np.random.default_rng(7)
     imgs = rng.integers(0, 256, (6, 40, 40)).astype(np.uint8)
