@@ -67,7 +67,7 @@ def load_library(path=None):
     global _lib
     if _lib is not None and path is None:
         return _lib
-    path = path or LIB_PATH
+    path = path or os.environ.get("RADB_LIB") or LIB_PATH  # RADB_LIB: A/B builds of the same CUDA library
     if not os.path.exists(path):
         raise RuntimeError(
             "radb: CUDA library %s is missing -- build it with `python -c 'import __graft_entry__ as g; "

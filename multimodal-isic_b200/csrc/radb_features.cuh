@@ -102,13 +102,13 @@ __device__ void fo_task_u8(const RadbParams& p, const int* hist, const int* lhis
         in_n += in ? h[k] : 0;
         in_s1 += in ? hk * v : 0.0;
     }
-    m2 = warp_sum(m2) / dN;
-    m3 = warp_sum(m3) / dN;
-    m4 = warp_sum(m4) / dN;
-    mad = warp_sum(mad) / dN;
-    en = warp_sum(en);
+    {
+        double r[6] = {m2, m3, m4, mad, en, in_s1};
+        warp_sum_n(r);
+        m2 = r[0] / dN; m3 = r[1] / dN; m4 = r[2] / dN; mad = r[3] / dN; en = r[4]; in_s1 = r[5];
+    }
     const int inN = warp_sum_i(in_n);
-    const double in_mean = warp_sum(in_s1) / (double)inN;
+    const double in_mean = in_s1 / (double)inN;
     double rmad = 0;
 #pragma unroll
     for (int k = 0; k < 8; k++) {
@@ -181,7 +181,7 @@ __device__ __forceinline__ int sturm_count(const double* d, const double* e2, in
 __device__ double tridiag_kth(const double* d, const double* e2, int m, int k, double lo, double hi,
                               int lane)
 {
-    for (int it = 0; it < 10; it++) {
+    for (int it = 0; it < 8; it++) {
         double w = (hi - lo) * (1.0 / 33.0);
         double x = lo + w * (double)(lane + 1);
         int c = sturm_count(d, e2, m, x);
@@ -192,7 +192,7 @@ __device__ double tridiag_kth(const double* d, const double* e2, int m, int k, d
         double nhi = (nl == 32) ? hi : lo + w * (double)(nl + 1);
         lo = nlo;
         hi = nhi;
-        if (hi - lo <= 1e-13) break;  // eigenvalues live in [-1, 1]; features need rtol 1e-6
+        if (hi - lo <= 2e-11) break;  // eigenvalues live in [-1, 1]; the feature needs rtol 1e-6
     }
     return 0.5 * (lo + hi);
 }
@@ -262,7 +262,10 @@ __device__ double mcc_task(const int* P, const int* px, const int* py, int n, in
         double kpart = 0;
         for (int r = k + 1 + lane; r < m; r += 32) {
             double s = 0;
-            for (int c = k + 1; c < m; c++) s += sym_get(M, r, c) * v[c];
+            const int rb = tri(r, 0);
+            for (int c = k + 1; c <= r; c++) s += M[rb + c] * v[c];
+            int ix = tri(r + 1, r);
+            for (int c = r + 1; c < m; c++) { s += M[ix] * v[c]; ix += c + 1; }
             s *= beta;
             w[r] = s;
             kpart += s * v[r];
@@ -273,8 +276,9 @@ __device__ double mcc_task(const int* P, const int* px, const int* py, int n, in
         __syncwarp();
         // M22 -= v w^T + w v^T (lower triangle)
         for (int r = k + 1 + lane; r < m; r += 32) {
-            double vr = v[r], wr = w[r];
-            for (int c = k + 1; c <= r; c++) M[tri(r, c)] -= vr * w[c] + wr * v[c];
+            const double vr = v[r], wr = w[r];
+            const int rb = tri(r, 0);
+            for (int c = k + 1; c <= r; c++) M[rb + c] -= vr * w[c] + wr * v[c];
         }
         __syncwarp();
         if (lane == 0) { d[k] = M[tri(k, k)]; e2[k] = alpha * alpha; }
@@ -304,8 +308,11 @@ __device__ double mcc_task(const int* P, const int* px, const int* py, int n, in
     ghi += 1e-12 * (span + 1.0);
     double l2 = tridiag_kth(d, e2, m, m - 2, glo, ghi, lane);
     if (symmetric) {
-        double l1 = tridiag_kth(d, e2, m, 0, glo, ghi, lane);
-        return fmax(fabs(l2), fabs(l1));
+        // second largest |lambda(A)|: lambda_min matters only if it lies below -|lambda_2|
+        const double t = fabs(l2);
+        if (sturm_count(d, e2, m, -t * (1.0 + 1e-9) - 1e-12) == 0) return t;
+        const double l1 = tridiag_kth(d, e2, m, 0, glo, ghi, lane);
+        return fmax(t, fabs(l1));
     }
     return sqrt(fmax(l2, 0.0));
 }
@@ -347,11 +354,13 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
     __syncwarp();
     if (sN == 0) return 0;
     const double N = (double)sN, rN = 1.0 / N;
-    const double ux = (double)warp_sum_ll(sI) * rN;
-    const double uy = (double)warp_sum_ll(sJ) * rN;
-    const double autoc = (double)warp_sum_ll(sIJ) * rN;
-    const double contrast = (double)warp_sum_ll(sD2) * rN;
-    const double energy = (double)warp_sum_ll(sC2) * rN * rN;
+    double r0[5] = {(double)sI, (double)sJ, (double)sIJ, (double)sD2, (double)sC2};  // exact integers < 2^53
+    warp_sum_n(r0);
+    const double ux = r0[0] * rN;
+    const double uy = r0[1] * rN;
+    const double autoc = r0[2] * rN;
+    const double contrast = r0[3] * rN;
+    const double energy = r0[4] * rN * rN;
     const double maxp = (double)warp_max_i(maxc) * rN;
     const double log2N = log2(N);
     nnz = warp_sum_i(nnz);
@@ -378,10 +387,11 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
         }
     }
     __syncwarp();
-    hx = warp_sum(hx);
-    hy = warp_sum(hy);
-    hx0 = warp_sum(hx0);
-    hy0 = warp_sum(hy0);
+    {
+        double r1[4] = {hx, hy, hx0, hy0};
+        warp_sum_n(r1);
+        hx = r1[0]; hy = r1[1]; hx0 = r1[2]; hy0 = r1[3];
+    }
     nx = warp_sum_i(nx);
     ny = warp_sum_i(ny);
     // pass B: cluster moments and correlation terms
@@ -407,14 +417,12 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
             sclog += dc * (tab_log2(tb, c) - log2N);
         }
     }
-    ct = warp_sum(ct);
-    cs = warp_sum(cs);
-    cp = warp_sum(cp);
-    ssq = warp_sum(ssq);
-    ssqy = warp_sum(ssqy);
-    corm = warp_sum(corm);
-    h1corr = warp_sum(h1corr);
-    const double hxy = -warp_sum(sclog) * rN - RADB_EPS_LN2 * (double)nnz;
+    {
+        double r2[8] = {ct, cs, cp, ssq, ssqy, corm, h1corr, sclog};
+        warp_sum_n(r2);
+        ct = r2[0]; cs = r2[1]; cp = r2[2]; ssq = r2[3]; ssqy = r2[4]; corm = r2[5]; h1corr = r2[6]; sclog = r2[7];
+    }
+    const double hxy = -sclog * rN - RADB_EPS_LN2 * (double)nnz;
     // log2(px*py + eps) = log2 px + log2 py + eps/(px*py*ln2) + O(eps^2): HXY1/HXY2 in closed form
     const double hxy1 = hx0 + hy0 - RADB_EPS_LN2 * h1corr;
     const double hxy2 = hx0 + hy0 - RADB_EPS_LN2 * (double)nx * (double)ny;
@@ -432,17 +440,6 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
         idn += q / (1.0 + dk / dn);
         if (k > 0) iv += q * tab_inv2(tb, k);
     }
-    da = warp_sum(da);
-    de = warp_sum(de);
-    idv = warp_sum(idv);
-    idm = warp_sum(idm);
-    idmn = warp_sum(idmn);
-    idn = warp_sum(idn);
-    iv = warp_sum(iv);
-    double dvar = 0;
-    for (int k = lane; k < n; k += 32)
-        if (psub[k]) dvar += (double)psub[k] * rN * ((double)k - da) * ((double)k - da);
-    dvar = warp_sum(dvar);
     // i+j marginal (index k <-> i+j = k+2)
     double sa = 0, se = 0;
     for (int k = lane; k < 2 * n - 1; k += 32) {
@@ -451,8 +448,15 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
         sa += (double)(k + 2) * q;
         se -= q * log2(q + RADB_EPS);
     }
-    sa = warp_sum(sa);
-    se = warp_sum(se);
+    {
+        double r3[9] = {da, de, idv, idm, idmn, idn, iv, sa, se};
+        warp_sum_n(r3);
+        da = r3[0]; de = r3[1]; idv = r3[2]; idm = r3[3]; idmn = r3[4]; idn = r3[5]; iv = r3[6]; sa = r3[7]; se = r3[8];
+    }
+    double dvar = 0;
+    for (int k = lane; k < n; k += 32)
+        if (psub[k]) dvar += (double)psub[k] * rN * ((double)k - da) * ((double)k - da);
+    dvar = warp_sum(dvar);
     __syncwarp();
     const double mcc = mcc_task(P, px, py, n, p.symmetric, ws, idx, lane);
     if (lane == 0) {
@@ -524,15 +528,12 @@ __device__ int glrlm_task(const RadbTabs& tb, const unsigned* R, int cell0, int 
     sN = warp_sum_ll(sN);
     __syncwarp();
     if (sN == 0) return 0;
-    sGI = warp_sum_ll(sGI);
-    sGI2 = warp_sum_ll(sGI2);
-    sG2 = warp_sum_ll(sG2);
-    lgl = warp_sum(lgl);
-    e1 = warp_sum(e1);
-    srl = warp_sum(srl);
-    srh = warp_sum(srh);
-    lrl = warp_sum(lrl);
-    lrh = warp_sum(lrh);
+    {
+        double r0[9] = {(double)sGI, (double)sGI2, (double)sG2, lgl, e1, srl, srh, lrl, lrh};  // first three: exact
+        warp_sum_n(r0);
+        sGI = (long long)r0[0]; sGI2 = (long long)r0[1]; sG2 = (long long)r0[2];
+        lgl = r0[3]; e1 = r0[4]; srl = r0[5]; srh = r0[6]; lrl = r0[7]; lrh = r0[8];
+    }
     nnz = warp_sum_i(nnz);
     long long sRJ = 0, sRJ2 = 0, sR2 = 0;
     double sre = 0;
@@ -544,10 +545,11 @@ __device__ int glrlm_task(const RadbTabs& tb, const unsigned* R, int cell0, int 
         sR2 += (long long)c * c;
         sre += (double)c * tab_inv2(tb, j + 1);
     }
-    sRJ = warp_sum_ll(sRJ);
-    sRJ2 = warp_sum_ll(sRJ2);
-    sR2 = warp_sum_ll(sR2);
-    sre = warp_sum(sre);
+    {
+        double r1[4] = {(double)sRJ, (double)sRJ2, (double)sR2, sre};
+        warp_sum_n(r1);
+        sRJ = (long long)r1[0]; sRJ2 = (long long)r1[1]; sR2 = (long long)r1[2]; sre = r1[3];
+    }
     if (lane == 0) {
         const double N = (double)sN, rN = 1.0 / N;
         o[0] = (double)sG2 * rN;
@@ -607,20 +609,12 @@ __device__ __forceinline__ void zs_level(ZoneSums& z, const RadbTabs& tb, int i,
 }
 __device__ __forceinline__ void zs_reduce(ZoneSums& z)
 {
-    z.N = warp_sum_ll(z.N);
-    z.GI = warp_sum_ll(z.GI);
-    z.GI2 = warp_sum_ll(z.GI2);
-    z.G2 = warp_sum_ll(z.G2);
-    z.J1 = warp_sum_ll(z.J1);
-    z.J2 = warp_sum_ll(z.J2);
-    z.PJ2 = warp_sum_ll(z.PJ2);
-    z.lgl = warp_sum(z.lgl);
-    z.e1 = warp_sum(z.e1);
-    z.small = warp_sum(z.small);
-    z.sl = warp_sum(z.sl);
-    z.sh = warp_sum(z.sh);
-    z.ll = warp_sum(z.ll);
-    z.lh = warp_sum(z.lh);
+    double r[14] = {(double)z.N, (double)z.GI, (double)z.GI2, (double)z.G2, (double)z.J1, (double)z.J2,
+                    (double)z.PJ2, z.lgl, z.e1, z.small, z.sl, z.sh, z.ll, z.lh};  // first seven: exact integers
+    warp_sum_n(r);
+    z.N = (long long)r[0]; z.GI = (long long)r[1]; z.GI2 = (long long)r[2]; z.G2 = (long long)r[3];
+    z.J1 = (long long)r[4]; z.J2 = (long long)r[5]; z.PJ2 = (long long)r[6];
+    z.lgl = r[7]; z.e1 = r[8]; z.small = r[9]; z.sl = r[10]; z.sh = r[11]; z.ll = r[12]; z.lh = r[13];
     z.nnz = warp_sum_i(z.nnz);
 }
 

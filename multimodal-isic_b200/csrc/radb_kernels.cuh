@@ -36,6 +36,24 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 #endif
 }
+// N independent butterflies interleaved: same instruction count as N warp_sum calls, but the
+// shuffle latencies overlap (the feature reductions are latency-bound).
+template <int N>
+__device__ __forceinline__ void warp_sum_n(double (&v)[N])
+{
+#ifdef RADB_EMU
+    for (int i = 0; i < N; i++) v[i] = warp_sum(v[i]);
+#else
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        double t[N];
+#pragma unroll
+        for (int i = 0; i < N; i++) t[i] = __shfl_xor_sync(FULLMASK, v[i], m);
+#pragma unroll
+        for (int i = 0; i < N; i++) v[i] += t[i];
+    }
+#endif
+}
 __device__ __forceinline__ long long warp_sum_ll(long long v)
 {
 #ifdef RADB_EMU
@@ -136,23 +154,38 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity)
 }
 #endif
 
-// ------------------------------------------------------------------ union-find on u16 labels
-__device__ __forceinline__ unsigned uf_find(volatile unsigned short* L, unsigned x)
+// ------------------------------------------------------------------ union-find over row runs
+// One 32-bit word per pixel: low 16 bits = parent pixel index, high 16 bits = size.  During the
+// union pass the high half of a run start holds its run length (static); after it, the run
+// lengths are folded into the zone root with one native 32-bit shared atomic per run.
+__device__ __forceinline__ unsigned uf_find(volatile unsigned* L, unsigned x)
 {
-    unsigned p;
-    while ((p = L[x]) != x) x = p;
+    unsigned w = L[x], p = w & 0xffffu;
+    while (p != x) {
+        const unsigned wp = L[p], g = wp & 0xffffu;
+        if (g != p) L[x] = (w & 0xffff0000u) | g;  // path halving: x is not a root, g is an ancestor
+        x = p;
+        w = wp;
+        p = g;
+    }
     return x;
 }
-__device__ __forceinline__ void uf_union(unsigned short* L, unsigned a, unsigned b)
+__device__ __forceinline__ unsigned uf_find_ro(const volatile unsigned* L, unsigned x)
+{
+    unsigned p;
+    while ((p = L[x] & 0xffffu) != x) x = p;
+    return x;
+}
+__device__ __forceinline__ void uf_union(unsigned* L, unsigned a, unsigned b)
 {
     while (true) {
         a = uf_find(L, a);
         b = uf_find(L, b);
         if (a == b) return;
         if (a < b) { unsigned t = a; a = b; b = t; }
-        unsigned short old = atomicCAS(&L[a], (unsigned short)a, (unsigned short)b);
-        if (old == (unsigned short)a) return;
-        a = old;
+        const unsigned wa = ((volatile unsigned*)L)[a];
+        if ((wa & 0xffffu) != a) continue;  // lost the race: a is no longer a root
+        if (atomicCAS(&L[a], wa, (wa & 0xffff0000u) | b) == wa) return;
     }
 }
 
@@ -184,14 +217,12 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
     const int H = p.H, W = p.W, HW = p.HW, WP = p.WP, NA = p.n_angles, NB = 2 * p.n_angles;
     PT* s_img = (PT*)(smem + p.o_stage);
     unsigned char* s_msk = smem + p.o_mask;
-    unsigned short* lab = (unsigned short*)(smem + p.o_stage);
+    unsigned* lab = (unsigned*)(smem + p.o_stage);  // union-find words (after the raw patch is consumed)
     unsigned char* lev = smem + p.o_lev;
-    unsigned* zsize = (unsigned*)(smem + p.o_zsize);
     int* hist = (int*)(smem + p.o_hist);
     unsigned char* lut = smem + p.o_lut;
     int* lhist = (int*)(smem + p.o_lhist);
     int* glcm = (int*)(smem + p.o_glcm);
-    unsigned* glrlm = (unsigned*)(smem + p.o_glrlm);
     int* gldm = (int*)(smem + p.o_gldm);
     int* ngc = (int*)(smem + p.o_ngc);
     int* ngn = (int*)(smem + p.o_ngn);
@@ -352,9 +383,8 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
     int a_row = -1;
     for (int a = 0; a < NA; a++)
         if (p.ang_y[a] == 0) a_row = a;
-    unsigned short* zs16 = (unsigned short*)zsize;
-    if (a_row < 0) {  // no along-row connectivity: every ROI pixel starts as its own run
-        for (int i = tid; i < HW; i += RADB_NT) { lab[i] = (unsigned short)i; zs16[i] = 1; }
+    if (a_row < 0) {  // no along-row connectivity: every ROI pixel starts as its own run of length 1
+        for (int i = tid; i < HW; i += RADB_NT) lab[i] = 0x10000u | (unsigned)i;
     }
 
     // ---- phase 3a: line walks.  One thread walks one line of the image along one angle, so
@@ -370,8 +400,8 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
             int first = tid - (t0 % RADB_NT);
             if (first < 0) first += RADB_NT;
             for (int l = first; l < nlines; l += RADB_NT) {
-                unsigned* R = glrlm;
-                const int cell0 = a * ng * nr;
+                unsigned* R = (unsigned*)(smem + p.o_glrlm + a * p.glrlm_stride);
+                const int cell0 = 0;
                 int cur = 0, len = 0;
                 if (dy == 0) {
                     const int base = (l + 1) * WP + 1, lbase = l * W;
@@ -379,15 +409,21 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
                     for (int x = 0; x < W; x++) {
                         const int g = lev[base + x];
                         if (g != cur) {
-                            if (cur) { add_u16(R, cell0 + (cur - 1) * nr + len - 1); zs16[lbase + st] = (unsigned short)len; }
+                            if (cur) {
+                                add_u16(R, cell0 + (cur - 1) * nr + len - 1);
+                                lab[lbase + st] = ((unsigned)len << 16) | (unsigned)(lbase + st);
+                            }
                             cur = g;
                             len = 0;
                             st = x;
                         }
                         len++;
-                        if (g) lab[lbase + x] = (unsigned short)(lbase + st);
+                        if (g) lab[lbase + x] = (unsigned)(lbase + st);
                     }
-                    if (cur) { add_u16(R, cell0 + (cur - 1) * nr + len - 1); zs16[lbase + st] = (unsigned short)len; }
+                    if (cur) {
+                        add_u16(R, cell0 + (cur - 1) * nr + len - 1);
+                        lab[lbase + st] = ((unsigned)len << 16) | (unsigned)(lbase + st);
+                    }
                 } else {
                     const int sdx = dx * dy;  // x step per +1 in y (runs are direction-agnostic)
                     int x = l, brk = 0;
@@ -421,14 +457,37 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
         }
         const int nd = NB + 1;
         const bool inplane = (NA == 4);  // all 8 neighbours: run-adjacency union rules apply
-        for (int base = 0; base < nbox; base += RADB_NT) {  // uniform trip count: __syncwarp below
+        // Union requests are queued per warp and executed 32 at a time, so that the
+        // data-dependent find loops run with (nearly) all lanes busy.
+        unsigned* uq = (unsigned*)(smem + p.o_uq) + warp * 64;
+        int qn = 0;
+        const unsigned lt_mask = (1u << lane) - 1u;
+        auto drain = [&](int count) {
+            if (lane < count) {
+                const unsigned pr = uq[qn - count + lane];
+                uf_union(lab, pr >> 16, pr & 0xffffu);
+            }
+            __syncwarp();
+            qn -= count;
+        };
+        auto push = [&](bool has, unsigned pair) {
+            const unsigned m = __ballot_sync(FULLMASK, has);
+            if (has) uq[qn + __popc(m & lt_mask)] = pair;
+            qn += __popc(m);
+            __syncwarp();
+            if (qn >= 32) drain(32);
+        };
+        for (int base = 0; base < nbox; base += RADB_NT) {  // uniform trip count (warp collectives below)
             const int idx = base + tid;
             const int yb = (int)(((float)idx + 0.5f) * inv_bw);
             const int y = by0 + yb, x = bx0 + (idx - yb * bw);
             const int ctr = (y + 1) * WP + x + 1;
             const int c = idx < nbox ? (int)lev[ctr] : 0;
+            const int li = y * W + x;
+            unsigned req[RADB_MAX_ANGLES];  // union partner + 1 (0 = none)
+#pragma unroll
+            for (int a = 0; a < RADB_MAX_ANGLES; a++) req[a] = 0;
             if (c) {
-                const int li = y * W + x;
                 int dep = 0, cnt = 0, sum = 0;
 #pragma unroll
                 for (int a = 0; a < RADB_MAX_ANGLES; a++) {
@@ -450,7 +509,7 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
                             db = db < 0 ? -db : db;
                             dep += (db <= p.alpha);
                         }
-                        if (!inplane && a != a_row && b == c) uf_union(lab, (unsigned)li, (unsigned)(li - loff[a]));
+                        if (!inplane && a != a_row && b == c) req[a] = (unsigned)(li - loff[a]) + 1u;
                     }
                 }
                 atomicAdd(&gldm[(c - 1) * nd + dep], 1);
@@ -465,15 +524,19 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
                     const int n_ = lev[ctr - WP], nw = lev[ctr - WP - 1], ne = lev[ctr - WP + 1];
                     const bool is_start = lev[ctr - 1] != c, is_end = lev[ctr + 1] != c;
                     if (n_ == c) {
-                        if (is_start || nw != c) uf_union(lab, (unsigned)li, (unsigned)(li - W));
+                        if (is_start || nw != c) req[0] = (unsigned)(li - W) + 1u;
                     } else {
-                        if (nw == c && is_start) uf_union(lab, (unsigned)li, (unsigned)(li - W - 1));
-                        if (ne == c && is_end) uf_union(lab, (unsigned)li, (unsigned)(li - W + 1));
+                        if (nw == c && is_start) req[0] = (unsigned)(li - W - 1) + 1u;
+                        if (ne == c && is_end) req[1] = (unsigned)(li - W + 1) + 1u;
                     }
                 }
             }
-            __syncwarp();  // reconverge after the data-dependent union loops
+            const int nreq = inplane ? 2 : NA;
+#pragma unroll
+            for (int a = 0; a < RADB_MAX_ANGLES; a++)
+                if (a < nreq) push(req[a] != 0, ((unsigned)li << 16) | (req[a] - 1u));
         }
+        if (qn) drain(qn);
     }
     __syncthreads();
 
@@ -485,8 +548,8 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
         const int c = lev[ctr];
         if (c && (a_row < 0 || lev[ctr - 1] != c)) {  // run start
             const int li = y * W + x;
-            const unsigned r = uf_find(lab, (unsigned)li);
-            if (r != (unsigned)li) atomicAdd(&zsize[r >> 1], (unsigned)zs16[li] << ((r & 1) * 16));
+            const unsigned r = uf_find_ro(lab, (unsigned)li);
+            if (r != (unsigned)li) atomicAdd(&lab[r], lab[li] & 0xffff0000u);  // only roots are ever added to
         }
     }
     if (p.symmetric) {
@@ -515,8 +578,9 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
         const int c = lev[ctr];
         if (!c || (a_row >= 0 && lev[ctr - 1] == c)) continue;
         const int li = y * W + x;
-        if (lab[li] != (unsigned short)li) continue;
-        const int s = zs16[li];
+        const unsigned wl = lab[li];
+        if ((wl & 0xffffu) != (unsigned)li) continue;
+        const int s = (int)(wl >> 16);
         if (s <= p.s0) {
             atomicAdd(&szm[(c - 1) * p.s0 + s - 1], 1);
         } else {
@@ -540,18 +604,18 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
         for (int a = 0; a < NA; a++)
             for (int t = tid; t < ng * p.nr; t += RADB_NT)
                 p.dbg_glrlm[((patch * NA + a) * p.max_ng + t / p.nr) * p.nr + t % p.nr] =
-                    get_u16(glrlm, a * ng * p.nr + t);
+                    get_u16((const unsigned*)(smem + p.o_glrlm + a * p.glrlm_stride), t);
     if (p.dbg_gldm)
         for (int t = tid; t < ng * (NB + 1); t += RADB_NT)
             p.dbg_gldm[patch * p.max_ng * (NB + 1) + t] = gldm[t];
 
     // ---- phase 6: warp-specialised feature reductions
-    //   tasks 0..NA-1      : GLCM features of angle t        -> fsc[t][0..23]
-    //   tasks NA..2NA-1    : GLRLM features of angle t-NA    -> fsc[t-NA][24..39]
-    //   then GLSZM, GLDM, NGTDM, first-order                 -> fsc[NA*40 + ...]
+    //   tasks 0..NA-1 : angle t: GLRLM features -> fsc[t][24..39], then GLCM features (+MCC, whose
+    //                   workspace re-uses the GLRLM slot of the same angle) -> fsc[t][0..23]
+    //   then GLSZM, GLDM, NGTDM, first-order -> fsc[NA*40 + ...]
     double* single = fsc + NA * RADB_FSC_STRIDE;  // [0..15] glszm, [16..29] gldm, [30..34] ngtdm, [35..52] fo
     int* valid = misc + 16;                       // [a] glcm angle valid, [4+a] glrlm angle valid
-    const int ntask = 2 * NA + 4;
+    const int ntask = NA + 4;
     RadbTabs tb;
     tb.inv2 = (const double*)(smem + p.o_inv2);
     tb.ninv = p.ninv;
@@ -559,23 +623,23 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
     for (int t = warp; t < ntask; t += RADB_NT / 32) {
         if (t < NA) {
             const int a = t;
-            int ok = glcm_task(p, tb, glcm + a * ng * ng, ng, (int*)(smem + p.o_px) + a * ng,
-                               (int*)(smem + p.o_py) + a * ng, (int*)(smem + p.o_padd) + a * 2 * ng,
-                               (int*)(smem + p.o_psub) + a * ng, (double*)(smem + p.o_mcc) + a * p.mcc_stride,
-                               smem + p.o_idx + a * ng, fsc + a * RADB_FSC_STRIDE, lane);
-            if (lane == 0) valid[a] = ok;
-        } else if (t < 2 * NA) {
-            const int a = t - NA;
-            int ok = glrlm_task(tb, glrlm, a * ng * p.nr, ng, p.nr, (int*)(smem + p.o_pr) + a * p.nr,
+            unsigned char* slot = smem + p.o_glrlm + a * p.glrlm_stride;
+            int ok = glrlm_task(tb, (const unsigned*)slot, 0, ng, p.nr, (int*)(smem + p.o_pr) + a * p.nr,
                                 fsc + a * RADB_FSC_STRIDE + RADB_GLCM_NF, lane);
             if (lane == 0) valid[4 + a] = ok;
-        } else if (t == 2 * NA) {
+            __syncwarp();
+            ok = glcm_task(p, tb, glcm + a * ng * ng, ng, (int*)(smem + p.o_px) + a * ng,
+                           (int*)(smem + p.o_py) + a * ng, (int*)(smem + p.o_padd) + a * 2 * ng,
+                           (int*)(smem + p.o_psub) + a * ng, (double*)slot, smem + p.o_idx + a * ng,
+                           fsc + a * RADB_FSC_STRIDE, lane);
+            if (lane == 0) valid[a] = ok;
+        } else if (t == NA) {
             int novf = misc[5] < p.ovf_cap ? misc[5] : p.ovf_cap;
             glszm_task(p, tb, szm, ovf, (unsigned*)(smem + p.o_ovf2), novf, ng, (int*)(smem + p.o_pg), single,
                        lane);
-        } else if (t == 2 * NA + 1) {
+        } else if (t == NA + 1) {
             gldm_task(tb, gldm, ng, NB + 1, single + 16, lane);
-        } else if (t == 2 * NA + 2) {
+        } else if (t == NA + 2) {
             double* pi = (double*)(smem + p.o_ngp);
             ngtdm_task(ngc, ngn, ng, NB, pi, pi + ng, single + 30, lane,
                        p.dbg_ngn ? p.dbg_ngn + patch * p.max_ng : (int*)0,

@@ -35,11 +35,12 @@ struct RadbParams {
     int off_fo, off_glcm, off_gldm, off_glrlm, off_glszm, off_ngtdm;  // output column of each class, -1 = off
     int use_tma;
     // shared-memory byte offsets
-    int o_stage, o_mask, o_mbar, o_zero, o_lev, o_zsize, o_hist, o_lut, o_lhist, o_glcm, o_px, o_py,
-        o_padd, o_psub, o_glrlm, o_pr, o_gldm, o_ngc, o_ngn, o_szm, o_ovf, o_mcc, o_idx, o_fsc, o_misc,
+    int o_stage, o_mask, o_mbar, o_zero, o_lev, o_uq, o_hist, o_lut, o_lhist, o_glcm, o_px, o_py,
+        o_padd, o_psub, o_glrlm, o_pr, o_gldm, o_ngc, o_ngn, o_szm, o_ovf, o_idx, o_fsc, o_misc,
         o_ngp, o_qv, o_pg, o_ovf2, o_inv2, o_clog, smem_total;
     int ninv;        // entries of the 1/k^2 table
-    int mcc_stride;  // doubles per angle in the MCC workspace
+    int mcc_stride;    // doubles per angle in the MCC workspace
+    int glrlm_stride;  // bytes per angle of the GLRLM / MCC slot
     // optional debug outputs (device pointers, may be null); dims use max_ng
     int* dbg_levels;   // [B][H][W]
     int* dbg_glcm;     // [B][Na][max_ng][max_ng]
@@ -63,16 +64,16 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->s0 = 16;
     p->ovf_cap = p->HW / (p->s0 + 1) + 1;
     int o = 0;
-    p->o_stage = o;                       // raw pixels (TMA destination); later CCL labels (u16[HW])
+    p->o_stage = o;                       // raw pixels (TMA destination); later union-find words (u32[HW])
     int stage_bytes = radb_align(p->HW * pix_bytes, 16);
     p->o_mask = o + stage_bytes;          // raw mask (TMA destination)
     int both = stage_bytes + radb_align(p->HW, 16);
-    int lab_bytes = radb_align(p->HW * 2, 16);
+    int lab_bytes = radb_align(p->HW * 4, 16);   // union-find words (parent | size << 16)
     o += both > lab_bytes ? both : lab_bytes;
     p->o_mbar = o; o += 16;
     p->o_zero = o;                        // everything from here on is zeroed at CTA start
     p->o_lev = o; o += radb_align((H + 2) * p->WP, 16);
-    p->o_zsize = o; o += radb_align(p->HW * 2, 16);
+    p->o_uq = o; o += (RADB_NT / 32) * 64 * 4;           // per-warp union request queues
     p->o_hist = o; o += 256 * 4;
     p->o_lut = o; o += 256;
     p->o_lhist = o; o += radb_align(ng * 4, 16);
@@ -81,7 +82,12 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->o_py = o; o += radb_align(na * ng * 4, 16);
     p->o_padd = o; o += radb_align(na * 2 * ng * 4, 16);
     p->o_psub = o; o += radb_align(na * ng * 4, 16);
-    p->o_glrlm = o; o += radb_align(na * ng * p->nr * 2, 16);
+    // GLRLM counters of angle a live at o_glrlm + a*glrlm_stride; the same slot is re-used as the
+    // fp64 MCC workspace of that angle once its GLRLM features are reduced (same warp, in order).
+    p->mcc_stride = ng * (ng + 1) / 2 + 4 * ng;
+    p->glrlm_stride = radb_align(ng * p->nr * 2, 16);
+    if (p->mcc_stride * 8 > p->glrlm_stride) p->glrlm_stride = radb_align(p->mcc_stride * 8, 16);
+    p->o_glrlm = o; o += na * p->glrlm_stride;
     p->o_pr = o; o += radb_align(na * p->nr * 4, 16);
     p->o_gldm = o; o += radb_align(ng * (2 * na + 1) * 4, 16);
     p->o_ngc = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] voxel counts per neighbour count
@@ -89,8 +95,6 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->o_szm = o; o += radb_align(ng * p->s0 * 4, 16);
     p->o_ovf = o; o += radb_align(p->ovf_cap * 4, 16);
     p->o_ovf2 = o; o += radb_align(p->ovf_cap * 4, 16);  // overflow zones sorted by key
-    p->mcc_stride = ng * (ng + 1) / 2 + 4 * ng;
-    p->o_mcc = o; o += radb_align(na * p->mcc_stride * 8, 16);
     p->o_idx = o; o += radb_align(na * ng, 16);
     p->o_fsc = o; o += radb_align((na * RADB_FSC_STRIDE + 64) * 8, 16);
     p->o_ngp = o; o += radb_align(2 * ng * 8, 16);
