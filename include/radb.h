@@ -7,8 +7,8 @@
  *
  * Conventions: plain pointers and sizes only; `img`, `mask`, `out`, `status` and every debug
  * buffer are DEVICE pointers owned by the caller; calls are asynchronous and ordered on the
- * given CUDA stream (a `cudaStream_t` passed as void*); no allocation happens after
- * radb_create.  Every function returns 0 on success and a negative code on misuse / CUDA
+ * given CUDA stream (a `cudaStream_t` passed as void*); the only allocation after radb_create
+ * is the grow-only record workspace (see radb_reserve).  Every function returns 0 on success and a negative code on misuse / CUDA
  * errors (text via radb_last_error); nothing aborts.  A handle is not thread-safe: one handle
  * per (thread, device).
  */
@@ -86,7 +86,12 @@ void radb_destroy(radb_handle* h);
 int radb_feature_count(const radb_handle* h);
 const char* radb_feature_name(const radb_handle* h, int i);
 
-/* Dynamic shared memory (bytes) one CTA needs for HxW patches of `dtype`; < 0 if it cannot fit. */
+/* Pre-allocates the per-chunk record workspace for batches of up to `max_batch` HxW patches, so
+ * that later radb_extract calls allocate nothing.  Without it the workspace grows on demand
+ * (cudaMalloc, grow-only) the first time a larger batch or record size is seen. */
+int radb_reserve(radb_handle* h, int H, int W, int dtype, int64_t max_batch);
+
+/* Dynamic shared memory (bytes) one CTA of the build kernel needs for HxW patches of `dtype`; < 0 if it cannot fit. */
 int radb_smem_bytes(const radb_handle* h, int H, int W, int dtype);
 
 /* extractor.execute(image, mask, label=label) (RadiomicExtractor.py:38,42,45,48), batched:
@@ -109,7 +114,8 @@ int radb_debug_matrices(radb_handle* h, const void* img, int dtype, const uint8_
 
 int radb_max_ng(const radb_handle* h);
 
-/* Number of kernel launches this handle has issued (bench.py's gpu_launches evidence). */
+/* Number of kernel launches this handle has issued (bench.py's gpu_launches evidence): three
+ * kernels (build, angle, misc) per chunk of 16384 patches. */
 int64_t radb_launch_count(const radb_handle* h);
 
 const char* radb_last_error(void);

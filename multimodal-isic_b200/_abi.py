@@ -82,6 +82,8 @@ def load_library(path=None):
     lib.radb_feature_count.restype = i32
     lib.radb_feature_name.argtypes = [vp, i32]
     lib.radb_feature_name.restype = ctypes.c_char_p
+    lib.radb_reserve.argtypes = [vp, i32, i32, i32, i64]
+    lib.radb_reserve.restype = i32
     lib.radb_smem_bytes.argtypes = [vp, i32, i32, i32]
     lib.radb_smem_bytes.restype = i32
     lib.radb_extract.argtypes = [vp, vp, i32, vp, i64, i32, i32, i64, i64, vp, vp, vp]
@@ -102,7 +104,7 @@ def load_library(path=None):
 
 
 EXPORTED_SYMBOLS = (
-    "radb_create", "radb_destroy", "radb_feature_count", "radb_feature_name", "radb_smem_bytes",
+    "radb_create", "radb_destroy", "radb_feature_count", "radb_feature_name", "radb_reserve", "radb_smem_bytes",
     "radb_extract", "radb_debug_matrices", "radb_max_ng", "radb_launch_count", "radb_last_error",
     "radb_version",
 )

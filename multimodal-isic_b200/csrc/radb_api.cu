@@ -11,12 +11,19 @@
 
 static thread_local std::string g_err;
 
+#define RADB_TAB_NINV 4096   // entries of the device 1/k^2 table (beyond it the kernels divide)
+#define RADB_CHUNK 16384     // patches per pass through the three kernels (bounds the workspace)
+
 struct radb_handle {
     radb::Plan plan;
     int device;
-    int smem_optin;     // max dynamic shared memory per block the device allows
-    int smem_set;       // currently configured attribute value
+    int smem_optin;              // max dynamic shared memory per block the device allows
+    int smem_set[4];             // configured MaxDynamicSharedMemorySize per kernel
     int64_t launches;
+    unsigned char* ws;           // per-patch records of one chunk
+    size_t ws_bytes;
+    double* d_inv2;
+    double* d_tlog;
 };
 
 static int fail(int code, const std::string& msg)
@@ -33,6 +40,8 @@ static int cuda_fail(cudaError_t e, const char* what)
 extern "C" const char* radb_last_error(void) { return g_err.c_str(); }
 extern "C" const char* radb_version(void) { return "radb 0.1 (sm_100a)"; }
 
+extern "C" void radb_destroy(radb_handle* h);
+
 extern "C" int radb_create(const radb_settings* s, radb_handle** out)
 {
     if (!s || !out) return fail(RADB_E_INVALID, "null argument");
@@ -42,7 +51,10 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
     if (rc) { delete h; return fail(rc, err); }
     h->device = s->device;
     h->launches = 0;
-    h->smem_set = 0;
+    h->smem_set[0] = h->smem_set[1] = h->smem_set[2] = h->smem_set[3] = 0;
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+    h->d_inv2 = h->d_tlog = nullptr;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -52,11 +64,61 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
     if (s->device < 0 || s->device >= ndev) { delete h; return fail(RADB_E_INVALID, "device ordinal out of range"); }
     e = cudaDeviceGetAttribute(&h->smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, s->device);
     if (e != cudaSuccess) { delete h; return cuda_fail(e, "cudaDeviceGetAttribute"); }
+    {   // device tables for the reduction kernels
+        int cur = -1;
+        cudaGetDevice(&cur);
+        cudaSetDevice(s->device);
+        std::vector<double> inv2, tlog;
+        radb::make_tables(RADB_TAB_NINV, inv2, tlog);
+        e = cudaMalloc(&h->d_inv2, inv2.size() * 8);
+        if (e == cudaSuccess) e = cudaMalloc(&h->d_tlog, tlog.size() * 8);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_inv2, inv2.data(), inv2.size() * 8, cudaMemcpyHostToDevice);
+        if (e == cudaSuccess) e = cudaMemcpy(h->d_tlog, tlog.data(), tlog.size() * 8, cudaMemcpyHostToDevice);
+        if (cur >= 0) cudaSetDevice(cur);
+        if (e != cudaSuccess) { radb_destroy(h); return cuda_fail(e, "radb_create: table allocation"); }
+    }
     *out = h;
     return RADB_OK;
 }
 
-extern "C" void radb_destroy(radb_handle* h) { delete h; }
+extern "C" void radb_destroy(radb_handle* h)
+{
+    if (!h) return;
+    if (h->ws) cudaFree(h->ws);
+    if (h->d_inv2) cudaFree(h->d_inv2);
+    if (h->d_tlog) cudaFree(h->d_tlog);
+    delete h;
+}
+
+// Grow-only workspace: one record per patch of a chunk.
+static int ensure_ws(radb_handle* h, const RadbParams& p, int64_t B)
+{
+    const int64_t n = B < RADB_CHUNK ? B : RADB_CHUNK;
+    const size_t need = (size_t)n * (size_t)p.rec_bytes;
+    if (need <= h->ws_bytes) return RADB_OK;
+    if (h->ws) cudaFree(h->ws);
+    h->ws = nullptr;
+    h->ws_bytes = 0;
+    cudaError_t e = cudaMalloc(&h->ws, need);
+    if (e != cudaSuccess) return cuda_fail(e, "workspace allocation");
+    h->ws_bytes = need;
+    return RADB_OK;
+}
+
+extern "C" int radb_reserve(radb_handle* h, int H, int W, int dtype, int64_t max_batch)
+{
+    if (!h || max_batch < 0) return fail(RADB_E_INVALID, "bad argument");
+    RadbParams p;
+    std::string err;
+    int rc = radb::fill_params(h->plan, H, W, dtype, p, err);
+    if (rc) return fail(rc, err);
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != h->device) cudaSetDevice(h->device);
+    rc = ensure_ws(h, p, max_batch);
+    if (cur >= 0 && cur != h->device) cudaSetDevice(cur);
+    return rc;
+}
 extern "C" int radb_feature_count(const radb_handle* h) { return h ? h->plan.F : RADB_E_INVALID; }
 extern "C" const char* radb_feature_name(const radb_handle* h, int i)
 {
@@ -76,6 +138,20 @@ extern "C" int radb_smem_bytes(const radb_handle* h, int H, int W, int dtype)
     return p.smem_total;
 }
 
+template <typename K>
+static int set_smem(radb_handle* h, K kernel, int which, int bytes)
+{
+    if (bytes > h->smem_optin) return fail(RADB_E_SMEM, "shared memory request exceeds the device opt-in limit");
+    if (bytes > h->smem_set[which]) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
+        cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
+        h->smem_set[which] = bytes;
+    }
+    return RADB_OK;
+}
+
+// One pass = three kernels over a chunk of patches, stream-ordered, sharing the record workspace.
 static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
 {
     (void)dtype;
@@ -86,31 +162,49 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         e = cudaSetDevice(h->device);
         if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     }
-    if (p.smem_total > h->smem_optin) return fail(RADB_E_SMEM, "shared memory request exceeds the device opt-in limit");
-    if (p.smem_total > h->smem_set) {
-        e = cudaFuncSetAttribute(radb_extract_kernel<unsigned char>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 p.smem_total);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
-        cudaFuncSetAttribute(radb_extract_kernel<unsigned char>, cudaFuncAttributePreferredSharedMemoryCarveout,
-                             cudaSharedmemCarveoutMaxShared);
-        h->smem_set = p.smem_total;
-    }
-    const long long maxgrid = 0x7fffffffLL;
+    const bool dbg = p.dbg_levels || p.dbg_glcm || p.dbg_glrlm || p.dbg_glszm || p.dbg_gldm || p.dbg_ng;
+    int rc = dbg ? set_smem(h, radb_build_kernel<unsigned char, true>, 3, p.smem_total)
+                 : set_smem(h, radb_build_kernel<unsigned char, false>, 0, p.smem_total);
+    if (!rc) rc = set_smem(h, radb_angle_kernel, 1, p.a_smem_total);
+    if (!rc) rc = set_smem(h, radb_misc_kernel, 2, p.m_smem_total);
+    if (!rc) rc = ensure_ws(h, p, p.B);
+    if (rc) return rc;
+    p.ws = h->ws;
+    p.g_inv2 = h->d_inv2;
+    p.g_tlog = h->d_tlog;
+    if (p.ninv > RADB_TAB_NINV) p.ninv = RADB_TAB_NINV;
+    cudaStream_t st = (cudaStream_t)stream;
     long long done = 0;
     while (done < p.B) {
-        long long n = p.B - done < maxgrid ? p.B - done : maxgrid;
+        const long long n = p.B - done < RADB_CHUNK ? p.B - done : RADB_CHUNK;
         RadbParams q = p;
         q.img = (const unsigned char*)p.img + done * p.img_stride;
         q.mask = p.mask + done * p.mask_stride;
         q.out = p.out + done * p.F;
         q.status = p.status + done;
-        // debug buffers are only used with small batches (one launch)
-        radb_extract_kernel<unsigned char><<<(unsigned)n, RADB_NT, p.smem_total, (cudaStream_t)stream>>>(q);
-        h->launches++;
+        q.B = n;
+        if (done) {  // debug buffers (parity tests) advance with the chunk
+            const long long HW = p.HW, NA = p.n_angles, NG = p.max_ng;
+            if (q.dbg_levels) q.dbg_levels += done * HW;
+            if (q.dbg_glcm) q.dbg_glcm += done * NA * NG * NG;
+            if (q.dbg_glrlm) q.dbg_glrlm += done * NA * NG * p.nr;
+            if (q.dbg_glszm) q.dbg_glszm += done * NG * HW;
+            if (q.dbg_gldm) q.dbg_gldm += done * NG * (2 * NA + 1);
+            if (q.dbg_ngn) q.dbg_ngn += done * NG;
+            if (q.dbg_ngs) q.dbg_ngs += done * NG;
+            if (q.dbg_ng) q.dbg_ng += done;
+        }
+        if (dbg)
+            radb_build_kernel<unsigned char, true><<<(unsigned)n, RADB_NT, p.smem_total, st>>>(q);
+        else
+            radb_build_kernel<unsigned char, false><<<(unsigned)n, RADB_NT, p.smem_total, st>>>(q);
+        radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, st>>>(q);
+        radb_misc_kernel<<<(unsigned)n, RADB_NT, p.m_smem_total, st>>>(q);
+        h->launches += 3;
         done += n;
     }
     e = cudaGetLastError();
-    if (e != cudaSuccess) return cuda_fail(e, "radb_extract_kernel launch");
+    if (e != cudaSuccess) return cuda_fail(e, "radb kernel launch");
     return RADB_OK;
 }
 
@@ -158,7 +252,6 @@ extern "C" int radb_debug_matrices(radb_handle* h, const void* img, int dtype, c
     int rc = setup(h, img, dtype, mask, B, H, W, img_stride_b, mask_stride_b, out, status, p);
     if (rc) return rc;
     if (B == 0) return RADB_OK;
-    if (B > 0x7fffffffLL) return fail(RADB_E_INVALID, "debug batches must fit one launch");
     p.dbg_levels = levels;
     p.dbg_glcm = glcm;
     p.dbg_glrlm = glrlm;

@@ -12,64 +12,71 @@
 //  * 1/k^2 comes from a per-CTA table (no fp64 divisions inside the cell loops).
 #pragma once
 
+// Out-of-line fp64 helpers: log2 / the table fallbacks expand to 25-70 instructions each; inlining
+// them at every call site is what made the kernels several times larger than the instruction cache.
+__device__ __noinline__ double radb_log2(double x) { return log2(x); }
+__device__ __noinline__ double radb_inv_sq(int k) { return 1.0 / ((double)k * (double)k); }
+__device__ __noinline__ double radb_div(double a, double b) { return a / b; }
+__device__ __noinline__ double radb_sqrt(double a) { return sqrt(a); }
+
 struct RadbTabs {
     const double* inv2;  // inv2[k-1] = 1/k^2, k = 1..ninv
     int ninv;
     const double* tlog;  // tlog[c] = log2(c), c = 1..127 (tlog[0] = 0)
+    double* red;         // this warp's reduction scratch (RADB_RED_DOUBLES doubles, shared memory)
 };
 __device__ __forceinline__ double tab_inv2(const RadbTabs& t, int k)
 {
-    return k <= t.ninv ? t.inv2[k - 1] : 1.0 / ((double)k * (double)k);
+    return k <= t.ninv ? t.inv2[k - 1] : radb_inv_sq(k);
 }
 __device__ __forceinline__ double tab_log2(const RadbTabs& t, int c)
 {
-    return c < 128 ? t.tlog[c] : log2((double)c);
+    return c < 128 ? t.tlog[c] : radb_log2((double)c);
 }
 __device__ __forceinline__ double tab_clog(const RadbTabs& t, int c) { return (double)c * tab_log2(t, c); }
 
 // ------------------------------------------------------------------ first-order (u8 raw histogram)
 // One warp.  A.5: everything except Entropy/Uniformity comes from the raw ROI values; for uint8
 // pixels those are exactly the 256-bin histogram (lane l owns bins 8l..8l+7).
-__device__ void fo_task_u8(const RadbParams& p, const int* hist, const int* lhist, int ng, double* qv,
+__device__ void fo_task_u8(const RadbParams& p, const RadbTabs& tb, const int* hist, const int* lhist, int ng, double* qv,
                            double* o, int lane)
 {
-    int h[8];
+    const int* h = hist + lane * 8;  // this lane's 8 bins (re-read in each pass: keeps the code small)
     long long s1 = 0;
     int n = 0, vmin = 256, vmax = -1;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 8; k++) {
-        const int v = lane * 8 + k;
-        h[k] = hist[v];
-        n += h[k];
-        s1 += (long long)h[k] * v;
-        vmin = (h[k] && v < vmin) ? v : vmin;
-        vmax = (h[k] && v > vmax) ? v : vmax;
+        const int v = lane * 8 + k, hk = h[k];
+        n += hk;
+        s1 += (long long)hk * v;
+        vmin = (hk && v < vmin) ? v : vmin;
+        vmax = (hk && v > vmax) ? v : vmax;
     }
     const int before = warp_excl_scan_i(n, lane);
     const int N = warp_sum_i(n);
-    const double dN = (double)N;
-    const double mean = (double)warp_sum_ll(s1) / dN;
+    const double dN = (double)N, rN = radb_div(1.0, dN);
+    const double mean = (double)warp_sum_ll(s1) * rN;
     const double shift = p.shift;
     vmin = warp_min_i(vmin);
     vmax = warp_max_i(vmax);
     // order statistics for the 10/25/50/75/90 percentiles (numpy 'linear' interpolation): rank r
     // lives in the lane whose cumulative range [before, before+n) contains it
     double fr[5];
-#pragma unroll
+#pragma unroll 1
     for (int q = 0; q < 5; q++) {
-        const double qq = q == 0 ? 10.0 : q == 1 ? 25.0 : q == 2 ? 50.0 : q == 3 ? 75.0 : 90.0;
-        const double pos = (qq / 100.0) * (dN - 1.0);
+        const double qq = q == 0 ? 0.1 : q == 1 ? 0.25 : q == 2 ? 0.5 : q == 3 ? 0.75 : 0.9;
+        const double pos = qq * (dN - 1.0);
         const double fl = floor(pos);
-        fr[q] = pos - fl;
+        if (lane == 0) qv[10 + q] = pos - fl;
         int lo = (int)fl;
         lo = lo > N - 1 ? N - 1 : lo;
         const int hi = lo + 1 > N - 1 ? N - 1 : lo + 1;
-#pragma unroll
+#pragma unroll 1
         for (int e = 0; e < 2; e++) {
             const int r = e ? hi : lo;
             if (r >= before && r < before + n) {
                 int cum = before, bin = 0;
-#pragma unroll
+#pragma unroll 1
                 for (int k = 0; k < 8; k++) {
                     bin = (r >= cum) ? k : bin;
                     cum += h[k];
@@ -79,17 +86,13 @@ __device__ void fo_task_u8(const RadbParams& p, const int* hist, const int* lhis
         }
     }
     __syncwarp();
-    double pc[5];
 #pragma unroll
-    for (int q = 0; q < 5; q++) {
-        const double a = qv[2 * q], b = qv[2 * q + 1];
-        pc[q] = a + (b - a) * fr[q];
-    }
-    const double p10 = pc[0], p25 = pc[1], med = pc[2], p75 = pc[3], p90 = pc[4];
-    // central moments, MAD, energy, robust MAD (branch-free over the 8 bins)
+    for (int q = 0; q < 5; q++) fr[q] = qv[2 * q] + (qv[2 * q + 1] - qv[2 * q]) * qv[10 + q];
+    const double p10 = fr[0], p25 = fr[1], med = fr[2], p75 = fr[3], p90 = fr[4];
+    // central moments, MAD, energy, robust MAD
     double m2 = 0, m3 = 0, m4 = 0, mad = 0, en = 0, in_s1 = 0;
     int in_n = 0;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 8; k++) {
         const double v = (double)(lane * 8 + k), hk = (double)h[k];
         const double d = v - mean, d2 = d * d;
@@ -104,35 +107,39 @@ __device__ void fo_task_u8(const RadbParams& p, const int* hist, const int* lhis
     }
     {
         double r[6] = {m2, m3, m4, mad, en, in_s1};
-        warp_sum_n(r);
-        m2 = r[0] / dN; m3 = r[1] / dN; m4 = r[2] / dN; mad = r[3] / dN; en = r[4]; in_s1 = r[5];
+        warp_sum_n(r, tb.red, lane);
+        m2 = r[0] * rN; m3 = r[1] * rN; m4 = r[2] * rN; mad = r[3] * rN; en = r[4]; in_s1 = r[5];
     }
     const int inN = warp_sum_i(in_n);
-    const double in_mean = in_s1 / (double)inN;
+    const double rin = radb_div(1.0, (double)inN);
+    const double in_mean = in_s1 * rin;
     double rmad = 0;
-#pragma unroll
+#pragma unroll 1
     for (int k = 0; k < 8; k++) {
         const double v = (double)(lane * 8 + k);
         const bool in = (v >= p10) && (v <= p90);
         rmad += in ? (double)h[k] * fabs(v - in_mean) : 0.0;
     }
-    rmad = warp_sum(rmad) / (double)inN;
     // discretised histogram: Entropy / Uniformity (A.5: p = level histogram / N)
     double ent = 0, uni = 0;
+#pragma unroll 1
     for (int i = lane; i < ng; i += 32) {
-        const double pi = (double)lhist[i] / dN;
-        if (lhist[i]) ent -= pi * log2(pi + RADB_EPS);
+        const double pi = (double)lhist[i] * rN;
+        if (lhist[i]) ent -= pi * radb_log2(pi + RADB_EPS);
         uni += pi * pi;
     }
-    ent = warp_sum(ent);
-    uni = warp_sum(uni);
+    {
+        double r[3] = {rmad, ent, uni};
+        warp_sum_n(r, tb.red, lane);
+        rmad = r[0] * rin; ent = r[1]; uni = r[2];
+    }
     if (lane == 0) {
         o[0] = p10;
         o[1] = p90;
         o[2] = en;
         o[3] = ent;
         o[4] = p75 - p25;
-        o[5] = (m2 == 0.0) ? 0.0 : m4 / (m2 * m2);
+        o[5] = (m2 == 0.0) ? 0.0 : radb_div(m4, m2 * m2);
         o[6] = (double)vmax;
         o[7] = mad;
         o[8] = mean;
@@ -140,8 +147,8 @@ __device__ void fo_task_u8(const RadbParams& p, const int* hist, const int* lhis
         o[10] = (double)vmin;
         o[11] = (double)(vmax - vmin);
         o[12] = rmad;
-        o[13] = sqrt(en / dN);
-        o[14] = (m2 == 0.0) ? 0.0 : m3 / (m2 * sqrt(m2));
+        o[13] = radb_sqrt(en * rN);
+        o[14] = (m2 == 0.0) ? 0.0 : radb_div(m3, m2 * radb_sqrt(m2));
         o[15] = en;  // TotalEnergy: pixel spacing is (1, 1) for GetImageFromArray images
         o[16] = uni;
         o[17] = m2;
@@ -197,10 +204,10 @@ __device__ double tridiag_kth(const double* d, const double* e2, int m, int k, d
     return 0.5 * (lo + hi);
 }
 
-// One warp per angle.  A.6: MCC = sqrt(second largest eigenvalue of Q),
+// One warp per angle.  A.6: MCC = radb_sqrt(second largest eigenvalue of Q),
 // Q[i][j] = sum_k P[i][k] P[j][k] / (px[i] py[k]); Q is similar to S = A A^T with
 // A = Dx^-1/2 P Dy^-1/2.  For a symmetric GLCM A is symmetric, so the eigenvalues of S are the
-// squares of those of A and sqrt(lambda_2(S)) = second largest |lambda(A)|.
+// squares of those of A and radb_sqrt(lambda_2(S)) = second largest |lambda(A)|.
 __device__ double mcc_task(const int* P, const int* px, const int* py, int n, int symmetric, double* ws,
                            unsigned char* idx, int lane)
 {
@@ -220,8 +227,8 @@ __device__ double mcc_task(const int* P, const int* px, const int* py, int n, in
     double* w = v + m;
     double* d = w + m;
     double* e2 = d + m;
-    // d doubles as scratch for 1/sqrt(px) while the matrix is built (d is first written below)
-    for (int r = lane; r < m; r += 32) d[r] = 1.0 / sqrt((double)px[idx[r]]);
+    // d doubles as scratch for 1/radb_sqrt(px) while the matrix is built (d is first written below)
+    for (int r = lane; r < m; r += 32) d[r] = radb_div(1.0, radb_sqrt((double)px[idx[r]]));
     __syncwarp();
     for (int r = 0; r < m; r++) {
         const int ir = idx[r];
@@ -234,7 +241,7 @@ __device__ double mcc_task(const int* P, const int* px, const int* py, int n, in
             } else {
                 val = 0;
                 for (int k = 0; k < n; k++)
-                    if (py[k] > 0) val += (double)P[ir * n + k] * (double)P[ic * n + k] / (double)py[k];
+                    if (py[k] > 0) val += radb_div((double)P[ir * n + k] * (double)P[ic * n + k], (double)py[k]);
             }
             M[tri(r, c)] = val * rr * d[c];
         }
@@ -251,11 +258,11 @@ __device__ double mcc_task(const int* P, const int* px, const int* py, int n, in
             __syncwarp();
             continue;
         }
-        double nrm = sqrt(tail + x0 * x0);
+        double nrm = radb_sqrt(tail + x0 * x0);
         double alpha = x0 > 0 ? -nrm : nrm;
         // v = x - alpha e1 (indices k+1..m-1), beta = 2 / v^T v
         double vtv = tail + (x0 - alpha) * (x0 - alpha);
-        double beta = 2.0 / vtv;
+        double beta = radb_div(2.0, vtv);
         for (int r = k + 1 + lane; r < m; r += 32) v[r] = (r == k + 1) ? x0 - alpha : M[tri(r, k)];
         __syncwarp();
         // w = beta * M22 v
@@ -294,7 +301,7 @@ __device__ double mcc_task(const int* P, const int* px, const int* py, int n, in
     // Gershgorin bounds
     double glo = 1e300, ghi = -1e300;
     for (int i = lane; i < m; i += 32) {
-        double r = (i > 0 ? sqrt(e2[i - 1]) : 0.0) + (i < m - 1 ? sqrt(e2[i]) : 0.0);
+        double r = (i > 0 ? radb_sqrt(e2[i - 1]) : 0.0) + (i < m - 1 ? radb_sqrt(e2[i]) : 0.0);
         glo = fmin(glo, d[i] - r);
         ghi = fmax(ghi, d[i] + r);
     }
@@ -314,7 +321,7 @@ __device__ double mcc_task(const int* P, const int* px, const int* py, int n, in
         const double l1 = tridiag_kth(d, e2, m, 0, glo, ghi, lane);
         return fmax(t, fabs(l1));
     }
-    return sqrt(fmax(l2, 0.0));
+    return radb_sqrt(fmax(l2, 0.0));
 }
 
 // ------------------------------------------------------------------ GLCM features (one warp, one angle)
@@ -353,16 +360,16 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
     sN = warp_sum_ll(sN);
     __syncwarp();
     if (sN == 0) return 0;
-    const double N = (double)sN, rN = 1.0 / N;
+    const double N = (double)sN, rN = radb_div(1.0, N);
     double r0[5] = {(double)sI, (double)sJ, (double)sIJ, (double)sD2, (double)sC2};  // exact integers < 2^53
-    warp_sum_n(r0);
+    warp_sum_n(r0, tb.red, lane);
     const double ux = r0[0] * rN;
     const double uy = r0[1] * rN;
     const double autoc = r0[2] * rN;
     const double contrast = r0[3] * rN;
     const double energy = r0[4] * rN * rN;
     const double maxp = (double)warp_max_i(maxc) * rN;
-    const double log2N = log2(N);
+    const double log2N = radb_log2(N);
     nnz = warp_sum_i(nnz);
     // marginals: entropies and reciprocal tables (ws is free until mcc_task builds its matrix)
     double* rpx = ws;       // N / px[i]
@@ -371,25 +378,25 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
     int nx = 0, ny = 0;
     for (int i = lane; i < n; i += 32) {
         const int a = px[i], b = py[i];
-        rpx[i] = a ? N / (double)a : 0.0;
-        rpy[i] = b ? 1.0 / (double)b : 0.0;
+        rpx[i] = a ? radb_div(N, (double)a) : 0.0;
+        rpy[i] = b ? radb_div(1.0, (double)b) : 0.0;
         if (a) {
             const double q = (double)a * rN;
-            hx -= q * log2(q + RADB_EPS);
-            hx0 -= q * (log2((double)a) - log2N);
+            hx -= q * radb_log2(q + RADB_EPS);
+            hx0 -= q * (radb_log2((double)a) - log2N);
             nx++;
         }
         if (b) {
             const double q = (double)b * rN;
-            hy -= q * log2(q + RADB_EPS);
-            hy0 -= q * (log2((double)b) - log2N);
+            hy -= q * radb_log2(q + RADB_EPS);
+            hy0 -= q * (radb_log2((double)b) - log2N);
             ny++;
         }
     }
     __syncwarp();
     {
         double r1[4] = {hx, hy, hx0, hy0};
-        warp_sum_n(r1);
+        warp_sum_n(r1, tb.red, lane);
         hx = r1[0]; hy = r1[1]; hx0 = r1[2]; hy0 = r1[3];
     }
     nx = warp_sum_i(nx);
@@ -419,7 +426,7 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
     }
     {
         double r2[8] = {ct, cs, cp, ssq, ssqy, corm, h1corr, sclog};
-        warp_sum_n(r2);
+        warp_sum_n(r2, tb.red, lane);
         ct = r2[0]; cs = r2[1]; cp = r2[2]; ssq = r2[3]; ssqy = r2[4]; corm = r2[5]; h1corr = r2[6]; sclog = r2[7];
     }
     const double hxy = -sclog * rN - RADB_EPS_LN2 * (double)nnz;
@@ -428,16 +435,16 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
     const double hxy2 = hx0 + hy0 - RADB_EPS_LN2 * (double)nx * (double)ny;
     // |i-j| marginal
     double da = 0, de = 0, idv = 0, idm = 0, idmn = 0, idn = 0, iv = 0;
-    const double dn = (double)n;
+    const double rdn = radb_div(1.0, (double)n);
     for (int k = lane; k < n; k += 32) {
         if (!psub[k]) continue;
         const double q = (double)psub[k] * rN, dk = (double)k;
         da += dk * q;
-        de -= q * log2(q + RADB_EPS);
-        idv += q / (1.0 + dk);
-        idm += q / (1.0 + dk * dk);
-        idmn += q / (1.0 + (dk * dk) / (dn * dn));
-        idn += q / (1.0 + dk / dn);
+        de -= q * radb_log2(q + RADB_EPS);
+        idv += radb_div(q, 1.0 + dk);
+        idm += radb_div(q, 1.0 + dk * dk);
+        idmn += radb_div(q, 1.0 + (dk * dk) * rdn * rdn);
+        idn += radb_div(q, 1.0 + dk * rdn);
         if (k > 0) iv += q * tab_inv2(tb, k);
     }
     // i+j marginal (index k <-> i+j = k+2)
@@ -446,11 +453,11 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
         if (!padd[k]) continue;
         const double q = (double)padd[k] * rN;
         sa += (double)(k + 2) * q;
-        se -= q * log2(q + RADB_EPS);
+        se -= q * radb_log2(q + RADB_EPS);
     }
     {
         double r3[9] = {da, de, idv, idm, idmn, idn, iv, sa, se};
-        warp_sum_n(r3);
+        warp_sum_n(r3, tb.red, lane);
         da = r3[0]; de = r3[1]; idv = r3[2]; idm = r3[3]; idmn = r3[4]; idn = r3[5]; iv = r3[6]; sa = r3[7]; se = r3[8];
     }
     double dvar = 0;
@@ -460,7 +467,7 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
     __syncwarp();
     const double mcc = mcc_task(P, px, py, n, p.symmetric, ws, idx, lane);
     if (lane == 0) {
-        const double sigx = sqrt(ssq), sigy = sqrt(ssqy);
+        const double sigx = radb_sqrt(ssq), sigy = radb_sqrt(ssqy);
         const double div = fmax(hx, hy);
         double im2 = 1.0 - exp(-2.0 * (hxy2 - hxy));
         im2 = im2 < 0.0 ? 0.0 : im2;
@@ -469,7 +476,7 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
         o[2] = cs;
         o[3] = ct;
         o[4] = contrast;
-        o[5] = (sigx * sigy == 0.0) ? 1.0 : corm / (sigx * sigy + RADB_EPS);
+        o[5] = (sigx * sigy == 0.0) ? 1.0 : radb_div(corm, sigx * sigy + RADB_EPS);
         o[6] = da;
         o[7] = de;
         o[8] = dvar;
@@ -477,8 +484,8 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
         o[10] = idm;
         o[11] = idmn;
         o[12] = idn;
-        o[13] = (div != 0.0) ? (hxy - hxy1) / div : 0.0;
-        o[14] = sqrt(im2);
+        o[13] = (div != 0.0) ? radb_div(hxy - hxy1, div) : 0.0;
+        o[14] = radb_sqrt(im2);
         o[15] = iv;
         o[16] = ux;
         o[17] = energy;
@@ -530,7 +537,7 @@ __device__ int glrlm_task(const RadbTabs& tb, const unsigned* R, int cell0, int 
     if (sN == 0) return 0;
     {
         double r0[9] = {(double)sGI, (double)sGI2, (double)sG2, lgl, e1, srl, srh, lrl, lrh};  // first three: exact
-        warp_sum_n(r0);
+        warp_sum_n(r0, tb.red, lane);
         sGI = (long long)r0[0]; sGI2 = (long long)r0[1]; sG2 = (long long)r0[2];
         lgl = r0[3]; e1 = r0[4]; srl = r0[5]; srh = r0[6]; lrl = r0[7]; lrh = r0[8];
     }
@@ -547,11 +554,11 @@ __device__ int glrlm_task(const RadbTabs& tb, const unsigned* R, int cell0, int 
     }
     {
         double r1[4] = {(double)sRJ, (double)sRJ2, (double)sR2, sre};
-        warp_sum_n(r1);
+        warp_sum_n(r1, tb.red, lane);
         sRJ = (long long)r1[0]; sRJ2 = (long long)r1[1]; sR2 = (long long)r1[2]; sre = r1[3];
     }
     if (lane == 0) {
-        const double N = (double)sN, rN = 1.0 / N;
+        const double N = (double)sN, rN = radb_div(1.0, N);
         o[0] = (double)sG2 * rN;
         o[1] = (double)sG2 * rN * rN;
         o[2] = (double)(sN * sGI2 - sGI * sGI) * rN * rN;
@@ -560,10 +567,10 @@ __device__ int glrlm_task(const RadbTabs& tb, const unsigned* R, int cell0, int 
         o[5] = lrh * rN;
         o[6] = lrl * rN;
         o[7] = lgl * rN;
-        o[8] = log2(N) - e1 * rN - RADB_EPS_LN2 * (double)nnz;
+        o[8] = radb_log2(N) - e1 * rN - RADB_EPS_LN2 * (double)nnz;
         o[9] = (double)sR2 * rN;
         o[10] = (double)sR2 * rN * rN;
-        o[11] = N / (double)sRJ;
+        o[11] = radb_div(N, (double)sRJ);
         o[12] = (double)(sN * sRJ2 - sRJ * sRJ) * rN * rN;
         o[13] = sre * rN;
         o[14] = srh * rN;
@@ -607,11 +614,11 @@ __device__ __forceinline__ void zs_level(ZoneSums& z, const RadbTabs& tb, int i,
     z.G2 += (long long)g * g;
     z.lgl += (double)g * tab_inv2(tb, i);
 }
-__device__ __forceinline__ void zs_reduce(ZoneSums& z)
+__device__ __forceinline__ void zs_reduce(ZoneSums& z, const RadbTabs& tb, int lane)
 {
     double r[14] = {(double)z.N, (double)z.GI, (double)z.GI2, (double)z.G2, (double)z.J1, (double)z.J2,
                     (double)z.PJ2, z.lgl, z.e1, z.small, z.sl, z.sh, z.ll, z.lh};  // first seven: exact integers
-    warp_sum_n(r);
+    warp_sum_n(r, tb.red, lane);
     z.N = (long long)r[0]; z.GI = (long long)r[1]; z.GI2 = (long long)r[2]; z.G2 = (long long)r[3];
     z.J1 = (long long)r[4]; z.J2 = (long long)r[5]; z.PJ2 = (long long)r[6];
     z.lgl = r[7]; z.e1 = r[8]; z.small = r[9]; z.sl = r[10]; z.sh = r[11]; z.ll = r[12]; z.lh = r[13];
@@ -669,26 +676,26 @@ __device__ void glszm_task(const RadbParams& p, const RadbTabs& tb, const int* Z
     __syncwarp();
     for (int i = lane; i < n; i += 32)
         if (pg[i]) zs_level(z, tb, i + 1, pg[i]);
-    zs_reduce(z);
+    zs_reduce(z, tb, lane);
     if (lane == 0) {
-        const double N = z.N ? (double)z.N : 1.0;
+        const double N = z.N ? (double)z.N : 1.0, rN = radb_div(1.0, N);
         const double Np = z.J1 ? (double)z.J1 : 1.0;
-        o[0] = (double)z.G2 / N;
-        o[1] = (double)z.G2 / (N * N);
-        o[2] = (double)(z.N * z.GI2 - z.GI * z.GI) / (N * N);
-        o[3] = (double)z.GI2 / N;
-        o[4] = (double)z.J2 / N;
-        o[5] = z.lh / N;
-        o[6] = z.ll / N;
-        o[7] = z.lgl / N;
-        o[8] = (double)z.PJ2 / N;
-        o[9] = (double)z.PJ2 / (N * N);
-        o[10] = z.small / N;
-        o[11] = z.sh / N;
-        o[12] = z.sl / N;
-        o[13] = z.N ? log2(N) - z.e1 / N - RADB_EPS_LN2 * (double)z.nnz : 0.0;
-        o[14] = N / Np;
-        o[15] = (double)(z.N * z.J2 - z.J1 * z.J1) / (N * N);
+        o[0] = (double)z.G2 * rN;
+        o[1] = (double)z.G2 * rN * rN;
+        o[2] = (double)(z.N * z.GI2 - z.GI * z.GI) * rN * rN;
+        o[3] = (double)z.GI2 * rN;
+        o[4] = (double)z.J2 * rN;
+        o[5] = z.lh * rN;
+        o[6] = z.ll * rN;
+        o[7] = z.lgl * rN;
+        o[8] = (double)z.PJ2 * rN;
+        o[9] = (double)z.PJ2 * rN * rN;
+        o[10] = z.small * rN;
+        o[11] = z.sh * rN;
+        o[12] = z.sl * rN;
+        o[13] = z.N ? radb_log2(N) - z.e1 * rN - RADB_EPS_LN2 * (double)z.nnz : 0.0;
+        o[14] = radb_div(N, Np);
+        o[15] = (double)(z.N * z.J2 - z.J1 * z.J1) * rN * rN;
     }
 }
 
@@ -720,23 +727,23 @@ __device__ void gldm_task(const RadbTabs& tb, const int* D, int n, int nd, doubl
         int cs = warp_sum_i(colsum[j]);
         if (lane == 0) z.PJ2 += (long long)cs * cs;
     }
-    zs_reduce(z);
+    zs_reduce(z, tb, lane);
     if (lane == 0) {
-        const double N = z.N ? (double)z.N : 1.0;
-        o[0] = z.N ? log2(N) - z.e1 / N - RADB_EPS_LN2 * (double)z.nnz : 0.0;
-        o[1] = (double)z.PJ2 / N;
-        o[2] = (double)z.PJ2 / (N * N);
-        o[3] = (double)(z.N * z.J2 - z.J1 * z.J1) / (N * N);
-        o[4] = (double)z.G2 / N;
-        o[5] = (double)(z.N * z.GI2 - z.GI * z.GI) / (N * N);
-        o[6] = (double)z.GI2 / N;
-        o[7] = (double)z.J2 / N;
-        o[8] = z.lh / N;
-        o[9] = z.ll / N;
-        o[10] = z.lgl / N;
-        o[11] = z.small / N;
-        o[12] = z.sh / N;
-        o[13] = z.sl / N;
+        const double N = z.N ? (double)z.N : 1.0, rN = radb_div(1.0, N);
+        o[0] = z.N ? radb_log2(N) - z.e1 * rN - RADB_EPS_LN2 * (double)z.nnz : 0.0;
+        o[1] = (double)z.PJ2 * rN;
+        o[2] = (double)z.PJ2 * rN * rN;
+        o[3] = (double)(z.N * z.J2 - z.J1 * z.J1) * rN * rN;
+        o[4] = (double)z.G2 * rN;
+        o[5] = (double)(z.N * z.GI2 - z.GI * z.GI) * rN * rN;
+        o[6] = (double)z.GI2 * rN;
+        o[7] = (double)z.J2 * rN;
+        o[8] = z.lh * rN;
+        o[9] = z.ll * rN;
+        o[10] = z.lgl * rN;
+        o[11] = z.small * rN;
+        o[12] = z.sh * rN;
+        o[13] = z.sl * rN;
     }
 }
 
@@ -752,7 +759,7 @@ __device__ void ngtdm_task(const int* C, const int* S, int n, int nb, double* pi
         double s = 0;
         for (int c = 0; c < nb; c++) {
             ni += C[i * nb + c];
-            s += (double)S[i * nb + c] / (double)(c + 1);
+            s += radb_div((double)S[i * nb + c], (double)(c + 1));
         }
         pi[i] = (double)ni;
         si[i] = s;
@@ -765,7 +772,8 @@ __device__ void ngtdm_task(const int* C, const int* S, int n, int nb, double* pi
         if (lane < 5) o[lane] = nan_f64();
         return;
     }
-    for (int i = lane; i < n; i += 32) pi[i] = pi[i] / Nvp;
+    const double rNvp = radb_div(1.0, Nvp);
+    for (int i = lane; i < n; i += 32) pi[i] = pi[i] * rNvp;
     __syncwarp();
     double sum_ps = 0, sum_s = 0, absd = 0, cplx = 0, contr = 0, stren = 0;
     int ngp = 0;
@@ -781,7 +789,7 @@ __device__ void ngtdm_task(const int* C, const int* S, int n, int nb, double* pi
             if (p_j == 0.0) continue;
             double dj = (double)(j + 1), dd = di - dj;
             absd += fabs(di * p_i - dj * p_j);
-            cplx += fabs(dd) * (p_i * s_i + p_j * si[j]) / (p_i + p_j);
+            cplx += radb_div(fabs(dd) * (p_i * s_i + p_j * si[j]), p_i + p_j);
             contr += p_i * p_j * dd * dd;
             stren += (p_i + p_j) * dd * dd;
         }
@@ -795,10 +803,10 @@ __device__ void ngtdm_task(const int* C, const int* S, int n, int nb, double* pi
     ngp = warp_sum_i(ngp);
     if (lane == 0) {
         double div = (double)ngp * (double)(ngp - 1);
-        o[0] = (absd != 0.0) ? sum_ps / absd : 0.0;
-        o[1] = (sum_ps != 0.0) ? 1.0 / sum_ps : 1e6;
-        o[2] = cplx / Nvp;
-        o[3] = (div != 0.0) ? contr * sum_s / Nvp / div : 0.0;
-        o[4] = (sum_s != 0.0) ? stren / sum_s : 0.0;
+        o[0] = (absd != 0.0) ? radb_div(sum_ps, absd) : 0.0;
+        o[1] = (sum_ps != 0.0) ? radb_div(1.0, sum_ps) : 1e6;
+        o[2] = cplx * rNvp;
+        o[3] = (div != 0.0) ? radb_div(contr * sum_s * rNvp, div) : 0.0;
+        o[4] = (sum_s != 0.0) ? radb_div(stren, sum_s) : 0.0;
     }
 }

@@ -124,8 +124,20 @@ static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParam
     p.off_glszm = pl.off[4];
     p.off_ngtdm = pl.off[5];
     radb_layout(&p, 1);
-    if (p.smem_total > 227 * 1024) { err = "patch size x gray levels need more than 227 KB of shared memory"; return RADB_E_SMEM; }
+    if (p.smem_total > 227 * 1024 || p.a_smem_total > 227 * 1024 || p.m_smem_total > 227 * 1024) {
+        err = "patch size x gray levels need more than 227 KB of shared memory";
+        return RADB_E_SMEM;
+    }
     return 0;
+}
+
+// 1/k^2 and log2(k) tables read by the reduction kernels (device copies are made at radb_create)
+static inline void make_tables(int ninv, std::vector<double>& inv2, std::vector<double>& tlog)
+{
+    inv2.resize(ninv);
+    for (int k = 0; k < ninv; k++) inv2[k] = 1.0 / ((double)(k + 1) * (double)(k + 1));
+    tlog.resize(128);
+    for (int k = 0; k < 128; k++) tlog[k] = k >= 2 ? log2((double)k) : 0.0;
 }
 
 }  // namespace radb

@@ -1,10 +1,16 @@
-// radb -- B200-native radiomic feature kernels (sm_100a).  One CTA (128 threads) per patch:
-//   stage   : TMA bulk copy (cp.async.bulk + mbarrier) of the raw patch + mask into shared memory
-//   discret.: ROI histogram / bbox / min-max -> value->level LUT -> padded level image (smem)
-//   build   : one neighbourhood pass feeds GLCM, GLDM, NGTDM, GLRLM (run walk) and the GLSZM
-//             union-find; every matrix lives in shared memory as privatised integer counters
-//   reduce  : warp-specialised fp64 feature reductions (warp w <-> angle w), shuffle reductions,
-//             MCC through Householder tridiagonalisation + Sturm multisection in shared memory
+// radb -- B200-native radiomic feature kernels (sm_100a).  Three kernels per batch, one CTA
+// (128 threads) per patch in each, so that every kernel's code stays small enough for the SM
+// instruction caches (a fused single kernel measured 55 % "no instruction" stalls, profiles/):
+//   radb_build_kernel : TMA bulk copy (cp.async.bulk + mbarrier) of the raw patch + mask into
+//                       shared memory -> ROI histogram / bbox -> value->level LUT -> padded level
+//                       image -> line walks (GLRLM runs + row-run labels) -> one neighbourhood
+//                       pass (GLCM, GLDM, NGTDM, run-adjacency unions for GLSZM) -> zone sizes.
+//                       Every matrix is a shared-memory privatised integer counter array; the
+//                       finished RECORD (header + matrices) is copied to a global workspace.
+//   radb_angle_kernel : warp a reduces GLRLM angle a (16 features) and GLCM angle a (24 features,
+//                       MCC through Householder tridiagonalisation + Sturm multisection), fp64,
+//                       then the CTA forms the nanmean over angles.
+//   radb_misc_kernel  : one warp each for GLSZM, GLDM, NGTDM and first-order features.
 // Semantics follow pyradiomics 3.1.0 as called from /root/reference/RadiomicExtractor.py:38-48
 // (settings /root/reference/params.yml:93-119); the algorithm restated is SURVEY.md Appendix A.
 // This header also compiles as plain C++ under tests/emu/cuda_emu.h (RADB_EMU) so that the same
@@ -36,23 +42,30 @@ __device__ __forceinline__ double warp_sum(double v)
     return v;
 #endif
 }
-// N independent butterflies interleaved: same instruction count as N warp_sum calls, but the
-// shuffle latencies overlap (the feature reductions are latency-bound).
+// N sums at once through a per-warp shared-memory scratch (N x 33 doubles): every lane stores its
+// N partials, lane i < N adds the 32 partials of value i in lane order, all lanes read the N
+// totals back.  Compared with N shuffle butterflies this is ~3x fewer instructions, one short
+// dependent chain instead of N, and a fraction of the code size (the inlined butterflies were
+// 25-40 % of the reduction kernels' instruction footprint).  Fixed order => reproducible.
+#define RADB_RED_MAX 14
+#define RADB_RED_DOUBLES (RADB_RED_MAX * 33)
 template <int N>
-__device__ __forceinline__ void warp_sum_n(double (&v)[N])
+__device__ __forceinline__ void warp_sum_n(double (&v)[N], double* scr, int lane)
 {
-#ifdef RADB_EMU
-    for (int i = 0; i < N; i++) v[i] = warp_sum(v[i]);
-#else
 #pragma unroll
-    for (int m = 16; m >= 1; m >>= 1) {
-        double t[N];
-#pragma unroll
-        for (int i = 0; i < N; i++) t[i] = __shfl_xor_sync(FULLMASK, v[i], m);
-#pragma unroll
-        for (int i = 0; i < N; i++) v[i] += t[i];
+    for (int i = 0; i < N; i++) scr[i * 33 + lane] = v[i];
+    __syncwarp();
+    if (lane < N) {
+        const double* r = scr + lane * 33;
+        double s0 = 0, s1 = 0;
+#pragma unroll 1
+        for (int j = 0; j < 32; j += 2) { s0 += r[j]; s1 += r[j + 1]; }
+        scr[lane * 33 + 32] = s0 + s1;
     }
-#endif
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < N; i++) v[i] = scr[i * 33 + 32];
+    __syncwarp();
 }
 __device__ __forceinline__ long long warp_sum_ll(long long v)
 {
@@ -209,9 +222,9 @@ __device__ __forceinline__ double py_mod(double a, double b)
 
 #include "radb_features.cuh"
 
-// ------------------------------------------------------------------ the per-patch CTA
-template <typename PT>
-__device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* smem)
+// ------------------------------------------------------------------ build kernel: one CTA per patch
+template <typename PT, bool DBG>
+__device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned char* smem)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, HW = p.HW, WP = p.WP, NA = p.n_angles, NB = 2 * p.n_angles;
@@ -228,7 +241,6 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
     int* ngn = (int*)(smem + p.o_ngn);
     int* szm = (int*)(smem + p.o_szm);
     unsigned* ovf = (unsigned*)(smem + p.o_ovf);
-    double* fsc = (double*)(smem + p.o_fsc);
     int* misc = (int*)(smem + p.o_misc);
     const PT* g_img = (const PT*)((const unsigned char*)p.img + patch * p.img_stride);
     const unsigned char* g_msk = p.mask + patch * p.mask_stride;
@@ -346,7 +358,7 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
             for (int f = tid; f < p.F; f += RADB_NT) out[f] = nan_f64();
             if (tid == 0) {
                 p.status[patch] = st;
-                if (p.dbg_ng) p.dbg_ng[patch] = 0;
+                if (DBG && p.dbg_ng) p.dbg_ng[patch] = 0;
             }
             return;
         }
@@ -364,12 +376,6 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
         }
     for (int v = tid; v < 256; v += RADB_NT)
         if (hist[v]) atomicAdd(&lhist[lut[v] - 1], hist[v]);
-    {   // per-CTA tables for the feature reductions: 1/k^2 and log2(c)
-        double* inv2 = (double*)(smem + p.o_inv2);
-        double* clog = (double*)(smem + p.o_clog);
-        for (int k = tid; k < p.ninv; k += RADB_NT) inv2[k] = 1.0 / ((double)(k + 1) * (double)(k + 1));
-        for (int k = tid; k < 128; k += RADB_NT) clog[k] = k >= 2 ? log2((double)k) : 0.0;
-    }
     __syncthreads();
 
     // ROI bounding box (every later pixel pass runs over the bbox only, linearised so that all
@@ -587,105 +593,156 @@ __device__ void radb_cta(const RadbParams& p, long long patch, unsigned char* sm
             int k = atomicAdd(&misc[5], 1);
             if (k < p.ovf_cap) ovf[k] = ((unsigned)c << 16) | (unsigned)s;
         }
-        if (p.dbg_glszm) atomicAdd(&p.dbg_glszm[(patch * p.max_ng + (c - 1)) * (long long)HW + s - 1], 1);
+        if (DBG && p.dbg_glszm) atomicAdd(&p.dbg_glszm[(patch * p.max_ng + (c - 1)) * (long long)HW + s - 1], 1);
     }
     __syncthreads();
 
     // ---- optional debug dump of the integer matrices (parity tests)
-    if (p.dbg_ng && tid == 0) p.dbg_ng[patch] = ng;
-    if (p.dbg_levels)
+    if (DBG && p.dbg_ng && tid == 0) p.dbg_ng[patch] = ng;
+    if (DBG && p.dbg_levels)
         for (int i = tid; i < HW; i += RADB_NT)
             p.dbg_levels[patch * HW + i] = lev[(i / W + 1) * WP + (i % W) + 1];
-    if (p.dbg_glcm)
+    if (DBG && p.dbg_glcm)
         for (int a = 0; a < NA; a++)
             for (int t = tid; t < ng * ng; t += RADB_NT)
                 p.dbg_glcm[((patch * NA + a) * p.max_ng + t / ng) * p.max_ng + t % ng] = glcm[a * ng * ng + t];
-    if (p.dbg_glrlm)
+    if (DBG && p.dbg_glrlm)
         for (int a = 0; a < NA; a++)
             for (int t = tid; t < ng * p.nr; t += RADB_NT)
                 p.dbg_glrlm[((patch * NA + a) * p.max_ng + t / p.nr) * p.nr + t % p.nr] =
                     get_u16((const unsigned*)(smem + p.o_glrlm + a * p.glrlm_stride), t);
-    if (p.dbg_gldm)
+    if (DBG && p.dbg_gldm)
         for (int t = tid; t < ng * (NB + 1); t += RADB_NT)
             p.dbg_gldm[patch * p.max_ng * (NB + 1) + t] = gldm[t];
 
-    // ---- phase 6: warp-specialised feature reductions
-    //   tasks 0..NA-1 : angle t: GLRLM features -> fsc[t][24..39], then GLCM features (+MCC, whose
-    //                   workspace re-uses the GLRLM slot of the same angle) -> fsc[t][0..23]
-    //   then GLSZM, GLDM, NGTDM, first-order -> fsc[NA*40 + ...]
-    double* single = fsc + NA * RADB_FSC_STRIDE;  // [0..15] glszm, [16..29] gldm, [30..34] ngtdm, [35..52] fo
-    int* valid = misc + 16;                       // [a] glcm angle valid, [4+a] glrlm angle valid
-    const int ntask = NA + 4;
+    // ---- phase 6: publish the record (header + every integer matrix) for the reduction kernels
+    if (tid == 0) {
+        int nroi = 0;  // number of gray levels present in the ROI (MCC: < 2 -> 1)
+        for (int i = 0; i < ng; i++) nroi += lhist[i] > 0;
+        misc[9] = nroi;
+    }
+    __syncthreads();
+    {
+        const uint4* src = (const uint4*)(smem + p.o_rec);
+        uint4* dst = (uint4*)(p.ws + patch * (long long)p.rec_bytes);
+        const int n16 = p.rec_bytes / 16;
+        for (int i = tid; i < n16; i += RADB_NT) dst[i] = src[i];
+    }
+}
+
+// ------------------------------------------------------------------ angle kernel: GLRLM + GLCM (+MCC)
+// One CTA per patch, warp a <-> angle a.  The matrices are read from the record in the global
+// workspace (L2-resident: the build kernel has just written them); scratch lives in shared memory.
+__device__ void radb_angle_cta(const RadbParams& p, long long patch, unsigned char* smem)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NA = p.n_angles;
+    if (p.status[patch] != 0) return;  // NaN row already written by the build kernel
+    const unsigned char* rec = p.ws + patch * (long long)p.rec_bytes;
+    const int* misc = (const int*)(rec + (p.o_misc - p.o_rec));
+    const int ng = misc[8], nroi = misc[9];
+    double* fsc = (double*)(smem + p.a_fsc);
+    int* valid = (int*)(smem + p.a_valid);
+    double* out = p.out + patch * (long long)p.F;
     RadbTabs tb;
-    tb.inv2 = (const double*)(smem + p.o_inv2);
+    tb.inv2 = p.g_inv2;
     tb.ninv = p.ninv;
-    tb.tlog = (const double*)(smem + p.o_clog);
-    for (int t = warp; t < ntask; t += RADB_NT / 32) {
-        if (t < NA) {
-            const int a = t;
-            unsigned char* slot = smem + p.o_glrlm + a * p.glrlm_stride;
-            int ok = glrlm_task(tb, (const unsigned*)slot, 0, ng, p.nr, (int*)(smem + p.o_pr) + a * p.nr,
-                                fsc + a * RADB_FSC_STRIDE + RADB_GLCM_NF, lane);
-            if (lane == 0) valid[4 + a] = ok;
-            __syncwarp();
-            ok = glcm_task(p, tb, glcm + a * ng * ng, ng, (int*)(smem + p.o_px) + a * ng,
-                           (int*)(smem + p.o_py) + a * ng, (int*)(smem + p.o_padd) + a * 2 * ng,
-                           (int*)(smem + p.o_psub) + a * ng, (double*)slot, smem + p.o_idx + a * ng,
-                           fsc + a * RADB_FSC_STRIDE, lane);
-            if (lane == 0) valid[a] = ok;
-        } else if (t == NA) {
-            int novf = misc[5] < p.ovf_cap ? misc[5] : p.ovf_cap;
-            glszm_task(p, tb, szm, ovf, (unsigned*)(smem + p.o_ovf2), novf, ng, (int*)(smem + p.o_pg), single,
+    tb.tlog = p.g_tlog;
+    tb.red = (double*)(smem + warp * p.a_warp_bytes + p.a_red);
+    for (int a = warp; a < NA; a += RADB_NT / 32) {
+        unsigned char* ws = smem + warp * p.a_warp_bytes;
+        // zero this warp's integer scratch (px, py, padd, psub, pr are contiguous)
+        for (int i = lane; i < (p.a_idx - p.a_px) / 4; i += 32) ((int*)(ws + p.a_px))[i] = 0;
+        __syncwarp();
+        const unsigned* R = (const unsigned*)(rec + (p.o_glrlm - p.o_rec) + a * p.glrlm_stride);
+        int ok = glrlm_task(tb, R, 0, ng, p.nr, (int*)(ws + p.a_pr), fsc + a * RADB_FSC_STRIDE + RADB_GLCM_NF, lane);
+        if (lane == 0) valid[4 + a] = ok;
+        const int* P = (const int*)(rec + (p.o_glcm - p.o_rec)) + a * ng * ng;
+        ok = glcm_task(p, tb, P, ng, (int*)(ws + p.a_px), (int*)(ws + p.a_py), (int*)(ws + p.a_padd),
+                       (int*)(ws + p.a_psub), (double*)(ws + p.a_mcc), ws + p.a_idx, fsc + a * RADB_FSC_STRIDE,
                        lane);
-        } else if (t == NA + 1) {
-            gldm_task(tb, gldm, ng, NB + 1, single + 16, lane);
-        } else if (t == NA + 2) {
-            double* pi = (double*)(smem + p.o_ngp);
-            ngtdm_task(ngc, ngn, ng, NB, pi, pi + ng, single + 30, lane,
+        if (lane == 0) valid[a] = ok;
+    }
+    __syncthreads();
+    // nanmean over the non-empty angles
+    if (p.off_glcm >= 0 && tid < RADB_GLCM_NF) {
+        double s = 0;
+        int k = 0;
+        for (int a = 0; a < NA; a++)
+            if (valid[a]) { s += fsc[a * RADB_FSC_STRIDE + tid]; k++; }
+        double v = k ? s / (double)k : nan_f64();
+        if (tid == 19 && nroi < 2) v = 1.0;
+        out[p.off_glcm + tid] = v;
+    }
+    if (p.off_glrlm >= 0 && tid >= 32 && tid < 32 + RADB_GLRLM_NF) {
+        const int f = tid - 32;
+        double s = 0;
+        int k = 0;
+        for (int a = 0; a < NA; a++)
+            if (valid[4 + a]) { s += fsc[a * RADB_FSC_STRIDE + RADB_GLCM_NF + f]; k++; }
+        out[p.off_glrlm + f] = k ? s / (double)k : nan_f64();
+    }
+}
+
+// ------------------------------------------------------------------ misc kernel: GLSZM, GLDM, NGTDM, first-order
+// One CTA per patch, one warp per feature class.
+__device__ void radb_misc_cta(const RadbParams& p, long long patch, unsigned char* smem)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int NB = 2 * p.n_angles;
+    if (p.status[patch] != 0) return;
+    const unsigned char* rec = p.ws + patch * (long long)p.rec_bytes;
+    const int* misc = (const int*)(rec + (p.o_misc - p.o_rec));
+    const int ng = misc[8];
+    double* out = p.out + patch * (long long)p.F;
+    RadbTabs tb;
+    tb.inv2 = p.g_inv2;
+    tb.ninv = p.ninv;
+    tb.tlog = p.g_tlog;
+    tb.red = (double*)(smem + p.m_red) + warp * RADB_RED_DOUBLES;
+    for (int t = warp; t < 4; t += RADB_NT / 32) {
+        if (t == 0) {
+            if (p.off_glszm < 0) continue;
+            int* pg = (int*)(smem + p.m_pg);
+            for (int i = lane; i < ng; i += 32) pg[i] = 0;
+            __syncwarp();
+            const int novf = misc[5] < p.ovf_cap ? misc[5] : p.ovf_cap;
+            glszm_task(p, tb, (const int*)(rec + (p.o_szm - p.o_rec)), (const unsigned*)(rec + (p.o_ovf - p.o_rec)),
+                       (unsigned*)(smem + p.m_ovf2), novf, ng, pg, out + p.off_glszm, lane);
+        } else if (t == 1) {
+            if (p.off_gldm < 0) continue;
+            gldm_task(tb, (const int*)(rec + (p.o_gldm - p.o_rec)), ng, NB + 1, out + p.off_gldm, lane);
+        } else if (t == 2) {
+            if (p.off_ngtdm < 0 && !p.dbg_ngn) continue;
+            double* pi = (double*)(smem + p.m_ngp);
+            double dummy[5];
+            ngtdm_task((const int*)(rec + (p.o_ngc - p.o_rec)), (const int*)(rec + (p.o_ngn - p.o_rec)), ng, NB, pi,
+                       pi + ng, p.off_ngtdm >= 0 ? out + p.off_ngtdm : dummy, lane,
                        p.dbg_ngn ? p.dbg_ngn + patch * p.max_ng : (int*)0,
                        p.dbg_ngs ? p.dbg_ngs + patch * p.max_ng : (double*)0);
         } else {
-            fo_task_u8(p, hist, lhist, ng, (double*)(smem + p.o_qv), single + 35, lane);
-        }
-    }
-    __syncthreads();
-
-    // ---- phase 7: nanmean over angles, write the feature row
-    {
-        int nroi = 0;  // number of gray levels present in the ROI (MCC: < 2 -> 1)
-        for (int i = 0; i < ng; i++) nroi += lhist[i] > 0;
-        if (p.off_glcm >= 0 && tid < RADB_GLCM_NF) {
-            double s = 0;
-            int k = 0;
-            for (int a = 0; a < NA; a++)
-                if (valid[a]) { s += fsc[a * RADB_FSC_STRIDE + tid]; k++; }
-            double v = k ? s / (double)k : nan_f64();
-            if (tid == 19 && nroi < 2) v = 1.0;
-            out[p.off_glcm + tid] = v;
-        }
-        if (p.off_glrlm >= 0 && tid >= 32 && tid < 32 + RADB_GLRLM_NF) {
-            const int f = tid - 32;
-            double s = 0;
-            int k = 0;
-            for (int a = 0; a < NA; a++)
-                if (valid[4 + a]) { s += fsc[a * RADB_FSC_STRIDE + RADB_GLCM_NF + f]; k++; }
-            out[p.off_glrlm + f] = k ? s / (double)k : nan_f64();
-        }
-        if (tid >= 64) {
-            const int f = tid - 64;
-            if (f < 16) { if (p.off_glszm >= 0) out[p.off_glszm + f] = single[f]; }
-            else if (f < 30) { if (p.off_gldm >= 0) out[p.off_gldm + f - 16] = single[f]; }
-            else if (f < 35) { if (p.off_ngtdm >= 0) out[p.off_ngtdm + f - 30] = single[f]; }
-            else if (f < 53) { if (p.off_fo >= 0) out[p.off_fo + f - 35] = single[f]; }
+            if (p.off_fo < 0) continue;
+            fo_task_u8(p, tb, (const int*)(rec + (p.o_hist - p.o_rec)), (const int*)(rec + (p.o_lhist - p.o_rec)), ng,
+                       (double*)(smem + p.m_qv), out + p.off_fo, lane);
         }
     }
 }
 
 #ifndef RADB_EMU
-template <typename PT>
-__global__ void __launch_bounds__(RADB_NT, 4) radb_extract_kernel(const RadbParams p)
+template <typename PT, bool DBG>
+__global__ void __launch_bounds__(RADB_NT, 4) radb_build_kernel(const RadbParams p)
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
-    radb_cta<PT>(p, (long long)blockIdx.x, radb_smem);
+    radb_build_cta<PT, DBG>(p, (long long)blockIdx.x, radb_smem);
+}
+__global__ void __launch_bounds__(RADB_NT, 6) radb_angle_kernel(const RadbParams p)
+{
+    extern __shared__ __align__(16) unsigned char radb_smem[];
+    radb_angle_cta(p, (long long)blockIdx.x, radb_smem);
+}
+__global__ void __launch_bounds__(RADB_NT, 8) radb_misc_kernel(const RadbParams p)
+{
+    extern __shared__ __align__(16) unsigned char radb_smem[];
+    radb_misc_cta(p, (long long)blockIdx.x, radb_smem);
 }
 #endif

@@ -34,13 +34,23 @@ struct RadbParams {
     int F;
     int off_fo, off_glcm, off_gldm, off_glrlm, off_glszm, off_ngtdm;  // output column of each class, -1 = off
     int use_tma;
-    // shared-memory byte offsets
-    int o_stage, o_mask, o_mbar, o_zero, o_lev, o_uq, o_hist, o_lut, o_lhist, o_glcm, o_px, o_py,
-        o_padd, o_psub, o_glrlm, o_pr, o_gldm, o_ngc, o_ngn, o_szm, o_ovf, o_idx, o_fsc, o_misc,
-        o_ngp, o_qv, o_pg, o_ovf2, o_inv2, o_clog, smem_total;
-    int ninv;        // entries of the 1/k^2 table
+    // ---- build kernel: shared-memory byte offsets.  [o_rec, o_rec + rec_bytes) is the per-patch
+    // RECORD (header + every integer matrix); the build kernel copies it to the global workspace
+    // and the reduction kernels read it from there at the same relative offsets.
+    int o_stage, o_mask, o_mbar, o_zero, o_lev, o_uq, o_lut, o_rec, o_misc, o_hist, o_lhist, o_glcm, o_glrlm,
+        o_gldm, o_ngc, o_ngn, o_szm, o_ovf, smem_total;
+    int rec_bytes;
+    int glrlm_stride;  // bytes per angle of the packed-u16 GLRLM counters
     int mcc_stride;    // doubles per angle in the MCC workspace
-    int glrlm_stride;  // bytes per angle of the GLRLM / MCC slot
+    int ninv;          // entries of the 1/k^2 table
+    // ---- angle kernel (GLRLM + GLCM + MCC, one warp per angle): per-warp scratch + CTA scratch
+    int a_px, a_py, a_padd, a_psub, a_pr, a_idx, a_mcc, a_red, a_warp_bytes, a_fsc, a_valid, a_smem_total;
+    // ---- misc kernel (GLSZM, GLDM, NGTDM, first-order: one warp each)
+    int m_pg, m_ovf2, m_ngp, m_qv, m_red, m_smem_total;
+    // global workspace + tables (device pointers)
+    unsigned char* ws;        // [B][rec_bytes]
+    const double* g_inv2;     // [ninv]  1/k^2
+    const double* g_tlog;     // [128]   log2(k)
     // optional debug outputs (device pointers, may be null); dims use max_ng
     int* dbg_levels;   // [B][H][W]
     int* dbg_glcm;     // [B][Na][max_ng][max_ng]
@@ -54,7 +64,7 @@ struct RadbParams {
 
 static inline int radb_align(int v, int a) { return (v + a - 1) / a * a; }
 
-// Fills WP/HW/nr/s0/ovf_cap and every o_* offset from H, W, max_ng, n_angles, pixel size.
+// Fills WP/HW/nr/s0/ovf_cap and every shared-memory / record offset from H, W, max_ng, n_angles.
 static inline void radb_layout(RadbParams* p, int pix_bytes)
 {
     const int H = p->H, W = p->W, ng = p->max_ng, na = p->n_angles;
@@ -63,7 +73,12 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->nr = H > W ? H : W;
     p->s0 = 16;
     p->ovf_cap = p->HW / (p->s0 + 1) + 1;
+    p->ninv = ng > p->nr ? ng : p->nr;
+    if (p->ninv < 16) p->ninv = 16;
+    p->mcc_stride = ng * (ng + 1) / 2 + 4 * ng;
+    if (p->mcc_stride < 2 * ng + 8) p->mcc_stride = 2 * ng + 8;
     int o = 0;
+    // ---- build kernel
     p->o_stage = o;                       // raw pixels (TMA destination); later union-find words (u32[HW])
     int stage_bytes = radb_align(p->HW * pix_bytes, 16);
     p->o_mask = o + stage_bytes;          // raw mask (TMA destination)
@@ -74,36 +89,42 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->o_zero = o;                        // everything from here on is zeroed at CTA start
     p->o_lev = o; o += radb_align((H + 2) * p->WP, 16);
     p->o_uq = o; o += (RADB_NT / 32) * 64 * 4;           // per-warp union request queues
-    p->o_hist = o; o += 256 * 4;
     p->o_lut = o; o += 256;
+    p->o_rec = o;
+    p->o_misc = o; o += 32 * 4;           // record header: [0] Np, [5] #overflow zones, [8] Ng, [9] #levels present
+    p->o_hist = o; o += 256 * 4;
     p->o_lhist = o; o += radb_align(ng * 4, 16);
     p->o_glcm = o; o += radb_align(na * ng * ng * 4, 16);
-    p->o_px = o; o += radb_align(na * ng * 4, 16);
-    p->o_py = o; o += radb_align(na * ng * 4, 16);
-    p->o_padd = o; o += radb_align(na * 2 * ng * 4, 16);
-    p->o_psub = o; o += radb_align(na * ng * 4, 16);
-    // GLRLM counters of angle a live at o_glrlm + a*glrlm_stride; the same slot is re-used as the
-    // fp64 MCC workspace of that angle once its GLRLM features are reduced (same warp, in order).
-    p->mcc_stride = ng * (ng + 1) / 2 + 4 * ng;
     p->glrlm_stride = radb_align(ng * p->nr * 2, 16);
-    if (p->mcc_stride * 8 > p->glrlm_stride) p->glrlm_stride = radb_align(p->mcc_stride * 8, 16);
     p->o_glrlm = o; o += na * p->glrlm_stride;
-    p->o_pr = o; o += radb_align(na * p->nr * 4, 16);
     p->o_gldm = o; o += radb_align(ng * (2 * na + 1) * 4, 16);
     p->o_ngc = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] voxel counts per neighbour count
     p->o_ngn = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] sum |cnt*i - sum(neigh)|
     p->o_szm = o; o += radb_align(ng * p->s0 * 4, 16);
     p->o_ovf = o; o += radb_align(p->ovf_cap * 4, 16);
-    p->o_ovf2 = o; o += radb_align(p->ovf_cap * 4, 16);  // overflow zones sorted by key
-    p->o_idx = o; o += radb_align(na * ng, 16);
-    p->o_fsc = o; o += radb_align((na * RADB_FSC_STRIDE + 64) * 8, 16);
-    p->o_ngp = o; o += radb_align(2 * ng * 8, 16);
-    p->o_qv = o; o += 16 * 8;
-    p->o_pg = o; o += radb_align(ng * 4, 16);
-    p->ninv = ng > p->nr ? ng : p->nr;
-    if (p->ninv < 16) p->ninv = 16;
-    p->o_inv2 = o; o += radb_align(p->ninv * 8, 16);
-    p->o_clog = o; o += 128 * 8;
-    p->o_misc = o; o += 32 * 4;
+    p->rec_bytes = o - p->o_rec;
     p->smem_total = o;
+    // ---- angle kernel
+    o = 0;
+    p->a_px = o; o += radb_align(ng * 4, 16);
+    p->a_py = o; o += radb_align(ng * 4, 16);
+    p->a_padd = o; o += radb_align(2 * ng * 4, 16);
+    p->a_psub = o; o += radb_align(ng * 4, 16);
+    p->a_pr = o; o += radb_align(p->nr * 4, 16);
+    p->a_idx = o; o += radb_align(ng, 16);
+    p->a_mcc = o; o += radb_align(p->mcc_stride * 8, 16);
+    p->a_red = o; o += 14 * 33 * 8;       // RADB_RED_DOUBLES
+    p->a_warp_bytes = o;
+    o = (RADB_NT / 32) * p->a_warp_bytes;
+    p->a_fsc = o; o += RADB_MAX_ANGLES * RADB_FSC_STRIDE * 8;
+    p->a_valid = o; o += 16 * 4;
+    p->a_smem_total = o;
+    // ---- misc kernel
+    o = 0;
+    p->m_pg = o; o += radb_align(ng * 4, 16);
+    p->m_ovf2 = o; o += radb_align(p->ovf_cap * 4, 16);
+    p->m_ngp = o; o += radb_align(2 * ng * 8, 16);
+    p->m_qv = o; o += 16 * 8;
+    p->m_red = o; o += (RADB_NT / 32) * 14 * 33 * 8;
+    p->m_smem_total = o;
 }

@@ -52,11 +52,19 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
     p.dbg_ngn = ngtdm_n;
     p.dbg_ngs = ngtdm_s;
     p.dbg_ng = ng;
-    std::vector<unsigned char> smem((size_t)p.smem_total + 64);
+    std::vector<double> inv2, tlog;
+    radb::make_tables(p.ninv, inv2, tlog);
+    p.g_inv2 = inv2.data();
+    p.g_tlog = tlog.data();
+    std::vector<unsigned char> ws((size_t)B * p.rec_bytes + 64);
+    p.ws = (unsigned char*)(((uintptr_t)ws.data() + 15) & ~(uintptr_t)15);
+    int mx = p.smem_total > p.a_smem_total ? p.smem_total : p.a_smem_total;
+    mx = mx > p.m_smem_total ? mx : p.m_smem_total;
+    std::vector<unsigned char> smem((size_t)mx + 64);
     unsigned char* sm = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
-    emu::launch((unsigned)B, RADB_NT, [&]() {
-        // poison the shared memory like a fresh CTA would find it (stale data from the last CTA)
-        radb_cta<unsigned char>(p, (long long)blockIdx.x, sm);
-    });
+    // the same three launches radb_api.cu issues, CTA by CTA on host threads
+    emu::launch((unsigned)B, RADB_NT, [&]() { radb_build_cta<unsigned char, true>(p, (long long)blockIdx.x, sm); });
+    emu::launch((unsigned)B, RADB_NT, [&]() { radb_angle_cta(p, (long long)blockIdx.x, sm); });
+    emu::launch((unsigned)B, RADB_NT, [&]() { radb_misc_cta(p, (long long)blockIdx.x, sm); });
     return 0;
 }
