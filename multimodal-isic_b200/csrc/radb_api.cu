@@ -195,9 +195,9 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
             if (q.dbg_ng) q.dbg_ng += done;
         }
         if (dbg)
-            radb_build_kernel<unsigned char, true><<<(unsigned)n, RADB_NT, p.smem_total, st>>>(q);
+            radb_build_kernel<unsigned char, true><<<(unsigned)n, RADB_NTB, p.smem_total, st>>>(q);
         else
-            radb_build_kernel<unsigned char, false><<<(unsigned)n, RADB_NT, p.smem_total, st>>>(q);
+            radb_build_kernel<unsigned char, false><<<(unsigned)n, RADB_NTB, p.smem_total, st>>>(q);
         radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, st>>>(q);
         radb_misc_kernel<<<(unsigned)n, RADB_NT, p.m_smem_total, st>>>(q);
         h->launches += 3;

@@ -19,10 +19,12 @@ __device__ __noinline__ double radb_inv_sq(int k) { return 1.0 / ((double)k * (d
 __device__ __noinline__ double radb_div(double a, double b) { return a / b; }
 __device__ __noinline__ double radb_sqrt(double a) { return sqrt(a); }
 
+#define RADB_TLOG_N 2048  // entries of the log2(count) table
+
 struct RadbTabs {
     const double* inv2;  // inv2[k-1] = 1/k^2, k = 1..ninv
     int ninv;
-    const double* tlog;  // tlog[c] = log2(c), c = 1..127 (tlog[0] = 0)
+    const double* tlog;  // tlog[c] = log2(c), c = 1..RADB_TLOG_N-1 (tlog[0] = 0)
     double* red;         // this warp's reduction scratch (RADB_RED_DOUBLES doubles, shared memory)
 };
 __device__ __forceinline__ double tab_inv2(const RadbTabs& t, int k)
@@ -31,7 +33,7 @@ __device__ __forceinline__ double tab_inv2(const RadbTabs& t, int k)
 }
 __device__ __forceinline__ double tab_log2(const RadbTabs& t, int c)
 {
-    return c < 128 ? t.tlog[c] : radb_log2((double)c);
+    return c < RADB_TLOG_N ? t.tlog[c] : radb_log2((double)c);
 }
 __device__ __forceinline__ double tab_clog(const RadbTabs& t, int c) { return (double)c * tab_log2(t, c); }
 
@@ -170,16 +172,20 @@ __device__ __forceinline__ int sturm_count(const double* d, const double* e2, in
     double p0 = 1.0, p1 = d[0] - x;
     bool neg = p1 < 0.0;
     int cnt = neg ? 1 : 0;
+#pragma unroll 1
     for (int i = 1; i < m; i++) {
-        double pn = (d[i] - x) * p1 - e2[i - 1] * p0;
-        bool nneg = (pn < 0.0) || (pn == 0.0 && neg);
+        const double pn = (d[i] - x) * p1 - e2[i - 1] * p0;
+        const bool nneg = (pn < 0.0) || (pn == 0.0 && neg);
         cnt += (nneg != neg) ? 1 : 0;
         neg = nneg;
         p0 = p1;
         p1 = pn;
-        double ap = fabs(p1);
-        if (ap > 1e100) { p0 *= 1e-100; p1 *= 1e-100; }
-        else if (ap < 1e-100) { p0 *= 1e100; p1 *= 1e100; }
+        if (i & 1) {  // |p| changes by at most ~1e17 per step: rescaling every other step is enough
+            const double ap = fabs(p1);
+            const double sc = ap > 1e100 ? 1e-100 : (ap < 1e-100 ? 1e100 : 1.0);
+            p0 *= sc;
+            p1 *= sc;
+        }
     }
     return cnt;
 }
@@ -369,7 +375,9 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
     const double contrast = r0[3] * rN;
     const double energy = r0[4] * rN * rN;
     const double maxp = (double)warp_max_i(maxc) * rN;
-    const double log2N = radb_log2(N);
+    // every log2 of an integer count goes through tab_log2 (same source for c, px and N), so that
+    // c*(log2 c - log2 N) and the marginal terms cancel exactly for a one-level ROI
+    const double log2N = tab_log2(tb, (int)sN);
     nnz = warp_sum_i(nnz);
     // marginals: entropies and reciprocal tables (ws is free until mcc_task builds its matrix)
     double* rpx = ws;       // N / px[i]
@@ -383,13 +391,13 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
         if (a) {
             const double q = (double)a * rN;
             hx -= q * radb_log2(q + RADB_EPS);
-            hx0 -= q * (radb_log2((double)a) - log2N);
+            hx0 -= q * (tab_log2(tb, a) - log2N);
             nx++;
         }
         if (b) {
             const double q = (double)b * rN;
             hy -= q * radb_log2(q + RADB_EPS);
-            hy0 -= q * (radb_log2((double)b) - log2N);
+            hy0 -= q * (tab_log2(tb, b) - log2N);
             ny++;
         }
     }

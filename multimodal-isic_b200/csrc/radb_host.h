@@ -136,8 +136,8 @@ static inline void make_tables(int ninv, std::vector<double>& inv2, std::vector<
 {
     inv2.resize(ninv);
     for (int k = 0; k < ninv; k++) inv2[k] = 1.0 / ((double)(k + 1) * (double)(k + 1));
-    tlog.resize(128);
-    for (int k = 0; k < 128; k++) tlog[k] = k >= 2 ? log2((double)k) : 0.0;
+    tlog.resize(2048);  // RADB_TLOG_N
+    for (int k = 0; k < 2048; k++) tlog[k] = k >= 2 ? log2((double)k) : 0.0;
 }
 
 }  // namespace radb

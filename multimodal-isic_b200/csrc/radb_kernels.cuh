@@ -264,7 +264,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         uint4* z = (uint4*)(smem + p.o_zero);
         const int nz = (p.smem_total - p.o_zero) / 16;
         const uint4 zero = {0u, 0u, 0u, 0u};
-        for (int i = tid; i < nz; i += RADB_NT) z[i] = zero;
+        for (int i = tid; i < nz; i += RADB_NTB) z[i] = zero;
     }
 #ifndef RADB_EMU
     if (p.use_tma) {
@@ -272,7 +272,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     } else
 #endif
     {
-        for (int i = tid; i < HW; i += RADB_NT) {
+        for (int i = tid; i < HW; i += RADB_NTB) {
             s_img[i] = g_img[i];
             s_msk[i] = g_msk[i];
         }
@@ -282,7 +282,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     // ---- phase 1: ROI histogram, bbox, voxel count
     {
         int np = 0, ymin = H, ymax = -1, xmin = W, xmax = -1;
-        for (int y = warp; y < H; y += RADB_NT / 32)
+        for (int y = warp; y < H; y += RADB_NTB / 32)
             for (int x = lane; x < W; x += 32) {
                 int i = y * W + x;
                 if ((int)s_msk[i] == p.label) {
@@ -333,7 +333,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             const double bw = p.bin_width;
             const double low = (double)vmin - py_mod((double)vmin, bw);
             ng = 0;
-            for (int v = tid; v < 256; v += RADB_NT) {
+            for (int v = tid; v < 256; v += RADB_NTB) {
                 int L = 0;
                 if (v >= vmin && v <= vmax) {
                     double x = (double)v;
@@ -355,7 +355,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             if (ng > p.max_ng) st = 4;
         }
         if (st) {
-            for (int f = tid; f < p.F; f += RADB_NT) out[f] = nan_f64();
+            for (int f = tid; f < p.F; f += RADB_NTB) out[f] = nan_f64();
             if (tid == 0) {
                 p.status[patch] = st;
                 if (DBG && p.dbg_ng) p.dbg_ng[patch] = 0;
@@ -368,13 +368,13 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     const int ng = misc[8];
 
     // ---- phase 2: discretised level image (padded, 0 outside the ROI) + level histogram
-    for (int y = warp; y < H; y += RADB_NT / 32)
+    for (int y = warp; y < H; y += RADB_NTB / 32)
         for (int x = lane; x < W; x += 32) {
             int i = y * W + x;
             unsigned char L = ((int)s_msk[i] == p.label) ? lut[(int)s_img[i]] : (unsigned char)0;
             lev[(y + 1) * WP + x + 1] = L;
         }
-    for (int v = tid; v < 256; v += RADB_NT)
+    for (int v = tid; v < 256; v += RADB_NTB)
         if (hist[v]) atomicAdd(&lhist[lut[v] - 1], hist[v]);
     __syncthreads();
 
@@ -390,33 +390,34 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     for (int a = 0; a < NA; a++)
         if (p.ang_y[a] == 0) a_row = a;
     if (a_row < 0) {  // no along-row connectivity: every ROI pixel starts as its own run of length 1
-        for (int i = tid; i < HW; i += RADB_NT) lab[i] = 0x10000u | (unsigned)i;
+        for (int i = tid; i < HW; i += RADB_NTB) lab[i] = 0x10000u | (unsigned)i;
     }
 
-    // ---- phase 3a: line walks.  One thread walks one line of the image along one angle, so
-    // every lane runs the same trip count: GLRLM runs for all angles; the along-row walk also
-    // writes label = run start and the run length (seed of the zone sizes).
+    // ---- phase 3a: line walks over the ROI bounding box.  One thread walks one line along one
+    // angle, so every lane runs the same trip count: GLRLM runs for all angles; the along-row
+    // walk also writes label = run start and the run length (seed of the zone sizes).  Diagonal
+    // lines are wrapped inside the bbox (a wrap forces a run break), so every angle is bw (or bh)
+    // lines of equal length.
     {
         const int nr = p.nr;
         int t0 = 0;
         for (int a = 0; a < NA; a++) {
             const int dy = p.ang_y[a], dx = p.ang_x[a];
-            const int nlines = (dy == 0) ? H : W;
+            const int nlines = (dy == 0) ? bh : bw;
             // tasks [t0, t0 + nlines) belong to angle a; thread tid takes tasks tid, tid+NT, ...
-            int first = tid - (t0 % RADB_NT);
-            if (first < 0) first += RADB_NT;
-            for (int l = first; l < nlines; l += RADB_NT) {
-                unsigned* R = (unsigned*)(smem + p.o_glrlm + a * p.glrlm_stride);
-                const int cell0 = 0;
+            int first = tid - (t0 % RADB_NTB);
+            if (first < 0) first += RADB_NTB;
+            unsigned* R = (unsigned*)(smem + p.o_glrlm + a * p.glrlm_stride);
+            for (int l = first; l < nlines; l += RADB_NTB) {
                 int cur = 0, len = 0;
                 if (dy == 0) {
-                    const int base = (l + 1) * WP + 1, lbase = l * W;
+                    const int base = (by0 + l + 1) * WP + bx0 + 1, lbase = (by0 + l) * W + bx0;
                     int st = 0;
-                    for (int x = 0; x < W; x++) {
+                    for (int x = 0; x < bw; x++) {
                         const int g = lev[base + x];
                         if (g != cur) {
                             if (cur) {
-                                add_u16(R, cell0 + (cur - 1) * nr + len - 1);
+                                add_u16(R, (cur - 1) * nr + len - 1);
                                 lab[lbase + st] = ((unsigned)len << 16) | (unsigned)(lbase + st);
                             }
                             cur = g;
@@ -427,26 +428,28 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                         if (g) lab[lbase + x] = (unsigned)(lbase + st);
                     }
                     if (cur) {
-                        add_u16(R, cell0 + (cur - 1) * nr + len - 1);
+                        add_u16(R, (cur - 1) * nr + len - 1);
                         lab[lbase + st] = ((unsigned)len << 16) | (unsigned)(lbase + st);
                     }
                 } else {
                     const int sdx = dx * dy;  // x step per +1 in y (runs are direction-agnostic)
                     int x = l, brk = 0;
-                    for (int y = 0; y < H; y++) {
-                        const int g = lev[(y + 1) * WP + x + 1];
+                    int pos = (by0 + 1) * WP + bx0 + 1;
+                    for (int y = 0; y < bh; y++) {
+                        const int g = lev[pos + x];
                         if (g != cur || brk) {
-                            if (cur) add_u16(R, cell0 + (cur - 1) * nr + len - 1);
+                            if (cur) add_u16(R, (cur - 1) * nr + len - 1);
                             cur = g;
                             len = 0;
                         }
                         len++;
+                        pos += WP;
                         x += sdx;
                         brk = 0;
-                        if (x >= W) { x = 0; brk = 1; }       // wrapped diagonal: the next pixel is not
-                        else if (x < 0) { x = W - 1; brk = 1; }  // a neighbour of this one
+                        if (x >= bw) { x = 0; brk = 1; }          // wrapped diagonal: the next pixel is not
+                        else if (x < 0) { x = bw - 1; brk = 1; }  // a neighbour of this one
                     }
-                    if (cur) add_u16(R, cell0 + (cur - 1) * nr + len - 1);
+                    if (cur) add_u16(R, (cur - 1) * nr + len - 1);
                 }
             }
             t0 += nlines;
@@ -483,7 +486,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             __syncwarp();
             if (qn >= 32) drain(32);
         };
-        for (int base = 0; base < nbox; base += RADB_NT) {  // uniform trip count (warp collectives below)
+        for (int base = 0; base < nbox; base += RADB_NTB) {  // uniform trip count (warp collectives below)
             const int idx = base + tid;
             const int yb = (int)(((float)idx + 0.5f) * inv_bw);
             const int y = by0 + yb, x = bx0 + (idx - yb * bw);
@@ -547,7 +550,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     __syncthreads();
 
     // ---- phase 4: fold run lengths into their zone root; symmetrise the GLCM
-    for (int idx = tid; idx < nbox; idx += RADB_NT) {
+    for (int idx = tid; idx < nbox; idx += RADB_NTB) {
         const int yb = (int)(((float)idx + 0.5f) * inv_bw);
         const int y = by0 + yb, x = bx0 + (idx - yb * bw);
         const int ctr = (y + 1) * WP + x + 1;
@@ -561,7 +564,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     if (p.symmetric) {
         for (int a = 0; a < NA; a++) {
             int* P = glcm + a * ng * ng;
-            for (int t = tid; t < ng * ng; t += RADB_NT) {
+            for (int t = tid; t < ng * ng; t += RADB_NTB) {
                 int i = t / ng, j = t - i * ng;
                 if (i > j) continue;
                 if (i == j) {
@@ -577,7 +580,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     __syncthreads();
 
     // ---- phase 5: zone roots -> GLSZM (dense + overflow)
-    for (int idx = tid; idx < nbox; idx += RADB_NT) {
+    for (int idx = tid; idx < nbox; idx += RADB_NTB) {
         const int yb = (int)(((float)idx + 0.5f) * inv_bw);
         const int y = by0 + yb, x = bx0 + (idx - yb * bw);
         const int ctr = (y + 1) * WP + x + 1;
@@ -600,19 +603,19 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     // ---- optional debug dump of the integer matrices (parity tests)
     if (DBG && p.dbg_ng && tid == 0) p.dbg_ng[patch] = ng;
     if (DBG && p.dbg_levels)
-        for (int i = tid; i < HW; i += RADB_NT)
+        for (int i = tid; i < HW; i += RADB_NTB)
             p.dbg_levels[patch * HW + i] = lev[(i / W + 1) * WP + (i % W) + 1];
     if (DBG && p.dbg_glcm)
         for (int a = 0; a < NA; a++)
-            for (int t = tid; t < ng * ng; t += RADB_NT)
+            for (int t = tid; t < ng * ng; t += RADB_NTB)
                 p.dbg_glcm[((patch * NA + a) * p.max_ng + t / ng) * p.max_ng + t % ng] = glcm[a * ng * ng + t];
     if (DBG && p.dbg_glrlm)
         for (int a = 0; a < NA; a++)
-            for (int t = tid; t < ng * p.nr; t += RADB_NT)
+            for (int t = tid; t < ng * p.nr; t += RADB_NTB)
                 p.dbg_glrlm[((patch * NA + a) * p.max_ng + t / p.nr) * p.nr + t % p.nr] =
                     get_u16((const unsigned*)(smem + p.o_glrlm + a * p.glrlm_stride), t);
     if (DBG && p.dbg_gldm)
-        for (int t = tid; t < ng * (NB + 1); t += RADB_NT)
+        for (int t = tid; t < ng * (NB + 1); t += RADB_NTB)
             p.dbg_gldm[patch * p.max_ng * (NB + 1) + t] = gldm[t];
 
     // ---- phase 6: publish the record (header + every integer matrix) for the reduction kernels
@@ -626,7 +629,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const uint4* src = (const uint4*)(smem + p.o_rec);
         uint4* dst = (uint4*)(p.ws + patch * (long long)p.rec_bytes);
         const int n16 = p.rec_bytes / 16;
-        for (int i = tid; i < n16; i += RADB_NT) dst[i] = src[i];
+        for (int i = tid; i < n16; i += RADB_NTB) dst[i] = src[i];
     }
 }
 
@@ -730,7 +733,7 @@ __device__ void radb_misc_cta(const RadbParams& p, long long patch, unsigned cha
 
 #ifndef RADB_EMU
 template <typename PT, bool DBG>
-__global__ void __launch_bounds__(RADB_NT, 4) radb_build_kernel(const RadbParams p)
+__global__ void __launch_bounds__(RADB_NTB, RADB_NTB_MINB) radb_build_kernel(const RadbParams p)
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
     radb_build_cta<PT, DBG>(p, (long long)blockIdx.x, radb_smem);

@@ -3,7 +3,13 @@
 #pragma once
 #include <stdint.h>
 
-#define RADB_NT 128          // threads per CTA (4 warps); one CTA per patch
+#define RADB_NT 128          // threads per CTA of the reduction kernels (4 warps); one CTA per patch
+#ifndef RADB_NTB
+#define RADB_NTB 256         // threads per CTA of the build kernel
+#endif
+#ifndef RADB_NTB_MINB
+#define RADB_NTB_MINB 4      // min resident build CTAs per SM (register cap)
+#endif
 #define RADB_MAX_ANGLES 4    // unidirectional offsets at distance 1 in a plane
 #define RADB_GLCM_NF 24
 #define RADB_GLRLM_NF 16
@@ -50,7 +56,7 @@ struct RadbParams {
     // global workspace + tables (device pointers)
     unsigned char* ws;        // [B][rec_bytes]
     const double* g_inv2;     // [ninv]  1/k^2
-    const double* g_tlog;     // [128]   log2(k)
+    const double* g_tlog;     // [2048]  log2(k)
     // optional debug outputs (device pointers, may be null); dims use max_ng
     int* dbg_levels;   // [B][H][W]
     int* dbg_glcm;     // [B][Na][max_ng][max_ng]
@@ -88,7 +94,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->o_mbar = o; o += 16;
     p->o_zero = o;                        // everything from here on is zeroed at CTA start
     p->o_lev = o; o += radb_align((H + 2) * p->WP, 16);
-    p->o_uq = o; o += (RADB_NT / 32) * 64 * 4;           // per-warp union request queues
+    p->o_uq = o; o += (RADB_NTB / 32) * 64 * 4;           // per-warp union request queues
     p->o_lut = o; o += 256;
     p->o_rec = o;
     p->o_misc = o; o += 32 * 4;           // record header: [0] Np, [5] #overflow zones, [8] Ng, [9] #levels present

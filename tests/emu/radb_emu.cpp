@@ -54,6 +54,8 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
     p.dbg_ng = ng;
     std::vector<double> inv2, tlog;
     radb::make_tables(p.ninv, inv2, tlog);
+    if (getenv("RADB_EMU_PERTURB_TABLES"))  // host-libm vs device-libm: the tables may differ by an ulp
+        for (size_t k = 2; k < tlog.size(); k++) tlog[k] = nextafter(tlog[k], (k & 1) ? 1e9 : -1e9);
     p.g_inv2 = inv2.data();
     p.g_tlog = tlog.data();
     std::vector<unsigned char> ws((size_t)B * p.rec_bytes + 64);
@@ -63,7 +65,7 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
     std::vector<unsigned char> smem((size_t)mx + 64);
     unsigned char* sm = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
     // the same three launches radb_api.cu issues, CTA by CTA on host threads
-    emu::launch((unsigned)B, RADB_NT, [&]() { radb_build_cta<unsigned char, true>(p, (long long)blockIdx.x, sm); });
+    emu::launch((unsigned)B, RADB_NTB, [&]() { radb_build_cta<unsigned char, true>(p, (long long)blockIdx.x, sm); });
     emu::launch((unsigned)B, RADB_NT, [&]() { radb_angle_cta(p, (long long)blockIdx.x, sm); });
     emu::launch((unsigned)B, RADB_NT, [&]() { radb_misc_cta(p, (long long)blockIdx.x, sm); });
     return 0;

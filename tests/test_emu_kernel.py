@@ -80,3 +80,12 @@ def test_emu_bitwise_reproducible(emu):
     for _ in range(3):
         b = emu.run(img, mask, 10, 255, INPLANE)["features"]
         assert a.tobytes() == b.tobytes()
+
+
+def test_emu_edge_cases_with_perturbed_tables(emu, monkeypatch):
+    # the device log2 and the host-built log2 table may differ in the last bit: degenerate ROIs
+    # (one gray level: Imc2 must be exactly 0) must not depend on it
+    monkeypatch.setenv("RADB_EMU_PERTURB_TABLES", "1")
+    imgs, masks = edge_case_batch()
+    r = emu.run(imgs, masks, 10, 255, INPLANE)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=False)) == 6
