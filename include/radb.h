@@ -86,10 +86,12 @@ void radb_destroy(radb_handle* h);
 int radb_feature_count(const radb_handle* h);
 const char* radb_feature_name(const radb_handle* h, int i);
 
-/* Pre-allocates the per-chunk record workspace for batches of up to `max_batch` HxW patches, so
- * that later radb_extract calls allocate nothing.  Without it the workspace grows on demand
- * (cudaMalloc, grow-only) the first time a larger batch or record size is seen. */
-int radb_reserve(radb_handle* h, int H, int W, int dtype, int64_t max_batch);
+/* Pre-allocates the per-chunk record workspace used by launches on `cuda_stream` for batches of
+ * up to `max_batch` HxW patches, so that later radb_extract calls on that stream allocate
+ * nothing.  Without it the workspace grows on demand (cudaMalloc, grow-only) the first time a
+ * larger batch or record size is seen.  The handle keeps one workspace per stream, so launches
+ * issued on different streams may overlap. */
+int radb_reserve(radb_handle* h, int H, int W, int dtype, int64_t max_batch, void* cuda_stream);
 
 /* Dynamic shared memory (bytes) one CTA of the build kernel needs for HxW patches of `dtype`; < 0 if it cannot fit. */
 int radb_smem_bytes(const radb_handle* h, int H, int W, int dtype);

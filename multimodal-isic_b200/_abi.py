@@ -82,7 +82,7 @@ def load_library(path=None):
     lib.radb_feature_count.restype = i32
     lib.radb_feature_name.argtypes = [vp, i32]
     lib.radb_feature_name.restype = ctypes.c_char_p
-    lib.radb_reserve.argtypes = [vp, i32, i32, i32, i64]
+    lib.radb_reserve.argtypes = [vp, i32, i32, i32, i64, vp]
     lib.radb_reserve.restype = i32
     lib.radb_smem_bytes.argtypes = [vp, i32, i32, i32]
     lib.radb_smem_bytes.restype = i32

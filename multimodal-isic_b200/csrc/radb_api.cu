@@ -20,8 +20,9 @@ struct radb_handle {
     int smem_optin;              // max dynamic shared memory per block the device allows
     int smem_set[4];             // configured MaxDynamicSharedMemorySize per kernel
     int64_t launches;
-    unsigned char* ws;           // per-patch records of one chunk
-    size_t ws_bytes;
+    struct Ws { void* stream; unsigned char* p; size_t bytes; };
+    std::vector<Ws> ws;          // per-patch records of one chunk, one workspace per CUDA stream
+                                 // (launches on different streams may overlap; each owns its records)
     double* d_inv2;
     double* d_tlog;
 };
@@ -52,8 +53,6 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
     h->device = s->device;
     h->launches = 0;
     h->smem_set[0] = h->smem_set[1] = h->smem_set[2] = h->smem_set[3] = 0;
-    h->ws = nullptr;
-    h->ws_bytes = 0;
     h->d_inv2 = h->d_tlog = nullptr;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -84,28 +83,38 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
 extern "C" void radb_destroy(radb_handle* h)
 {
     if (!h) return;
-    if (h->ws) cudaFree(h->ws);
+    for (auto& w : h->ws)
+        if (w.p) cudaFree(w.p);
     if (h->d_inv2) cudaFree(h->d_inv2);
     if (h->d_tlog) cudaFree(h->d_tlog);
     delete h;
 }
 
-// Grow-only workspace: one record per patch of a chunk.
-static int ensure_ws(radb_handle* h, const RadbParams& p, int64_t B)
+// Grow-only workspace: one record per patch of a chunk, keyed by the stream the kernels run on.
+static int ensure_ws(radb_handle* h, const RadbParams& p, int64_t B, void* stream, unsigned char** out)
 {
     const int64_t n = B < RADB_CHUNK ? B : RADB_CHUNK;
     const size_t need = (size_t)n * (size_t)p.rec_bytes;
-    if (need <= h->ws_bytes) return RADB_OK;
-    if (h->ws) cudaFree(h->ws);
-    h->ws = nullptr;
-    h->ws_bytes = 0;
-    cudaError_t e = cudaMalloc(&h->ws, need);
-    if (e != cudaSuccess) return cuda_fail(e, "workspace allocation");
-    h->ws_bytes = need;
+    radb_handle::Ws* w = nullptr;
+    for (auto& e : h->ws)
+        if (e.stream == stream) w = &e;
+    if (!w) {
+        h->ws.push_back({stream, nullptr, 0});
+        w = &h->ws.back();
+    }
+    if (need > w->bytes) {
+        if (w->p) cudaFree(w->p);  // synchronises the device: nothing is still reading it
+        w->p = nullptr;
+        w->bytes = 0;
+        cudaError_t e = cudaMalloc(&w->p, need);
+        if (e != cudaSuccess) return cuda_fail(e, "workspace allocation");
+        w->bytes = need;
+    }
+    *out = w->p;
     return RADB_OK;
 }
 
-extern "C" int radb_reserve(radb_handle* h, int H, int W, int dtype, int64_t max_batch)
+extern "C" int radb_reserve(radb_handle* h, int H, int W, int dtype, int64_t max_batch, void* cuda_stream)
 {
     if (!h || max_batch < 0) return fail(RADB_E_INVALID, "bad argument");
     RadbParams p;
@@ -115,7 +124,8 @@ extern "C" int radb_reserve(radb_handle* h, int H, int W, int dtype, int64_t max
     int cur = -1;
     cudaGetDevice(&cur);
     if (cur != h->device) cudaSetDevice(h->device);
-    rc = ensure_ws(h, p, max_batch);
+    unsigned char* unused = nullptr;
+    rc = ensure_ws(h, p, max_batch, cuda_stream, &unused);
     if (cur >= 0 && cur != h->device) cudaSetDevice(cur);
     return rc;
 }
@@ -167,9 +177,10 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
                  : set_smem(h, radb_build_kernel<unsigned char, false>, 0, p.smem_total);
     if (!rc) rc = set_smem(h, radb_angle_kernel, 1, p.a_smem_total);
     if (!rc) rc = set_smem(h, radb_misc_kernel, 2, p.m_smem_total);
-    if (!rc) rc = ensure_ws(h, p, p.B);
+    unsigned char* wsp = nullptr;
+    if (!rc) rc = ensure_ws(h, p, p.B, stream, &wsp);
     if (rc) return rc;
-    p.ws = h->ws;
+    p.ws = wsp;
     p.g_inv2 = h->d_inv2;
     p.g_tlog = h->d_tlog;
     if (p.ninv > RADB_TAB_NINV) p.ninv = RADB_TAB_NINV;

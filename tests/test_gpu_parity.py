@@ -122,6 +122,17 @@ def test_host_pipeline_matches_device_path(gpu_pkg):
         ex.extract_batch(imgs, np.zeros_like(masks), strict=True)
 
 
+def test_host_pipeline_overlapping_streams(gpu_pkg):
+    # two pipeline slots = two CUDA streams in flight on one handle: each stream owns its records
+    B = 40000
+    imgs, masks = gpu_pkg.synth.make_patches_torch(B, 64, seed=7, device="cuda")
+    ex = gpu_pkg.RadiomicsExtractor({"setting": {"label": 255, "binWidth": 25}}, chunk=4096)
+    dev, _ = ex.extract_batch(imgs, masks)
+    host, st = ex.extract_batch(imgs.cpu().numpy(), masks.cpu().numpy())
+    assert not st.any()
+    np.testing.assert_array_equal(host, dev.cpu().numpy())
+
+
 def test_record_path_matches_reference_call_pattern(gpu_pkg, tmp_path):
     """RadiomicExtractor.py:23-55 end to end: PNG files -> cv2 -> gray/R/G/B executes."""
     import cv2
