@@ -18,7 +18,7 @@ struct radb_handle {
     radb::Plan plan;
     int device;
     int smem_optin;              // max dynamic shared memory per block the device allows
-    int smem_set[4];             // configured MaxDynamicSharedMemorySize per kernel
+    int smem_set[8];             // configured MaxDynamicSharedMemorySize per kernel
     int64_t launches;
     struct Ws { void* stream; unsigned char* p; size_t bytes; };
     std::vector<Ws> ws;          // per-patch records of one chunk, one workspace per CUDA stream
@@ -52,7 +52,7 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
     if (rc) { delete h; return fail(rc, err); }
     h->device = s->device;
     h->launches = 0;
-    h->smem_set[0] = h->smem_set[1] = h->smem_set[2] = h->smem_set[3] = 0;
+    for (int i = 0; i < 8; i++) h->smem_set[i] = 0;
     h->d_inv2 = h->d_tlog = nullptr;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -90,11 +90,21 @@ extern "C" void radb_destroy(radb_handle* h)
     delete h;
 }
 
-// Grow-only workspace: one record per patch of a chunk, keyed by the stream the kernels run on.
+// Patches per pass through the three kernels: bounds the workspace (records + wide-mode scratch).
+static int64_t chunk_for(const RadbParams& p, int64_t B)
+{
+    const size_t per = (size_t)p.rec_bytes + (size_t)p.scr_bytes;
+    int64_t n = (int64_t)(((size_t)1 << 30) / per);  // <= 1 GiB
+    if (n > RADB_CHUNK) n = RADB_CHUNK;
+    if (n < 1) n = 1;
+    return B < n ? B : n;
+}
+
+// Grow-only workspace: one record (+ scratch) per patch of a chunk, keyed by the stream the kernels run on.
 static int ensure_ws(radb_handle* h, const RadbParams& p, int64_t B, void* stream, unsigned char** out)
 {
-    const int64_t n = B < RADB_CHUNK ? B : RADB_CHUNK;
-    const size_t need = (size_t)n * (size_t)p.rec_bytes;
+    const int64_t n = chunk_for(p, B);
+    const size_t need = (size_t)n * ((size_t)p.rec_bytes + (size_t)p.scr_bytes);
     radb_handle::Ws* w = nullptr;
     for (auto& e : h->ws)
         if (e.stream == stream) w = &e;
@@ -173,21 +183,25 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
     }
     const bool dbg = p.dbg_levels || p.dbg_glcm || p.dbg_glrlm || p.dbg_glszm || p.dbg_gldm || p.dbg_ng;
-    int rc = dbg ? set_smem(h, radb_build_kernel<unsigned char, true>, 3, p.smem_total)
-                 : set_smem(h, radb_build_kernel<unsigned char, false>, 0, p.smem_total);
+    typedef void (*build_fn)(const RadbParams);
+    const build_fn build = p.wide ? (dbg ? radb_build_kernel<unsigned char, true, true> : radb_build_kernel<unsigned char, false, true>)
+                                  : (dbg ? radb_build_kernel<unsigned char, true, false> : radb_build_kernel<unsigned char, false, false>);
+    int rc = set_smem(h, build, (p.wide ? 4 : 0) + (dbg ? 3 : 0), p.smem_total);
     if (!rc) rc = set_smem(h, radb_angle_kernel, 1, p.a_smem_total);
     if (!rc) rc = set_smem(h, radb_misc_kernel, 2, p.m_smem_total);
     unsigned char* wsp = nullptr;
     if (!rc) rc = ensure_ws(h, p, p.B, stream, &wsp);
     if (rc) return rc;
+    const long long chunk = chunk_for(p, p.B);
     p.ws = wsp;
+    p.ws_scr = wsp + (size_t)chunk * (size_t)p.rec_bytes;
     p.g_inv2 = h->d_inv2;
     p.g_tlog = h->d_tlog;
     if (p.ninv > RADB_TAB_NINV) p.ninv = RADB_TAB_NINV;
     cudaStream_t st = (cudaStream_t)stream;
     long long done = 0;
     while (done < p.B) {
-        const long long n = p.B - done < RADB_CHUNK ? p.B - done : RADB_CHUNK;
+        const long long n = p.B - done < chunk ? p.B - done : chunk;
         RadbParams q = p;
         q.img = (const unsigned char*)p.img + done * p.img_stride;
         q.mask = p.mask + done * p.mask_stride;
@@ -205,10 +219,7 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
             if (q.dbg_ngs) q.dbg_ngs += done * NG;
             if (q.dbg_ng) q.dbg_ng += done;
         }
-        if (dbg)
-            radb_build_kernel<unsigned char, true><<<(unsigned)n, RADB_NTB, p.smem_total, st>>>(q);
-        else
-            radb_build_kernel<unsigned char, false><<<(unsigned)n, RADB_NTB, p.smem_total, st>>>(q);
+        build<<<(unsigned)n, RADB_NTB, p.smem_total, st>>>(q);
         radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, st>>>(q);
         radb_misc_kernel<<<(unsigned)n, RADB_NT, p.m_smem_total, st>>>(q);
         h->launches += 3;
@@ -237,7 +248,7 @@ static int setup(radb_handle* h, const void* img, int dtype, const uint8_t* mask
     p.status = status;
     p.B = B;
     // TMA bulk copies need 16-byte aligned sources and sizes
-    p.use_tma = ((uintptr_t)img % 16 == 0) && ((uintptr_t)mask % 16 == 0) && (img_stride_b % 16 == 0) &&
+    p.use_tma = !p.wide && ((uintptr_t)img % 16 == 0) && ((uintptr_t)mask % 16 == 0) && (img_stride_b % 16 == 0) &&
                 (mask_stride_b % 16 == 0) && (p.HW % 16 == 0);
     return RADB_OK;
 }

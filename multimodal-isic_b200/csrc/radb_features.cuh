@@ -508,8 +508,8 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
 }
 
 // ------------------------------------------------------------------ GLRLM features (one warp, one angle)
-// A.7.  R = packed u16 counters [n][nr] starting at cell0; pr = int scratch [nr] (zeroed).
-__device__ int glrlm_task(const RadbTabs& tb, const unsigned* R, int cell0, int n, int nr, int* pr, double* o,
+// A.7.  R = run counters [n][nr] (packed u16, or u32 in wide mode); pr = int scratch [nr] (zeroed).
+__device__ int glrlm_task(const RadbTabs& tb, const unsigned* R, int wide, int n, int nr, int* pr, double* o,
                           int lane)
 {
     long long sN = 0, sGI = 0, sGI2 = 0, sG2 = 0;
@@ -519,7 +519,7 @@ __device__ int glrlm_task(const RadbTabs& tb, const unsigned* R, int cell0, int 
         int rs = 0;
         const double i2 = (double)(i + 1) * (double)(i + 1), ri2 = tab_inv2(tb, i + 1);
         for (int j = lane; j < nr; j += 32) {
-            const int c = get_u16(R, cell0 + i * nr + j);
+            const int c = get_run(R, i * nr + j, wide);
             if (!c) continue;
             rs += c;
             pr[j] += c;
@@ -633,7 +633,7 @@ __device__ __forceinline__ void zs_reduce(ZoneSums& z, const RadbTabs& tb, int l
     z.nnz = warp_sum_i(z.nnz);
 }
 
-// A.8.  Dense counters Z[n][s0] (sizes 1..s0) + overflow list of (level << 16 | size) zones with
+// A.8.  Dense counters Z[n][s0] (sizes 1..s0) + overflow list of (level << 24 | size) zones with
 // size > s0.  pg = int scratch [n] (zeroed), sorted = scratch for the rank-sorted overflow list.
 __device__ void glszm_task(const RadbParams& p, const RadbTabs& tb, const int* Z, const unsigned* ovf,
                            unsigned* sorted, int novf, int n, int* pg, double* o, int lane)
@@ -669,7 +669,7 @@ __device__ void glszm_task(const RadbParams& p, const RadbTabs& tb, const int* Z
     __syncwarp();
     for (int e = lane; e < novf; e += 32) {
         unsigned key = sorted[e];
-        int sz = (int)(key & 0xffffu), lv = (int)(key >> 16);
+        int sz = (int)(key & 0xffffffu), lv = (int)(key >> 24);
         atomicAdd(&pg[lv - 1], 1);
         if (e == 0 || sorted[e - 1] != key) {  // first of its (level, size) cell
             int cnt = 1;
@@ -678,7 +678,7 @@ __device__ void glszm_task(const RadbParams& p, const RadbTabs& tb, const int* Z
         }
         int same_size = 0, first_size = 1;
         for (int f = 0; f < novf; f++)
-            if ((int)(sorted[f] & 0xffffu) == sz) { same_size++; if (f < e) first_size = 0; }
+            if ((int)(sorted[f] & 0xffffffu) == sz) { same_size++; if (f < e) first_size = 0; }
         if (first_size) z.PJ2 += (long long)same_size * same_size;
     }
     __syncwarp();

@@ -104,7 +104,10 @@ static inline int make_plan(const radb_settings& s, Plan& pl, std::string& err)
 static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParams& p, std::string& err)
 {
     if (dtype != RADB_DTYPE_U8) { err = "only uint8 pixels are implemented in this build (u16/f32 pending)"; return RADB_E_UNSUPPORTED; }
-    if (H < 1 || W < 1 || (long long)H * W > 65535) { err = "patch must have 1..65535 pixels"; return RADB_E_INVALID; }
+    if (H < 1 || W < 1 || H > 4096 || W > 4096 || (long long)H * W >= (1 << 24)) {
+        err = "image must be 1..4096 pixels per side and < 2^24 pixels";
+        return RADB_E_INVALID;
+    }
     memset(&p, 0, sizeof(p));
     p.H = H;
     p.W = W;
@@ -123,9 +126,16 @@ static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParam
     p.off_glrlm = pl.off[3];
     p.off_glszm = pl.off[4];
     p.off_ngtdm = pl.off[5];
+    // narrow mode (everything in shared memory) when the patch fits with >= 2 CTAs per SM,
+    // otherwise wide mode (level image, union-find words, GLRLM, overflow list in global memory)
+    p.wide = 0;
     radb_layout(&p, 1);
+    if ((long long)H * W > 65535 || p.smem_total > 110 * 1024) {
+        p.wide = 1;
+        radb_layout(&p, 1);
+    }
     if (p.smem_total > 227 * 1024 || p.a_smem_total > 227 * 1024 || p.m_smem_total > 227 * 1024) {
-        err = "patch size x gray levels need more than 227 KB of shared memory";
+        err = "image size x gray levels need more than 227 KB of shared memory";
         return RADB_E_SMEM;
     }
     return 0;

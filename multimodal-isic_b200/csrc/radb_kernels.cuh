@@ -168,41 +168,54 @@ __device__ __forceinline__ void mbar_wait(void* bar, unsigned parity)
 #endif
 
 // ------------------------------------------------------------------ union-find over row runs
-// One 32-bit word per pixel: low 16 bits = parent pixel index, high 16 bits = size.  During the
-// union pass the high half of a run start holds its run length (static); after it, the run
-// lengths are folded into the zone root with one native 32-bit shared atomic per run.
-__device__ __forceinline__ unsigned uf_find(volatile unsigned* L, unsigned x)
+// One word per pixel: low half = parent pixel index, high half = size.  During the union pass the
+// high half of a run start holds its run length (static); after it, the run lengths are folded
+// into the zone root with one native atomic per run.  Narrow mode (patches that fit shared
+// memory, <= 65535 pixels): 32-bit words (16 | 16) in shared memory.  Wide mode (whole images):
+// 64-bit words (32 | 32) in the global scratch.
+template <bool WIDE> struct UF { typedef unsigned W; enum { S = 16 }; };
+template <> struct UF<true> { typedef unsigned long long W; enum { S = 32 }; };
+
+template <typename W, int S>
+__device__ __forceinline__ unsigned uf_find(volatile W* L, unsigned x)
 {
-    unsigned w = L[x], p = w & 0xffffu;
+    const W lo = (((W)1) << S) - 1;
+    W w = L[x];
+    unsigned p = (unsigned)(w & lo);
     while (p != x) {
-        const unsigned wp = L[p], g = wp & 0xffffu;
-        if (g != p) L[x] = (w & 0xffff0000u) | g;  // path halving: x is not a root, g is an ancestor
+        const W wp = L[p];
+        const unsigned g = (unsigned)(wp & lo);
+        if (g != p) L[x] = (w & ~lo) | (W)g;  // path halving: x is not a root, g is an ancestor
         x = p;
         w = wp;
         p = g;
     }
     return x;
 }
-__device__ __forceinline__ unsigned uf_find_ro(const volatile unsigned* L, unsigned x)
+template <typename W, int S>
+__device__ __forceinline__ unsigned uf_find_ro(const volatile W* L, unsigned x)
 {
+    const W lo = (((W)1) << S) - 1;
     unsigned p;
-    while ((p = L[x] & 0xffffu) != x) x = p;
+    while ((p = (unsigned)(L[x] & lo)) != x) x = p;
     return x;
 }
-__device__ __forceinline__ void uf_union(unsigned* L, unsigned a, unsigned b)
+template <typename W, int S>
+__device__ __forceinline__ void uf_union(W* L, unsigned a, unsigned b)
 {
+    const W lo = (((W)1) << S) - 1;
     while (true) {
-        a = uf_find(L, a);
-        b = uf_find(L, b);
+        a = uf_find<W, S>(L, a);
+        b = uf_find<W, S>(L, b);
         if (a == b) return;
         if (a < b) { unsigned t = a; a = b; b = t; }
-        const unsigned wa = ((volatile unsigned*)L)[a];
-        if ((wa & 0xffffu) != a) continue;  // lost the race: a is no longer a root
-        if (atomicCAS(&L[a], wa, (wa & 0xffff0000u) | b) == wa) return;
+        const W wa = ((volatile W*)L)[a];
+        if ((unsigned)(wa & lo) != a) continue;  // lost the race: a is no longer a root
+        if (atomicCAS(&L[a], wa, (wa & ~lo) | (W)b) == wa) return;
     }
 }
 
-// packed u16 counters updated with one 32-bit shared atomic
+// GLRLM counters: packed u16 pairs updated with one 32-bit atomic (narrow) or plain u32 (wide)
 __device__ __forceinline__ void add_u16(unsigned* base, int cell)
 {
     atomicAdd(&base[cell >> 1], (cell & 1) ? 0x10000u : 1u);
@@ -210,6 +223,16 @@ __device__ __forceinline__ void add_u16(unsigned* base, int cell)
 __device__ __forceinline__ int get_u16(const unsigned* base, int cell)
 {
     return (int)((base[cell >> 1] >> ((cell & 1) * 16)) & 0xffffu);
+}
+template <bool WIDE>
+__device__ __forceinline__ void add_run(unsigned* base, int cell)
+{
+    if (WIDE) atomicAdd(&base[cell], 1u);
+    else add_u16(base, cell);
+}
+__device__ __forceinline__ int get_run(const unsigned* base, int cell, int wide)
+{
+    return wide ? (int)base[cell] : get_u16(base, cell);
 }
 
 // Python-style modulo (sign of the divisor), as numpy's % in imageoperations.getBinEdges
@@ -223,15 +246,24 @@ __device__ __forceinline__ double py_mod(double a, double b)
 #include "radb_features.cuh"
 
 // ------------------------------------------------------------------ build kernel: one CTA per patch
-template <typename PT, bool DBG>
+template <typename PT, bool DBG, bool WIDE>
 __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned char* smem)
 {
+    typedef typename UF<WIDE>::W UW;  // union-find word
+    const int US = UF<WIDE>::S;
+    const UW ULO = (((UW)1) << US) - 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, HW = p.HW, WP = p.WP, NA = p.n_angles, NB = 2 * p.n_angles;
-    PT* s_img = (PT*)(smem + p.o_stage);
-    unsigned char* s_msk = smem + p.o_mask;
-    unsigned* lab = (unsigned*)(smem + p.o_stage);  // union-find words (after the raw patch is consumed)
-    unsigned char* lev = smem + p.o_lev;
+    const PT* g_img = (const PT*)((const unsigned char*)p.img + patch * p.img_stride);
+    const unsigned char* g_msk = p.mask + patch * p.mask_stride;
+    unsigned char* g_rec = p.ws + patch * (long long)p.rec_bytes;              // this patch's record (global)
+    unsigned char* g_scr = WIDE ? p.ws_scr + patch * p.scr_bytes : (unsigned char*)0;  // wide-mode scratch (global)
+    // narrow: the raw patch is staged in shared memory and the level image / union-find words live
+    // there too; wide: pixels are read straight from global memory and those arrays are global.
+    const PT* s_img = WIDE ? g_img : (const PT*)(smem + p.o_stage);
+    const unsigned char* s_msk = WIDE ? g_msk : smem + p.o_mask;
+    UW* lab = WIDE ? (UW*)(g_scr + p.g_lab) : (UW*)(smem + p.o_stage);
+    unsigned char* lev = WIDE ? g_scr + p.g_lev : smem + p.o_lev;
     int* hist = (int*)(smem + p.o_hist);
     unsigned char* lut = smem + p.o_lut;
     int* lhist = (int*)(smem + p.o_lhist);
@@ -240,23 +272,22 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     int* ngc = (int*)(smem + p.o_ngc);
     int* ngn = (int*)(smem + p.o_ngn);
     int* szm = (int*)(smem + p.o_szm);
-    unsigned* ovf = (unsigned*)(smem + p.o_ovf);
+    unsigned* ovf = WIDE ? (unsigned*)(g_rec + (p.o_ovf - p.o_rec)) : (unsigned*)(smem + p.o_ovf);
+    unsigned char* glrlm_base = WIDE ? g_rec + (p.o_glrlm - p.o_rec) : smem + p.o_glrlm;
     int* misc = (int*)(smem + p.o_misc);
-    const PT* g_img = (const PT*)((const unsigned char*)p.img + patch * p.img_stride);
-    const unsigned char* g_msk = p.mask + patch * p.mask_stride;
     double* out = p.out + patch * (long long)p.F;
 
     // ---- phase 0: stage the patch, zero the counters
 #ifndef RADB_EMU
-    if (p.use_tma) {
+    if (!WIDE && p.use_tma) {
         void* bar = smem + p.o_mbar;
         if (tid == 0) mbar_init(bar, 1);
         __syncthreads();
         if (tid == 0) {
             const unsigned ib = (unsigned)(HW * sizeof(PT)), mb = (unsigned)HW;
             mbar_expect_tx(bar, ib + mb);
-            tma_load_1d(s_img, g_img, ib, bar);
-            tma_load_1d(s_msk, g_msk, mb, bar);
+            tma_load_1d(smem + p.o_stage, g_img, ib, bar);
+            tma_load_1d(smem + p.o_mask, g_msk, mb, bar);
         }
     }
 #endif
@@ -265,16 +296,28 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int nz = (p.smem_total - p.o_zero) / 16;
         const uint4 zero = {0u, 0u, 0u, 0u};
         for (int i = tid; i < nz; i += RADB_NTB) z[i] = zero;
+        if (WIDE) {  // level image + GLRLM counters in global memory
+            uint4* zl = (uint4*)lev;
+            const int nl = (int)(p.g_lab / 16);
+            for (int i = tid; i < nl; i += RADB_NTB) zl[i] = zero;
+            uint4* zr = (uint4*)glrlm_base;
+            const int nrr = NA * p.glrlm_stride / 16;
+            for (int i = tid; i < nrr; i += RADB_NTB) zr[i] = zero;
+        }
     }
+    if (!WIDE) {
 #ifndef RADB_EMU
-    if (p.use_tma) {
-        mbar_wait(smem + p.o_mbar, 0);
-    } else
+        if (p.use_tma) {
+            mbar_wait(smem + p.o_mbar, 0);
+        } else
 #endif
-    {
-        for (int i = tid; i < HW; i += RADB_NTB) {
-            s_img[i] = g_img[i];
-            s_msk[i] = g_msk[i];
+        {
+            PT* d_img = (PT*)(smem + p.o_stage);
+            unsigned char* d_msk = smem + p.o_mask;
+            for (int i = tid; i < HW; i += RADB_NTB) {
+                d_img[i] = g_img[i];
+                d_msk[i] = g_msk[i];
+            }
         }
     }
     __syncthreads();
@@ -390,7 +433,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     for (int a = 0; a < NA; a++)
         if (p.ang_y[a] == 0) a_row = a;
     if (a_row < 0) {  // no along-row connectivity: every ROI pixel starts as its own run of length 1
-        for (int i = tid; i < HW; i += RADB_NTB) lab[i] = 0x10000u | (unsigned)i;
+        for (int i = tid; i < HW; i += RADB_NTB) lab[i] = (((UW)1) << US) | (UW)i;
     }
 
     // ---- phase 3a: line walks over the ROI bounding box.  One thread walks one line along one
@@ -407,7 +450,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             // tasks [t0, t0 + nlines) belong to angle a; thread tid takes tasks tid, tid+NT, ...
             int first = tid - (t0 % RADB_NTB);
             if (first < 0) first += RADB_NTB;
-            unsigned* R = (unsigned*)(smem + p.o_glrlm + a * p.glrlm_stride);
+            unsigned* R = (unsigned*)(glrlm_base + a * p.glrlm_stride);
             for (int l = first; l < nlines; l += RADB_NTB) {
                 int cur = 0, len = 0;
                 if (dy == 0) {
@@ -417,19 +460,19 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                         const int g = lev[base + x];
                         if (g != cur) {
                             if (cur) {
-                                add_u16(R, (cur - 1) * nr + len - 1);
-                                lab[lbase + st] = ((unsigned)len << 16) | (unsigned)(lbase + st);
+                                add_run<WIDE>(R, (cur - 1) * nr + len - 1);
+                                lab[lbase + st] = ((UW)len << US) | (UW)(lbase + st);
                             }
                             cur = g;
                             len = 0;
                             st = x;
                         }
                         len++;
-                        if (g) lab[lbase + x] = (unsigned)(lbase + st);
+                        if (g) lab[lbase + x] = (UW)(lbase + st);
                     }
                     if (cur) {
-                        add_u16(R, (cur - 1) * nr + len - 1);
-                        lab[lbase + st] = ((unsigned)len << 16) | (unsigned)(lbase + st);
+                        add_run<WIDE>(R, (cur - 1) * nr + len - 1);
+                        lab[lbase + st] = ((UW)len << US) | (UW)(lbase + st);
                     }
                 } else {
                     const int sdx = dx * dy;  // x step per +1 in y (runs are direction-agnostic)
@@ -438,7 +481,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                     for (int y = 0; y < bh; y++) {
                         const int g = lev[pos + x];
                         if (g != cur || brk) {
-                            if (cur) add_u16(R, (cur - 1) * nr + len - 1);
+                            if (cur) add_run<WIDE>(R, (cur - 1) * nr + len - 1);
                             cur = g;
                             len = 0;
                         }
@@ -449,7 +492,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                         if (x >= bw) { x = 0; brk = 1; }          // wrapped diagonal: the next pixel is not
                         else if (x < 0) { x = bw - 1; brk = 1; }  // a neighbour of this one
                     }
-                    if (cur) add_u16(R, (cur - 1) * nr + len - 1);
+                    if (cur) add_run<WIDE>(R, (cur - 1) * nr + len - 1);
                 }
             }
             t0 += nlines;
@@ -468,18 +511,18 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const bool inplane = (NA == 4);  // all 8 neighbours: run-adjacency union rules apply
         // Union requests are queued per warp and executed 32 at a time, so that the
         // data-dependent find loops run with (nearly) all lanes busy.
-        unsigned* uq = (unsigned*)(smem + p.o_uq) + warp * 64;
+        UW* uq = (UW*)(smem + p.o_uq) + warp * 64;
         int qn = 0;
         const unsigned lt_mask = (1u << lane) - 1u;
         auto drain = [&](int count) {
             if (lane < count) {
-                const unsigned pr = uq[qn - count + lane];
-                uf_union(lab, pr >> 16, pr & 0xffffu);
+                const UW pr = uq[qn - count + lane];
+                uf_union<UW, UF<WIDE>::S>(lab, (unsigned)(pr >> US), (unsigned)(pr & ULO));
             }
             __syncwarp();
             qn -= count;
         };
-        auto push = [&](bool has, unsigned pair) {
+        auto push = [&](bool has, UW pair) {
             const unsigned m = __ballot_sync(FULLMASK, has);
             if (has) uq[qn + __popc(m & lt_mask)] = pair;
             qn += __popc(m);
@@ -488,7 +531,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         };
         for (int base = 0; base < nbox; base += RADB_NTB) {  // uniform trip count (warp collectives below)
             const int idx = base + tid;
-            const int yb = (int)(((float)idx + 0.5f) * inv_bw);
+            const int yb = WIDE ? idx / bw : (int)(((float)idx + 0.5f) * inv_bw);
             const int y = by0 + yb, x = bx0 + (idx - yb * bw);
             const int ctr = (y + 1) * WP + x + 1;
             const int c = idx < nbox ? (int)lev[ctr] : 0;
@@ -543,7 +586,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             const int nreq = inplane ? 2 : NA;
 #pragma unroll
             for (int a = 0; a < RADB_MAX_ANGLES; a++)
-                if (a < nreq) push(req[a] != 0, ((unsigned)li << 16) | (req[a] - 1u));
+                if (a < nreq) push(req[a] != 0, ((UW)(unsigned)li << US) | (UW)(req[a] - 1u));
         }
         if (qn) drain(qn);
     }
@@ -551,14 +594,14 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
 
     // ---- phase 4: fold run lengths into their zone root; symmetrise the GLCM
     for (int idx = tid; idx < nbox; idx += RADB_NTB) {
-        const int yb = (int)(((float)idx + 0.5f) * inv_bw);
+        const int yb = WIDE ? idx / bw : (int)(((float)idx + 0.5f) * inv_bw);
         const int y = by0 + yb, x = bx0 + (idx - yb * bw);
         const int ctr = (y + 1) * WP + x + 1;
         const int c = lev[ctr];
         if (c && (a_row < 0 || lev[ctr - 1] != c)) {  // run start
             const int li = y * W + x;
-            const unsigned r = uf_find_ro(lab, (unsigned)li);
-            if (r != (unsigned)li) atomicAdd(&lab[r], lab[li] & 0xffff0000u);  // only roots are ever added to
+            const unsigned r = uf_find_ro<UW, UF<WIDE>::S>(lab, (unsigned)li);
+            if (r != (unsigned)li) atomicAdd(&lab[r], (UW)(lab[li] & ~ULO));  // only roots are ever added to
         }
     }
     if (p.symmetric) {
@@ -581,20 +624,20 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
 
     // ---- phase 5: zone roots -> GLSZM (dense + overflow)
     for (int idx = tid; idx < nbox; idx += RADB_NTB) {
-        const int yb = (int)(((float)idx + 0.5f) * inv_bw);
+        const int yb = WIDE ? idx / bw : (int)(((float)idx + 0.5f) * inv_bw);
         const int y = by0 + yb, x = bx0 + (idx - yb * bw);
         const int ctr = (y + 1) * WP + x + 1;
         const int c = lev[ctr];
         if (!c || (a_row >= 0 && lev[ctr - 1] == c)) continue;
         const int li = y * W + x;
-        const unsigned wl = lab[li];
-        if ((wl & 0xffffu) != (unsigned)li) continue;
-        const int s = (int)(wl >> 16);
+        const UW wl = lab[li];
+        if ((unsigned)(wl & ULO) != (unsigned)li) continue;
+        const int s = (int)(wl >> US);
         if (s <= p.s0) {
             atomicAdd(&szm[(c - 1) * p.s0 + s - 1], 1);
         } else {
             int k = atomicAdd(&misc[5], 1);
-            if (k < p.ovf_cap) ovf[k] = ((unsigned)c << 16) | (unsigned)s;
+            if (k < p.ovf_cap) ovf[k] = ((unsigned)c << 24) | (unsigned)s;  // sizes < 2^24
         }
         if (DBG && p.dbg_glszm) atomicAdd(&p.dbg_glszm[(patch * p.max_ng + (c - 1)) * (long long)HW + s - 1], 1);
     }
@@ -613,7 +656,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         for (int a = 0; a < NA; a++)
             for (int t = tid; t < ng * p.nr; t += RADB_NTB)
                 p.dbg_glrlm[((patch * NA + a) * p.max_ng + t / p.nr) * p.nr + t % p.nr] =
-                    get_u16((const unsigned*)(smem + p.o_glrlm + a * p.glrlm_stride), t);
+                    get_run((const unsigned*)(glrlm_base + a * p.glrlm_stride), t, WIDE);
     if (DBG && p.dbg_gldm)
         for (int t = tid; t < ng * (NB + 1); t += RADB_NTB)
             p.dbg_gldm[patch * p.max_ng * (NB + 1) + t] = gldm[t];
@@ -627,8 +670,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     __syncthreads();
     {
         const uint4* src = (const uint4*)(smem + p.o_rec);
-        uint4* dst = (uint4*)(p.ws + patch * (long long)p.rec_bytes);
-        const int n16 = p.rec_bytes / 16;
+        uint4* dst = (uint4*)g_rec;
+        const int n16 = p.rec_copy_bytes / 16;  // wide: GLRLM and the overflow list are already in place
         for (int i = tid; i < n16; i += RADB_NTB) dst[i] = src[i];
     }
 }
@@ -658,7 +701,7 @@ __device__ void radb_angle_cta(const RadbParams& p, long long patch, unsigned ch
         for (int i = lane; i < (p.a_idx - p.a_px) / 4; i += 32) ((int*)(ws + p.a_px))[i] = 0;
         __syncwarp();
         const unsigned* R = (const unsigned*)(rec + (p.o_glrlm - p.o_rec) + a * p.glrlm_stride);
-        int ok = glrlm_task(tb, R, 0, ng, p.nr, (int*)(ws + p.a_pr), fsc + a * RADB_FSC_STRIDE + RADB_GLCM_NF, lane);
+        int ok = glrlm_task(tb, R, p.wide, ng, p.nr, (int*)(ws + p.a_pr), fsc + a * RADB_FSC_STRIDE + RADB_GLCM_NF, lane);
         if (lane == 0) valid[4 + a] = ok;
         const int* P = (const int*)(rec + (p.o_glcm - p.o_rec)) + a * ng * ng;
         ok = glcm_task(p, tb, P, ng, (int*)(ws + p.a_px), (int*)(ws + p.a_py), (int*)(ws + p.a_padd),
@@ -732,11 +775,11 @@ __device__ void radb_misc_cta(const RadbParams& p, long long patch, unsigned cha
 }
 
 #ifndef RADB_EMU
-template <typename PT, bool DBG>
+template <typename PT, bool DBG, bool WIDE>
 __global__ void __launch_bounds__(RADB_NTB, RADB_NTB_MINB) radb_build_kernel(const RadbParams p)
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
-    radb_build_cta<PT, DBG>(p, (long long)blockIdx.x, radb_smem);
+    radb_build_cta<PT, DBG, WIDE>(p, (long long)blockIdx.x, radb_smem);
 }
 __global__ void __launch_bounds__(RADB_NT, 6) radb_angle_kernel(const RadbParams p)
 {

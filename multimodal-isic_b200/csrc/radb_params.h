@@ -40,12 +40,16 @@ struct RadbParams {
     int F;
     int off_fo, off_glcm, off_gldm, off_glrlm, off_glszm, off_ngtdm;  // output column of each class, -1 = off
     int use_tma;
+    int wide;      // 1: whole-image mode (level image, union-find words, GLRLM and overflow list in global memory)
     // ---- build kernel: shared-memory byte offsets.  [o_rec, o_rec + rec_bytes) is the per-patch
     // RECORD (header + every integer matrix); the build kernel copies it to the global workspace
     // and the reduction kernels read it from there at the same relative offsets.
     int o_stage, o_mask, o_mbar, o_zero, o_lev, o_uq, o_lut, o_rec, o_misc, o_hist, o_lhist, o_glcm, o_glrlm,
         o_gldm, o_ngc, o_ngn, o_szm, o_ovf, smem_total;
-    int rec_bytes;
+    int rec_bytes;       // record size in the global workspace
+    int rec_copy_bytes;  // leading part of the record that is built in shared memory and copied out
+    long long scr_bytes; // wide mode: per-patch global scratch (level image + union-find words)
+    long long g_lev, g_lab;  // offsets inside that scratch
     int glrlm_stride;  // bytes per angle of the packed-u16 GLRLM counters
     int mcc_stride;    // doubles per angle in the MCC workspace
     int ninv;          // entries of the 1/k^2 table
@@ -55,6 +59,7 @@ struct RadbParams {
     int m_pg, m_ovf2, m_ngp, m_qv, m_red, m_smem_total;
     // global workspace + tables (device pointers)
     unsigned char* ws;        // [B][rec_bytes]
+    unsigned char* ws_scr;    // [B][scr_bytes] (wide mode)
     const double* g_inv2;     // [ninv]  1/k^2
     const double* g_tlog;     // [2048]  log2(k)
     // optional debug outputs (device pointers, may be null); dims use max_ng
@@ -70,46 +75,56 @@ struct RadbParams {
 
 static inline int radb_align(int v, int a) { return (v + a - 1) / a * a; }
 
-// Fills WP/HW/nr/s0/ovf_cap and every shared-memory / record offset from H, W, max_ng, n_angles.
+// Fills WP/HW/nr/s0/ovf_cap and every shared-memory / record offset from H, W, max_ng, n_angles
+// and p->wide.  Record layout (both modes): header, hist, lhist, glcm, gldm, ngc, ngn, szm | glrlm, ovf.
 static inline void radb_layout(RadbParams* p, int pix_bytes)
 {
-    const int H = p->H, W = p->W, ng = p->max_ng, na = p->n_angles;
+    const int H = p->H, W = p->W, ng = p->max_ng, na = p->n_angles, wide = p->wide;
     p->HW = H * W;
     p->WP = radb_align(W + 2, 4);
     p->nr = H > W ? H : W;
-    p->s0 = 16;
+    p->s0 = wide ? 64 : 16;
     p->ovf_cap = p->HW / (p->s0 + 1) + 1;
     p->ninv = ng > p->nr ? ng : p->nr;
-    if (p->ninv < 16) p->ninv = 16;
+    if (p->ninv < p->s0) p->ninv = p->s0;
     p->mcc_stride = ng * (ng + 1) / 2 + 4 * ng;
     if (p->mcc_stride < 2 * ng + 8) p->mcc_stride = 2 * ng + 8;
     int o = 0;
     // ---- build kernel
     p->o_stage = o;                       // raw pixels (TMA destination); later union-find words (u32[HW])
-    int stage_bytes = radb_align(p->HW * pix_bytes, 16);
-    p->o_mask = o + stage_bytes;          // raw mask (TMA destination)
-    int both = stage_bytes + radb_align(p->HW, 16);
-    int lab_bytes = radb_align(p->HW * 4, 16);   // union-find words (parent | size << 16)
-    o += both > lab_bytes ? both : lab_bytes;
+    p->o_mask = o;
+    if (!wide) {
+        int stage_bytes = radb_align(p->HW * pix_bytes, 16);
+        p->o_mask = o + stage_bytes;      // raw mask (TMA destination)
+        int both = stage_bytes + radb_align(p->HW, 16);
+        int lab_bytes = radb_align(p->HW * 4, 16);   // union-find words (parent | size << 16)
+        o += both > lab_bytes ? both : lab_bytes;
+    }
     p->o_mbar = o; o += 16;
     p->o_zero = o;                        // everything from here on is zeroed at CTA start
-    p->o_lev = o; o += radb_align((H + 2) * p->WP, 16);
-    p->o_uq = o; o += (RADB_NTB / 32) * 64 * 4;           // per-warp union request queues
+    p->o_lev = o;
+    if (!wide) o += radb_align((H + 2) * p->WP, 16);
+    p->o_uq = o; o += (RADB_NTB / 32) * 64 * (wide ? 8 : 4);   // per-warp union request queues
     p->o_lut = o; o += 256;
     p->o_rec = o;
     p->o_misc = o; o += 32 * 4;           // record header: [0] Np, [5] #overflow zones, [8] Ng, [9] #levels present
     p->o_hist = o; o += 256 * 4;
     p->o_lhist = o; o += radb_align(ng * 4, 16);
     p->o_glcm = o; o += radb_align(na * ng * ng * 4, 16);
-    p->glrlm_stride = radb_align(ng * p->nr * 2, 16);
-    p->o_glrlm = o; o += na * p->glrlm_stride;
     p->o_gldm = o; o += radb_align(ng * (2 * na + 1) * 4, 16);
     p->o_ngc = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] voxel counts per neighbour count
     p->o_ngn = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] sum |cnt*i - sum(neigh)|
     p->o_szm = o; o += radb_align(ng * p->s0 * 4, 16);
-    p->o_ovf = o; o += radb_align(p->ovf_cap * 4, 16);
+    p->rec_copy_bytes = o - p->o_rec;
+    p->glrlm_stride = radb_align(ng * p->nr * (wide ? 4 : 2), 16);
+    p->o_glrlm = o; o += na * p->glrlm_stride;             // wide: lives in the global record only
+    p->o_ovf = o; o += radb_align(p->ovf_cap * 4, 16);     // wide: lives in the global record only
     p->rec_bytes = o - p->o_rec;
-    p->smem_total = o;
+    p->smem_total = wide ? p->o_rec + p->rec_copy_bytes : o;
+    if (!wide) p->rec_copy_bytes = p->rec_bytes;
+    p->g_lev = 0;
+    p->g_lab = radb_align((H + 2) * p->WP, 16);
+    p->scr_bytes = wide ? p->g_lab + (long long)p->HW * 8 : 0;
     // ---- angle kernel
     o = 0;
     p->a_px = o; o += radb_align(ng * 4, 16);

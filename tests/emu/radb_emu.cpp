@@ -18,6 +18,14 @@ extern "C" int radb_emu_feature_count(const radb_settings* s)
     if (radb::make_plan(*s, pl, g_err)) return -1;
     return pl.F;
 }
+extern "C" int radb_emu_is_wide(const radb_settings* s, int H, int W)
+{
+    radb::Plan pl;
+    if (radb::make_plan(*s, pl, g_err)) return -1;
+    RadbParams p;
+    if (radb::fill_params(pl, H, W, RADB_DTYPE_U8, p, g_err)) return -1;
+    return p.wide;
+}
 extern "C" int radb_emu_max_ng(const radb_settings* s)
 {
     radb::Plan pl;
@@ -58,14 +66,18 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
         for (size_t k = 2; k < tlog.size(); k++) tlog[k] = nextafter(tlog[k], (k & 1) ? 1e9 : -1e9);
     p.g_inv2 = inv2.data();
     p.g_tlog = tlog.data();
-    std::vector<unsigned char> ws((size_t)B * p.rec_bytes + 64);
+    std::vector<unsigned char> ws((size_t)B * p.rec_bytes + 64), scr((size_t)B * p.scr_bytes + 64);
     p.ws = (unsigned char*)(((uintptr_t)ws.data() + 15) & ~(uintptr_t)15);
+    p.ws_scr = (unsigned char*)(((uintptr_t)scr.data() + 15) & ~(uintptr_t)15);
     int mx = p.smem_total > p.a_smem_total ? p.smem_total : p.a_smem_total;
     mx = mx > p.m_smem_total ? mx : p.m_smem_total;
     std::vector<unsigned char> smem((size_t)mx + 64);
     unsigned char* sm = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
     // the same three launches radb_api.cu issues, CTA by CTA on host threads
-    emu::launch((unsigned)B, RADB_NTB, [&]() { radb_build_cta<unsigned char, true>(p, (long long)blockIdx.x, sm); });
+    if (p.wide)
+        emu::launch((unsigned)B, RADB_NTB, [&]() { radb_build_cta<unsigned char, true, true>(p, (long long)blockIdx.x, sm); });
+    else
+        emu::launch((unsigned)B, RADB_NTB, [&]() { radb_build_cta<unsigned char, true, false>(p, (long long)blockIdx.x, sm); });
     emu::launch((unsigned)B, RADB_NT, [&]() { radb_angle_cta(p, (long long)blockIdx.x, sm); });
     emu::launch((unsigned)B, RADB_NT, [&]() { radb_misc_cta(p, (long long)blockIdx.x, sm); });
     return 0;

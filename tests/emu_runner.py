@@ -17,6 +17,10 @@ class EmuRunner:
         self.lib.radb_emu_extract.argtypes = [vp, vp, i32, vp, i64, i32, i32, i64, i64] + [vp] * 10
         self.lib.radb_emu_last_error.restype = ctypes.c_char_p
 
+    def is_wide(self, H, W, bin_width=10, angles=((0, 1),)):
+        s = _abi.make_settings(bin_width, 255, angles)
+        return self.lib.radb_emu_is_wide(ctypes.byref(s), H, W)
+
     def run(self, imgs, masks, bin_width=10, label=255, angles=((0, 1),), symmetrical=True, alpha=0):
         imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
         masks = np.ascontiguousarray(masks, dtype=np.uint8)

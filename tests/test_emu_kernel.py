@@ -89,3 +89,23 @@ def test_emu_edge_cases_with_perturbed_tables(emu, monkeypatch):
     imgs, masks = edge_case_batch()
     r = emu.run(imgs, masks, 10, 255, INPLANE)
     assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=False)) == 6
+
+
+def test_emu_wide_mode_whole_image(emu):
+    # > 65535 pixels: level image, union-find words, GLRLM and the zone overflow list move to global
+    # memory (whole dermoscopy images, RadiomicExtractor.py:29-38, are this size class)
+    imgs, masks = synth.make_patches(1, 270, 300, seed=11)
+    assert emu.is_wide(270, 300, 10, INPLANE) == 1
+    r = emu.run(imgs, masks, 10, 255, INPLANE)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=False)) == 1
+
+
+def test_emu_wide_mode_literal_and_smooth(emu):
+    H, W = 260, 256
+    yy, xx = np.mgrid[:H, :W]
+    img = np.clip(120 + 50 * np.sin(xx / 23.0) + 40 * np.cos(yy / 17.0), 0, 255).astype(np.uint8)[None]
+    mask = np.zeros((1, H, W), np.uint8)
+    mask[0, 5:250, 3:251] = 255
+    assert emu.is_wide(H, W, 25, LITERAL) == 1
+    r = emu.run(img, mask, 25, 255, LITERAL)
+    assert compare_with_oracle(r, img, mask, dict(label=255, binWidth=25, force2D=True)) == 1

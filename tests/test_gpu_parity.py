@@ -76,6 +76,22 @@ def test_force2d_dimension1_column_only(gpu_pkg):
     assert compare_with_oracle(r, imgs, masks, s) == 6
 
 
+@pytest.mark.parametrize("hw,n", [((224, 224), 3), ((450, 600), 1), ((300, 200), 2)])
+def test_wide_mode_large_images(gpu_pkg, hw, n):
+    """Images that do not fit shared memory (224x224 patches of BASELINE.json configs[3]; whole
+    600x450 dermoscopy images as the reference feeds them, RadiomicExtractor.py:29-38)."""
+    H, W = hw
+    imgs, masks = gpu_pkg.synth.make_patches(n, H, W, seed=12)
+    r = _dbg(_engine(gpu_pkg), imgs, masks)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=False)) == n
+
+
+def test_wide_mode_literal_whole_image(gpu_pkg):
+    imgs, masks = gpu_pkg.synth.make_patches(2, 450, 600, seed=13)
+    r = _dbg(_engine(gpu_pkg, 10, LITERAL), imgs, masks)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=True)) == 2
+
+
 def test_random_noise_many_levels(gpu_pkg):
     rng = np.random.default_rng(7)
     imgs = rng.integers(0, 256, (6, 40, 40)).astype(np.uint8)
@@ -140,7 +156,7 @@ def test_record_path_matches_reference_call_pattern(gpu_pkg, tmp_path):
     rng = np.random.default_rng(9)
     recs = []
     for k in range(3):
-        g, m = gpu_pkg.synth.make_patches(1, 48, 64, seed=20 + k)
+        g, m = gpu_pkg.synth.make_patches(1, *((48, 64) if k < 2 else (300, 400)), seed=20 + k)  # last: whole-image size
         bgr = np.stack([np.clip(g[0].astype(int) + rng.integers(-20, 20, g[0].shape), 0, 255) for _ in range(3)],
                        -1).astype(np.uint8)
         ip, sp = str(tmp_path / ("img%d.png" % k)), str(tmp_path / ("seg%d.png" % k))
