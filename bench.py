@@ -131,7 +131,7 @@ def reference_arm(args):
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": tot / args.steps * 1e3,
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": workload_config(args, n, F),
+        "config": dict(workload_config(args, n, F), l2_policy="n/a (CPU arm)"),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": "port",
                          "sample": "%d of the workload's 64x64 patches per step, oracle (C matrices + NumPy features), "
                                    "multiprocessing pool over %d cores" % (n, arm.cores)},
@@ -242,8 +242,15 @@ def gpu_arm(args):
     l0 = ex.engine.launches
     ms = timed(step, args.steps)
     launches = ex.engine.launches - l0
-    # kernel-only duration (same kernel, events directly around the launches on its stream)
-    kms = timed(lambda: ex.engine.extract_device(imgs, masks, out, status), args.steps) / args.steps
+    # per-kernel device time (CUDA events recorded by the library on the launching stream around the
+    # build / angle / misc kernels of every chunk), averaged over the same number of steps
+    ex.engine.set_profiling(True)
+    for _ in range(args.steps):
+        ex.engine.extract_device(imgs, masks, out, status)
+    torch.cuda.synchronize()
+    kparts = {k: v / args.steps for k, v in ex.engine.kernel_ms().items()}
+    ex.engine.set_profiling(False)
+    kms = sum(kparts.values())
     bad = int((status != 0).sum().item())
 
     # ---- end to end through the public API with HOST buffers (pinned), copies in the timed region
@@ -309,6 +316,7 @@ def gpu_arm(args):
         peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6.65 TB/s"
         bpp = bytes_per_patch(H, H, F)
         achieved = B * bpp / (kms / 1e3) / 1e9
+        dom = max(kparts, key=kparts.get)
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
@@ -322,10 +330,16 @@ def gpu_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, B, F),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "radb_extract_kernel<uint8>", "kernel_ms": kms,
+                         "traffic": traffic, "kernel": "radb_build_kernel + radb_angle_kernel + radb_misc_kernel "
+                                                       "(one pass of the hot path; chunks of 16384 patches)",
+                         "kernel_ms": kms, "kernel_ms_parts": kparts, "dominant_kernel": "radb_%s_kernel" % dom,
+                         "dominant_share": kparts[dom] / kms,
+                         "dominant_achieved": B * bpp / (kparts[dom] / 1e3) / 1e9,
                          "bytes_per_patch": bpp, "peak_source": peak_src,
-                         "note": "algorithmic bytes = H*W px + H*W mask + 8*F; the matrix stages are shared-memory-"
-                                 "atomic / fp64 bound, not HBM bound (DESIGN.md)"},
+                         "note": "algorithmic bytes = H*W px + H*W mask + 8*F per patch over the summed duration of "
+                                 "the three kernels of a pass; dominant_achieved uses the dominant kernel's duration "
+                                 "alone. The pass is issue/latency bound (shared-memory atomics, fp64), not HBM "
+                                 "bound (DESIGN.md, profiles/)"},
             "cpu_baseline": cpu,
             "e2e": {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(world * B * H * H * 2),
                     "d2h_bytes_per_step": int(world * B * (F * 8 + 4)), "matches_device_path": same},

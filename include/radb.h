@@ -120,6 +120,12 @@ int radb_max_ng(const radb_handle* h);
  * kernels (build, angle, misc) per chunk of 16384 patches. */
 int64_t radb_launch_count(const radb_handle* h);
 
+/* Per-kernel device timing for bench.py's roofline: with profiling on, every launch records CUDA
+ * events on its stream around the build / angle / misc kernels; radb_kernel_ms waits for them,
+ * returns the accumulated milliseconds per kernel in ms3[0..2] and clears the record. */
+int radb_set_profiling(radb_handle* h, int on);
+int radb_kernel_ms(radb_handle* h, double* ms3);
+
 const char* radb_last_error(void);
 const char* radb_version(void);
 

@@ -25,6 +25,8 @@ struct radb_handle {
                                  // (launches on different streams may overlap; each owns its records)
     double* d_inv2;
     double* d_tlog;
+    bool profiling;              // record CUDA events around every kernel (radb_set_profiling)
+    std::vector<cudaEvent_t> events;  // 4 per chunk: start, after build, after angle, after misc
 };
 
 static int fail(int code, const std::string& msg)
@@ -54,6 +56,7 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
     h->launches = 0;
     for (int i = 0; i < 8; i++) h->smem_set[i] = 0;
     h->d_inv2 = h->d_tlog = nullptr;
+    h->profiling = false;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -219,9 +222,20 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
             if (q.dbg_ngs) q.dbg_ngs += done * NG;
             if (q.dbg_ng) q.dbg_ng += done;
         }
+        auto mark = [&]() {
+            if (!h->profiling) return;
+            cudaEvent_t ev;
+            cudaEventCreate(&ev);
+            cudaEventRecord(ev, st);
+            h->events.push_back(ev);
+        };
+        mark();
         build<<<(unsigned)n, RADB_NTB, p.smem_total, st>>>(q);
+        mark();
         radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, st>>>(q);
+        mark();
         radb_misc_kernel<<<(unsigned)n, RADB_NT, p.m_smem_total, st>>>(q);
+        mark();
         h->launches += 3;
         done += n;
     }
@@ -283,4 +297,31 @@ extern "C" int radb_debug_matrices(radb_handle* h, const void* img, int dtype, c
     p.dbg_ngs = ngtdm_s;
     p.dbg_ng = ng;
     return launch(h, p, dtype, cuda_stream);
+}
+
+extern "C" int radb_set_profiling(radb_handle* h, int on)
+{
+    if (!h) return fail(RADB_E_INVALID, "null handle");
+    for (auto ev : h->events) cudaEventDestroy(ev);
+    h->events.clear();
+    h->profiling = on != 0;
+    return RADB_OK;
+}
+
+extern "C" int radb_kernel_ms(radb_handle* h, double* ms3)
+{
+    if (!h || !ms3) return fail(RADB_E_INVALID, "null argument");
+    ms3[0] = ms3[1] = ms3[2] = 0.0;
+    for (size_t i = 0; i + 3 < h->events.size(); i += 4) {
+        cudaError_t e = cudaEventSynchronize(h->events[i + 3]);
+        if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
+        for (int k = 0; k < 3; k++) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, h->events[i + k], h->events[i + k + 1]);
+            ms3[k] += ms;
+        }
+    }
+    for (auto ev : h->events) cudaEventDestroy(ev);
+    h->events.clear();
+    return RADB_OK;
 }

@@ -49,6 +49,17 @@ class Engine:
     def launches(self):
         return int(self.lib.radb_launch_count(self._h))
 
+    def set_profiling(self, on):
+        self.lib.radb_set_profiling(self._h, int(bool(on)))
+
+    def kernel_ms(self):
+        """Accumulated device milliseconds of the (build, angle, misc) kernels since profiling was switched on."""
+        ms = (ctypes.c_double * 3)()
+        rc = self.lib.radb_kernel_ms(self._h, ctypes.byref(ms))
+        if rc != 0:
+            raise RadbError("radb_kernel_ms failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+        return dict(build=ms[0], angle=ms[1], misc=ms[2])
+
     def smem_bytes(self, H, W, dtype=_abi.DTYPE_U8):
         return int(self.lib.radb_smem_bytes(self._h, H, W, dtype))
 
