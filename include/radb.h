@@ -22,7 +22,7 @@ extern "C" {
 
 typedef struct radb_handle radb_handle;
 
-/* feature classes, in the output order (params.yml:164-171 order without shape2D) */
+/* feature classes; output order = shape2D (if enabled), then the order below (params.yml:164-171) */
 enum {
     RADB_CLASS_FIRSTORDER = 1u << 0,
     RADB_CLASS_GLCM = 1u << 1,
@@ -30,7 +30,8 @@ enum {
     RADB_CLASS_GLRLM = 1u << 3,
     RADB_CLASS_GLSZM = 1u << 4,
     RADB_CLASS_NGTDM = 1u << 5,
-    RADB_CLASS_ALL = 0x3fu
+    RADB_CLASS_SHAPE2D = 1u << 6, /* mask-only; its 9 columns come first (pyradiomics computes shape first) */
+    RADB_CLASS_ALL = 0x7fu
 };
 
 /* pixel types of `img` */

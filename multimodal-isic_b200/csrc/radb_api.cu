@@ -18,7 +18,7 @@ struct radb_handle {
     radb::Plan plan;
     int device;
     int smem_optin;              // max dynamic shared memory per block the device allows
-    int smem_set[8];             // configured MaxDynamicSharedMemorySize per kernel
+    int smem_set[9];             // configured MaxDynamicSharedMemorySize per kernel
     int64_t launches;
     struct Ws { void* stream; unsigned char* p; size_t bytes; };
     std::vector<Ws> ws;          // per-patch records of one chunk, one workspace per CUDA stream
@@ -54,7 +54,7 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
     if (rc) { delete h; return fail(rc, err); }
     h->device = s->device;
     h->launches = 0;
-    for (int i = 0; i < 8; i++) h->smem_set[i] = 0;
+    for (int i = 0; i < 9; i++) h->smem_set[i] = 0;
     h->d_inv2 = h->d_tlog = nullptr;
     h->profiling = false;
     int ndev = 0;
@@ -191,6 +191,7 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
                                   : (dbg ? radb_build_kernel<unsigned char, true, false> : radb_build_kernel<unsigned char, false, false>);
     int rc = set_smem(h, build, (p.wide ? 4 : 0) + (dbg ? 3 : 0), p.smem_total);
     if (!rc) rc = set_smem(h, radb_angle_kernel, 1, p.a_smem_total);
+    if (!rc && p.off_shape >= 0) rc = set_smem(h, radb_shape_kernel, 8, p.s_smem_total);
     if (!rc) rc = set_smem(h, radb_misc_kernel, 2, p.m_smem_total);
     unsigned char* wsp = nullptr;
     if (!rc) rc = ensure_ws(h, p, p.B, stream, &wsp);
@@ -235,6 +236,10 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, st>>>(q);
         mark();
         radb_misc_kernel<<<(unsigned)n, RADB_NT, p.m_smem_total, st>>>(q);
+        if (p.off_shape >= 0) {
+            radb_shape_kernel<<<(unsigned)n, RADB_NT, p.s_smem_total, st>>>(q);
+            h->launches += 1;
+        }
         mark();
         h->launches += 3;
         done += n;

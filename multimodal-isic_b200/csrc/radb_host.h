@@ -58,6 +58,7 @@ struct Plan {
     int max_ng;
     int F;
     int off[6];
+    int off_shape;
     std::vector<std::string> names;
 };
 
@@ -88,6 +89,15 @@ static inline int make_plan(const radb_settings& s, Plan& pl, std::string& err)
     pl.max_ng = ng;
     pl.F = 0;
     pl.names.clear();
+    pl.off_shape = -1;
+    if (s.class_mask & RADB_CLASS_SHAPE2D) {  // A.1 step 3: shape keys come first
+        static const char* shape_names[9] = {"Elongation", "MajorAxisLength", "MaximumDiameter", "MeshSurface",
+                                             "MinorAxisLength", "Perimeter", "PerimeterSurfaceRatio", "PixelSurface",
+                                             "Sphericity"};
+        pl.off_shape = 0;
+        for (auto f : shape_names) pl.names.push_back(std::string("original_shape2D_") + f);
+        pl.F = 9;
+    }
     int k = 0;
     for (const auto& c : classes()) {
         if (s.class_mask & c.bit) {
@@ -126,6 +136,7 @@ static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParam
     p.off_glrlm = pl.off[3];
     p.off_glszm = pl.off[4];
     p.off_ngtdm = pl.off[5];
+    p.off_shape = pl.off_shape;
     // narrow mode (everything in shared memory) when the patch fits with >= 2 CTAs per SM,
     // otherwise wide mode (level image, union-find words, GLRLM, overflow list in global memory)
     p.wide = 0;
@@ -134,7 +145,7 @@ static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParam
         p.wide = 1;
         radb_layout(&p, 1);
     }
-    if (p.smem_total > 227 * 1024 || p.a_smem_total > 227 * 1024 || p.m_smem_total > 227 * 1024) {
+    if (p.smem_total > 227 * 1024 || p.a_smem_total > 227 * 1024 || p.m_smem_total > 227 * 1024 || p.s_smem_total > 227 * 1024) {
         err = "image size x gray levels need more than 227 KB of shared memory";
         return RADB_E_SMEM;
     }

@@ -774,6 +774,129 @@ __device__ void radb_misc_cta(const RadbParams& p, long long patch, unsigned cha
     }
 }
 
+// ------------------------------------------------------------------ shape kernel: shape2D (9 features)
+// pyradiomics shape2D.py + cshape.c:calculate_coefficients2D (SURVEY.md section 8 f rank 1), mask only:
+// marching squares over the zero-padded mask.  Everything reduces to integers: the perimeter is
+// (#axis-aligned segments) + sqrt(1/2) * (#diagonal segments), the mesh surface is a sum of
+// eighths per 2x2 cell (equal to the |shoelace| sum of the contour), the maximum diameter is the
+// largest distance between contour vertices (edge midpoints; only the extreme vertices of every
+// row can be hull vertices, so 2 candidates per half-row are kept), the axes come from the exact
+// second moments of the ROI pixel coordinates.
+__device__ void radb_shape_cta(const RadbParams& p, long long patch, unsigned char* smem)
+{
+    const int tid = threadIdx.x, lane = tid & 31;
+    const int H = p.H, W = p.W;
+    if (p.status[patch] != 0 || p.off_shape < 0) return;
+    const unsigned char* m = p.mask + patch * p.mask_stride;
+    double* out = p.out + patch * (long long)p.F + p.off_shape;
+    const int nrow = 2 * H + 1;                     // doubled y coordinates 0..2H of contour vertices (shifted by +1)
+    int* xmin = (int*)smem;                         // [nrow]
+    int* xmax = xmin + nrow;                        // [nrow]
+    unsigned long long* cta = (unsigned long long*)(smem + ((2 * nrow * 4 + 15) & ~15));  // [9] integer totals
+    int* wmax = (int*)(cta + 10);                   // [RADB_NT / 32][2]
+    for (int i = tid; i < nrow; i += RADB_NT) { xmin[i] = 0x7fffffff; xmax[i] = -1; }
+    if (tid < 9) cta[tid] = 0;
+    __syncthreads();
+    const int label = p.label;
+    long long n = 0, sy = 0, sx = 0, syy = 0, sxx = 0, sxy = 0, eighths = 0;
+    int nstraight = 0, ndiag = 0;
+    // one thread per 2x2 cell of the padded mask: cell (iy, ix) has corners (iy..iy+1, ix..ix+1), iy, ix >= -1
+    const int cw = W + 1, ncell = (H + 1) * cw;
+    for (int t = tid; t < ncell; t += RADB_NT) {
+        const int iy = t / cw - 1, ix = t - (iy + 1) * cw - 1;
+        const bool in0 = iy >= 0, in1 = iy + 1 < H, jn0 = ix >= 0, jn1 = ix + 1 < W;
+        const int c0 = (in0 && jn0) ? ((int)m[iy * W + ix] == label) : 0;
+        const int c1 = (in0 && jn1) ? ((int)m[iy * W + ix + 1] == label) : 0;
+        const int c2 = (in1 && jn1) ? ((int)m[(iy + 1) * W + ix + 1] == label) : 0;
+        const int c3 = (in1 && jn0) ? ((int)m[(iy + 1) * W + ix] == label) : 0;
+        const int k = c0 + c1 + c2 + c3;
+        if (c2) {  // pixel (iy+1, ix+1) is visited exactly once as corner 2
+            const long long y = iy + 1, x = ix + 1;
+            n++; sy += y; sx += x; syy += y * y; sxx += x * x; sxy += x * y;
+        }
+        if (k == 0) continue;
+        const bool diagonal = (k == 2) && (c0 == c2);
+        eighths += k == 4 ? 8 : k == 3 ? 7 : k == 1 ? 1 : diagonal ? 2 : 4;
+        if (k == 4) continue;
+        if (k == 2 && !diagonal) nstraight++; else ndiag += diagonal ? 2 : 1;
+        // contour vertices owned by this cell: midpoints of its top edge (c0|c1) and left edge (c0|c3);
+        // coordinates doubled and shifted by +1 so they are non-negative
+        if (c0 != c1) {
+            const int y2 = 2 * iy + 1, x2 = 2 * ix + 2;
+            atomicMin(&xmin[y2], x2);
+            atomicMax(&xmax[y2], x2);
+        }
+        if (c0 != c3) {
+            const int y2 = 2 * iy + 2, x2 = 2 * ix + 1;
+            atomicMin(&xmin[y2], x2);
+            atomicMax(&xmax[y2], x2);
+        }
+    }
+    // CTA reduction of the integer sums
+    {
+        long long v[9] = {n, sy, sx, syy, sxx, sxy, eighths, (long long)nstraight, (long long)ndiag};
+#pragma unroll 1
+        for (int i = 0; i < 9; i++) {
+            const long long t = warp_sum_ll(v[i]);
+            if (lane == 0 && t) atomicAdd(&cta[i], (unsigned long long)t);
+        }
+    }
+    __syncthreads();
+    // maximum squared distance between candidate vertices (doubled coordinates -> exact integers)
+    long long best = 0;
+    for (int a = tid; a < 2 * nrow; a += RADB_NT) {
+        const int ya = a >> 1, xa = (a & 1) ? xmax[ya] : xmin[ya];
+        if (xmax[ya] < 0) continue;
+        for (int yb = ya; yb < nrow; yb++) {
+            if (xmax[yb] < 0) continue;
+            const long long dy = yb - ya;
+            long long d0 = xmin[yb] - xa, d1 = xmax[yb] - xa;
+            d0 = d0 * d0 + dy * dy;
+            d1 = d1 * d1 + dy * dy;
+            best = d0 > best ? d0 : best;
+            best = d1 > best ? d1 : best;
+        }
+    }
+    {
+        int hi = (int)(best >> 31), lo = (int)(best & 0x7fffffff);
+        // 64-bit max across the CTA through two 31-bit halves (values < 2^62)
+        int mhi = warp_max_i(hi);
+        lo = (hi == mhi) ? lo : -1;
+        int mlo = warp_max_i(lo);
+        if (lane == 0) { wmax[(tid >> 5) * 2] = mhi; wmax[(tid >> 5) * 2 + 1] = mlo; }
+    }
+    __syncthreads();
+    if (tid == 0) {
+        long long bestall = 0;
+        for (int w = 0; w < RADB_NT / 32; w++) {
+            long long b = ((long long)wmax[w * 2] << 31) | (long long)wmax[w * 2 + 1];
+            bestall = b > bestall ? b : bestall;
+        }
+        const long long* T = (const long long*)cta;  // n, sy, sx, syy, sxx, sxy, eighths, #straight, #diagonal
+        const double N = (double)T[0];
+        const double rN2 = 1.0 / (N * N);
+        // covariance of the coordinates / sqrt(N): population second moments
+        const double a = (double)(T[0] * T[3] - T[1] * T[1]) * rN2;  // var(y)
+        const double c = (double)(T[0] * T[4] - T[2] * T[2]) * rN2;  // var(x)
+        const double b = (double)(T[0] * T[5] - T[1] * T[2]) * rN2;  // cov(x, y)
+        const double hd = 0.5 * (a - c), rad = sqrt(hd * hd + b * b), mid = 0.5 * (a + c);
+        double e1 = mid + rad, e0 = mid - rad;
+        if (e0 < 0 && e0 > -1e-10) e0 = 0;
+        if (e1 < 0 && e1 > -1e-10) e1 = 0;
+        const double surface = (double)T[6] / 8.0;
+        const double perimeter = (double)T[7] + (double)T[8] * 0.70710678118654752440;
+        out[0] = (e0 < 0 || e1 < 0) ? nan_f64() : sqrt(e0 / e1);
+        out[1] = e1 < 0 ? nan_f64() : sqrt(e1) * 4.0;
+        out[2] = sqrt((double)bestall) * 0.5;
+        out[3] = surface;
+        out[4] = e0 < 0 ? nan_f64() : sqrt(e0) * 4.0;
+        out[5] = perimeter;
+        out[6] = perimeter / surface;
+        out[7] = N;
+        out[8] = 2.0 * sqrt(3.14159265358979323846 * surface) / perimeter;
+    }
+}
+
 #ifndef RADB_EMU
 template <typename PT, bool DBG, bool WIDE>
 __global__ void __launch_bounds__(RADB_NTB, RADB_NTB_MINB) radb_build_kernel(const RadbParams p)
@@ -790,5 +913,10 @@ __global__ void __launch_bounds__(RADB_NT, 8) radb_misc_kernel(const RadbParams 
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
     radb_misc_cta(p, (long long)blockIdx.x, radb_smem);
+}
+__global__ void __launch_bounds__(RADB_NT, 8) radb_shape_kernel(const RadbParams p)
+{
+    extern __shared__ __align__(16) unsigned char radb_smem[];
+    radb_shape_cta(p, (long long)blockIdx.x, radb_smem);
 }
 #endif

@@ -39,6 +39,7 @@ struct RadbParams {
     int ovf_cap;
     int F;
     int off_fo, off_glcm, off_gldm, off_glrlm, off_glszm, off_ngtdm;  // output column of each class, -1 = off
+    int off_shape;                                                    // shape2D (always first when enabled)
     int use_tma;
     int wide;      // 1: whole-image mode (level image, union-find words, GLRLM and overflow list in global memory)
     // ---- build kernel: shared-memory byte offsets.  [o_rec, o_rec + rec_bytes) is the per-patch
@@ -57,6 +58,7 @@ struct RadbParams {
     int a_px, a_py, a_padd, a_psub, a_pr, a_idx, a_mcc, a_red, a_warp_bytes, a_fsc, a_valid, a_smem_total;
     // ---- misc kernel (GLSZM, GLDM, NGTDM, first-order: one warp each)
     int m_pg, m_ovf2, m_ngp, m_qv, m_red, m_smem_total;
+    int s_smem_total;  // shape kernel
     // global workspace + tables (device pointers)
     unsigned char* ws;        // [B][rec_bytes]
     unsigned char* ws_scr;    // [B][scr_bytes] (wide mode)
@@ -148,4 +150,6 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->m_qv = o; o += 16 * 8;
     p->m_red = o; o += (RADB_NT / 32) * 14 * 33 * 8;
     p->m_smem_total = o;
+    // ---- shape kernel: row extremes of the contour vertices + integer totals
+    p->s_smem_total = radb_align(2 * (2 * H + 1) * 4, 16) + 10 * 8 + (RADB_NT / 32) * 2 * 4 + 16;
 }

@@ -44,8 +44,10 @@ FEATURE_NAMES = {
               "SizeZoneNonUniformityNormalized", "SmallAreaEmphasis", "SmallAreaHighGrayLevelEmphasis",
               "SmallAreaLowGrayLevelEmphasis", "ZoneEntropy", "ZonePercentage", "ZoneVariance"],
     "ngtdm": ["Busyness", "Coarseness", "Complexity", "Contrast", "Strength"],
+    "shape2D": ["Elongation", "MajorAxisLength", "MaximumDiameter", "MeshSurface", "MinorAxisLength", "Perimeter",
+                "PerimeterSurfaceRatio", "PixelSurface", "Sphericity"],
 }
-SUPPORTED_CLASSES = set(CLASS_ORDER)
+SUPPORTED_CLASSES = set(CLASS_ORDER) | {"shape2D"}
 SUPPORTED_IMAGE_TYPES = {"Original"}
 # settings whose non-default value would change results and that the engine does not implement
 _UNSUPPORTED_IF_SET = ("normalize", "removeOutliers", "resampledPixelSpacing", "resegmentRange", "weightingNorm",
@@ -131,6 +133,11 @@ class Settings:
         if skipped_cls:
             self._complain("feature classes %s are not implemented yet and are skipped" % skipped_cls)
         self.classes = [c for c in self.enabledFeatures if c in SUPPORTED_CLASSES]
+        if "shape2D" in self.classes and not s.get("force2D", False):
+            # pyradiomics featureextractor.computeShape: shape2D is only extracted with force2D
+            warnings.warn("parameter force2D must be set to True to enable shape2D extraction", RuntimeWarning,
+                          stacklevel=4)
+            self.classes.remove("shape2D")
         if not self.classes:
             raise ValueError("no implemented feature class is enabled")
         for c in self.classes:
@@ -154,7 +161,8 @@ class Settings:
     def feature_names(self):
         """Output keys in pyradiomics order: image type, then class (file order), then A.2 order."""
         names = []
-        for c in self.classes:
+        # shape descriptors are computed first, whatever their position in the file (A.1 step 3)
+        for c in sorted(self.classes, key=lambda c: c != "shape2D"):
             sel = self.enabledFeatures[c]
             for f in FEATURE_NAMES[c]:
                 if not sel or f in sel:
@@ -163,7 +171,7 @@ class Settings:
 
     def engine_columns(self):
         """(engine class order, column permutation) mapping engine rows to ``feature_names()``."""
-        eng_classes = [c for c in CLASS_ORDER if c in self.classes]
+        eng_classes = [c for c in ("shape2D",) + tuple(CLASS_ORDER) if c in self.classes]
         eng_names = ["original_%s_%s" % (c, f) for c in eng_classes for f in FEATURE_NAMES[c]]
         pos = {n: i for i, n in enumerate(eng_names)}
         return eng_classes, [pos[n] for n in self.feature_names()]

@@ -20,6 +20,8 @@ import numpy as np
 EPS = float(np.spacing(1))  # pyradiomics' ``eps = numpy.spacing(1)``
 
 CLASS_ORDER = ("firstorder", "glcm", "gldm", "glrlm", "glszm", "ngtdm")
+SHAPE2D_NAMES = ["Elongation", "MajorAxisLength", "MaximumDiameter", "MeshSurface", "MinorAxisLength", "Perimeter",
+                 "PerimeterSurfaceRatio", "PixelSurface", "Sphericity"]  # [A.2] (SphericalDisproportion is deprecated)
 
 # [A.2] feature names, alphabetical by getXxxFeatureValue (inspect.getmembers order),
 # deprecated features excluded (they are off when the class list is ``[]``,
@@ -559,6 +561,73 @@ def ngtdm_features(n, s):
     return f
 
 
+# --------------------------------------------------------------------------- shape2D
+# pyradiomics ``src/cshape.c`` marching-squares tables (corner order, segments per case, edge midpoints)
+_GRID_ANGLES_2D = ((0, 0), (0, 1), (1, 1), (1, 0))
+_LINE_TABLE_2D = ((), (3, 0), (0, 1), (3, 1), (1, 2), (1, 2, 3, 0), (0, 2), (3, 2), (2, 3), (2, 0), (0, 1, 2, 3),
+                  (2, 1), (1, 3), (1, 0), (0, 3), ())
+_VERT_LIST_2D = ((0.0, 0.5), (0.5, 1.0), (1.0, 0.5), (0.5, 0.0))
+
+
+def shape2d_coefficients(mask_arr, spacing=(1.0, 1.0)):
+    """pyradiomics ``cshape.c:calculate_coefficients2D`` on the zero-padded mask (shape2D.py pads by 1):
+    marching-squares perimeter, mesh surface (|shoelace sum| / 2) and the maximum distance between
+    contour vertices.  (SURVEY.md section 8 f rank 1; reached from RadiomicExtractor.py:38 when
+    ``shape2D`` is enabled, params.yml:165.)"""
+    m = np.pad(np.asarray(mask_arr, dtype=bool), 1)
+    H, W = m.shape
+    perimeter = 0.0
+    surface = 0.0
+    verts = []
+    for iy in range(H - 1):
+        for ix in range(W - 1):
+            idx = 0
+            for a, (dy, dx) in enumerate(_GRID_ANGLES_2D):
+                if m[iy + dy, ix + dx]:
+                    idx |= 1 << a
+            seg = _LINE_TABLE_2D[idx]
+            for t in range(0, len(seg), 2):
+                a = [(iy + _VERT_LIST_2D[seg[t]][0]) * spacing[0], (ix + _VERT_LIST_2D[seg[t]][1]) * spacing[1]]
+                b = [(iy + _VERT_LIST_2D[seg[t + 1]][0]) * spacing[0], (ix + _VERT_LIST_2D[seg[t + 1]][1]) * spacing[1]]
+                surface += a[0] * b[1] - b[0] * a[1]
+                perimeter += np.sqrt((a[0] - b[0]) ** 2 + (a[1] - b[1]) ** 2)
+                verts.append(a)
+                verts.append(b)
+    surface = abs(surface) / 2.0
+    v = np.unique(np.asarray(verts), axis=0) if verts else np.zeros((0, 2))
+    diameter = 0.0
+    for i in range(0, len(v), 512):
+        d = np.sqrt(((v[i:i + 512, None, :] - v[None, :, :]) ** 2).sum(-1))
+        diameter = max(diameter, float(d.max()))
+    return perimeter, surface, diameter
+
+
+def shape2d_features(mask_arr, spacing=(1.0, 1.0)):
+    """pyradiomics ``shape2D.py`` (9 non-deprecated features, A.2 order)."""
+    mask_arr = np.asarray(mask_arr, dtype=bool)
+    perimeter, surface, diameter = shape2d_coefficients(mask_arr, spacing)
+    coords = np.array(np.nonzero(mask_arr), dtype="int").transpose((1, 0))
+    Np = len(coords)
+    phys = coords * np.asarray(spacing, dtype=np.float64)[None, :]
+    phys = phys - np.mean(phys, axis=0)
+    phys = phys / np.sqrt(Np)
+    cov = np.dot(phys.T.copy(), phys)
+    ev = np.linalg.eigvals(cov)
+    ev[(ev < 0) & (ev > -1e-10)] = 0
+    ev = np.sort(ev)
+    f = OrderedDict()
+    f["Elongation"] = float("nan") if (ev[0] < 0 or ev[1] < 0) else float(np.sqrt(ev[0] / ev[1]))
+    f["MajorAxisLength"] = float("nan") if ev[1] < 0 else float(np.sqrt(ev[1]) * 4)
+    f["MaximumDiameter"] = diameter
+    f["MeshSurface"] = surface
+    f["MinorAxisLength"] = float("nan") if ev[0] < 0 else float(np.sqrt(ev[0]) * 4)
+    f["Perimeter"] = perimeter
+    f["PerimeterSurfaceRatio"] = perimeter / surface
+    f["PixelSurface"] = Np * float(spacing[0] * spacing[1])
+    f["Sphericity"] = (2 * np.sqrt(np.pi * surface)) / perimeter
+    return f
+
+
 # --------------------------------------------------------------------------- execute
 def resolve_settings(settings=None):
     s = dict(DEFAULT_SETTINGS)
@@ -602,7 +671,13 @@ def execute(image, mask, settings=None, classes=CLASS_ORDER, image_type="origina
     gl, Ng = m["gray_levels"], m["Ng"]
     image = np.asarray(image)
     out = OrderedDict()
+    if "shape2D" in classes:  # [A.1 step 3] shape keys come first, whatever the class order
+        f = shape2d_features(m["mask"])
+        for k in SHAPE2D_NAMES:
+            out["%s_shape2D_%s" % (image_type, k)] = float(f[k])
     for cls in classes:
+        if cls == "shape2D":
+            continue
         if cls == "firstorder":
             f = firstorder_features(image[m["mask"]], m["levels"][m["mask"]], s["voxelArrayShift"])
         elif cls == "glcm":
@@ -623,4 +698,5 @@ def execute(image, mask, settings=None, classes=CLASS_ORDER, image_type="origina
 
 
 def feature_names(classes=CLASS_ORDER, image_type="original"):
-    return ["%s_%s_%s" % (image_type, c, k) for c in classes for k in FEATURE_NAMES[c]]
+    names = ["%s_shape2D_%s" % (image_type, k) for k in SHAPE2D_NAMES] if "shape2D" in classes else []
+    return names + ["%s_%s_%s" % (image_type, c, k) for c in classes if c != "shape2D" for k in FEATURE_NAMES[c]]

@@ -71,6 +71,7 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
     p.ws_scr = (unsigned char*)(((uintptr_t)scr.data() + 15) & ~(uintptr_t)15);
     int mx = p.smem_total > p.a_smem_total ? p.smem_total : p.a_smem_total;
     mx = mx > p.m_smem_total ? mx : p.m_smem_total;
+    mx = mx > p.s_smem_total ? mx : p.s_smem_total;
     std::vector<unsigned char> smem((size_t)mx + 64);
     unsigned char* sm = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
     // the same three launches radb_api.cu issues, CTA by CTA on host threads
@@ -80,5 +81,6 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
         emu::launch((unsigned)B, RADB_NTB, [&]() { radb_build_cta<unsigned char, true, false>(p, (long long)blockIdx.x, sm); });
     emu::launch((unsigned)B, RADB_NT, [&]() { radb_angle_cta(p, (long long)blockIdx.x, sm); });
     emu::launch((unsigned)B, RADB_NT, [&]() { radb_misc_cta(p, (long long)blockIdx.x, sm); });
+    if (p.off_shape >= 0) emu::launch((unsigned)B, RADB_NT, [&]() { radb_shape_cta(p, (long long)blockIdx.x, sm); });
     return 0;
 }

@@ -21,11 +21,12 @@ class EmuRunner:
         s = _abi.make_settings(bin_width, 255, angles)
         return self.lib.radb_emu_is_wide(ctypes.byref(s), H, W)
 
-    def run(self, imgs, masks, bin_width=10, label=255, angles=((0, 1),), symmetrical=True, alpha=0):
+    def run(self, imgs, masks, bin_width=10, label=255, angles=((0, 1),), symmetrical=True, alpha=0,
+            classes=_abi.CLASS_ORDER):
         imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
         masks = np.ascontiguousarray(masks, dtype=np.uint8)
         B, H, W = imgs.shape
-        s = _abi.make_settings(bin_width, label, angles, symmetrical, alpha)
+        s = _abi.make_settings(bin_width, label, angles, symmetrical, alpha, classes=classes)
         F = self.lib.radb_emu_feature_count(ctypes.byref(s))
         ng = self.lib.radb_emu_max_ng(ctypes.byref(s))
         assert F > 0 and ng > 0, self.lib.radb_emu_last_error()
@@ -45,11 +46,11 @@ class EmuRunner:
 RTOL, ATOL = 1e-6, 1e-9  # BASELINE.json north_star: every floating-point feature
 
 
-def compare_with_oracle(r, imgs, masks, settings, check_matrices=True):
+def compare_with_oracle(r, imgs, masks, settings, check_matrices=True, classes=orc.CLASS_ORDER):
     """Bit-exact discretised image + integer matrices, features within rtol 1e-6 / atol 1e-9.
     ``r``: dict from EmuRunner.run or Engine.debug_matrices.  Returns the number of valid patches."""
     s = orc.resolve_settings(settings)
-    names = orc.feature_names()
+    names = orc.feature_names(classes)
     nvalid = 0
     for b in range(len(imgs)):
         try:
@@ -75,7 +76,7 @@ def compare_with_oracle(r, imgs, masks, settings, check_matrices=True):
             np.testing.assert_array_equal(r["gldm"][b][:Ng], m["gldm"])
             np.testing.assert_array_equal(r["ngtdm_n"][b][:Ng], m["ngtdm_n"])
             np.testing.assert_allclose(r["ngtdm_s"][b][:Ng], m["ngtdm_s"], rtol=1e-12, atol=1e-12)
-        f = orc.execute(imgs[b], masks[b], s, matrix_backend=cmatrices)
+        f = orc.execute(imgs[b], masks[b], s, classes=classes, matrix_backend=cmatrices)
         ref = np.array([f[k] for k in names])
         got = r["features"][b]
         bad = [(k, a, g) for k, a, g in zip(names, ref, got) if not np.isclose(g, a, rtol=RTOL, atol=ATOL, equal_nan=True)]

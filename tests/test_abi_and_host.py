@@ -75,12 +75,13 @@ def test_settings_reference_like_file(tmp_path):
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
         s = pkg.Settings(str(f))
-    assert any("Wavelet" in str(x.message) for x in w) and any("shape2D" in str(x.message) for x in w)
+    assert any("Wavelet" in str(x.message) for x in w)
     assert s.label == 255 and s.bin_width == 10.0
     assert s.angles() == orc.angles(2, force2D=True)[0] == [(0, 1)]          # literal force2D on 2-D input
     assert list(s.enabledImagetypes) == ["Original", "Wavelet", "LoG"]
     assert list(s.enabledFeatures) == ["firstorder", "shape2D", "glcm", "gldm", "glrlm", "glszm", "ngtdm"]
-    assert s.feature_names() == orc.feature_names()
+    # 102 = 9 shape2D + 93 (dataset.py:42), shape keys first
+    assert s.feature_names() == orc.feature_names(("shape2D",) + orc.CLASS_ORDER) and len(s.feature_names()) == 102
     with pytest.raises(NotImplementedError):
         pkg.Settings(str(f), strict=True)
 
@@ -100,7 +101,16 @@ def test_settings_class_order_and_feature_subset():
 
 
 def test_feature_name_tables_agree():
-    assert pkg.FEATURE_NAMES == {k: v for k, v in orc.FEATURE_NAMES.items()}
+    assert {k: v for k, v in pkg.FEATURE_NAMES.items() if k != "shape2D"} == dict(orc.FEATURE_NAMES)
+    assert pkg.FEATURE_NAMES["shape2D"] == orc.SHAPE2D_NAMES
+
+
+def test_shape2d_needs_force2d():
+    with pytest.warns(RuntimeWarning, match="force2D must be set"):
+        s = pkg.Settings({"setting": {"force2D": False}, "featureClass": {"shape2D": [], "glcm": []}})
+    assert s.classes == ["glcm"]
+    s = pkg.Settings({"setting": {"force2D": True}, "featureClass": {"glcm": [], "shape2D": ["Perimeter"]}})
+    assert s.feature_names()[0] == "original_shape2D_Perimeter" and s.engine_columns()[0] == ["shape2D", "glcm"]
 
 
 def test_shard_bounds():

@@ -109,3 +109,22 @@ def test_emu_wide_mode_literal_and_smooth(emu):
     assert emu.is_wide(H, W, 25, LITERAL) == 1
     r = emu.run(img, mask, 25, 255, LITERAL)
     assert compare_with_oracle(r, img, mask, dict(label=255, binWidth=25, force2D=True)) == 1
+
+
+ALL_CLASSES = ("shape2D",) + tuple(orc.CLASS_ORDER)
+
+
+def test_emu_shape2d_102_features(emu):
+    # the reference's full vector: 9 shape2D + 93 = 102 (dataset.py:42), shape keys first
+    imgs, masks = synth.make_patches(3, 48, 40, seed=5)
+    masks[2, 10:14, 10:14] = 0  # a hole in the ROI
+    r = emu.run(imgs, masks, 10, 255, LITERAL, classes=ALL_CLASSES)
+    assert r["features"].shape[1] == 102
+    s = dict(label=255, binWidth=10, force2D=True)
+    assert compare_with_oracle(r, imgs, masks, s, classes=ALL_CLASSES) == 3
+
+
+def test_emu_shape2d_edge_cases(emu):
+    imgs, masks = edge_case_batch()
+    r = emu.run(imgs, masks, 10, 255, INPLANE, classes=ALL_CLASSES)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=False), classes=ALL_CLASSES) == 6

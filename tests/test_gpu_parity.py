@@ -92,6 +92,27 @@ def test_wide_mode_literal_whole_image(gpu_pkg):
     assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=True)) == 2
 
 
+ALL_CLASSES = ("shape2D",) + tuple(orc.CLASS_ORDER)
+
+
+@pytest.mark.parametrize("hw", [(64, 64), (37, 53), (300, 260)])
+def test_shape2d_102_features(gpu_pkg, hw):
+    """9 shape2D + 93 = 102 features per execute (dataset.py:42), shape keys first."""
+    imgs, masks = gpu_pkg.synth.make_patches(4, hw[0], hw[1], seed=14)
+    masks[1, 10:14, 10:15] = 0  # a hole
+    eng = _engine(gpu_pkg, 10, LITERAL, classes=ALL_CLASSES)
+    assert eng.F == 102 and eng.names == orc.feature_names(ALL_CLASSES)
+    r = _dbg(eng, imgs, masks)
+    s = dict(label=255, binWidth=10, force2D=True)
+    assert compare_with_oracle(r, imgs, masks, s, classes=ALL_CLASSES) == 4
+
+
+def test_shape2d_edge_cases(gpu_pkg):
+    imgs, masks = edge_case_batch()
+    r = _dbg(_engine(gpu_pkg, classes=ALL_CLASSES), imgs, masks)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=False), classes=ALL_CLASSES) == 6
+
+
 def test_random_noise_many_levels(gpu_pkg):
     rng = np.random.default_rng(7)
     imgs = rng.integers(0, 256, (6, 40, 40)).astype(np.uint8)
@@ -166,7 +187,7 @@ def test_record_path_matches_reference_call_pattern(gpu_pkg, tmp_path):
     params = {"setting": {"label": 255, "binWidth": 10, "force2D": True, "symmetricalGLCM": True,
                           "additionalInfo": False},
               "imageType": {"Original": {}},
-              "featureClass": {c: [] for c in ("firstorder", "glcm", "gldm", "glrlm", "glszm", "ngtdm")}}
+              "featureClass": {c: [] for c in ("firstorder", "shape2D", "glcm", "gldm", "glrlm", "glszm", "ngtdm")}}
     ex = gpu_pkg.RadiomicsExtractor(params)
     res = ex.parallell_extraction(recs)
     ser = ex.serial_extraction(recs)
@@ -179,12 +200,12 @@ def test_record_path_matches_reference_call_pattern(gpu_pkg, tmp_path):
         planes = {"grayscale": cv2.cvtColor(im, cv2.COLOR_BGR2GRAY), "red": im[:, :, 2], "green": im[:, :, 1],
                   "blue": im[:, :, 0]}
         for ch, arr in planes.items():
-            ref = orc.execute(arr, sg, params["setting"], matrix_backend=cmatrices)
-            assert list(res[k][ch].keys()) == list(ref.keys())
+            ref = orc.execute(arr, sg, params["setting"], classes=ALL_CLASSES, matrix_backend=cmatrices)
+            assert list(res[k][ch].keys()) == list(ref.keys()) and len(ref) == 102
             np.testing.assert_allclose(list(res[k][ch].values()), list(ref.values()), rtol=RTOL, atol=ATOL)
             assert res[k][ch] == ser[k][ch]
     df = gpu_pkg.features_to_dataframe(res)
-    assert df.shape == (3, 4 * 93)
+    assert df.shape == (3, 4 * 102)
 
 
 def test_full_size_properties(gpu_pkg):

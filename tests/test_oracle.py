@@ -130,3 +130,31 @@ def test_check_mask_errors():
         orc.check_mask(m, 255)
     m[3, 3] = 255
     assert orc.check_mask(m, 255) == [(2, 3), (2, 3)]
+
+
+def test_shape2d_oracle_against_independent_area_and_known_shapes():
+    """The marching-squares tables are typed from memory of pyradiomics' cshape.c; their
+    orientation is validated by comparing the shoelace surface with an independent count of
+    eighths per 2x2 cell, and by closed-form values for simple shapes."""
+    def area_indep(m):
+        m = np.pad(np.asarray(m, bool), 1)
+        a, b, c, d = (m[:-1, :-1].astype(int), m[:-1, 1:].astype(int), m[1:, 1:].astype(int), m[1:, :-1].astype(int))
+        n = a + b + c + d
+        diag = (a == c) & (b == d) & (a != b)
+        e = np.zeros(n.shape)
+        e[n == 1] = 1
+        e[n == 2] = 4
+        e[(n == 2) & diag] = 2
+        e[n == 3] = 7
+        e[n == 4] = 8
+        return e.sum() / 8
+    p, s, d = orc.shape2d_coefficients(np.ones((1, 1)))
+    assert np.isclose(p, 4 * np.sqrt(0.5)) and s == 0.5 and d == 1.0
+    p, s, d = orc.shape2d_coefficients(np.ones((3, 5)))
+    assert np.isclose(p, 2 * (2 + 4) + 4 * np.sqrt(0.5)) and s == 15 - 0.5 and np.isclose(d, np.hypot(5, 2))
+    rng = np.random.default_rng(3)
+    for _ in range(10):
+        m = rng.random((9, 11)) < 0.6
+        assert np.isclose(orc.shape2d_coefficients(m)[1], area_indep(m))
+    f = orc.shape2d_features(np.ones((4, 10), bool))
+    assert np.isclose(f["Elongation"], np.sqrt((4 ** 2 - 1) / (10 ** 2 - 1))) and f["PixelSurface"] == 40
