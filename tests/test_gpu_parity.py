@@ -242,3 +242,51 @@ def test_full_size_properties(gpu_pkg):
     for k, b in enumerate(idx):
         ref = list(orc.execute(hi[k], hm[k], dict(label=255, binWidth=25), matrix_backend=cmatrices).values())
         np.testing.assert_allclose(o[b], ref, rtol=RTOL, atol=ATOL)
+
+
+def test_dataframe_feeds_the_feature_selection_stage(gpu_pkg, tmp_path):
+    """Contract of the live consumer, /root/reference/reduce_dim.py:81-128: the pickled frame must be
+    all-numeric, have 4 equal channel blocks with _gs/_red/_green/_blue suffixes, and survive the
+    variance filter -> z-score -> L1-logistic CV selection -> |corr| > 0.95 drop sequence."""
+    import pandas as pd
+    from sklearn.feature_selection import SelectFromModel, VarianceThreshold
+    from sklearn.linear_model import LogisticRegressionCV
+    from sklearn.model_selection import StratifiedKFold
+    from sklearn.preprocessing import StandardScaler
+
+    n = 80
+    ex = gpu_pkg.RadiomicsExtractor({"setting": {"label": 255, "binWidth": 10, "force2D": True},
+                                     "featureClass": {c: [] for c in ("firstorder", "shape2D", "glcm", "gldm", "glrlm",
+                                                                      "glszm", "ngtdm")}})
+    rng = np.random.default_rng(0)
+    g, m = gpu_pkg.synth.make_patches(n, 64, seed=30)
+    y = (m.reshape(n, -1).mean(1) > np.median(m.reshape(n, -1).mean(1))).astype(int)  # a label the features can learn
+    results = []
+    planes = [np.clip(g.astype(int) + rng.integers(-25, 25, g.shape), 0, 255).astype(np.uint8) for _ in range(4)]
+    feats = [ex.extract_batch(pl, m, strict=True)[0] for pl in planes]
+    for i in range(n):
+        results.append({ch: dict(zip(ex.feature_names, feats[c][i])) for c, ch in
+                        enumerate(("grayscale", "red", "green", "blue"))})
+    df = gpu_pkg.features_to_dataframe(results)
+    path = tmp_path / "radiomics.pkl"
+    df.to_pickle(path)
+    df = pd.read_pickle(path)
+    assert len(df.columns) % 4 == 0 and len(df.columns) // 4 == 102
+    for sfx in ("_gs", "_red", "_green", "_blue"):
+        assert sum(sfx in c for c in df.columns) == 102
+    assert np.isfinite(df.to_numpy()).all()
+    tr, te = df.iloc[:60], df.iloc[60:]
+    sel = VarianceThreshold(1e-3).fit(tr)
+    tr = pd.DataFrame(sel.transform(tr), columns=df.columns[sel.get_support()])
+    te = pd.DataFrame(sel.transform(te), columns=tr.columns)
+    sc = StandardScaler().fit(tr)
+    tr = pd.DataFrame(sc.transform(tr), columns=tr.columns)
+    model = LogisticRegressionCV(Cs=np.logspace(-2, 1, 5), cv=StratifiedKFold(5, shuffle=True, random_state=42),
+                                 penalty="l1", solver="liblinear", class_weight="balanced", scoring="f1",
+                                 max_iter=2000).fit(tr, y[:60])
+    keep = tr.columns[SelectFromModel(model, prefit=True).get_support()]
+    assert len(keep) >= 1
+    corr = tr[keep].corr().abs()
+    upper = corr.where(np.triu(np.ones(corr.shape), k=1).astype(bool))
+    dropped = [c for c in upper.columns if (upper[c] > 0.95).any()]
+    assert len(keep) - len(dropped) >= 1
