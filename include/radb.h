@@ -103,6 +103,15 @@ int radb_smem_bytes(const radb_handle* h, int H, int W, int dtype);
 int radb_extract(radb_handle* h, const void* img, int dtype, const uint8_t* mask, int64_t B, int H, int W,
                  int64_t img_stride_b, int64_t mask_stride_b, double* out, int32_t* status, void* cuda_stream);
 
+/* RadiomicsExtractor.extract_radiomics (RadiomicExtractor.py:23-55) for a batch of decoded records:
+ * `bgr` = interleaved BGR uint8 images [n][H][W][3] exactly as cv2.imread returns them (:29), `mask`
+ * = one uint8 mask per image [n][H][W] (:33-36).  A front-end kernel writes the gray (cv2 BGR2GRAY
+ * fixed point, :30), R, G, B planes (:41-47) into the caller's device scratch `planes`
+ * ([n][4][H][W] bytes) and the four executes of every image share its mask.
+ * out: [n*4][F], status: [n*4], rows in gray, R, G, B order per image. */
+int radb_extract_bgr(radb_handle* h, const uint8_t* bgr, const uint8_t* mask, int64_t n_images, int H, int W,
+                     uint8_t* planes, double* out, int32_t* status, void* cuda_stream);
+
 /* Same launch as radb_extract, additionally dumping the discretised image and the integer
  * texture matrices the features were reduced from (what pyradiomics' cMatrices.calculate_*
  * return) for bit-exact parity tests.  Any debug pointer may be NULL.  All buffers must be

@@ -99,7 +99,8 @@ static int64_t chunk_for(const RadbParams& p, int64_t B)
     const size_t per = (size_t)p.rec_bytes + (size_t)p.scr_bytes;
     int64_t n = (int64_t)(((size_t)1 << 30) / per);  // <= 1 GiB
     if (n > RADB_CHUNK) n = RADB_CHUNK;
-    if (n < 1) n = 1;
+    n -= n % 4;  // keeps the 4 planes of an image (shared mask) in one chunk
+    if (n < 4) n = 4;
     return B < n ? B : n;
 }
 
@@ -208,7 +209,7 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         const long long n = p.B - done < chunk ? p.B - done : chunk;
         RadbParams q = p;
         q.img = (const unsigned char*)p.img + done * p.img_stride;
-        q.mask = p.mask + done * p.mask_stride;
+        q.mask = p.mask + (done / p.mask_group) * p.mask_stride;  // chunks are multiples of mask_group
         q.out = p.out + done * p.F;
         q.status = p.status + done;
         q.B = n;
@@ -329,4 +330,27 @@ extern "C" int radb_kernel_ms(radb_handle* h, double* ms3)
     for (auto ev : h->events) cudaEventDestroy(ev);
     h->events.clear();
     return RADB_OK;
+}
+
+// RadiomicExtractor.extract_radiomics (RadiomicExtractor.py:23-55) for a batch of decoded records:
+// interleaved BGR images + one mask each -> gray/R/G/B planes (device scratch `planes`, 4*H*W bytes
+// per image) -> 4 executes per image sharing the mask.  out: [n_images*4][F] in gray, R, G, B order.
+extern "C" int radb_extract_bgr(radb_handle* h, const uint8_t* bgr, const uint8_t* mask, int64_t n_images, int H,
+                                int W, uint8_t* planes, double* out, int32_t* status, void* cuda_stream)
+{
+    if (!h || !bgr || !mask || !planes || !out || !status) return fail(RADB_E_INVALID, "null argument");
+    if (n_images < 0) return fail(RADB_E_INVALID, "negative batch size");
+    if (n_images == 0) return RADB_OK;
+    RadbParams p;
+    const int64_t HW = (int64_t)H * W;
+    int rc = setup(h, planes, RADB_DTYPE_U8, mask, n_images * 4, H, W, HW, HW, out, status, p);
+    if (rc) return rc;
+    p.mask_group = 4;
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != h->device) cudaSetDevice(h->device);
+    const long long threads = n_images * ((HW + 3) / 4);
+    radb_bgr_planes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(bgr, planes, n_images, HW);
+    h->launches += 1;
+    return launch(h, p, RADB_DTYPE_U8, cuda_stream);
 }

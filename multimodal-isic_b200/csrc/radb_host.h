@@ -121,6 +121,7 @@ static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParam
     memset(&p, 0, sizeof(p));
     p.H = H;
     p.W = W;
+    p.mask_group = 1;
     p.label = pl.s.label;
     p.n_angles = pl.s.n_angles;
     for (int a = 0; a < pl.s.n_angles; a++) { p.ang_y[a] = pl.s.angles[a][0]; p.ang_x[a] = pl.s.angles[a][1]; }

@@ -255,7 +255,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, HW = p.HW, WP = p.WP, NA = p.n_angles, NB = 2 * p.n_angles;
     const PT* g_img = (const PT*)((const unsigned char*)p.img + patch * p.img_stride);
-    const unsigned char* g_msk = p.mask + patch * p.mask_stride;
+    const unsigned char* g_msk = p.mask + (patch / p.mask_group) * p.mask_stride;
     unsigned char* g_rec = p.ws + patch * (long long)p.rec_bytes;              // this patch's record (global)
     unsigned char* g_scr = WIDE ? p.ws_scr + patch * p.scr_bytes : (unsigned char*)0;  // wide-mode scratch (global)
     // narrow: the raw patch is staged in shared memory and the level image / union-find words live
@@ -774,6 +774,30 @@ __device__ void radb_misc_cta(const RadbParams& p, long long patch, unsigned cha
     }
 }
 
+// ------------------------------------------------------------------ channel front-end
+// RadiomicExtractor.py:29-30,41-47: cv2.imread gives interleaved BGR uint8; the reference then runs
+// execute() on cvtColor(BGR2GRAY), R = im[:,:,2], G = im[:,:,1], B = im[:,:,0].  This kernel reads the
+// interleaved pixels once and writes the four planes [image][gray, R, G, B][H][W].  Gray is OpenCV's
+// 8-bit fixed-point BT.601: (R*9798 + G*19235 + B*3735 + 2^14) >> 15 (bit-exact against
+// opencv 4.13, tests/test_emu_kernel.py).  One thread converts 4 pixels (12 bytes in, 4x4 bytes out).
+__device__ void radb_bgr_planes_thread(const unsigned char* bgr, unsigned char* planes, long long n_images,
+                                       long long HW, long long q)
+{
+    const long long quads = (HW + 3) / 4;
+    if (q >= n_images * quads) return;
+    const long long img = q / quads, p0 = (q - img * quads) * 4;
+    const unsigned char* src = bgr + (img * HW + p0) * 3;
+    unsigned char* dst = planes + img * 4 * HW + p0;
+    const int cnt = (int)(HW - p0 < 4 ? HW - p0 : 4);
+    for (int k = 0; k < cnt; k++) {
+        const int b = src[3 * k], g = src[3 * k + 1], r = src[3 * k + 2];
+        dst[k] = (unsigned char)((r * 9798 + g * 19235 + b * 3735 + 16384) >> 15);
+        dst[HW + k] = (unsigned char)r;
+        dst[2 * HW + k] = (unsigned char)g;
+        dst[3 * HW + k] = (unsigned char)b;
+    }
+}
+
 // ------------------------------------------------------------------ shape kernel: shape2D (9 features)
 // pyradiomics shape2D.py + cshape.c:calculate_coefficients2D (SURVEY.md section 8 f rank 1), mask only:
 // marching squares over the zero-padded mask.  Everything reduces to integers: the perimeter is
@@ -787,7 +811,7 @@ __device__ void radb_shape_cta(const RadbParams& p, long long patch, unsigned ch
     const int tid = threadIdx.x, lane = tid & 31;
     const int H = p.H, W = p.W;
     if (p.status[patch] != 0 || p.off_shape < 0) return;
-    const unsigned char* m = p.mask + patch * p.mask_stride;
+    const unsigned char* m = p.mask + (patch / p.mask_group) * p.mask_stride;
     double* out = p.out + patch * (long long)p.F + p.off_shape;
     const int nrow = 2 * H + 1;                     // doubled y coordinates 0..2H of contour vertices (shifted by +1)
     int* xmin = (int*)smem;                         // [nrow]
@@ -904,7 +928,10 @@ __global__ void __launch_bounds__(RADB_NTB, RADB_NTB_MINB) radb_build_kernel(con
     extern __shared__ __align__(16) unsigned char radb_smem[];
     radb_build_cta<PT, DBG, WIDE>(p, (long long)blockIdx.x, radb_smem);
 }
-__global__ void __launch_bounds__(RADB_NT, 6) radb_angle_kernel(const RadbParams p)
+#ifndef RADB_ANGLE_MINB
+#define RADB_ANGLE_MINB 6
+#endif
+__global__ void __launch_bounds__(RADB_NT, RADB_ANGLE_MINB) radb_angle_kernel(const RadbParams p)
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
     radb_angle_cta(p, (long long)blockIdx.x, radb_smem);
@@ -913,6 +940,10 @@ __global__ void __launch_bounds__(RADB_NT, 8) radb_misc_kernel(const RadbParams 
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
     radb_misc_cta(p, (long long)blockIdx.x, radb_smem);
+}
+__global__ void radb_bgr_planes_kernel(const unsigned char* bgr, unsigned char* planes, long long n_images, long long HW)
+{
+    radb_bgr_planes_thread(bgr, planes, n_images, HW, (long long)blockIdx.x * blockDim.x + threadIdx.x);
 }
 __global__ void __launch_bounds__(RADB_NT, 8) radb_shape_kernel(const RadbParams p)
 {

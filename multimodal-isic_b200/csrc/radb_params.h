@@ -21,7 +21,8 @@ struct RadbParams {
     const void* img;
     const uint8_t* mask;
     long long img_stride;   // bytes between patches
-    long long mask_stride;  // bytes between patches
+    long long mask_stride;  // bytes between masks
+    int mask_group;         // consecutive patches sharing one mask (1; 4 for the gray/R/G/B planes of an image)
     double* out;            // [B][F]
     int* status;            // [B]
     long long B;

@@ -91,6 +91,28 @@ class Engine:
             raise RadbError("radb_extract failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
         return out, status
 
+    def extract_bgr(self, bgr, masks, stream=None):
+        """Decoded records in, four feature rows per record out (gray, R, G, B): ``bgr`` [n, H, W, 3]
+        uint8 (cv2.imread layout), ``masks`` [n, H, W] uint8, both on the device.  The gray/R/G/B planes
+        are produced by the front-end kernel; the four executes share the mask."""
+        if bgr.dtype != torch.uint8 or masks.dtype != torch.uint8:
+            raise TypeError("bgr and masks must be uint8")
+        if bgr.dim() != 4 or bgr.shape[3] != 3 or tuple(bgr.shape[:3]) != tuple(masks.shape):
+            raise ValueError("bgr must be [n, H, W, 3] and masks [n, H, W]")
+        if not (bgr.is_cuda and masks.is_cuda and bgr.is_contiguous() and masks.is_contiguous()):
+            raise ValueError("bgr / masks must be contiguous CUDA tensors")
+        n, H, W, _ = bgr.shape
+        dev = bgr.device
+        planes = torch.empty((n, 4, H, W), dtype=torch.uint8, device=dev)
+        out = torch.empty((n * 4, self.F), dtype=torch.float64, device=dev)
+        status = torch.empty((n * 4,), dtype=torch.int32, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = self.lib.radb_extract_bgr(self._h, bgr.data_ptr(), masks.data_ptr(), n, H, W, planes.data_ptr(),
+                                       out.data_ptr(), status.data_ptr(), st.cuda_stream)
+        if rc != 0:
+            raise RadbError("radb_extract_bgr failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+        return out, status
+
     def debug_matrices(self, images, masks):
         """Features plus the integer matrices (numpy, trimmed to shapes the oracle uses)."""
         self._check(images, masks)

@@ -60,45 +60,54 @@ class RadiomicsExtractor:
 
     @staticmethod
     def _load_record(record):
-        """cv2 decode exactly as RadiomicExtractor.py:29-36 (host side)."""
+        """cv2 decode exactly as RadiomicExtractor.py:29,33-35 (host side): interleaved BGR image and
+        the mask, nearest-resized to the image if needed.  The gray / R / G / B planes of :30,41-47
+        are produced on the GPU by the front-end kernel (bit-exact with cv2.cvtColor)."""
         import cv2
 
         im = cv2.imread(record["image_path"], cv2.IMREAD_COLOR)
         if im is None:
             raise FileNotFoundError(record["image_path"])
-        gray = cv2.cvtColor(im, cv2.COLOR_BGR2GRAY)
         sg = cv2.imread(record["segmentation_path"], cv2.IMREAD_GRAYSCALE)
         if sg is None:
             raise FileNotFoundError(record["segmentation_path"])
         if im.shape[:2] != sg.shape[:2]:
             sg = cv2.resize(sg, (im.shape[1], im.shape[0]), interpolation=cv2.INTER_NEAREST)
-        planes = np.stack([gray, im[:, :, 2], im[:, :, 1], im[:, :, 0]])  # gray, R, G, B
-        return np.ascontiguousarray(planes), np.ascontiguousarray(sg)
+        return np.ascontiguousarray(im), np.ascontiguousarray(sg)
+
+    def _extract_records(self, loaded, max_bytes=256 << 20):
+        """loaded: list of (bgr [H,W,3], mask [H,W]) -> list of per-record channel dicts (input order)."""
+        results = [None] * len(loaded)
+        groups = {}
+        for i, (im, _) in enumerate(loaded):
+            groups.setdefault(im.shape[:2], []).append(i)
+        dev = torch.device("cuda", self.device)
+        for (H, W), idxs in groups.items():
+            per = max(1, max_bytes // (H * W * 3))
+            for s0 in range(0, len(idxs), per):
+                part = idxs[s0:s0 + per]
+                bgr = torch.as_tensor(np.stack([loaded[i][0] for i in part])).to(dev, non_blocking=True)
+                msk = torch.as_tensor(np.stack([loaded[i][1] for i in part])).to(dev, non_blocking=True)
+                out, status = self.engine.extract_bgr(bgr, msk)
+                feats = self._permute(out).cpu().numpy()
+                status = status.cpu().numpy()
+                if status.any():  # the reference has no try/except: pyradiomics' ValueError aborts the run
+                    raise _status_error(int(status[np.nonzero(status)[0][0]]), self.params.label)
+                for k, i in enumerate(part):
+                    results[i] = {ch: OrderedDict(zip(self.feature_names, feats[4 * k + c].tolist()))
+                                  for c, ch in enumerate(CHANNELS)}
+        return results
 
     def extract_radiomics(self, list_of_dicts):  # RadiomicExtractor.py:23-55 (one record)
-        planes, sg = self._load_record(list_of_dicts)
-        masks = np.ascontiguousarray(np.broadcast_to(sg, planes.shape))
-        feats, status = self.extract_batch(planes, masks, strict=True)
-        return {ch: OrderedDict(zip(self.feature_names, feats[i].tolist())) for i, ch in enumerate(CHANNELS)}
+        return self._extract_records([self._load_record(list_of_dicts)])[0]
 
     def parallell_extraction(self, list_of_dicts, n_processes=None):  # RadiomicExtractor.py:58-71
         """Order-preserving extraction of all records.  ``n_processes`` is accepted for
         signature compatibility; the fan-out is over GPU CTAs, not host processes.  Records of
-        equal image size are batched into one launch."""
+        equal image size are batched into one launch sequence."""
         logger.info("Extraction mode: parallel")
         t0 = time.time()
-        loaded = [self._load_record(r) for r in list_of_dicts]
-        results = [None] * len(loaded)
-        groups = {}
-        for i, (planes, _) in enumerate(loaded):
-            groups.setdefault(planes.shape[1:], []).append(i)
-        for shape, idxs in groups.items():
-            imgs = np.concatenate([loaded[i][0] for i in idxs])
-            msks = np.concatenate([np.broadcast_to(loaded[i][1], loaded[i][0].shape) for i in idxs])
-            feats, _ = self.extract_batch(imgs, np.ascontiguousarray(msks), strict=True)
-            for k, i in enumerate(idxs):
-                results[i] = {ch: OrderedDict(zip(self.feature_names, feats[4 * k + c].tolist()))
-                              for c, ch in enumerate(CHANNELS)}
+        results = self._extract_records([self._load_record(r) for r in list_of_dicts])
         h, m, s = self._convert_time(t0, time.time())
         logger.info(f" Time taken: {h}h:{m}m:{s}s")
         return results

@@ -84,3 +84,10 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
     if (p.off_shape >= 0) emu::launch((unsigned)B, RADB_NT, [&]() { radb_shape_cta(p, (long long)blockIdx.x, sm); });
     return 0;
 }
+
+// Host twin of radb_bgr_planes_kernel (one "thread" per 4 pixels).
+extern "C" void radb_emu_bgr_planes(const uint8_t* bgr, uint8_t* planes, int64_t n_images, int64_t HW)
+{
+    const long long threads = n_images * ((HW + 3) / 4);
+    for (long long q = 0; q < threads; q++) radb_bgr_planes_thread(bgr, planes, n_images, HW, q);
+}

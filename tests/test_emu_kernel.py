@@ -128,3 +128,20 @@ def test_emu_shape2d_edge_cases(emu):
     imgs, masks = edge_case_batch()
     r = emu.run(imgs, masks, 10, 255, INPLANE, classes=ALL_CLASSES)
     assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=False), classes=ALL_CLASSES) == 6
+
+
+def test_emu_bgr_front_end_matches_cv2(emu):
+    # RadiomicExtractor.py:29-30,41-47: gray = cv2.cvtColor(BGR2GRAY), R/G/B = channels 2/1/0
+    import ctypes
+
+    import cv2
+
+    rng = np.random.default_rng(0)
+    bgr = rng.integers(0, 256, (3, 37, 53, 3)).astype(np.uint8)
+    planes = np.zeros((3, 4, 37, 53), np.uint8)
+    emu.lib.radb_emu_bgr_planes.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64]
+    emu.lib.radb_emu_bgr_planes(bgr.ctypes.data, planes.ctypes.data, 3, 37 * 53)
+    for i in range(3):
+        np.testing.assert_array_equal(planes[i, 0], cv2.cvtColor(bgr[i], cv2.COLOR_BGR2GRAY))
+        for k, ch in ((1, 2), (2, 1), (3, 0)):
+            np.testing.assert_array_equal(planes[i, k], bgr[i, :, :, ch])
