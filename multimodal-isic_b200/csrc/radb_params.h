@@ -8,7 +8,7 @@
 #define RADB_NTB 256         // threads per CTA of the build kernel
 #endif
 #ifndef RADB_NTB_MINB
-#define RADB_NTB_MINB 4      // min resident build CTAs per SM (register cap)
+#define RADB_NTB_MINB 5      // min resident build CTAs per SM (register cap: 48)
 #endif
 #define RADB_MAX_ANGLES 4    // unidirectional offsets at distance 1 in a plane
 #define RADB_GLCM_NF 24
