@@ -320,7 +320,7 @@ def gpu_arm(args):
         traffic = None
         try:
             with open(os.path.join(ROOT, "profiles", "traffic.json")) as fh:
-                traffic = json.load(fh).get("dram_bytes_per_launch")
+                traffic = json.load(fh)["dram_bytes_per_patch"] * B  # ncu capture, scaled to the patches of one pass
         except Exception:
             pass
         total = world * B * args.steps

@@ -245,6 +245,244 @@ __device__ __forceinline__ double py_mod(double a, double b)
 
 #include "radb_features.cuh"
 
+// ------------------------------------------------------------------ first-order for non-uint8 pixels
+// uint8 patches get all 18 first-order features from the 256-bin raw histogram (fo_task_u8, misc
+// kernel).  For uint16 / float32 / float64 pixels the build kernel computes them from the ROI values
+// themselves while the raw patch is still staged: fp64 moment passes with fixed-order CTA
+// reductions, and the ten order statistics behind the 10/25/50/75/90 percentiles by a multi-rank
+// radix select (8 key bits per pass over order-preserving integer keys).
+template <typename PT> struct PixKey;
+template <> struct PixKey<unsigned char> { enum { BITS = 8 }; };
+template <> struct PixKey<unsigned short> {
+    enum { BITS = 16 };
+    static __device__ __forceinline__ unsigned long long key(unsigned short v) { return v; }
+    static __device__ __forceinline__ double value(unsigned long long k) { return (double)k; }
+};
+template <> struct PixKey<float> {
+    enum { BITS = 32 };
+    static __device__ __forceinline__ unsigned long long key(float v)
+    {
+        unsigned b;
+        memcpy(&b, &v, 4);
+        return (b & 0x80000000u) ? (unsigned)~b : (b | 0x80000000u);
+    }
+    static __device__ __forceinline__ double value(unsigned long long k)
+    {
+        unsigned b = (unsigned)k;
+        b = (b & 0x80000000u) ? (b & 0x7fffffffu) : ~b;
+        float v;
+        memcpy(&v, &b, 4);
+        return (double)v;
+    }
+};
+template <> struct PixKey<double> {
+    enum { BITS = 64 };
+    static __device__ __forceinline__ unsigned long long key(double v)
+    {
+        unsigned long long b;
+        memcpy(&b, &v, 8);
+        return (b >> 63) ? ~b : (b | 0x8000000000000000ULL);
+    }
+    static __device__ __forceinline__ double value(unsigned long long k)
+    {
+        unsigned long long b = (k >> 63) ? (k & 0x7fffffffffffffffULL) : ~k;
+        double v;
+        memcpy(&v, &b, 8);
+        return v;
+    }
+};
+
+// fixed-order CTA sum of K doubles per thread: warp butterflies, one slot per warp, everyone adds the slots
+template <int K>
+__device__ __forceinline__ void cta_sum(double (&v)[K], double* slots /*[K][RADB_NTB/32]*/, int tid)
+{
+    const int lane = tid & 31, warp = tid >> 5, NW = RADB_NTB / 32;
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        const double t = warp_sum(v[k]);
+        if (lane == 0) slots[k * NW + warp] = t;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < K; k++) {
+        double t = 0;
+        for (int w = 0; w < NW; w++) t += slots[k * NW + w];
+        v[k] = t;
+    }
+    __syncthreads();
+}
+
+#define RADB_FO_RANKS 10
+// scratch layout (bytes from `scr`): slots double[8*8] | fr double[16] | prefix u64[10] | gprefix u64[10] |
+//                                    rem int[10] | grp int[10] | ngroups int[2] | hist int[10][256]
+#define RADB_FO_SCRATCH (64 * 8 + 16 * 8 + 10 * 8 + 10 * 8 + 10 * 4 + 10 * 4 + 8 + 10 * 256 * 4 + 64)
+
+template <typename PT>
+__device__ void fo_generic(const RadbParams& p, const PT* img, const unsigned char* msk, int HW, int N,
+                           const int* lhist, int ng, unsigned char* scr, double* o, int tid)
+{
+    typedef PixKey<PT> KY;
+    double* slots = (double*)scr;
+    double* fr = slots + 64;                                  // [0..9] order statistics, [10..14] fractions
+    unsigned long long* prefix = (unsigned long long*)(fr + 16);
+    unsigned long long* gprefix = prefix + 10;
+    int* rem = (int*)(gprefix + 10);
+    int* grp = rem + 10;
+    int* ngroups = grp + 10;
+    int* hist = ngroups + 2;
+    const double dN = (double)N, rN = 1.0 / dN, shift = p.shift;
+    // ---- pass 1: mean; pass 2: central moments, MAD, energy
+    double a1[2] = {0, 0};
+    for (int i = tid; i < HW; i += RADB_NTB)
+        if ((int)msk[i] == p.label) { const double x = (double)img[i]; a1[0] += x; a1[1] += (x + shift) * (x + shift); }
+    cta_sum(a1, slots, tid);
+    const double mean = a1[0] * rN, en = a1[1];
+    double a2[4] = {0, 0, 0, 0};
+    double vmn = 1e308, vmx = -1e308;
+    for (int i = tid; i < HW; i += RADB_NTB)
+        if ((int)msk[i] == p.label) {
+            const double x = (double)img[i], d = x - mean, d2 = d * d;
+            a2[0] += d2; a2[1] += d2 * d; a2[2] += d2 * d2; a2[3] += fabs(d);
+            vmn = fmin(vmn, x); vmx = fmax(vmx, x);
+        }
+    cta_sum(a2, slots, tid);
+    {   // min / max (exact: no rounding in min/max)
+        const int lane = tid & 31, warp = tid >> 5, NW = RADB_NTB / 32;
+#pragma unroll
+        for (int m = 16; m >= 1; m >>= 1) {
+            vmn = fmin(vmn, __shfl_xor_sync(FULLMASK, vmn, m));
+            vmx = fmax(vmx, __shfl_xor_sync(FULLMASK, vmx, m));
+        }
+        if (lane == 0) { slots[warp] = vmn; slots[NW + warp] = vmx; }
+        __syncthreads();
+        for (int w = 0; w < NW; w++) { vmn = fmin(vmn, slots[w]); vmx = fmax(vmx, slots[NW + w]); }
+        __syncthreads();
+    }
+    const double m2 = a2[0] * rN, m3 = a2[1] * rN, m4 = a2[2] * rN, mad = a2[3] * rN;
+    // ---- multi-rank radix select: ranks lo/hi of the 10/25/50/75/90 percentiles (numpy 'linear')
+    if (tid < 5) {
+        const double qq = tid == 0 ? 0.1 : tid == 1 ? 0.25 : tid == 2 ? 0.5 : tid == 3 ? 0.75 : 0.9;
+        const double pos = qq * (dN - 1.0), fl = floor(pos);
+        int lo = (int)fl;
+        lo = lo > N - 1 ? N - 1 : lo;
+        const int hi = lo + 1 > N - 1 ? N - 1 : lo + 1;
+        fr[10 + tid] = pos - fl;
+        rem[2 * tid] = lo;
+        rem[2 * tid + 1] = hi;
+    }
+    if (tid < RADB_FO_RANKS) { prefix[tid] = 0; grp[tid] = 0; }
+    if (tid == 0) { ngroups[0] = 1; gprefix[0] = 0; }
+    for (int i = tid; i < RADB_FO_RANKS * 256; i += RADB_NTB) hist[i] = 0;
+    __syncthreads();
+    for (int sh = KY::BITS - 8; sh >= 0; sh -= 8) {
+        const int ngr = ngroups[0];
+        const bool first = (sh == KY::BITS - 8);
+        for (int i = tid; i < HW; i += RADB_NTB)
+            if ((int)msk[i] == p.label) {
+                const unsigned long long k = KY::key(img[i]);
+                const unsigned long long kh = first ? 0ULL : (k >> (sh + 8));
+                const int b = (int)((k >> sh) & 255ULL);
+                for (int g = 0; g < ngr; g++)
+                    if (kh == gprefix[g]) atomicAdd(&hist[g * 256 + b], 1);
+            }
+        __syncthreads();
+        if (tid < RADB_FO_RANKS) {
+            const int* hg = hist + grp[tid] * 256;
+            int cum = 0, bucket = 255;
+            for (int b = 0; b < 256; b++) {
+                const int c = hg[b];
+                if (rem[tid] < cum + c) { bucket = b; break; }
+                cum += c;
+            }
+            prefix[tid] = (prefix[tid] << 8) | (unsigned long long)bucket;
+            rem[tid] -= cum;
+        }
+        __syncthreads();
+        if (tid == 0) {  // ranks that still share a prefix share a histogram in the next pass
+            int n = 0;
+            for (int q = 0; q < RADB_FO_RANKS; q++) {
+                int g = -1;
+                for (int h = 0; h < n; h++)
+                    if (gprefix[h] == prefix[q]) g = h;
+                if (g < 0) { g = n; gprefix[n++] = prefix[q]; }
+                grp[q] = g;
+            }
+            ngroups[0] = n;
+        }
+        for (int i = tid; i < RADB_FO_RANKS * 256; i += RADB_NTB) hist[i] = 0;
+        __syncthreads();
+    }
+    if (tid < RADB_FO_RANKS) fr[tid] = KY::value(prefix[tid]);
+    __syncthreads();
+    double pc[5];
+#pragma unroll
+    for (int q = 0; q < 5; q++) pc[q] = fr[2 * q] + (fr[2 * q + 1] - fr[2 * q]) * fr[10 + q];
+    const double p10 = pc[0], p25 = pc[1], med = pc[2], p75 = pc[3], p90 = pc[4];
+    // ---- robust MAD: values inside [p10, p90]
+    double a3[2] = {0, 0};
+    for (int i = tid; i < HW; i += RADB_NTB)
+        if ((int)msk[i] == p.label) {
+            const double x = (double)img[i];
+            if (x >= p10 && x <= p90) { a3[0] += x; a3[1] += 1.0; }
+        }
+    cta_sum(a3, slots, tid);
+    const double rin = 1.0 / a3[1], in_mean = a3[0] * rin;
+    double a4[3] = {0, 0, 0};
+    for (int i = tid; i < HW; i += RADB_NTB)
+        if ((int)msk[i] == p.label) {
+            const double x = (double)img[i];
+            if (x >= p10 && x <= p90) a4[0] += fabs(x - in_mean);
+        }
+    for (int i = tid; i < ng; i += RADB_NTB) {
+        const double pi = (double)lhist[i] * rN;
+        if (lhist[i]) a4[1] -= pi * radb_log2(pi + RADB_EPS);
+        a4[2] += pi * pi;
+    }
+    cta_sum(a4, slots, tid);
+    if (tid == 0) {
+        o[0] = p10;
+        o[1] = p90;
+        o[2] = en;
+        o[3] = a4[1];
+        o[4] = p75 - p25;
+        o[5] = (m2 == 0.0) ? 0.0 : m4 / (m2 * m2);
+        o[6] = vmx;
+        o[7] = mad;
+        o[8] = mean;
+        o[9] = med;
+        o[10] = vmn;
+        o[11] = vmx - vmn;
+        o[12] = a4[0] * rin;
+        o[13] = sqrt(en * rN);
+        o[14] = (m2 == 0.0) ? 0.0 : m3 / (m2 * sqrt(m2));
+        o[15] = en;  // TotalEnergy: pixel spacing is (1, 1)
+        o[16] = a4[2];
+        o[17] = m2;
+    }
+    __syncthreads();
+}
+
+// A.3 binImage: gray level of x = number of fp64 edges (low + k*bw, as numpy.arange builds them) <= x
+__device__ __noinline__ int radb_level(double x, double low, double bw)
+{
+    long long k = (long long)floor((x - low) / bw);
+    while (low + (double)k * bw > x) k--;
+    while (low + (double)(k + 1) * bw <= x) k++;
+    return (int)(k + 1);
+}
+
+template <typename PT> struct fo_dispatch {
+    static __device__ __forceinline__ void run(const RadbParams& p, const PT* img, const unsigned char* msk, int HW, int N,
+                                               const int* lhist, int ng, unsigned char* scr, double* o, int tid)
+    {
+        fo_generic<PT>(p, img, msk, HW, N, lhist, ng, scr, o, tid);
+    }
+};
+template <> struct fo_dispatch<unsigned char> {
+    static __device__ __forceinline__ void run(const RadbParams&, const unsigned char*, const unsigned char*, int, int,
+                                               const int*, int, unsigned char*, double*, int) {}
+};
+
 // ------------------------------------------------------------------ build kernel: one CTA per patch
 template <typename PT, bool DBG, bool WIDE>
 __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned char* smem)
@@ -322,9 +560,12 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     }
     __syncthreads();
 
-    // ---- phase 1: ROI histogram, bbox, voxel count
+    // ---- phase 1: ROI histogram (uint8) or value range (other pixel types), bbox, voxel count
+    const bool U8 = sizeof(PT) == 1;
+    double* wrange = (double*)(smem + p.o_fo);  // non-uint8: per-warp min / max slots
     {
         int np = 0, ymin = H, ymax = -1, xmin = W, xmax = -1;
+        double vmn = 1e308, vmx = -1e308;
         for (int y = warp; y < H; y += RADB_NTB / 32)
             for (int x = lane; x < W; x += 32) {
                 int i = y * W + x;
@@ -334,7 +575,13 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                     ymax = y > ymax ? y : ymax;
                     xmin = x < xmin ? x : xmin;
                     xmax = x > xmax ? x : xmax;
-                    atomicAdd(&hist[(int)s_img[i]], 1);
+                    if (U8) {
+                        atomicAdd(&hist[(int)s_img[i]], 1);
+                    } else {
+                        const double v = (double)s_img[i];
+                        vmn = fmin(vmn, v);
+                        vmx = fmax(vmx, v);
+                    }
                 }
             }
         np = warp_sum_i(np);
@@ -342,6 +589,14 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         ymax = warp_max_i(ymax);
         xmin = warp_min_i(xmin);
         xmax = warp_max_i(xmax);
+        if (!U8) {
+#pragma unroll
+            for (int m = 16; m >= 1; m >>= 1) {
+                vmn = fmin(vmn, __shfl_xor_sync(FULLMASK, vmn, m));
+                vmx = fmax(vmx, __shfl_xor_sync(FULLMASK, vmx, m));
+            }
+            if (lane == 0) { wrange[warp] = vmn; wrange[RADB_NTB / 32 + warp] = vmx; }
+        }
         if (lane == 0 && np) {
             atomicAdd(&misc[0], np);
             // zero-neutral encodings so the zeroed scratch needs no separate init
@@ -352,7 +607,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         }
     }
     __syncthreads();
-    // ROI validity (A.1 step 2, imageoperations.checkMask)
+    // ROI validity (A.1 step 2, imageoperations.checkMask) and the bin edges (A.3 getBinEdges)
+    double low = 0;
     {
         const int np = misc[0];
         int st = 0;
@@ -363,38 +619,36 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             if (nd == 0) st = 2;
             else if (nd < 2) st = 3;
         }
-        int vmin = 256, vmax = -1;
-        for (int k = 0; k < 8; k++) {
-            int v = lane * 8 + k;
-            if (hist[v]) { vmin = v < vmin ? v : vmin; vmax = v > vmax ? v : vmax; }
+        double vmin = 1e308, vmax = -1e308;
+        if (U8) {
+            int imin = 256, imax = -1;
+            for (int k = 0; k < 8; k++) {
+                int v = lane * 8 + k;
+                if (hist[v]) { imin = v < imin ? v : imin; imax = v > imax ? v : imax; }
+            }
+            vmin = (double)warp_min_i(imin);
+            vmax = (double)warp_max_i(imax);
+        } else {
+            for (int w = 0; w < RADB_NTB / 32; w++) {
+                vmin = fmin(vmin, wrange[w]);
+                vmax = fmax(vmax, wrange[RADB_NTB / 32 + w]);
+            }
         }
-        vmin = warp_min_i(vmin);
-        vmax = warp_max_i(vmax);
-        // A.3 getBinEdges / binImage: level = #edges <= x, edges = low + k*binWidth
         int ng = 0;
         if (!st) {
             const double bw = p.bin_width;
-            const double low = (double)vmin - py_mod((double)vmin, bw);
-            ng = 0;
-            for (int v = tid; v < 256; v += RADB_NTB) {
-                int L = 0;
-                if (v >= vmin && v <= vmax) {
-                    double x = (double)v;
-                    long long k = (long long)floor((x - low) / bw);
-                    while (low + (double)k * bw > x) k--;
-                    while (low + (double)(k + 1) * bw <= x) k++;
-                    L = (int)(k + 1);
-                    if (L > 255) L = 255;  // reported through status 4 below
+            low = vmin - py_mod(vmin, bw);
+            if (U8) {  // value -> level LUT: level = #edges <= x, edges = low + k*binWidth
+                for (int v = tid; v < 256; v += RADB_NTB) {
+                    int L = 0;
+                    if ((double)v >= vmin && (double)v <= vmax) {
+                        L = radb_level((double)v, low, bw);
+                        if (L > 255) L = 255;  // reported through status 4 below
+                    }
+                    lut[v] = (unsigned char)L;
                 }
-                lut[v] = (unsigned char)L;
             }
-            {
-                double x = (double)vmax;
-                long long k = (long long)floor((x - low) / bw);
-                while (low + (double)k * bw > x) k--;
-                while (low + (double)(k + 1) * bw <= x) k++;
-                ng = (int)(k + 1);
-            }
+            ng = radb_level(vmax, low, bw);
             if (ng > p.max_ng) st = 4;
         }
         if (st) {
@@ -414,12 +668,23 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     for (int y = warp; y < H; y += RADB_NTB / 32)
         for (int x = lane; x < W; x += 32) {
             int i = y * W + x;
-            unsigned char L = ((int)s_msk[i] == p.label) ? lut[(int)s_img[i]] : (unsigned char)0;
+            unsigned char L = 0;
+            if ((int)s_msk[i] == p.label) {
+                if (U8) {
+                    L = lut[(int)s_img[i]];
+                } else {
+                    L = (unsigned char)radb_level((double)s_img[i], low, p.bin_width);
+                    atomicAdd(&lhist[L - 1], 1);
+                }
+            }
             lev[(y + 1) * WP + x + 1] = L;
         }
-    for (int v = tid; v < 256; v += RADB_NTB)
-        if (hist[v]) atomicAdd(&lhist[lut[v] - 1], hist[v]);
+    if (U8)
+        for (int v = tid; v < 256; v += RADB_NTB)
+            if (hist[v]) atomicAdd(&lhist[lut[v] - 1], hist[v]);
     __syncthreads();
+    if (!U8 && p.off_fo >= 0)  // first-order features need the raw values: now, before the stage is re-used
+        fo_dispatch<PT>::run(p, s_img, s_msk, HW, misc[0], lhist, ng, smem + p.o_fo, out + p.off_fo, tid);
 
     // ROI bounding box (every later pixel pass runs over the bbox only, linearised so that all
     // lanes of a warp have work)
@@ -767,7 +1032,7 @@ __device__ void radb_misc_cta(const RadbParams& p, long long patch, unsigned cha
                        p.dbg_ngn ? p.dbg_ngn + patch * p.max_ng : (int*)0,
                        p.dbg_ngs ? p.dbg_ngs + patch * p.max_ng : (double*)0);
         } else {
-            if (p.off_fo < 0) continue;
+            if (p.off_fo < 0 || p.pix_bytes != 1) continue;  // non-uint8: done by the build kernel
             fo_task_u8(p, tb, (const int*)(rec + (p.o_hist - p.o_rec)), (const int*)(rec + (p.o_lhist - p.o_rec)), ng,
                        (double*)(smem + p.m_qv), out + p.off_fo, lane);
         }

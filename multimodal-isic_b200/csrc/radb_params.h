@@ -15,7 +15,7 @@
 #define RADB_GLRLM_NF 16
 #define RADB_FSC_STRIDE 40   // per-angle scratch: 24 GLCM + 16 GLRLM features
 
-enum { RADB_U8 = 0, RADB_U16 = 1, RADB_F32 = 2 };
+enum { RADB_U8 = 0, RADB_U16 = 1, RADB_F32 = 2, RADB_F64 = 3 };
 
 struct RadbParams {
     const void* img;
@@ -42,11 +42,12 @@ struct RadbParams {
     int off_fo, off_glcm, off_gldm, off_glrlm, off_glszm, off_ngtdm;  // output column of each class, -1 = off
     int off_shape;                                                    // shape2D (always first when enabled)
     int use_tma;
+    int pix_bytes; // 1 uint8, 2 uint16, 4 float32, 8 float64
     int wide;      // 1: whole-image mode (level image, union-find words, GLRLM and overflow list in global memory)
     // ---- build kernel: shared-memory byte offsets.  [o_rec, o_rec + rec_bytes) is the per-patch
     // RECORD (header + every integer matrix); the build kernel copies it to the global workspace
     // and the reduction kernels read it from there at the same relative offsets.
-    int o_stage, o_mask, o_mbar, o_zero, o_lev, o_uq, o_lut, o_rec, o_misc, o_hist, o_lhist, o_glcm, o_glrlm,
+    int o_stage, o_mask, o_mbar, o_zero, o_lev, o_uq, o_lut, o_fo, o_rec, o_misc, o_hist, o_lhist, o_glcm, o_glrlm,
         o_gldm, o_ngc, o_ngn, o_szm, o_ovf, smem_total;
     int rec_bytes;       // record size in the global workspace
     int rec_copy_bytes;  // leading part of the record that is built in shared memory and copied out
@@ -83,6 +84,7 @@ static inline int radb_align(int v, int a) { return (v + a - 1) / a * a; }
 static inline void radb_layout(RadbParams* p, int pix_bytes)
 {
     const int H = p->H, W = p->W, ng = p->max_ng, na = p->n_angles, wide = p->wide;
+    p->pix_bytes = pix_bytes;
     p->HW = H * W;
     p->WP = radb_align(W + 2, 4);
     p->nr = H > W ? H : W;
@@ -109,6 +111,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     if (!wide) o += radb_align((H + 2) * p->WP, 16);
     p->o_uq = o; o += (RADB_NTB / 32) * 64 * (wide ? 8 : 4);   // per-warp union request queues
     p->o_lut = o; o += 256;
+    p->o_fo = o; o += pix_bytes == 1 ? 16 : radb_align(64 * 8 + 16 * 8 + 10 * 8 + 10 * 8 + 10 * 4 + 10 * 4 + 8 + 10 * 256 * 4 + 64, 16);  // RADB_FO_SCRATCH
     p->o_rec = o;
     p->o_misc = o; o += 32 * 4;           // record header: [0] Np, [5] #overflow zones, [8] Ng, [9] #levels present
     p->o_hist = o; o += 256 * 4;
