@@ -35,7 +35,7 @@ enum {
 };
 
 /* pixel types of `img` */
-enum { RADB_DTYPE_U8 = 0, RADB_DTYPE_U16 = 1, RADB_DTYPE_F32 = 2 };
+enum { RADB_DTYPE_U8 = 0, RADB_DTYPE_U16 = 1, RADB_DTYPE_F32 = 2, RADB_DTYPE_F64 = 3 };
 
 /* per-patch status written to `status[b]`; rows with status != 0 are NaN.
  * 1-3 are the ValueErrors pyradiomics' imageoperations.checkMask raises through
@@ -73,8 +73,8 @@ typedef struct radb_settings {
     double gldm_alpha;         /* gldm_a (0) */
     double voxel_array_shift;  /* voxelArrayShift (0) */
     uint32_t class_mask;       /* RADB_CLASS_* bits: params.yml:164-171 featureClass */
-    int32_t max_ng;            /* shared-memory sizing bound on gray levels; 0 = derive from
-                                  dtype and bin_width */
+    int32_t max_ng;            /* sizing bound on gray levels (<= 255); 0 = derive from bin_width for
+                                  uint8 pixels; required for the other pixel types */
     int32_t device;            /* CUDA device ordinal */
 } radb_settings;
 

@@ -11,7 +11,7 @@ LIB_PATH = os.path.join(HERE, "csrc", "libradb_b200.so")
 
 CLASS_BITS = {"firstorder": 1, "glcm": 2, "gldm": 4, "glrlm": 8, "glszm": 16, "ngtdm": 32, "shape2D": 64}
 CLASS_ORDER = ("firstorder", "glcm", "gldm", "glrlm", "glszm", "ngtdm")
-DTYPE_U8, DTYPE_U16, DTYPE_F32 = 0, 1, 2
+DTYPE_U8, DTYPE_U16, DTYPE_F32, DTYPE_F64 = 0, 1, 2, 3
 
 STATUS_MESSAGES = {
     1: "Label (%s) not present in mask",

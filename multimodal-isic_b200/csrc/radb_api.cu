@@ -18,7 +18,7 @@ struct radb_handle {
     radb::Plan plan;
     int device;
     int smem_optin;              // max dynamic shared memory per block the device allows
-    int smem_set[9];             // configured MaxDynamicSharedMemorySize per kernel
+    int smem_set[32];             // configured MaxDynamicSharedMemorySize per kernel
     int64_t launches;
     struct Ws { void* stream; unsigned char* p; size_t bytes; };
     std::vector<Ws> ws;          // per-patch records of one chunk, one workspace per CUDA stream
@@ -54,7 +54,7 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
     if (rc) { delete h; return fail(rc, err); }
     h->device = s->device;
     h->launches = 0;
-    for (int i = 0; i < 9; i++) h->smem_set[i] = 0;
+    for (int i = 0; i < 32; i++) h->smem_set[i] = 0;
     h->d_inv2 = h->d_tlog = nullptr;
     h->profiling = false;
     int ndev = 0;
@@ -178,7 +178,6 @@ static int set_smem(radb_handle* h, K kernel, int which, int bytes)
 // One pass = three kernels over a chunk of patches, stream-ordered, sharing the record workspace.
 static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
 {
-    (void)dtype;
     cudaError_t e;
     int cur = -1;
     cudaGetDevice(&cur);
@@ -188,9 +187,18 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     }
     const bool dbg = p.dbg_levels || p.dbg_glcm || p.dbg_glrlm || p.dbg_glszm || p.dbg_gldm || p.dbg_ng;
     typedef void (*build_fn)(const RadbParams);
-    const build_fn build = p.wide ? (dbg ? radb_build_kernel<unsigned char, true, true> : radb_build_kernel<unsigned char, false, true>)
-                                  : (dbg ? radb_build_kernel<unsigned char, true, false> : radb_build_kernel<unsigned char, false, false>);
-    int rc = set_smem(h, build, (p.wide ? 4 : 0) + (dbg ? 3 : 0), p.smem_total);
+    build_fn build = nullptr;
+#define RADB_PICK(PT) (p.wide ? (dbg ? radb_build_kernel<PT, true, true> : radb_build_kernel<PT, false, true>) \
+                              : (dbg ? radb_build_kernel<PT, true, false> : radb_build_kernel<PT, false, false>))
+    switch (dtype) {
+        case RADB_DTYPE_U8: build = RADB_PICK(unsigned char); break;
+        case RADB_DTYPE_U16: build = RADB_PICK(unsigned short); break;
+        case RADB_DTYPE_F32: build = RADB_PICK(float); break;
+        case RADB_DTYPE_F64: build = RADB_PICK(double); break;
+        default: return fail(RADB_E_INVALID, "unknown pixel dtype");
+    }
+#undef RADB_PICK
+    int rc = set_smem(h, build, 9 + dtype * 4 + (p.wide ? 2 : 0) + (dbg ? 1 : 0), p.smem_total);
     if (!rc) rc = set_smem(h, radb_angle_kernel, 1, p.a_smem_total);
     if (!rc && p.off_shape >= 0) rc = set_smem(h, radb_shape_kernel, 8, p.s_smem_total);
     if (!rc) rc = set_smem(h, radb_misc_kernel, 2, p.m_smem_total);
@@ -258,7 +266,7 @@ static int setup(radb_handle* h, const void* img, int dtype, const uint8_t* mask
     std::string err;
     int rc = radb::fill_params(h->plan, H, W, dtype, p, err);
     if (rc) return fail(rc, err);
-    if (img_stride_b < (int64_t)H * W || mask_stride_b < (int64_t)H * W)
+    if (img_stride_b < (int64_t)H * W * p.pix_bytes || mask_stride_b < (int64_t)H * W)
         return fail(RADB_E_INVALID, "patch stride smaller than the patch");
     p.img = img;
     p.mask = mask;
@@ -269,7 +277,7 @@ static int setup(radb_handle* h, const void* img, int dtype, const uint8_t* mask
     p.B = B;
     // TMA bulk copies need 16-byte aligned sources and sizes
     p.use_tma = !p.wide && ((uintptr_t)img % 16 == 0) && ((uintptr_t)mask % 16 == 0) && (img_stride_b % 16 == 0) &&
-                (mask_stride_b % 16 == 0) && (p.HW % 16 == 0);
+                (mask_stride_b % 16 == 0) && (p.HW % 16 == 0) && (img_stride_b % p.pix_bytes == 0);
     return RADB_OK;
 }
 

@@ -113,7 +113,18 @@ static inline int make_plan(const radb_settings& s, Plan& pl, std::string& err)
 
 static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParams& p, std::string& err)
 {
-    if (dtype != RADB_DTYPE_U8) { err = "only uint8 pixels are implemented in this build (u16/f32 pending)"; return RADB_E_UNSUPPORTED; }
+    int pix_bytes = 0;
+    switch (dtype) {
+        case RADB_DTYPE_U8: pix_bytes = 1; break;
+        case RADB_DTYPE_U16: pix_bytes = 2; break;
+        case RADB_DTYPE_F32: pix_bytes = 4; break;
+        case RADB_DTYPE_F64: pix_bytes = 8; break;
+        default: err = "unknown pixel dtype"; return RADB_E_INVALID;
+    }
+    if (dtype != RADB_DTYPE_U8 && pl.s.max_ng <= 0) {
+        err = "max_ng must be given for non-uint8 pixels (the gray-level count cannot be bounded from the dtype)";
+        return RADB_E_INVALID;
+    }
     if (H < 1 || W < 1 || H > 4096 || W > 4096 || (long long)H * W >= (1 << 24)) {
         err = "image must be 1..4096 pixels per side and < 2^24 pixels";
         return RADB_E_INVALID;
@@ -141,10 +152,10 @@ static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParam
     // narrow mode (everything in shared memory) when the patch fits with >= 2 CTAs per SM,
     // otherwise wide mode (level image, union-find words, GLRLM, overflow list in global memory)
     p.wide = 0;
-    radb_layout(&p, 1);
+    radb_layout(&p, pix_bytes);
     if ((long long)H * W > 65535 || p.smem_total > 110 * 1024) {
         p.wide = 1;
-        radb_layout(&p, 1);
+        radb_layout(&p, pix_bytes);
     }
     if (p.smem_total > 227 * 1024 || p.a_smem_total > 227 * 1024 || p.m_smem_total > 227 * 1024 || p.s_smem_total > 227 * 1024) {
         err = "image size x gray levels need more than 227 KB of shared memory";

@@ -318,8 +318,8 @@ __device__ __forceinline__ void cta_sum(double (&v)[K], double* slots /*[K][RADB
 #define RADB_FO_SCRATCH (64 * 8 + 16 * 8 + 10 * 8 + 10 * 8 + 10 * 4 + 10 * 4 + 8 + 10 * 256 * 4 + 64)
 
 template <typename PT>
-__device__ void fo_generic(const RadbParams& p, const PT* img, const unsigned char* msk, int HW, int N,
-                           const int* lhist, int ng, unsigned char* scr, double* o, int tid)
+__device__ void fo_generic(const RadbParams& p, const PT* img, const unsigned char* msk, int HW, int N, double vmn,
+                           double vmx, const int* lhist, int ng, unsigned char* scr, double* o, int tid)
 {
     typedef PixKey<PT> KY;
     double* slots = (double*)scr;
@@ -336,28 +336,15 @@ __device__ void fo_generic(const RadbParams& p, const PT* img, const unsigned ch
     for (int i = tid; i < HW; i += RADB_NTB)
         if ((int)msk[i] == p.label) { const double x = (double)img[i]; a1[0] += x; a1[1] += (x + shift) * (x + shift); }
     cta_sum(a1, slots, tid);
-    const double mean = a1[0] * rN, en = a1[1];
+    // a flat ROI has mean == its value exactly (a rounded sum/N would leave spurious 1e-30 moments)
+    const double mean = (vmn == vmx) ? vmn : a1[0] * rN, en = a1[1];
     double a2[4] = {0, 0, 0, 0};
-    double vmn = 1e308, vmx = -1e308;
     for (int i = tid; i < HW; i += RADB_NTB)
         if ((int)msk[i] == p.label) {
             const double x = (double)img[i], d = x - mean, d2 = d * d;
             a2[0] += d2; a2[1] += d2 * d; a2[2] += d2 * d2; a2[3] += fabs(d);
-            vmn = fmin(vmn, x); vmx = fmax(vmx, x);
         }
     cta_sum(a2, slots, tid);
-    {   // min / max (exact: no rounding in min/max)
-        const int lane = tid & 31, warp = tid >> 5, NW = RADB_NTB / 32;
-#pragma unroll
-        for (int m = 16; m >= 1; m >>= 1) {
-            vmn = fmin(vmn, __shfl_xor_sync(FULLMASK, vmn, m));
-            vmx = fmax(vmx, __shfl_xor_sync(FULLMASK, vmx, m));
-        }
-        if (lane == 0) { slots[warp] = vmn; slots[NW + warp] = vmx; }
-        __syncthreads();
-        for (int w = 0; w < NW; w++) { vmn = fmin(vmn, slots[w]); vmx = fmax(vmx, slots[NW + w]); }
-        __syncthreads();
-    }
     const double m2 = a2[0] * rN, m3 = a2[1] * rN, m4 = a2[2] * rN, mad = a2[3] * rN;
     // ---- multi-rank radix select: ranks lo/hi of the 10/25/50/75/90 percentiles (numpy 'linear')
     if (tid < 5) {
@@ -473,14 +460,15 @@ __device__ __noinline__ int radb_level(double x, double low, double bw)
 
 template <typename PT> struct fo_dispatch {
     static __device__ __forceinline__ void run(const RadbParams& p, const PT* img, const unsigned char* msk, int HW, int N,
-                                               const int* lhist, int ng, unsigned char* scr, double* o, int tid)
+                                               double vmn, double vmx, const int* lhist, int ng, unsigned char* scr,
+                                               double* o, int tid)
     {
-        fo_generic<PT>(p, img, msk, HW, N, lhist, ng, scr, o, tid);
+        fo_generic<PT>(p, img, msk, HW, N, vmn, vmx, lhist, ng, scr, o, tid);
     }
 };
 template <> struct fo_dispatch<unsigned char> {
     static __device__ __forceinline__ void run(const RadbParams&, const unsigned char*, const unsigned char*, int, int,
-                                               const int*, int, unsigned char*, double*, int) {}
+                                               double, double, const int*, int, unsigned char*, double*, int) {}
 };
 
 // ------------------------------------------------------------------ build kernel: one CTA per patch
@@ -608,7 +596,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     }
     __syncthreads();
     // ROI validity (A.1 step 2, imageoperations.checkMask) and the bin edges (A.3 getBinEdges)
-    double low = 0;
+    double low = 0, roi_min = 0, roi_max = 0;
     {
         const int np = misc[0];
         int st = 0;
@@ -634,6 +622,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 vmax = fmax(vmax, wrange[RADB_NTB / 32 + w]);
             }
         }
+        roi_min = vmin;
+        roi_max = vmax;
         int ng = 0;
         if (!st) {
             const double bw = p.bin_width;
@@ -684,7 +674,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             if (hist[v]) atomicAdd(&lhist[lut[v] - 1], hist[v]);
     __syncthreads();
     if (!U8 && p.off_fo >= 0)  // first-order features need the raw values: now, before the stage is re-used
-        fo_dispatch<PT>::run(p, s_img, s_msk, HW, misc[0], lhist, ng, smem + p.o_fo, out + p.off_fo, tid);
+        fo_dispatch<PT>::run(p, s_img, s_msk, HW, misc[0], roi_min, roi_max, lhist, ng, smem + p.o_fo, out + p.off_fo, tid);
 
     // ROI bounding box (every later pixel pass runs over the bbox only, linearised so that all
     // lanes of a warp have work)

@@ -63,9 +63,14 @@ class Engine:
     def smem_bytes(self, H, W, dtype=_abi.DTYPE_U8):
         return int(self.lib.radb_smem_bytes(self._h, H, W, dtype))
 
+    DTYPES = {torch.uint8: _abi.DTYPE_U8, torch.uint16: _abi.DTYPE_U16, torch.float32: _abi.DTYPE_F32,
+              torch.float64: _abi.DTYPE_F64}
+
     def _check(self, images, masks):
-        if images.dtype != torch.uint8:
-            raise NotImplementedError("only uint8 images are implemented (got %s)" % images.dtype)
+        if images.dtype not in self.DTYPES:
+            raise NotImplementedError("pixel dtype %s is not implemented (uint8, uint16, float32, float64)" % images.dtype)
+        if images.dtype != torch.uint8 and self._settings.max_ng <= 0:
+            raise RadbError("non-uint8 pixels need an engine created with max_ng (gray-level bound)")
         if masks.dtype != torch.uint8:
             raise TypeError("masks must be uint8")
         if images.dim() != 3 or images.shape != masks.shape:
@@ -85,8 +90,9 @@ class Engine:
         if status is None:
             status = torch.empty((B,), dtype=torch.int32, device=dev)
         st = stream if stream is not None else torch.cuda.current_stream(dev)
-        rc = self.lib.radb_extract(self._h, images.data_ptr(), _abi.DTYPE_U8, masks.data_ptr(), B, H, W, H * W,
-                                   H * W, out.data_ptr(), status.data_ptr(), st.cuda_stream)
+        rc = self.lib.radb_extract(self._h, images.data_ptr(), self.DTYPES[images.dtype], masks.data_ptr(), B, H, W,
+                                   H * W * images.element_size(), H * W, out.data_ptr(), status.data_ptr(),
+                                   st.cuda_stream)
         if rc != 0:
             raise RadbError("radb_extract failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
         return out, status
@@ -126,8 +132,8 @@ class Engine:
                     glszm=z((B, ng, H * W)), gldm=z((B, ng, 2 * na + 1)), ngtdm_n=z((B, ng)),
                     ngtdm_s=z((B, ng), torch.float64), ng=z((B,)))
         st = torch.cuda.current_stream(dev)
-        rc = self.lib.radb_debug_matrices(self._h, images.data_ptr(), _abi.DTYPE_U8, masks.data_ptr(), B, H, W,
-                                          H * W, H * W, out.data_ptr(), status.data_ptr(),
+        rc = self.lib.radb_debug_matrices(self._h, images.data_ptr(), self.DTYPES[images.dtype], masks.data_ptr(), B, H, W,
+                                          H * W * images.element_size(), H * W, out.data_ptr(), status.data_ptr(),
                                           *[bufs[k].data_ptr() for k in ("levels", "glcm", "glrlm", "glszm", "gldm",
                                                                           "ngtdm_n", "ngtdm_s", "ng")],
                                           st.cuda_stream)
@@ -150,8 +156,8 @@ class HostPipeline:
         self._bufs = None
         self._key = None
 
-    def _ensure(self, H, W):
-        key = (H, W)
+    def _ensure(self, H, W, dtype=torch.uint8):
+        key = (H, W, dtype)
         if self._key == key:
             return
         dev = torch.device("cuda", self.engine.device)
@@ -159,9 +165,9 @@ class HostPipeline:
         self._bufs = []
         for _ in range(2):
             self._bufs.append(dict(
-                h_img=torch.empty((n, H, W), dtype=torch.uint8).pin_memory(),
+                h_img=torch.empty((n, H, W), dtype=dtype).pin_memory(),
                 h_msk=torch.empty((n, H, W), dtype=torch.uint8).pin_memory(),
-                d_img=torch.empty((n, H, W), dtype=torch.uint8, device=dev),
+                d_img=torch.empty((n, H, W), dtype=dtype, device=dev),
                 d_msk=torch.empty((n, H, W), dtype=torch.uint8, device=dev),
                 d_out=torch.empty((n, F), dtype=torch.float64, device=dev),
                 d_st=torch.empty((n,), dtype=torch.int32, device=dev),
@@ -169,7 +175,7 @@ class HostPipeline:
         self._key = key
 
     def run(self, images, masks, out=None, status=None):
-        """``images``/``masks``: host arrays [B, H, W] uint8 (NumPy or CPU tensors; pinned tensors
+        """``images``/``masks``: host arrays [B, H, W] (images uint8/uint16/float32/float64, masks uint8; NumPy or CPU tensors; pinned tensors
         skip the staging copy).  Returns host ``(features [B, F] float64, status [B] int32)``."""
         images = torch.as_tensor(images)
         masks = torch.as_tensor(masks)
@@ -177,7 +183,7 @@ class HostPipeline:
             raise ValueError("HostPipeline takes host buffers; use Engine.extract_device for device tensors")
         B, H, W = images.shape
         F = self.engine.F
-        self._ensure(H, W)
+        self._ensure(H, W, images.dtype)
         if out is None:
             out = torch.empty((B, F), dtype=torch.float64).pin_memory()
         if status is None:

@@ -46,6 +46,9 @@ class RadiomicsExtractor:
         self.engine = Engine(self.params.bin_width, self.params.label, self.params.angles(2),
                              bool(s["symmetricalGLCM"]), float(s["gldm_a"]), float(s["voxelArrayShift"]),
                              eng_classes, max_ng, self.device)
+        self._engine_args = (self.params.bin_width, self.params.label, self.params.angles(2),
+                             bool(s["symmetricalGLCM"]), float(s["gldm_a"]), float(s["voxelArrayShift"]), eng_classes)
+        self._engines_ng = {}  # engines for non-uint8 pixels, keyed by their gray-level bound
         self.feature_names = self.params.feature_names()
         self._perm_t = None
         self._identity = self._perm == list(range(self.engine.F))
@@ -132,21 +135,43 @@ class RadiomicsExtractor:
             self._perm_t = torch.as_tensor(self._perm, device=out.device)
         return out.index_select(1, self._perm_t)
 
+    def _engine_for(self, images, masks):
+        """uint8 pixels: the engine sized from binWidth.  Other pixel types: the gray-level count depends
+        on the data, so an engine sized for this batch's largest ROI range (rounded up to a multiple of
+        8 levels) is created on demand and cached."""
+        t = torch.as_tensor(images)
+        if t.dtype == torch.uint8:
+            return self.engine, self.pipeline
+        m = torch.as_tensor(masks) == self.params.label
+        f = t.to(torch.float64) if t.dtype != torch.uint16 else t.to(torch.int32).to(torch.float64)
+        big = torch.finfo(torch.float64).max
+        lo = torch.where(m, f, torch.full_like(f, big)).flatten(1).amin(1)
+        hi = torch.where(m, f, torch.full_like(f, -big)).flatten(1).amax(1)
+        ok = hi >= lo
+        span = float(((hi - lo)[ok] / self.params.bin_width).max().item()) if bool(ok.any()) else 0.0
+        ng = min(255, (int(span) + 3 + 7) // 8 * 8)
+        if ng not in self._engines_ng:
+            eng = Engine(*self._engine_args, max_ng=ng, device=self.device)
+            self._engines_ng[ng] = (eng, HostPipeline(eng, self.pipeline.chunk))
+        return self._engines_ng[ng]
+
     def extract_batch(self, images, masks, strict=False):
-        """``images``/``masks`` ``[B, H, W]`` uint8.  CUDA tensors -> CUDA tensors
+        """``images`` ``[B, H, W]`` uint8 (the reference's cv2 planes), uint16, float32 or float64; ``masks``
+        ``[B, H, W]`` uint8.  CUDA tensors -> CUDA tensors
         ``(features [B, F] float64, status [B] int32)``, asynchronous on the current stream;
         host arrays -> NumPy arrays through the pinned, chunk-pipelined path.
         ``strict=True`` raises the ValueError pyradiomics would raise for an invalid ROI
         (the reference has no try/except, RadiomicExtractor.py:23-55); otherwise such rows are NaN."""
+        engine, pipeline = self._engine_for(images, masks)
         if isinstance(images, torch.Tensor) and images.is_cuda:
-            out, status = self.engine.extract_device(images, masks)
+            out, status = engine.extract_device(images, masks)
             out = self._permute(out)
             if strict:
                 bad = torch.nonzero(status)
                 if bad.numel():
                     raise _status_error(int(status[bad[0, 0]]), self.params.label)
             return out, status
-        out, status = self.pipeline.run(images, masks)
+        out, status = pipeline.run(images, masks)
         out = self._permute(out).numpy()
         status = status.numpy()
         if strict and status.any():

@@ -75,10 +75,18 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
     std::vector<unsigned char> smem((size_t)mx + 64);
     unsigned char* sm = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
     // the same three launches radb_api.cu issues, CTA by CTA on host threads
-    if (p.wide)
-        emu::launch((unsigned)B, RADB_NTB, [&]() { radb_build_cta<unsigned char, true, true>(p, (long long)blockIdx.x, sm); });
-    else
-        emu::launch((unsigned)B, RADB_NTB, [&]() { radb_build_cta<unsigned char, true, false>(p, (long long)blockIdx.x, sm); });
+#define EMU_BUILD(PT)                                                                                             \
+    if (p.wide)                                                                                                   \
+        emu::launch((unsigned)B, RADB_NTB, [&]() { radb_build_cta<PT, true, true>(p, (long long)blockIdx.x, sm); }); \
+    else                                                                                                          \
+        emu::launch((unsigned)B, RADB_NTB, [&]() { radb_build_cta<PT, true, false>(p, (long long)blockIdx.x, sm); });
+    switch (dtype) {
+        case RADB_DTYPE_U8: EMU_BUILD(unsigned char) break;
+        case RADB_DTYPE_U16: EMU_BUILD(unsigned short) break;
+        case RADB_DTYPE_F32: EMU_BUILD(float) break;
+        case RADB_DTYPE_F64: EMU_BUILD(double) break;
+        default: g_err = "unknown dtype"; return -1;
+    }
     emu::launch((unsigned)B, RADB_NT, [&]() { radb_angle_cta(p, (long long)blockIdx.x, sm); });
     emu::launch((unsigned)B, RADB_NT, [&]() { radb_misc_cta(p, (long long)blockIdx.x, sm); });
     if (p.off_shape >= 0) emu::launch((unsigned)B, RADB_NT, [&]() { radb_shape_cta(p, (long long)blockIdx.x, sm); });

@@ -22,11 +22,12 @@ class EmuRunner:
         return self.lib.radb_emu_is_wide(ctypes.byref(s), H, W)
 
     def run(self, imgs, masks, bin_width=10, label=255, angles=((0, 1),), symmetrical=True, alpha=0,
-            classes=_abi.CLASS_ORDER):
-        imgs = np.ascontiguousarray(imgs, dtype=np.uint8)
+            classes=_abi.CLASS_ORDER, max_ng=0):
+        imgs = np.ascontiguousarray(imgs)
+        dtype = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3}[imgs.dtype]
         masks = np.ascontiguousarray(masks, dtype=np.uint8)
         B, H, W = imgs.shape
-        s = _abi.make_settings(bin_width, label, angles, symmetrical, alpha, classes=classes)
+        s = _abi.make_settings(bin_width, label, angles, symmetrical, alpha, classes=classes, max_ng=max_ng)
         F = self.lib.radb_emu_feature_count(ctypes.byref(s))
         ng = self.lib.radb_emu_max_ng(ctypes.byref(s))
         assert F > 0 and ng > 0, self.lib.radb_emu_last_error()
@@ -36,7 +37,7 @@ class EmuRunner:
                  glszm=np.zeros((B, ng, H * W), np.int32), gldm=np.zeros((B, ng, 2 * na + 1), np.int32),
                  ngtdm_n=np.zeros((B, ng), np.int32), ngtdm_s=np.zeros((B, ng)), ng=np.zeros(B, np.int32))
         p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
-        rc = self.lib.radb_emu_extract(ctypes.byref(s), p(imgs), 0, p(masks), B, H, W, H * W, H * W,
+        rc = self.lib.radb_emu_extract(ctypes.byref(s), p(imgs), dtype, p(masks), B, H, W, H * W * imgs.itemsize, H * W,
                                        *[p(r[k]) for k in ("features", "status", "levels", "glcm", "glrlm", "glszm",
                                                            "gldm", "ngtdm_n", "ngtdm_s", "ng")])
         assert rc == 0, self.lib.radb_emu_last_error()

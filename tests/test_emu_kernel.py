@@ -145,3 +145,22 @@ def test_emu_bgr_front_end_matches_cv2(emu):
         np.testing.assert_array_equal(planes[i, 0], cv2.cvtColor(bgr[i], cv2.COLOR_BGR2GRAY))
         for k, ch in ((1, 2), (2, 1), (3, 0)):
             np.testing.assert_array_equal(planes[i, k], bgr[i, :, :, ch])
+
+
+@pytest.mark.parametrize("dt", [np.uint16, np.float32, np.float64])
+def test_emu_other_pixel_types(emu, dt):
+    """uint16 / float pixels (derived image types, BASELINE.json configs[4]): per-pixel fp64 binning,
+    first-order features from the raw values (radix-select percentiles)."""
+    rng = np.random.default_rng(4)
+    g, masks = synth.make_patches(3, 40, 36, seed=6)
+    if dt == np.uint16:
+        imgs = (g.astype(np.uint16) * 7 + rng.integers(0, 7, g.shape).astype(np.uint16))     # range ~[0, 1800)
+        bw = 64
+    else:
+        imgs = (np.sqrt(g.astype(np.float64)) * 11.3 - 40.0 + rng.normal(0, 0.3, g.shape)).astype(dt)  # negatives too
+        bw = 7.5
+    # a flat patch.  (A dyadic value: numpy's mean of N copies is then exact.  For other values upstream's
+    # Skewness/Kurtosis of a flat float ROI are rounding noise, +-1 or 0; the engine returns the documented 0.)
+    imgs[2] = 37.25 if dt != np.uint16 else 640
+    r = emu.run(imgs, masks, bw, 255, INPLANE, max_ng=40)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=bw, force2D=False)) == 3

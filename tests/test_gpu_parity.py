@@ -292,3 +292,34 @@ def test_dataframe_feeds_the_feature_selection_stage(gpu_pkg, tmp_path):
     upper = corr.where(np.triu(np.ones(corr.shape), k=1).astype(bool))
     dropped = [c for c in upper.columns if (upper[c] > 0.95).any()]
     assert len(keep) - len(dropped) >= 1
+
+
+@pytest.mark.parametrize("dt", [np.uint16, np.float32, np.float64])
+def test_other_pixel_types(gpu_pkg, dt):
+    rng = np.random.default_rng(4)
+    g, masks = gpu_pkg.synth.make_patches(6, 64, seed=6)
+    if dt == np.uint16:
+        imgs = (g.astype(np.uint16) * 7 + rng.integers(0, 7, g.shape).astype(np.uint16))
+        bw = 64
+    else:
+        imgs = (np.sqrt(g.astype(np.float64)) * 11.3 - 40.0 + rng.normal(0, 0.3, g.shape)).astype(dt)
+        bw = 7.5
+    imgs[2] = 37.25 if dt != np.uint16 else 640
+    eng = gpu_pkg.Engine(bw, 255, INPLANE, max_ng=40)
+    tt = torch.as_tensor(imgs.view(np.int16) if dt == np.uint16 else imgs).cuda()
+    if dt == np.uint16:
+        tt = tt.view(torch.uint16)
+    r = eng.debug_matrices(tt, torch.as_tensor(masks).cuda())
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=bw, force2D=False)) == 6
+    # the drop-in class sizes an engine from the data range
+    ex = gpu_pkg.RadiomicsExtractor({"setting": {"label": 255, "binWidth": bw}})
+    out, st = ex.extract_batch(tt, torch.as_tensor(masks).cuda())
+    np.testing.assert_allclose(out.cpu().numpy(), r["features"], rtol=1e-12, atol=0)
+
+
+def test_float_wide_mode(gpu_pkg):
+    g, masks = gpu_pkg.synth.make_patches(1, 300, 280, seed=8)
+    imgs = np.log1p(g.astype(np.float64)) * 40.0
+    eng = gpu_pkg.Engine(5.0, 255, LITERAL, max_ng=64)
+    r = eng.debug_matrices(torch.as_tensor(imgs).cuda(), torch.as_tensor(masks).cuda())
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=5.0, force2D=True)) == 1
