@@ -112,6 +112,13 @@ int radb_extract(radb_handle* h, const void* img, int dtype, const uint8_t* mask
 int radb_extract_bgr(radb_handle* h, const uint8_t* bgr, const uint8_t* mask, int64_t n_images, int H, int W,
                      uint8_t* planes, double* out, int32_t* status, void* cuda_stream);
 
+/* imageType filters of the parameter file (params.yml:141-144; pyradiomics imageoperations.getSquareImage,
+ * getSquareRootImage, getLogarithmImage, getExponentialImage) for uint8 images, computed in float64:
+ * type 1 Square, 2 SquareRoot, 3 Logarithm, 4 Exponential.  img [n][H*W] uint8 -> out [n][H*W] float64
+ * (feed it to radb_extract with RADB_DTYPE_F64); mx = int32 [n] device scratch. */
+int radb_derive_image(radb_handle* h, const uint8_t* img, int64_t n_images, int64_t HW, int type, double* out,
+                      int32_t* mx, void* cuda_stream);
+
 /* Same launch as radb_extract, additionally dumping the discretised image and the integer
  * texture matrices the features were reduced from (what pyradiomics' cMatrices.calculate_*
  * return) for bit-exact parity tests.  Any debug pointer may be NULL.  All buffers must be

@@ -362,3 +362,27 @@ extern "C" int radb_extract_bgr(radb_handle* h, const uint8_t* bgr, const uint8_
     h->launches += 1;
     return launch(h, p, RADB_DTYPE_U8, cuda_stream);
 }
+
+// imageType filters of the pyradiomics parameter file (params.yml:141-144) for uint8 images:
+// type 1 Square, 2 SquareRoot, 3 Logarithm, 4 Exponential.  img [n][H*W] uint8 -> out [n][H*W] float64;
+// `mx` is an int32 [n] device scratch (per-image maximum).
+extern "C" int radb_derive_image(radb_handle* h, const uint8_t* img, int64_t n_images, int64_t HW, int type,
+                                 double* out, int32_t* mx, void* cuda_stream)
+{
+    if (!h || !img || !out || !mx) return fail(RADB_E_INVALID, "null argument");
+    if (type < 1 || type > 4) return fail(RADB_E_UNSUPPORTED, "image type not implemented (1 Square, 2 SquareRoot, 3 Logarithm, 4 Exponential)");
+    if (n_images <= 0 || HW <= 0) return RADB_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != h->device) cudaSetDevice(h->device);
+    cudaError_t e = cudaMemsetAsync(mx, 0, (size_t)n_images * 4, st);
+    if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
+    const long long t1 = n_images * ((HW + 3) / 4), t2 = n_images * HW;
+    radb_image_max_kernel<<<(unsigned)((t1 + 255) / 256), 256, 0, st>>>(img, n_images, HW, mx);
+    radb_derive_kernel<<<(unsigned)((t2 + 255) / 256), 256, 0, st>>>(img, n_images, HW, mx, type, out);
+    h->launches += 2;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "radb_derive_image launch");
+    return RADB_OK;
+}

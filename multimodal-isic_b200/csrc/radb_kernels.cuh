@@ -1053,6 +1053,30 @@ __device__ void radb_bgr_planes_thread(const unsigned char* bgr, unsigned char* 
     }
 }
 
+// ------------------------------------------------------------------ derived image types (point-wise)
+// pyradiomics imageoperations.get{Square,SquareRoot,Logarithm,Exponential}Image (params.yml:141-144):
+// y = g(x; M) in float64 with M = max |x| over the whole image (for the logarithm the second
+// normalisation max|log(|x|+1)| = log(M+1) because the transform is monotone in |x|).
+enum { RADB_IT_SQUARE = 1, RADB_IT_SQUAREROOT = 2, RADB_IT_LOGARITHM = 3, RADB_IT_EXPONENTIAL = 4 };
+__device__ __forceinline__ double radb_derive_px(int type, double x, double M)
+{
+    switch (type) {
+        case RADB_IT_SQUARE: {
+            const double c = 1.0 / sqrt(M);
+            return (c * x) * (c * x);
+        }
+        case RADB_IT_SQUAREROOT:
+            return x > 0 ? sqrt(x * M) : (x < 0 ? -sqrt(-x * M) : x);
+        case RADB_IT_LOGARITHM: {
+            const double y = x > 0 ? log(x + 1.0) : (x < 0 ? -log(-(x - 1.0)) : x);
+            return y * (M / log(M + 1.0));
+        }
+        case RADB_IT_EXPONENTIAL:
+            return exp((log(M) / M) * x);
+    }
+    return x;
+}
+
 // ------------------------------------------------------------------ shape kernel: shape2D (9 features)
 // pyradiomics shape2D.py + cshape.c:calculate_coefficients2D (SURVEY.md section 8 f rank 1), mask only:
 // marching squares over the zero-padded mask.  Everything reduces to integers: the perimeter is
@@ -1195,6 +1219,31 @@ __global__ void __launch_bounds__(RADB_NT, 8) radb_misc_kernel(const RadbParams 
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
     radb_misc_cta(p, (long long)blockIdx.x, radb_smem);
+}
+// per-image max of uint8 pixels (|x| = x), then the point-wise transform
+__global__ void radb_image_max_kernel(const unsigned char* img, long long n_images, long long HW, int* mx)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long words = (HW + 3) / 4;
+    int m = 0;
+    long long image = 0;
+    if (t < n_images * words) {
+        image = t / words;
+        const long long p0 = (t - image * words) * 4;
+        const unsigned char* s = img + image * HW + p0;
+        const int cnt = (int)(HW - p0 < 4 ? HW - p0 : 4);
+        for (int k = 0; k < cnt; k++) m = s[k] > m ? s[k] : m;
+    }
+    // lanes of a warp may straddle two images only at image boundaries: plain atomics are enough
+    if (t < n_images * words && m) atomicMax(&mx[image], m);
+}
+__global__ void radb_derive_kernel(const unsigned char* img, long long n_images, long long HW, const int* mx, int type,
+                                   double* out)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= n_images * HW) return;
+    const long long image = t / HW;
+    out[t] = radb_derive_px(type, (double)img[t], (double)mx[image]);
 }
 __global__ void radb_bgr_planes_kernel(const unsigned char* bgr, unsigned char* planes, long long n_images, long long HW)
 {

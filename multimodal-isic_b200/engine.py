@@ -97,7 +97,7 @@ class Engine:
             raise RadbError("radb_extract failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
         return out, status
 
-    def extract_bgr(self, bgr, masks, stream=None):
+    def extract_bgr(self, bgr, masks, stream=None, return_planes=False):
         """Decoded records in, four feature rows per record out (gray, R, G, B): ``bgr`` [n, H, W, 3]
         uint8 (cv2.imread layout), ``masks`` [n, H, W] uint8, both on the device.  The gray/R/G/B planes
         are produced by the front-end kernel; the four executes share the mask."""
@@ -117,7 +117,24 @@ class Engine:
                                        out.data_ptr(), status.data_ptr(), st.cuda_stream)
         if rc != 0:
             raise RadbError("radb_extract_bgr failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+        if return_planes:
+            return out, status, planes
         return out, status
+
+    def derive_image(self, images, type_code, stream=None):
+        """Point-wise derived image type (1 Square, 2 SquareRoot, 3 Logarithm, 4 Exponential) of uint8
+        device images [B, H, W] -> float64 [B, H, W] (pyradiomics imageoperations.get*Image)."""
+        if images.dtype != torch.uint8 or not images.is_cuda or not images.is_contiguous():
+            raise ValueError("derive_image takes contiguous uint8 CUDA images")
+        B, H, W = images.shape
+        out = torch.empty((B, H, W), dtype=torch.float64, device=images.device)
+        mx = torch.empty((B,), dtype=torch.int32, device=images.device)
+        st = stream if stream is not None else torch.cuda.current_stream(images.device)
+        rc = self.lib.radb_derive_image(self._h, images.data_ptr(), B, H * W, int(type_code), out.data_ptr(),
+                                        mx.data_ptr(), st.cuda_stream)
+        if rc != 0:
+            raise RadbError("radb_derive_image failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+        return out
 
     def debug_matrices(self, images, masks):
         """Features plus the integer matrices (numpy, trimmed to shapes the oracle uses)."""

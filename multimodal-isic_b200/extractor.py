@@ -14,7 +14,7 @@ import torch
 
 from . import _abi
 from .engine import Engine, HostPipeline
-from .settings import Settings
+from .settings import IMAGE_TYPE_CODES, Settings
 
 logger = logging.getLogger(__name__)
 
@@ -49,6 +49,15 @@ class RadiomicsExtractor:
         self._engine_args = (self.params.bin_width, self.params.label, self.params.angles(2),
                              bool(s["symmetricalGLCM"]), float(s["gldm_a"]), float(s["voxelArrayShift"]), eng_classes)
         self._engines_ng = {}  # engines for non-uint8 pixels, keyed by their gray-level bound
+        # derived image types (params.yml:141-144) are float64 images in the original intensity range
+        self.derived_types = [t for t in self.params.image_types if t != "Original"]
+        self._has_original = "Original" in self.params.image_types
+        self._derived_engine = None
+        if self.derived_types:
+            tex_classes = [c for c in eng_classes if c != "shape2D"]
+            self._derived_engine = Engine(self.params.bin_width, self.params.label, self.params.angles(2),
+                                          bool(s["symmetricalGLCM"]), float(s["gldm_a"]), float(s["voxelArrayShift"]),
+                                          tex_classes, min(255, int(255.0 // self.params.bin_width) + 3), self.device)
         self.feature_names = self.params.feature_names()
         self._perm_t = None
         self._identity = self._perm == list(range(self.engine.F))
@@ -91,7 +100,12 @@ class RadiomicsExtractor:
                 part = idxs[s0:s0 + per]
                 bgr = torch.as_tensor(np.stack([loaded[i][0] for i in part])).to(dev, non_blocking=True)
                 msk = torch.as_tensor(np.stack([loaded[i][1] for i in part])).to(dev, non_blocking=True)
-                out, status = self.engine.extract_bgr(bgr, msk)
+                if self.derived_types or not self._has_original:
+                    out, status, planes = self.engine.extract_bgr(bgr, msk, return_planes=True)
+                    out, status = self._device_blocks(planes.view(-1, H, W), msk.repeat_interleave(4, dim=0),
+                                                      first=(out, status))
+                else:
+                    out, status = self.engine.extract_bgr(bgr, msk)
                 feats = self._permute(out).cpu().numpy()
                 status = status.cpu().numpy()
                 if status.any():  # the reference has no try/except: pyradiomics' ValueError aborts the run
@@ -162,6 +176,8 @@ class RadiomicsExtractor:
         host arrays -> NumPy arrays through the pinned, chunk-pipelined path.
         ``strict=True`` raises the ValueError pyradiomics would raise for an invalid ROI
         (the reference has no try/except, RadiomicExtractor.py:23-55); otherwise such rows are NaN."""
+        if self.derived_types or not self._has_original:
+            return self._extract_multi_type(images, masks, strict)
         engine, pipeline = self._engine_for(images, masks)
         if isinstance(images, torch.Tensor) and images.is_cuda:
             out, status = engine.extract_device(images, masks)
@@ -177,6 +193,42 @@ class RadiomicsExtractor:
         if strict and status.any():
             raise _status_error(int(status[np.nonzero(status)[0][0]]), self.params.label)
         return out, status
+
+
+    # ---- several image types ------------------------------------------------------------------
+    def _device_blocks(self, images, masks, first=None):
+        """[shape | block per image type] for uint8 device images; ``first`` = precomputed (out, status) of
+        the Original/shape engine."""
+        if images.dtype != torch.uint8:
+            raise NotImplementedError("derived image types are implemented for uint8 input images")
+        out0, status = first if first is not None else self.engine.extract_device(images, masks)
+        nshape = 9 if "shape2D" in self.params.classes else 0
+        blocks = [out0 if self._has_original else out0[:, :nshape]]
+        for t in self.derived_types:
+            der = self.engine.derive_image(images, IMAGE_TYPE_CODES[t])
+            o, st = self._derived_engine.extract_device(der, masks)
+            blocks.append(o)
+            status = torch.maximum(status, st)
+        return torch.cat(blocks, dim=1), status
+
+    def _extract_multi_type(self, images, masks, strict):
+        on_device = isinstance(images, torch.Tensor) and images.is_cuda
+        dev = torch.device("cuda", self.device)
+        if on_device:
+            out, status = self._device_blocks(images, masks)
+            out = self._permute(out)
+        else:
+            images, masks = torch.as_tensor(images), torch.as_tensor(masks)
+            outs, sts = [], []
+            for s0 in range(0, len(images), self.pipeline.chunk):
+                o, st = self._device_blocks(images[s0:s0 + self.pipeline.chunk].to(dev),
+                                            masks[s0:s0 + self.pipeline.chunk].to(dev))
+                outs.append(self._permute(o).cpu())
+                sts.append(st.cpu())
+            out, status = torch.cat(outs), torch.cat(sts)
+        if strict and bool((status != 0).any()):
+            raise _status_error(int(status[status != 0][0]), self.params.label)
+        return (out, status) if on_device else (out.numpy(), status.numpy())
 
 
 def features_to_dataframe(results, suffixes=("gs", "red", "green", "blue")):

@@ -48,7 +48,8 @@ FEATURE_NAMES = {
                 "PerimeterSurfaceRatio", "PixelSurface", "Sphericity"],
 }
 SUPPORTED_CLASSES = set(CLASS_ORDER) | {"shape2D"}
-SUPPORTED_IMAGE_TYPES = {"Original"}
+SUPPORTED_IMAGE_TYPES = {"Original", "Square", "SquareRoot", "Logarithm", "Exponential"}
+IMAGE_TYPE_CODES = {"Square": 1, "SquareRoot": 2, "Logarithm": 3, "Exponential": 4}  # radb_derive_image
 # settings whose non-default value would change results and that the engine does not implement
 _UNSUPPORTED_IF_SET = ("normalize", "removeOutliers", "resampledPixelSpacing", "resegmentRange", "weightingNorm",
                        "binCount", "minimumROISize")
@@ -124,11 +125,10 @@ class Settings:
             raise ValueError("binWidth must be > 0")
         skipped_types = [t for t in self.enabledImagetypes if t not in SUPPORTED_IMAGE_TYPES]
         if skipped_types:
-            self._complain("image types %s are not implemented yet; only 'Original' features are computed"
-                           % skipped_types)
+            self._complain("image types %s are not implemented yet and are skipped" % skipped_types)
         self.image_types = [t for t in self.enabledImagetypes if t in SUPPORTED_IMAGE_TYPES]
         if not self.image_types:
-            raise NotImplementedError("no implemented image type is enabled (need 'Original')")
+            raise NotImplementedError("no implemented image type is enabled")
         skipped_cls = [c for c in self.enabledFeatures if c not in SUPPORTED_CLASSES]
         if skipped_cls:
             self._complain("feature classes %s are not implemented yet and are skipped" % skipped_cls)
@@ -158,20 +158,29 @@ class Settings:
         s = self.settings
         return in_plane_angles(ndim, s["distances"], bool(s["force2D"]), int(s["force2Ddimension"]))
 
+    def _class_features(self, c):
+        sel = self.enabledFeatures[c]
+        return [f for f in FEATURE_NAMES[c] if not sel or f in sel]
+
     def feature_names(self):
-        """Output keys in pyradiomics order: image type, then class (file order), then A.2 order."""
+        """Output keys in pyradiomics order: shape descriptors first (A.1 step 3, always ``original_``),
+        then for every enabled image type (file order) every class (file order) in A.2 order."""
         names = []
-        # shape descriptors are computed first, whatever their position in the file (A.1 step 3)
-        for c in sorted(self.classes, key=lambda c: c != "shape2D"):
-            sel = self.enabledFeatures[c]
-            for f in FEATURE_NAMES[c]:
-                if not sel or f in sel:
-                    names.append("original_%s_%s" % (c, f))
+        if "shape2D" in self.classes:
+            names += ["original_shape2D_%s" % f for f in self._class_features("shape2D")]
+        for t in self.image_types:
+            for c in self.classes:
+                if c != "shape2D":
+                    names += ["%s_%s_%s" % (t.lower(), c, f) for f in self._class_features(c)]
         return names
 
     def engine_columns(self):
-        """(engine class order, column permutation) mapping engine rows to ``feature_names()``."""
+        """(engine classes, column permutation): the engine emits, per image type, the classes in its fixed
+        order with all their features; the extractor concatenates [shape | block(type 1) | block(type 2) ...].
+        ``perm`` maps that super-row to ``feature_names()``."""
         eng_classes = [c for c in ("shape2D",) + tuple(CLASS_ORDER) if c in self.classes]
-        eng_names = ["original_%s_%s" % (c, f) for c in eng_classes for f in FEATURE_NAMES[c]]
+        eng_names = ["original_shape2D_%s" % f for f in FEATURE_NAMES["shape2D"]] if "shape2D" in eng_classes else []
+        for t in self.image_types:
+            eng_names += ["%s_%s_%s" % (t.lower(), c, f) for c in eng_classes if c != "shape2D" for f in FEATURE_NAMES[c]]
         pos = {n: i for i, n in enumerate(eng_names)}
         return eng_classes, [pos[n] for n in self.feature_names()]

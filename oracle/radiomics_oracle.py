@@ -628,6 +628,36 @@ def shape2d_features(mask_arr, spacing=(1.0, 1.0)):
     return f
 
 
+# --------------------------------------------------------------------------- derived image types
+def derived_image(image, image_type):
+    """pyradiomics ``imageoperations.get{Square,SquareRoot,Logarithm,Exponential}Image`` (params.yml:141-144):
+    point-wise transforms of the WHOLE image in float64, rescaled to the original intensity range.
+    Returns ``(array, name)`` with the lower-case name pyradiomics prefixes the feature keys with."""
+    im = np.asarray(image).astype("float64")
+    if image_type == "Original":
+        return np.asarray(image), "original"
+    if image_type == "Square":
+        coeff = 1 / np.sqrt(np.max(np.abs(im)))
+        return (coeff * im) ** 2, "square"
+    if image_type == "SquareRoot":
+        coeff = np.max(np.abs(im))
+        out = im.copy()
+        out[im > 0] = np.sqrt(im[im > 0] * coeff)
+        out[im < 0] = -np.sqrt(-im[im < 0] * coeff)
+        return out, "squareroot"
+    if image_type == "Logarithm":
+        im_max = np.max(np.abs(im))
+        out = im.copy()
+        out[im > 0] = np.log(im[im > 0] + 1)
+        out[im < 0] = -np.log(-(im[im < 0] - 1))
+        return out * (im_max / np.max(np.abs(out))), "logarithm"
+    if image_type == "Exponential":
+        im_max = np.max(np.abs(im))
+        coeff = np.log(im_max) / im_max
+        return np.exp(coeff * im), "exponential"
+    raise ValueError("image type %r is not restated in the oracle" % image_type)
+
+
 # --------------------------------------------------------------------------- execute
 def resolve_settings(settings=None):
     s = dict(DEFAULT_SETTINGS)
@@ -659,6 +689,19 @@ def matrices(image, mask, settings=None, matrix_backend=None):
         out["glszm"] = mb.glszm(levels, Ng, bi)
         out["gldm"] = mb.gldm(levels, Ng, bi, s["gldm_a"])
         out["ngtdm_n"], out["ngtdm_s"] = mb.ngtdm(levels, Ng, bi)
+    return out
+
+
+def execute_image_types(image, mask, settings=None, classes=CLASS_ORDER, image_types=("Original",), matrix_backend=None):
+    """``execute`` over several enabled image types in file order: shape first (once), then one block of
+    texture / first-order features per image type, keys prefixed with the image-type name."""
+    out = OrderedDict()
+    if "shape2D" in classes:
+        out.update(execute(image, mask, settings, classes=("shape2D",)))
+    rest = tuple(c for c in classes if c != "shape2D")
+    for t in image_types:
+        arr, name = derived_image(image, t)
+        out.update(execute(arr, mask, settings, classes=rest, image_type=name, matrix_backend=matrix_backend))
     return out
 
 

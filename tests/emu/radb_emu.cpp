@@ -99,3 +99,13 @@ extern "C" void radb_emu_bgr_planes(const uint8_t* bgr, uint8_t* planes, int64_t
     const long long threads = n_images * ((HW + 3) / 4);
     for (long long q = 0; q < threads; q++) radb_bgr_planes_thread(bgr, planes, n_images, HW, q);
 }
+
+// Host twin of radb_image_max_kernel + radb_derive_kernel.
+extern "C" void radb_emu_derive(const uint8_t* img, int64_t n_images, int64_t HW, int type, double* out)
+{
+    for (int64_t i = 0; i < n_images; i++) {
+        int m = 0;
+        for (int64_t k = 0; k < HW; k++) m = img[i * HW + k] > m ? img[i * HW + k] : m;
+        for (int64_t k = 0; k < HW; k++) out[i * HW + k] = radb_derive_px(type, (double)img[i * HW + k], (double)m);
+    }
+}

@@ -134,3 +134,16 @@ def test_dataframe_contract():
     assert df.columns[0] == names[0] + "_gs" and df.columns[93] == names[0] + "_red"
     assert df.columns[-1] == names[-1] + "_blue"
     assert all(str(t) == "float64" for t in df.dtypes)
+
+
+def test_settings_derived_image_types():
+    p = yaml.safe_load(REFERENCE_LIKE_PARAMS)
+    p["imageType"].update({"Square": {}, "SquareRoot": {}, "Logarithm": {}, "Exponential": {}, "Gradient": {}})
+    with pytest.warns(RuntimeWarning, match="Wavelet"):
+        s = pkg.Settings(p)
+    assert s.image_types == ["Original", "Square", "SquareRoot", "Logarithm", "Exponential"]
+    names = s.feature_names()
+    assert len(names) == 102 + 4 * 93                      # shape once, one 93-block per image type
+    assert names[:9] == ["original_shape2D_%s" % f for f in orc.SHAPE2D_NAMES]
+    assert names[102] == "square_firstorder_10Percentile" and names[-1] == "exponential_ngtdm_Strength"
+    assert s.engine_columns()[1] == list(range(len(names)))

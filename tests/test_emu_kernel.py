@@ -164,3 +164,20 @@ def test_emu_other_pixel_types(emu, dt):
     imgs[2] = 37.25 if dt != np.uint16 else 640
     r = emu.run(imgs, masks, bw, 255, INPLANE, max_ng=40)
     assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=bw, force2D=False)) == 3
+
+
+def test_emu_derived_image_types(emu):
+    # Square / SquareRoot / Logarithm / Exponential (params.yml:141-144): transform, then the f64 engine path
+    import ctypes
+
+    imgs, masks = synth.make_patches(2, 40, 44, seed=9)
+    emu.lib.radb_emu_derive.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int64, ctypes.c_int, ctypes.c_void_p]
+    for code, name in ((1, "Square"), (2, "SquareRoot"), (3, "Logarithm"), (4, "Exponential")):
+        out = np.zeros(imgs.shape, np.float64)
+        emu.lib.radb_emu_derive(imgs.ctypes.data, 2, 40 * 44, code, out.ctypes.data)
+        for b in range(2):
+            ref, prefix = orc.derived_image(imgs[b], name)
+            np.testing.assert_allclose(out[b], ref, rtol=1e-14, atol=1e-13)
+            assert prefix == name.lower()
+        r = emu.run(out, masks, 10, 255, LITERAL, max_ng=32)
+        assert compare_with_oracle(r, out, masks, dict(label=255, binWidth=10, force2D=True)) == 2

@@ -323,3 +323,39 @@ def test_float_wide_mode(gpu_pkg):
     eng = gpu_pkg.Engine(5.0, 255, LITERAL, max_ng=64)
     r = eng.debug_matrices(torch.as_tensor(imgs).cuda(), torch.as_tensor(masks).cuda())
     assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=5.0, force2D=True)) == 1
+
+
+def test_derived_image_types_batch_and_record_path(gpu_pkg, tmp_path):
+    """params.yml:137-145 with the point-wise image types: shape once, then a 93-feature block per type
+    (original_, square_, squareroot_, logarithm_, exponential_), on tensors and on decoded records."""
+    import cv2
+
+    params = {"setting": {"label": 255, "binWidth": 10, "force2D": True},
+              "imageType": {"Original": {}, "Square": {}, "SquareRoot": {}, "Logarithm": {}, "Exponential": {}},
+              "featureClass": {c: [] for c in ("firstorder", "shape2D", "glcm", "gldm", "glrlm", "glszm", "ngtdm")}}
+    types = list(params["imageType"])
+    ex = gpu_pkg.RadiomicsExtractor(params)
+    assert len(ex.feature_names) == 102 + 4 * 93
+    imgs, masks = gpu_pkg.synth.make_patches(3, 56, 48, seed=15)
+    out, st = ex.extract_batch(torch.as_tensor(imgs).cuda(), torch.as_tensor(masks).cuda())
+    out_h, _ = ex.extract_batch(imgs, masks)
+    np.testing.assert_array_equal(out.cpu().numpy(), out_h)
+    for b in range(3):
+        ref = orc.execute_image_types(imgs[b], masks[b], params["setting"], classes=ALL_CLASSES, image_types=types,
+                                      matrix_backend=cmatrices)
+        assert list(ref.keys()) == ex.feature_names
+        np.testing.assert_allclose(out_h[b], list(ref.values()), rtol=RTOL, atol=ATOL)
+    # record path (cv2 files -> BGR front-end -> every image type of every plane)
+    rng = np.random.default_rng(1)
+    bgr = np.stack([np.clip(imgs[0].astype(int) + rng.integers(-20, 20, imgs[0].shape), 0, 255) for _ in range(3)],
+                   -1).astype(np.uint8)
+    ip, sp = str(tmp_path / "i.png"), str(tmp_path / "s.png")
+    cv2.imwrite(ip, bgr)
+    cv2.imwrite(sp, masks[0])
+    res = ex.extract_radiomics({"image_path": ip, "segmentation_path": sp})
+    gray = cv2.cvtColor(bgr, cv2.COLOR_BGR2GRAY)
+    for ch, arr in (("grayscale", gray), ("blue", bgr[:, :, 0])):
+        ref = orc.execute_image_types(arr, masks[0], params["setting"], classes=ALL_CLASSES, image_types=types,
+                                      matrix_backend=cmatrices)
+        assert list(res[ch].keys()) == list(ref.keys())
+        np.testing.assert_allclose(list(res[ch].values()), list(ref.values()), rtol=RTOL, atol=ATOL)
