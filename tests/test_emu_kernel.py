@@ -181,3 +181,24 @@ def test_emu_derived_image_types(emu):
             assert prefix == name.lower()
         r = emu.run(out, masks, 10, 255, LITERAL, max_ng=32)
         assert compare_with_oracle(r, out, masks, dict(label=255, binWidth=10, force2D=True)) == 2
+
+
+def test_emu_address_sanitizer(tmp_path):
+    """The kernel source, emulated thread for thread, under AddressSanitizer: out-of-bounds accesses to
+    the global buffers / the shared-memory arena abort the run (stand-in for compute-sanitizer memcheck,
+    which is closed on the GPU pool)."""
+    import subprocess
+    import sys
+
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    asan = subprocess.run(["gcc", "-print-file-name=libasan.so"], capture_output=True, text=True).stdout.strip()
+    if not os.path.isabs(asan) or not os.path.exists(asan):
+        pytest.skip("libasan not available")
+    so = str(tmp_path / "libradb_emu_asan.so")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++20", "-fPIC", "-shared", "-pthread", "-fsanitize=address",
+                           "-fno-omit-frame-pointer", "-o", so, os.path.join(root, "tests", "emu", "radb_emu.cpp")])
+    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "emu", "asan_cases.py"), so], env=env,
+                       capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stderr[-2000:]
+    assert "u16 [0 0]" in r.stdout
