@@ -194,7 +194,7 @@ __device__ __forceinline__ int sturm_count(const double* d, const double* e2, in
 __device__ double tridiag_kth(const double* d, const double* e2, int m, int k, double lo, double hi,
                               int lane)
 {
-    for (int it = 0; it < 8; it++) {
+    for (int it = 0; it < 7; it++) {
         double w = (hi - lo) * (1.0 / 33.0);
         double x = lo + w * (double)(lane + 1);
         int c = sturm_count(d, e2, m, x);
@@ -205,7 +205,7 @@ __device__ double tridiag_kth(const double* d, const double* e2, int m, int k, d
         double nhi = (nl == 32) ? hi : lo + w * (double)(nl + 1);
         lo = nlo;
         hi = nhi;
-        if (hi - lo <= 2e-11) break;  // eigenvalues live in [-1, 1]; the feature needs rtol 1e-6
+        if (hi - lo <= 1e-10) break;  // eigenvalues live in [-1, 1] (33^7 = 4e10 shrink); the feature needs rtol 1e-6
     }
     return 0.5 * (lo + hi);
 }
@@ -253,7 +253,11 @@ __device__ double mcc_task(const int* P, const int* px, const int* py, int n, in
         }
     }
     __syncwarp();
-    // Householder tridiagonalisation, column k eliminates rows k+2..m-1
+    // Householder tridiagonalisation, column k eliminates rows k+2..m-1.  Small matrices (m <= 16) would
+    // leave most lanes idle with one lane per row: L = 4 / 2 / 1 consecutive lanes share a row and split
+    // its columns (c = first + sub, first + sub + L, ...), combined with xor shuffles.
+    const int L = m <= 8 ? 4 : (m <= 16 ? 2 : 1);
+    const int rpi = 32 / L, roff = lane / L, sub = lane & (L - 1);
     for (int k = 0; k < m - 2; k++) {
         double part = 0;
         for (int r = k + 2 + lane; r < m; r += 32) { double x = M[tri(r, k)]; part += x * x; }
@@ -273,25 +277,32 @@ __device__ double mcc_task(const int* P, const int* px, const int* py, int n, in
         __syncwarp();
         // w = beta * M22 v
         double kpart = 0;
-        for (int r = k + 1 + lane; r < m; r += 32) {
+        for (int r0 = k + 1; r0 < m; r0 += rpi) {
+            const int r = r0 + roff;
             double s = 0;
-            const int rb = tri(r, 0);
-            for (int c = k + 1; c <= r; c++) s += M[rb + c] * v[c];
-            int ix = tri(r + 1, r);
-            for (int c = r + 1; c < m; c++) { s += M[ix] * v[c]; ix += c + 1; }
-            s *= beta;
-            w[r] = s;
-            kpart += s * v[r];
+            if (r < m) {
+                const int rb = tri(r, 0);
+                for (int c = k + 1 + sub; c < m; c += L) s += (c <= r ? M[rb + c] : M[tri(c, r)]) * v[c];
+            }
+            for (int mm = 1; mm < L; mm <<= 1) s += __shfl_xor_sync(FULLMASK, s, mm);
+            if (r < m && sub == 0) {
+                s *= beta;
+                w[r] = s;
+                kpart += s * v[r];
+            }
         }
-        double K = 0.5 * beta * warp_sum(kpart);
+        const double K = 0.5 * beta * warp_sum(kpart);
         __syncwarp();
-        for (int r = k + 1 + lane; r < m; r += 32) w[r] -= K * v[r];
-        __syncwarp();
-        // M22 -= v w^T + w v^T (lower triangle)
-        for (int r = k + 1 + lane; r < m; r += 32) {
-            const double vr = v[r], wr = w[r];
+        // M22 -= v w'^T + w' v^T with w' = w - K v (lower triangle)
+        for (int r0 = k + 1; r0 < m; r0 += rpi) {
+            const int r = r0 + roff;
+            if (r >= m) continue;
+            const double vr = v[r], wr = w[r] - K * vr;
             const int rb = tri(r, 0);
-            for (int c = k + 1; c <= r; c++) M[rb + c] -= vr * w[c] + wr * v[c];
+            for (int c = k + 1 + sub; c <= r; c += L) {
+                const double vc = v[c];
+                M[rb + c] -= vr * (w[c] - K * vc) + wr * vc;
+            }
         }
         __syncwarp();
         if (lane == 0) { d[k] = M[tri(k, k)]; e2[k] = alpha * alpha; }
@@ -341,27 +352,35 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
     long long sN = 0, sI = 0, sJ = 0, sIJ = 0, sD2 = 0, sC2 = 0;
     double sclog = 0;
     int maxc = 0, nnz = 0;
-    for (int i = 0; i < n; i++) {
+    // Small matrices (n <= 16: binWidth 25 gives n <= 11) would leave most lanes idle with one row per
+    // warp iteration: the warp is split into 32/gw groups of gw lanes and every group takes its own row.
+    const int gw = n <= 8 ? 8 : (n <= 16 ? 16 : 32);
+    const int ngrp = 32 / gw, gi = lane / gw, gl = lane & (gw - 1);
+    for (int i0 = 0; i0 < n; i0 += ngrp) {
+        const int i = i0 + gi;
         int rs = 0;
-        for (int j = lane; j < n; j += 32) {
-            const int c = P[i * n + j];
-            if (c) {
-                rs += c;
-                sIJ += (long long)c * (i + 1) * (j + 1);
-                sD2 += (long long)c * (i - j) * (i - j);
-                sC2 += (long long)c * c;
-                sJ += (long long)c * (j + 1);
-                nnz++;
-                maxc = c > maxc ? c : maxc;
-                if (!sym) py[j] += c;  // lane (j mod 32) owns column j
-                atomicAdd(&padd[i + j], c);
-                atomicAdd(&psub[i > j ? i - j : j - i], c);
+        if (i < n)
+            for (int j = gl; j < n; j += gw) {
+                const int c = P[i * n + j];
+                if (c) {
+                    rs += c;
+                    sIJ += (long long)c * (i + 1) * (j + 1);
+                    sD2 += (long long)c * (i - j) * (i - j);
+                    sC2 += (long long)c * c;
+                    sJ += (long long)c * (j + 1);
+                    nnz++;
+                    maxc = c > maxc ? c : maxc;
+                    if (!sym) atomicAdd(&py[j], c);
+                    atomicAdd(&padd[i + j], c);
+                    atomicAdd(&psub[i > j ? i - j : j - i], c);
+                }
             }
+        rs = group_sum_i(rs, gw, lane);
+        if (gl == 0 && i < n) {
+            px[i] = rs;
+            sN += rs;
+            sI += (long long)rs * (i + 1);
         }
-        rs = warp_sum_i(rs);
-        if (lane == 0) px[i] = rs;
-        sN += (lane == 0) ? rs : 0;
-        sI += (lane == 0) ? (long long)rs * (i + 1) : 0;
     }
     sN = warp_sum_ll(sN);
     __syncwarp();
@@ -411,10 +430,12 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
     ny = warp_sum_i(ny);
     // pass B: cluster moments and correlation terms
     double ct = 0, cs = 0, cp = 0, ssq = 0, ssqy = 0, corm = 0, h1corr = 0;
-    for (int i = 0; i < n; i++) {
+    for (int i0 = 0; i0 < n; i0 += ngrp) {
+        const int i = i0 + gi;
+        if (i >= n) continue;
         const double di = (double)(i + 1) - ux;
         const double rpxi = rpx[i];
-        for (int j = lane; j < n; j += 32) {
+        for (int j = gl; j < n; j += gw) {
             const int c = P[i * n + j];
             if (!c) continue;
             const double dc = (double)c;

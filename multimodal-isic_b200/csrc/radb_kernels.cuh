@@ -102,6 +102,26 @@ __device__ __forceinline__ int warp_max_i(int v)
 #endif
 }
 __device__ __forceinline__ int warp_min_i(int v) { return -warp_max_i(-v); }
+// segmented sum: lanes are split into groups of `w` consecutive lanes (w = 8, 16 or 32, warp-uniform);
+// every lane gets the sum of its group
+__device__ __forceinline__ int group_sum_i(int v, int w, int lane)
+{
+#ifdef RADB_EMU
+    int all[32];
+    emu::gather<int>(v, all);
+    int s = 0;
+    for (int i = lane - (lane & (w - 1)), e = i + w; i < e; i++) s += all[i];
+    return s;
+#else
+    (void)lane;
+#pragma unroll
+    for (int m = 16; m >= 1; m >>= 1) {
+        const int t = __shfl_xor_sync(FULLMASK, v, m);
+        if (m < w) v += t;
+    }
+    return v;
+#endif
+}
 // exclusive prefix sum over lanes
 __device__ __forceinline__ int warp_excl_scan_i(int v, int lane)
 {
