@@ -49,14 +49,11 @@ def main():
     lines += ["", "DRAM bytes per launch (read + write): " + ", ".join("%s %.1f MB" % (k, v / 1e6) for k, v in traffic.items()),
               "= %.0f B per patch over the pass (grid %d patches); algorithmic bytes 8 936 B/patch." % (sum(traffic.values()) / grid, grid)]
     src = ncu(["-i", rep, "--page", "source", "--csv", "--print-source", "cuda,sass"])
-    for blk in re.split(r'(?m)^"Function Name",', src)[1:]:
-        rows = list(csv.reader(io.StringIO('"Function Name",' + blk)))
-        fname = re.sub(r"\(.*", "", rows[0][1]).replace("void ", "")
-        fpath = ""
+    for blk in re.split(r'(?m)^"File Path",', src)[1:]:
+        rows = list(csv.reader(io.StringIO('"File Path",' + blk)))
+        fpath = rows[0][1].split("/")[-1]
+        fname = re.sub(r"\(.*", "", rows[1][1]).replace("void ", "")
         hi = next(i for i, r in enumerate(rows) if r and r[0] == "Line No")
-        for r in rows[:hi]:
-            if r and r[0] == "File Path":
-                fpath = r[1].split("/")[-1]
         if not fpath.startswith("radb_"):
             continue
         h = rows[hi]
