@@ -236,10 +236,13 @@ __device__ double mcc_task(const int* P, const int* px, const int* py, int n, in
     // d doubles as scratch for 1/radb_sqrt(px) while the matrix is built (d is first written below)
     for (int r = lane; r < m; r += 32) d[r] = radb_div(1.0, radb_sqrt((double)px[idx[r]]));
     __syncwarp();
-    for (int r = 0; r < m; r++) {
+    const int bgw = m <= 8 ? 8 : (m <= 16 ? 16 : 32), bng = 32 / bgw;
+    for (int r0 = 0; r0 < m; r0 += bng) {
+        const int r = r0 + lane / bgw;
+        if (r >= m) continue;
         const int ir = idx[r];
         const double rr = d[r];
-        for (int c = lane; c <= r; c += 32) {
+        for (int c = lane & (bgw - 1); c <= r; c += bgw) {
             const int ic = idx[c];
             double val;
             if (symmetric) {
@@ -530,20 +533,25 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
 
 // ------------------------------------------------------------------ GLRLM features (one warp, one angle)
 // A.7.  R = run counters [n][nr] (packed u16, or u32 in wide mode); pr = int scratch [nr] (zeroed).
-__device__ int glrlm_task(const RadbTabs& tb, const unsigned* R, int wide, int n, int nr, int* pr, double* o,
-                          int lane)
+__device__ int glrlm_task(const RadbTabs& tb, const unsigned* R, int wide, int n, int nr, int maxlen, int* pr,
+                          double* o, int lane)
 {
     long long sN = 0, sGI = 0, sGI2 = 0, sG2 = 0;
     double lgl = 0, e1 = 0, srl = 0, srh = 0, lrl = 0, lrh = 0;
     int nnz = 0;
-    for (int i = 0; i < n; i++) {
+    // only run lengths 1..maxlen occur (recorded by the build kernel); short maxima let several rows
+    // share one warp iteration (groups of gw lanes, one row per group)
+    const int gw = maxlen <= 8 ? 8 : (maxlen <= 16 ? 16 : 32);
+    const int ngrp = 32 / gw, gi = lane / gw, gl = lane & (gw - 1);
+    for (int i0 = 0; i0 < n; i0 += ngrp) {
+        const int i = i0 + gi;
         int rs = 0;
-        const double i2 = (double)(i + 1) * (double)(i + 1), ri2 = tab_inv2(tb, i + 1);
-        for (int j = lane; j < nr; j += 32) {
+        const double i2 = (double)(i + 1) * (double)(i + 1), ri2 = tab_inv2(tb, i < n ? i + 1 : 1);
+        for (int j = gl; j < maxlen && i < n; j += gw) {
             const int c = get_run(R, i * nr + j, wide);
             if (!c) continue;
             rs += c;
-            pr[j] += c;
+            if (ngrp == 1) pr[j] += c; else atomicAdd(&pr[j], c);
             const double dc = (double)c, j2 = (double)(j + 1) * (double)(j + 1), rj2 = tab_inv2(tb, j + 1);
             e1 += tab_clog(tb, c);
             nnz++;
@@ -552,8 +560,8 @@ __device__ int glrlm_task(const RadbTabs& tb, const unsigned* R, int wide, int n
             lrl += dc * j2 * ri2;
             lrh += dc * i2 * j2;
         }
-        rs = warp_sum_i(rs);
-        if (lane == 0 && rs) {
+        rs = group_sum_i(rs, gw, lane);
+        if (gl == 0 && rs) {
             sN += rs;
             sGI += (long long)rs * (i + 1);
             sGI2 += (long long)rs * (i + 1) * (i + 1);
@@ -573,7 +581,7 @@ __device__ int glrlm_task(const RadbTabs& tb, const unsigned* R, int wide, int n
     nnz = warp_sum_i(nnz);
     long long sRJ = 0, sRJ2 = 0, sR2 = 0;
     double sre = 0;
-    for (int j = lane; j < nr; j += 32) {
+    for (int j = lane; j < maxlen; j += 32) {
         const int c = pr[j];
         if (!c) continue;
         sRJ += (long long)c * (j + 1);

@@ -726,6 +726,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             int first = tid - (t0 % RADB_NTB);
             if (first < 0) first += RADB_NTB;
             unsigned* R = (unsigned*)(glrlm_base + a * p.glrlm_stride);
+            int mylen = 0;  // longest run this thread saw: one atomicMax per thread, not per run
             for (int l = first; l < nlines; l += RADB_NTB) {
                 int cur = 0, len = 0;
                 if (dy == 0) {
@@ -737,6 +738,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                             if (cur) {
                                 add_run<WIDE>(R, (cur - 1) * nr + len - 1);
                                 lab[lbase + st] = ((UW)len << US) | (UW)(lbase + st);
+                                mylen = len > mylen ? len : mylen;
                             }
                             cur = g;
                             len = 0;
@@ -748,6 +750,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                     if (cur) {
                         add_run<WIDE>(R, (cur - 1) * nr + len - 1);
                         lab[lbase + st] = ((UW)len << US) | (UW)(lbase + st);
+                        mylen = len > mylen ? len : mylen;
                     }
                 } else {
                     const int sdx = dx * dy;  // x step per +1 in y (runs are direction-agnostic)
@@ -756,7 +759,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                     for (int y = 0; y < bh; y++) {
                         const int g = lev[pos + x];
                         if (g != cur || brk) {
-                            if (cur) add_run<WIDE>(R, (cur - 1) * nr + len - 1);
+                            if (cur) { add_run<WIDE>(R, (cur - 1) * nr + len - 1); mylen = len > mylen ? len : mylen; }
                             cur = g;
                             len = 0;
                         }
@@ -767,9 +770,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                         if (x >= bw) { x = 0; brk = 1; }          // wrapped diagonal: the next pixel is not
                         else if (x < 0) { x = bw - 1; brk = 1; }  // a neighbour of this one
                     }
-                    if (cur) add_run<WIDE>(R, (cur - 1) * nr + len - 1);
+                    if (cur) { add_run<WIDE>(R, (cur - 1) * nr + len - 1); mylen = len > mylen ? len : mylen; }
                 }
             }
+            if (mylen) atomicMax(&misc[10 + a], mylen);  // record header: longest run of angle a
             t0 += nlines;
         }
     }
@@ -875,7 +879,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int c = lev[ctr];
         if (c && (a_row < 0 || lev[ctr - 1] != c)) {  // run start
             const int li = y * W + x;
-            const unsigned r = uf_find_ro<UW, UF<WIDE>::S>(lab, (unsigned)li);
+            // (path halving only rewrites non-root words, whose size half is static: safe next to the atomicAdd)
+            const unsigned r = uf_find<UW, UF<WIDE>::S>(lab, (unsigned)li);
             if (r != (unsigned)li) atomicAdd(&lab[r], (UW)(lab[li] & ~ULO));  // only roots are ever added to
         }
     }
@@ -976,7 +981,7 @@ __device__ void radb_angle_cta(const RadbParams& p, long long patch, unsigned ch
         for (int i = lane; i < (p.a_idx - p.a_px) / 4; i += 32) ((int*)(ws + p.a_px))[i] = 0;
         __syncwarp();
         const unsigned* R = (const unsigned*)(rec + (p.o_glrlm - p.o_rec) + a * p.glrlm_stride);
-        int ok = glrlm_task(tb, R, p.wide, ng, p.nr, (int*)(ws + p.a_pr), fsc + a * RADB_FSC_STRIDE + RADB_GLCM_NF, lane);
+        int ok = glrlm_task(tb, R, p.wide, ng, p.nr, misc[10 + a], (int*)(ws + p.a_pr), fsc + a * RADB_FSC_STRIDE + RADB_GLCM_NF, lane);
         if (lane == 0) valid[4 + a] = ok;
         const int* P = (const int*)(rec + (p.o_glcm - p.o_rec)) + a * ng * ng;
         ok = glcm_task(p, tb, P, ng, (int*)(ws + p.a_px), (int*)(ws + p.a_py), (int*)(ws + p.a_padd),

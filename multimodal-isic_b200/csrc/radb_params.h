@@ -113,7 +113,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->o_lut = o; o += 256;
     p->o_fo = o; o += pix_bytes == 1 ? 16 : radb_align(64 * 8 + 16 * 8 + 10 * 8 + 10 * 8 + 10 * 4 + 10 * 4 + 8 + 10 * 256 * 4 + 64, 16);  // RADB_FO_SCRATCH
     p->o_rec = o;
-    p->o_misc = o; o += 32 * 4;           // record header: [0] Np, [5] #overflow zones, [8] Ng, [9] #levels present
+    p->o_misc = o; o += 32 * 4;           // record header: [0] Np, [5] #overflow zones, [8] Ng, [9] #levels present, [10+a] longest run of angle a
     p->o_hist = o; o += 256 * 4;
     p->o_lhist = o; o += radb_align(ng * 4, 16);
     p->o_glcm = o; o += radb_align(na * ng * ng * 4, 16);
