@@ -411,26 +411,25 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
         rpx[i] = a ? radb_div(N, (double)a) : 0.0;
         rpy[i] = b ? radb_div(1.0, (double)b) : 0.0;
         if (a) {
-            const double q = (double)a * rN;
-            hx -= q * radb_log2(q + RADB_EPS);
-            hx0 -= q * (tab_log2(tb, a) - log2N);
+            hx0 -= (double)a * rN * (tab_log2(tb, a) - log2N);
             nx++;
         }
         if (b) {
-            const double q = (double)b * rN;
-            hy -= q * radb_log2(q + RADB_EPS);
-            hy0 -= q * (tab_log2(tb, b) - log2N);
+            hy0 -= (double)b * rN * (tab_log2(tb, b) - log2N);
             ny++;
         }
     }
     __syncwarp();
     {
-        double r1[4] = {hx, hy, hx0, hy0};
+        double r1[2] = {hx0, hy0};
         warp_sum_n(r1, tb.red, lane);
-        hx = r1[0]; hy = r1[1]; hx0 = r1[2]; hy0 = r1[3];
+        hx0 = r1[0]; hy0 = r1[1];
     }
     nx = warp_sum_i(nx);
     ny = warp_sum_i(ny);
+    // HX = -sum px*log2(px + eps) = HX0 - nx*eps/ln2 to first order in eps (as for HXY)
+    hx = hx0 - RADB_EPS_LN2 * (double)nx;
+    hy = hy0 - RADB_EPS_LN2 * (double)ny;
     // pass B: cluster moments and correlation terms
     double ct = 0, cs = 0, cp = 0, ssq = 0, ssqy = 0, corm = 0, h1corr = 0;
     for (int i0 = 0; i0 < n; i0 += ngrp) {
@@ -472,7 +471,7 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
         if (!psub[k]) continue;
         const double q = (double)psub[k] * rN, dk = (double)k;
         da += dk * q;
-        de -= q * radb_log2(q + RADB_EPS);
+        de -= q * (tab_log2(tb, psub[k]) - log2N) + RADB_EPS_LN2;
         idv += radb_div(q, 1.0 + dk);
         idm += radb_div(q, 1.0 + dk * dk);
         idmn += radb_div(q, 1.0 + (dk * dk) * rdn * rdn);
@@ -485,7 +484,7 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
         if (!padd[k]) continue;
         const double q = (double)padd[k] * rN;
         sa += (double)(k + 2) * q;
-        se -= q * radb_log2(q + RADB_EPS);
+        se -= q * (tab_log2(tb, padd[k]) - log2N) + RADB_EPS_LN2;
     }
     {
         double r3[9] = {da, de, idv, idm, idmn, idn, iv, sa, se};

@@ -255,6 +255,13 @@ __device__ __forceinline__ int get_run(const unsigned* base, int cell, int wide)
     return wide ? (int)base[cell] : get_u16(base, cell);
 }
 
+// per-byte equality of two packed 4-byte words: 0x80 in every byte position where a == b (exact)
+__device__ __forceinline__ unsigned bytes_eq4(unsigned a, unsigned b)
+{
+    const unsigned t = a ^ b;
+    return ~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) & 0x80808080u;
+}
+
 // Python-style modulo (sign of the divisor), as numpy's % in imageoperations.getBinEdges
 __device__ __forceinline__ double py_mod(double a, double b)
 {
@@ -499,7 +506,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     const int US = UF<WIDE>::S;
     const UW ULO = (((UW)1) << US) - 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int H = p.H, W = p.W, HW = p.HW, WP = p.WP, NA = p.n_angles, NB = 2 * p.n_angles;
+    const int H = p.H, W = p.W, HW = p.HW, WP = p.WP, XO = p.xo, NA = p.n_angles, NB = 2 * p.n_angles;
     const PT* g_img = (const PT*)((const unsigned char*)p.img + patch * p.img_stride);
     const unsigned char* g_msk = p.mask + (patch / p.mask_group) * p.mask_stride;
     unsigned char* g_rec = p.ws + patch * (long long)p.rec_bytes;              // this patch's record (global)
@@ -574,6 +581,31 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     {
         int np = 0, ymin = H, ymax = -1, xmin = W, xmax = -1;
         double vmn = 1e308, vmx = -1e308;
+        if (U8 && p.vec4) {
+            // uint8 patches whose width is a multiple of 4: four pixels per 32-bit shared-memory load
+            const int WQ = W >> 2, NQ = HW >> 2;
+            const float inv_wq = 1.0f / (float)WQ;
+            const unsigned l4 = (unsigned)(p.label & 0xff) * 0x01010101u;
+            const unsigned* m4p = (const unsigned*)s_msk;
+            const unsigned* v4p = (const unsigned*)s_img;
+            if (p.label >= 0 && p.label <= 255)
+                for (int q = tid; q < NQ; q += RADB_NTB) {
+                    const unsigned eq = bytes_eq4(m4p[q], l4);
+                    if (!eq) continue;
+                    const int y = (int)(((float)q + 0.5f) * inv_wq), x0 = (q - y * WQ) << 2;
+                    const unsigned v4 = v4p[q];
+                    ymin = y < ymin ? y : ymin;
+                    ymax = y > ymax ? y : ymax;
+#pragma unroll
+                    for (int k = 0; k < 4; k++)
+                        if (eq & (0x80u << (8 * k))) {
+                            np++;
+                            xmin = x0 + k < xmin ? x0 + k : xmin;
+                            xmax = x0 + k > xmax ? x0 + k : xmax;
+                            atomicAdd(&hist[(v4 >> (8 * k)) & 0xffu], 1);
+                        }
+                }
+        } else
         for (int y = warp; y < H; y += RADB_NTB / 32)
             for (int x = lane; x < W; x += 32) {
                 int i = y * W + x;
@@ -675,6 +707,25 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     const int ng = misc[8];
 
     // ---- phase 2: discretised level image (padded, 0 outside the ROI) + level histogram
+    if (U8 && p.vec4) {
+        const int WQ = W >> 2, NQ = HW >> 2;
+        const float inv_wq = 1.0f / (float)WQ;
+        const unsigned l4 = (unsigned)(p.label & 0xff) * 0x01010101u;
+        const unsigned* m4p = (const unsigned*)s_msk;
+        const unsigned* v4p = (const unsigned*)s_img;
+        if (p.label >= 0 && p.label <= 255)
+            for (int q = tid; q < NQ; q += RADB_NTB) {
+                const unsigned eq = bytes_eq4(m4p[q], l4);
+                if (!eq) continue;  // the level image is pre-zeroed
+                const int y = (int)(((float)q + 0.5f) * inv_wq), xq = q - y * WQ;
+                const unsigned v4 = v4p[q];
+                unsigned w = 0;
+#pragma unroll
+                for (int k = 0; k < 4; k++)
+                    if (eq & (0x80u << (8 * k))) w |= (unsigned)lut[(v4 >> (8 * k)) & 0xffu] << (8 * k);
+                ((unsigned*)(lev + (y + 1) * WP + XO))[xq] = w;  // XO = 4 and WP % 4 == 0: aligned
+            }
+    } else
     for (int y = warp; y < H; y += RADB_NTB / 32)
         for (int x = lane; x < W; x += 32) {
             int i = y * W + x;
@@ -687,7 +738,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                     atomicAdd(&lhist[L - 1], 1);
                 }
             }
-            lev[(y + 1) * WP + x + 1] = L;
+            lev[(y + 1) * WP + x + XO] = L;
         }
     if (U8)
         for (int v = tid; v < 256; v += RADB_NTB)
@@ -730,7 +781,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             for (int l = first; l < nlines; l += RADB_NTB) {
                 int cur = 0, len = 0;
                 if (dy == 0) {
-                    const int base = (by0 + l + 1) * WP + bx0 + 1, lbase = (by0 + l) * W + bx0;
+                    const int base = (by0 + l + 1) * WP + bx0 + XO, lbase = (by0 + l) * W + bx0;
                     int st = 0;
                     for (int x = 0; x < bw; x++) {
                         const int g = lev[base + x];
@@ -755,7 +806,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 } else {
                     const int sdx = dx * dy;  // x step per +1 in y (runs are direction-agnostic)
                     int x = l, brk = 0;
-                    int pos = (by0 + 1) * WP + bx0 + 1;
+                    int pos = (by0 + 1) * WP + bx0 + XO;
                     for (int y = 0; y < bh; y++) {
                         const int g = lev[pos + x];
                         if (g != cur || brk) {
@@ -812,7 +863,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             const int idx = base + tid;
             const int yb = WIDE ? idx / bw : (int)(((float)idx + 0.5f) * inv_bw);
             const int y = by0 + yb, x = bx0 + (idx - yb * bw);
-            const int ctr = (y + 1) * WP + x + 1;
+            const int ctr = (y + 1) * WP + x + XO;
             const int c = idx < nbox ? (int)lev[ctr] : 0;
             const int li = y * W + x;
             unsigned req[RADB_MAX_ANGLES];  // union partner + 1 (0 = none)
@@ -875,7 +926,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     for (int idx = tid; idx < nbox; idx += RADB_NTB) {
         const int yb = WIDE ? idx / bw : (int)(((float)idx + 0.5f) * inv_bw);
         const int y = by0 + yb, x = bx0 + (idx - yb * bw);
-        const int ctr = (y + 1) * WP + x + 1;
+        const int ctr = (y + 1) * WP + x + XO;
         const int c = lev[ctr];
         if (c && (a_row < 0 || lev[ctr - 1] != c)) {  // run start
             const int li = y * W + x;
@@ -906,7 +957,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     for (int idx = tid; idx < nbox; idx += RADB_NTB) {
         const int yb = WIDE ? idx / bw : (int)(((float)idx + 0.5f) * inv_bw);
         const int y = by0 + yb, x = bx0 + (idx - yb * bw);
-        const int ctr = (y + 1) * WP + x + 1;
+        const int ctr = (y + 1) * WP + x + XO;
         const int c = lev[ctr];
         if (!c || (a_row >= 0 && lev[ctr - 1] == c)) continue;
         const int li = y * W + x;
@@ -927,7 +978,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     if (DBG && p.dbg_ng && tid == 0) p.dbg_ng[patch] = ng;
     if (DBG && p.dbg_levels)
         for (int i = tid; i < HW; i += RADB_NTB)
-            p.dbg_levels[patch * HW + i] = lev[(i / W + 1) * WP + (i % W) + 1];
+            p.dbg_levels[patch * HW + i] = lev[(i / W + 1) * WP + (i % W) + XO];
     if (DBG && p.dbg_glcm)
         for (int a = 0; a < NA; a++)
             for (int t = tid; t < ng * ng; t += RADB_NTB)

@@ -27,6 +27,8 @@ struct RadbParams {
     int* status;            // [B]
     long long B;
     int H, W, WP, HW;
+    int xo;        // column of pixel x = 0 inside a padded level-image row (left border width)
+    int vec4;      // uint8 narrow patches with W % 4 == 0: 4 pixels per shared-memory load in the discretise phases
     int label;
     int n_angles;
     int ang_y[RADB_MAX_ANGLES], ang_x[RADB_MAX_ANGLES];
@@ -86,7 +88,10 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     const int H = p->H, W = p->W, ng = p->max_ng, na = p->n_angles, wide = p->wide;
     p->pix_bytes = pix_bytes;
     p->HW = H * W;
-    p->WP = radb_align(W + 2, 4);
+    p->vec4 = (!wide && pix_bytes == 1 && W % 4 == 0) ? 1 : 0;
+    p->xo = p->vec4 ? 4 : 1;
+    p->WP = radb_align(W + p->xo + 1, 4);
+    if (p->vec4 && (p->WP / 4) % 2 == 0) p->WP += 4;  // odd word stride: row walks stay bank-conflict free
     p->nr = H > W ? H : W;
     p->s0 = wide ? 64 : 16;
     p->ovf_cap = p->HW / (p->s0 + 1) + 1;
