@@ -4,6 +4,7 @@
 // launches the CUDA kernel on the caller's stream or returns an error code.
 #include <cuda_runtime.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include <string>
 #include "radb_host.h"
@@ -12,7 +13,18 @@
 static thread_local std::string g_err;
 
 #define RADB_TAB_NINV 4096   // entries of the device 1/k^2 table (beyond it the kernels divide)
-#define RADB_CHUNK 16384     // patches per pass through the three kernels (bounds the workspace)
+#define RADB_CHUNK_DEFAULT 16384  // patches per pass through the three kernels (bounds the workspace)
+static int64_t g_chunk = 0;
+static int64_t radb_chunk()
+{
+    if (!g_chunk) {
+        const char* e = getenv("RADB_CHUNK");  // tuning knob, multiples of 4
+        long v = e ? atol(e) : 0;
+        g_chunk = (v >= 4) ? (v - v % 4) : RADB_CHUNK_DEFAULT;
+    }
+    return g_chunk;
+}
+#define RADB_CHUNK radb_chunk()
 
 struct radb_handle {
     radb::Plan plan;
