@@ -172,20 +172,24 @@ __device__ __forceinline__ int sturm_count(const double* d, const double* e2, in
     double p0 = 1.0, p1 = d[0] - x;
     bool neg = p1 < 0.0;
     int cnt = neg ? 1 : 0;
+    int i = 1;
 #pragma unroll 1
-    for (int i = 1; i < m; i++) {
+    for (; i + 1 < m; i += 2) {  // two steps per iteration, one rescale (|p| changes by < 1e17 per step)
+        const double pa = (d[i] - x) * p1 - e2[i - 1] * p0;
+        const bool na = (pa < 0.0) || (pa == 0.0 && neg);
+        const double pb = (d[i + 1] - x) * pa - e2[i] * p1;
+        const bool nb = (pb < 0.0) || (pb == 0.0 && na);
+        cnt += (na != neg) + (nb != na);
+        neg = nb;
+        const double ap = fabs(pb);
+        const double sc = ap > 1e100 ? 1e-100 : (ap < 1e-100 ? 1e100 : 1.0);
+        p0 = pa * sc;
+        p1 = pb * sc;
+    }
+    if (i < m) {
         const double pn = (d[i] - x) * p1 - e2[i - 1] * p0;
         const bool nneg = (pn < 0.0) || (pn == 0.0 && neg);
         cnt += (nneg != neg) ? 1 : 0;
-        neg = nneg;
-        p0 = p1;
-        p1 = pn;
-        if (i & 1) {  // |p| changes by at most ~1e17 per step: rescaling every other step is enough
-            const double ap = fabs(p1);
-            const double sc = ap > 1e100 ? 1e-100 : (ap < 1e-100 ? 1e100 : 1.0);
-            p0 *= sc;
-            p1 *= sc;
-        }
     }
     return cnt;
 }

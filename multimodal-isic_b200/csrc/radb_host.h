@@ -83,6 +83,21 @@ static inline int make_plan(const radb_settings& s, Plan& pl, std::string& err)
     if ((s.class_mask & RADB_CLASS_ALL) == 0) { err = "no feature class enabled"; return RADB_E_INVALID; }
     if (s.gldm_alpha < 0) { err = "gldm_alpha must be >= 0"; return RADB_E_INVALID; }
     pl.s = s;
+    if (s.n_angles == 4) {
+        // four distinct distance-1 offsets up to sign = the in-plane set: bring them into the canonical
+        // order (1,1), (0,1), (-1,1), (1,0) (pyradiomics' generator order) the kernel's fast path assumes
+        static const int canon[4][2] = {{1, 1}, {0, 1}, {-1, 1}, {1, 0}};
+        for (int a = 0; a < 4; a++) {
+            bool found = false;
+            for (int b = 0; b < 4; b++)
+                if ((s.angles[b][0] == canon[a][0] && s.angles[b][1] == canon[a][1]) ||
+                    (s.angles[b][0] == -canon[a][0] && s.angles[b][1] == -canon[a][1]))
+                    found = true;
+            if (!found) { err = "four angles must be the in-plane set"; return RADB_E_INVALID; }
+            pl.s.angles[a][0] = (int8_t)canon[a][0];
+            pl.s.angles[a][1] = (int8_t)canon[a][1];
+        }
+    }
     int ng = s.max_ng;
     if (ng <= 0) ng = (int)floor(255.0 / s.bin_width) + 1;  // uint8 pixels: levels 1..floor(255/bw)+1
     if (ng > 255) { err = "more than 255 gray levels (binWidth too small for the u8 level image)"; return RADB_E_UNSUPPORTED; }

@@ -869,7 +869,41 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             unsigned req[RADB_MAX_ANGLES];  // union partner + 1 (0 = none)
 #pragma unroll
             for (int a = 0; a < RADB_MAX_ANGLES; a++) req[a] = 0;
-            if (c) {
+            if (c && inplane) {
+                // the four in-plane angles in their canonical order (radb_host.h: make_plan):
+                // 0 (1,1) f=SE b=NW | 1 (0,1) f=E b=W | 2 (-1,1) f=NE b=SW | 3 (1,0) f=S b=N
+                const int nw = lev[ctr - WP - 1], n_ = lev[ctr - WP], ne = lev[ctr - WP + 1];
+                const int w_ = lev[ctr - 1], e_ = lev[ctr + 1];
+                const int sw = lev[ctr + WP - 1], s_ = lev[ctr + WP], se = lev[ctr + WP + 1];
+                int* g0 = glcm + (c - 1) * ng - 1;
+                const int ngng = ng * ng;
+                if (se) atomicAdd(&g0[se], 1);
+                if (e_) atomicAdd(&g0[ngng + e_], 1);
+                if (ne) atomicAdd(&g0[2 * ngng + ne], 1);
+                if (s_) atomicAdd(&g0[3 * ngng + s_], 1);
+                const int cnt = (nw != 0) + (n_ != 0) + (ne != 0) + (w_ != 0) + (e_ != 0) + (sw != 0) + (s_ != 0) + (se != 0);
+                const int sum = nw + n_ + ne + w_ + e_ + sw + s_ + se;  // levels outside the ROI are 0
+                const int al = p.alpha;
+#define RADB_DEP(v) ((v) != 0 && ((v) - c <= al) && (c - (v) <= al))
+                const int dep = RADB_DEP(nw) + RADB_DEP(n_) + RADB_DEP(ne) + RADB_DEP(w_) + RADB_DEP(e_) + RADB_DEP(sw) +
+                                RADB_DEP(s_) + RADB_DEP(se);
+#undef RADB_DEP
+                atomicAdd(&gldm[(c - 1) * nd + dep], 1);
+                if (cnt) {
+                    int num = cnt * c - sum;
+                    num = num < 0 ? -num : num;
+                    atomicAdd(&ngc[(c - 1) * NB + cnt - 1], 1);
+                    atomicAdd(&ngn[(c - 1) * NB + cnt - 1], num);
+                }
+                // 8-connectivity between row runs: one union per pair of touching runs.
+                const bool is_start = w_ != c, is_end = e_ != c;
+                if (n_ == c) {
+                    if (is_start || nw != c) req[0] = (unsigned)(li - W) + 1u;
+                } else {
+                    if (nw == c && is_start) req[0] = (unsigned)(li - W - 1) + 1u;
+                    if (ne == c && is_end) req[1] = (unsigned)(li - W + 1) + 1u;
+                }
+            } else if (c) {
                 int dep = 0, cnt = 0, sum = 0;
 #pragma unroll
                 for (int a = 0; a < RADB_MAX_ANGLES; a++) {
@@ -891,7 +925,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                             db = db < 0 ? -db : db;
                             dep += (db <= p.alpha);
                         }
-                        if (!inplane && a != a_row && b == c) req[a] = (unsigned)(li - loff[a]) + 1u;
+                        if (a != a_row && b == c) req[a] = (unsigned)(li - loff[a]) + 1u;
                     }
                 }
                 atomicAdd(&gldm[(c - 1) * nd + dep], 1);
@@ -900,17 +934,6 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                     num = num < 0 ? -num : num;
                     atomicAdd(&ngc[(c - 1) * NB + cnt - 1], 1);
                     atomicAdd(&ngn[(c - 1) * NB + cnt - 1], num);
-                }
-                if (inplane) {
-                    // 8-connectivity between row runs: one union per pair of touching runs.
-                    const int n_ = lev[ctr - WP], nw = lev[ctr - WP - 1], ne = lev[ctr - WP + 1];
-                    const bool is_start = lev[ctr - 1] != c, is_end = lev[ctr + 1] != c;
-                    if (n_ == c) {
-                        if (is_start || nw != c) req[0] = (unsigned)(li - W) + 1u;
-                    } else {
-                        if (nw == c && is_start) req[0] = (unsigned)(li - W - 1) + 1u;
-                        if (ne == c && is_end) req[1] = (unsigned)(li - W + 1) + 1u;
-                    }
                 }
             }
             const int nreq = inplane ? 2 : NA;
@@ -930,8 +953,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int c = lev[ctr];
         if (c && (a_row < 0 || lev[ctr - 1] != c)) {  // run start
             const int li = y * W + x;
-            // (path halving only rewrites non-root words, whose size half is static: safe next to the atomicAdd)
-            const unsigned r = uf_find<UW, UF<WIDE>::S>(lab, (unsigned)li);
+            const unsigned r = uf_find_ro<UW, UF<WIDE>::S>(lab, (unsigned)li);
             if (r != (unsigned)li) atomicAdd(&lab[r], (UW)(lab[li] & ~ULO));  // only roots are ever added to
         }
     }
