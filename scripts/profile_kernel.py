@@ -27,4 +27,9 @@ for i in range(a.launches):
     e1.record()
     torch.cuda.synchronize()
     print("launch %d: %.3f ms, %.0f patches/s" % (i, e0.elapsed_time(e1), a.patches / e0.elapsed_time(e1) * 1e3))
+ex.engine.set_profiling(True)
+for i in range(3):
+    ex.extract_batch(imgs, masks)
+torch.cuda.synchronize()
+print("per-kernel ms (3 launches):", {k: round(v, 3) for k, v in ex.engine.kernel_ms().items()})
 print("smem bytes/CTA:", ex.engine.smem_bytes(a.size, a.size), "status!=0:", int((st != 0).sum()))
