@@ -135,7 +135,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     if (!wide) p->rec_copy_bytes = p->rec_bytes;
     p->g_lev = 0;
     p->g_lab = radb_align((H + 2) * p->WP, 16);
-    p->scr_bytes = wide ? p->g_lab + (long long)p->HW * 8 : 0;
+    p->scr_bytes = wide ? (p->g_lab + (long long)p->HW * 8 + 15) / 16 * 16 : 0;  // 16-byte multiple: uint4 stores
     // ---- angle kernel
     o = 0;
     p->a_px = o; o += radb_align(ng * 4, 16);

@@ -8,7 +8,7 @@ from oracle import radiomics_oracle as orc
 emu=EmuRunner(sys.argv[1])
 ALL=("shape2D",)+tuple(orc.CLASS_ORDER)
 INPLANE=orc.angles(2)[0]; LIT=orc.angles(2,force2D=True)[0]
-for (H,W,n,ang) in ((64,64,2,INPLANE),(37,53,2,LIT),(120,150,1,INPLANE),(270,300,1,INPLANE)):
+for (H,W,n,ang) in ((64,64,2,INPLANE),(37,53,2,LIT),(120,150,1,INPLANE),(270,300,1,INPLANE),(121,151,3,INPLANE)):  # last: wide mode, odd pixel count, several patches
     im,mk=synth.make_patches(n,H,W,seed=1)
     r=emu.run(im,mk,10,255,ang,classes=ALL); print(H,W,'ok',r['status'])
 im,mk=edge_case_batch(); r=emu.run(im,mk,10,255,INPLANE,classes=ALL); print('edge',r['status'])

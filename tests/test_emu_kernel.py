@@ -195,10 +195,11 @@ def test_emu_address_sanitizer(tmp_path):
     if not os.path.isabs(asan) or not os.path.exists(asan):
         pytest.skip("libasan not available")
     so = str(tmp_path / "libradb_emu_asan.so")
-    subprocess.check_call(["g++", "-O1", "-g", "-std=c++20", "-fPIC", "-shared", "-pthread", "-fsanitize=address",
-                           "-fno-omit-frame-pointer", "-o", so, os.path.join(root, "tests", "emu", "radb_emu.cpp")])
-    env = dict(os.environ, LD_PRELOAD=asan, ASAN_OPTIONS="detect_leaks=0")
+    subprocess.check_call(["g++", "-O1", "-g", "-std=c++20", "-fPIC", "-shared", "-pthread", "-fsanitize=address,alignment",
+                           "-fno-sanitize-recover=alignment", "-fno-omit-frame-pointer", "-o", so, os.path.join(root, "tests", "emu", "radb_emu.cpp")])
+    ubsan = subprocess.run(["gcc", "-print-file-name=libubsan.so"], capture_output=True, text=True).stdout.strip()
+    env = dict(os.environ, LD_PRELOAD=asan + (":" + ubsan if os.path.isabs(ubsan) else ""), ASAN_OPTIONS="detect_leaks=0")
     r = subprocess.run([sys.executable, os.path.join(root, "tests", "emu", "asan_cases.py"), so], env=env,
                        capture_output=True, text=True, timeout=900)
-    assert r.returncode == 0 and "AddressSanitizer" not in r.stderr, r.stderr[-2000:]
+    assert r.returncode == 0 and "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-2000:]
     assert "u16 [0 0]" in r.stdout

@@ -359,3 +359,48 @@ def test_derived_image_types_batch_and_record_path(gpu_pkg, tmp_path):
                                       matrix_backend=cmatrices)
         assert list(res[ch].keys()) == list(ref.keys())
         np.testing.assert_allclose(list(res[ch].values()), list(ref.values()), rtol=RTOL, atol=ATOL)
+
+
+def _fuzz_patch(rng, H, W, kind):
+    yy, xx = np.mgrid[:H, :W]
+    if kind == 0:      # white noise
+        img = rng.integers(0, 256, (H, W))
+    elif kind == 1:    # few levels, big zones
+        img = (rng.integers(0, 4, (H // 4 + 1, W // 4 + 1)).repeat(4, 0).repeat(4, 1)[:H, :W]) * 60 + 20
+    elif kind == 2:    # smooth gradient + noise
+        img = 30 + 180 * (xx / max(W - 1, 1)) * (yy / max(H - 1, 1)) + rng.normal(0, 6, (H, W))
+    elif kind == 3:    # stripes (runs along one direction only)
+        img = np.where((xx // 3) % 2 == 0, 70, 150) + rng.integers(0, 3, (H, W))
+    else:              # checkerboard of blocks
+        img = np.where(((xx // 5) + (yy // 5)) % 2 == 0, 40, 210)
+    img = np.clip(img, 0, 255).astype(np.uint8)
+    mk = rng.integers(0, 4)
+    if mk == 0:
+        mask = np.full((H, W), 255)
+    elif mk == 1:
+        mask = np.where(rng.random((H, W)) < rng.uniform(0.2, 0.9), 255, 0)
+    elif mk == 2:
+        mask = np.where((yy - H / 2) ** 2 / (H / 2.2) ** 2 + (xx - W / 2) ** 2 / (W / 2.5) ** 2 < 1, 255, 0)
+    else:
+        mask = np.zeros((H, W), int)
+        y0, x0 = rng.integers(0, H // 2), rng.integers(0, W // 2)
+        mask[y0:y0 + rng.integers(2, H // 2 + 2), x0:x0 + rng.integers(2, W // 2 + 2)] = 255
+    return img, mask.astype(np.uint8)
+
+
+def test_fuzz_random_shapes_patterns_masks(gpu_pkg):
+    """Randomised shapes / textures / masks / bin widths / angle sets: integer matrices bit-exact and every
+    feature (102 per patch, shape2D included) within tolerance of the oracle."""
+    rng = np.random.default_rng(2026)
+    total = 0
+    for trial in range(36):
+        H, W = int(rng.integers(6, 90)), int(rng.integers(6, 90))
+        bw = [4, 10, 25, 7.5][trial % 4]
+        literal = trial % 3 == 0
+        ang = LITERAL if literal else INPLANE
+        pats = [_fuzz_patch(rng, H, W, int(rng.integers(0, 5))) for _ in range(5)]
+        imgs = np.stack([p[0] for p in pats])
+        masks = np.stack([p[1] for p in pats])
+        r = _dbg(_engine(gpu_pkg, bw, ang, classes=ALL_CLASSES), imgs, masks)
+        total += compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=bw, force2D=literal), classes=ALL_CLASSES)
+    assert total > 120
