@@ -813,7 +813,7 @@ __device__ void ngtdm_task(const int* C, const int* S, int n, int nb, double* pi
         return;
     }
     const double rNvp = radb_div(1.0, Nvp);
-    for (int i = lane; i < n; i += 32) pi[i] = pi[i] * rNvp;
+    for (int i = lane; i < n; i += 32) pi[i] = radb_div(pi[i], Nvp);  // true division, as upstream: see absd below
     __syncwarp();
     double sum_ps = 0, sum_s = 0, absd = 0, cplx = 0, contr = 0, stren = 0;
     int ngp = 0;
@@ -828,7 +828,9 @@ __device__ void ngtdm_task(const int* C, const int* S, int n, int nb, double* pi
             double p_j = pi[j];
             if (p_j == 0.0) continue;
             double dj = (double)(j + 1), dd = di - dj;
-            absd += fabs(di * p_i - dj * p_j);
+            // upstream tests this sum against exactly 0 (Busyness): the two products must be rounded
+            // separately -- an fma would leave a spurious 1e-17 when i*p_i == j*p_j
+            absd += fabs(__dmul_rn(di, p_i) - __dmul_rn(dj, p_j));
             cplx += radb_div(fabs(dd) * (p_i * s_i + p_j * si[j]), p_i + p_j);
             contr += p_i * p_j * dd * dd;
             stren += (p_i + p_j) * dd * dd;
