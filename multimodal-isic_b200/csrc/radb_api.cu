@@ -211,7 +211,9 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     }
 #undef RADB_PICK
     int rc = set_smem(h, build, 9 + dtype * 4 + (p.wide ? 2 : 0) + (dbg ? 1 : 0), p.smem_total);
-    if (!rc) rc = set_smem(h, radb_angle_kernel, 1, p.a_smem_total);
+    static const bool no_lane = getenv("RADB_NO_LANE") != nullptr;  // A/B switch: force the warp-per-angle kernel
+    if (no_lane) p.use_lane = 0;
+    if (!rc) rc = p.use_lane ? set_smem(h, radb_angle_lane_kernel, 3, p.l_smem_total) : set_smem(h, radb_angle_kernel, 1, p.a_smem_total);
     if (!rc && p.off_shape >= 0) rc = set_smem(h, radb_shape_kernel, 8, p.s_smem_total);
     if (!rc) rc = set_smem(h, radb_misc_kernel, 2, p.m_smem_total);
     unsigned char* wsp = nullptr;
@@ -254,7 +256,10 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         mark();
         build<<<(unsigned)n, RADB_NTB, p.smem_total, st>>>(q);
         mark();
-        radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, st>>>(q);
+        if (p.use_lane)
+            radb_angle_lane_kernel<<<(unsigned)((n * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, p.l_smem_total, st>>>(q);
+        else
+            radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, st>>>(q);
         mark();
         radb_misc_kernel<<<(unsigned)n, RADB_NT, p.m_smem_total, st>>>(q);
         if (p.off_shape >= 0) {

@@ -271,6 +271,7 @@ __device__ __forceinline__ double py_mod(double a, double b)
 }
 
 #include "radb_features.cuh"
+#include "radb_lane.cuh"
 
 // ------------------------------------------------------------------ first-order for non-uint8 pixels
 // uint8 patches get all 18 first-order features from the 256-bin raw histogram (fo_task_u8, misc
@@ -1312,6 +1313,11 @@ __global__ void __launch_bounds__(RADB_NT, RADB_ANGLE_MINB) radb_angle_kernel(co
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
     radb_angle_cta(p, (long long)blockIdx.x, radb_smem);
+}
+__global__ void __launch_bounds__(RADB_NTL) radb_angle_lane_kernel(const RadbParams p)
+{
+    extern __shared__ __align__(16) unsigned char radb_smem[];
+    radb_angle_lane_cta(p, (long long)blockIdx.x, radb_smem);
 }
 __global__ void __launch_bounds__(RADB_NT, 8) radb_misc_kernel(const RadbParams p)
 {

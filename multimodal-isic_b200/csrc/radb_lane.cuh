@@ -1,0 +1,463 @@
+// Thread-level ("lane") feature reductions: one THREAD per (patch, angle) instead of one warp.
+// Included by radb_kernels.cuh.
+//
+// Why: at the gray-level counts the reference's settings produce (binWidth 25 -> Ng <= 11, binWidth 10
+// -> Ng <= 26 for uint8 pixels) a GLCM / GLRLM angle is a few hundred cells.  Spread over a warp that is
+// 4 cells per lane followed by a dozen warp reductions, and the MCC eigenproblem (Householder + Sturm) is
+// a chain of ~10 dependent steps each ending in a warp reduction: ncu showed 37 k warp instructions per
+// patch in the warp-per-angle kernel, half of them reduction / synchronisation overhead and most at
+// 16-19 active lanes.  A thread that walks its own matrix serially needs no reduction at all; 32
+// independent matrices per warp keep every lane busy and the per-patch instruction count drops ~20x.
+//
+// Storage: every thread owns `l_doubles` fp64 slots of shared memory, slot-major (slot k of thread t at
+// smem[k * RADB_NTL + t]: consecutive lanes -> consecutive banks, conflict-free).  Integer scratch is
+// packed two-per-slot inside the thread's own slots (never aliases another thread's data, so no CTA
+// barriers are needed).  Layout for a patch with n gray levels (T = n(n+1)/2):
+//   M [0, T)        packed lower triangle: GLCM counts as doubles, later A = Dx^-1/2 P Dx^-1/2 (compacted)
+//   D [T, T+n)      ints px | psub during the count pass; later 1/sqrt(px); later Householder d / v
+//   E [T+n, T+2n)   ints padd during the count pass; later N/px; later Householder e^2 / w
+// The GLRLM task runs first and keeps its column sums (ints) at the start of the region.
+// Formulas: pyradiomics glcm.py / glrlm.py as restated in SURVEY.md A.6 / A.7 (same closed forms as the
+// warp-level tasks in radb_features.cuh); symmetric GLCMs only (symmetricalGLCM: True, params.yml:119) --
+// the asymmetric case stays on the warp kernel.
+#pragma once
+
+struct LaneMem {
+    double* d;  // this thread's slot 0 (fp64 view)
+    int* i;     // this thread's slot 0 (int view)
+};
+#define LMD(m, k) (m).d[(k) * RADB_NTL]
+#define LMI(m, k) (m).i[((k) >> 1) * (2 * RADB_NTL) + ((k) & 1)]
+
+// ------------------------------------------------------------------ GLRLM, one thread
+// R = run counters [n][nr] of one angle (packed u16, or u32 in wide mode); returns 0 for an empty angle.
+__device__ int glrlm_lane(const RadbTabs& tb, const unsigned* R, int wide, int n, int nr, int maxlen, LaneMem lm,
+                          double* o)
+{
+    for (int j = 0; j < maxlen; j++) LMI(lm, j) = 0;  // column sums p_r(j)
+    long long sN = 0, sGI = 0, sGI2 = 0, sG2 = 0;
+    double lgl = 0, e1 = 0, srl = 0, srh = 0, lrl = 0, lrh = 0;
+    int nnz = 0;
+    for (int i = 0; i < n; i++) {
+        int rs = 0;
+        long long bj2 = 0;  // sum_j c * j^2 (exact)
+        double arj = 0;     // sum_j c / j^2
+        const int c0 = i * nr;
+        for (int j = 0; j < maxlen; j++) {
+            const int c = get_run(R, c0 + j, wide);
+            if (!c) continue;
+            rs += c;
+            LMI(lm, j) += c;
+            e1 += tab_clog(tb, c);
+            nnz++;
+            arj += (double)c * tab_inv2(tb, j + 1);
+            bj2 += (long long)c * (j + 1) * (j + 1);
+        }
+        if (rs) {
+            const double i2 = (double)(i + 1) * (double)(i + 1), ri2 = tab_inv2(tb, i + 1);
+            sN += rs;
+            sGI += (long long)rs * (i + 1);
+            sGI2 += (long long)rs * (i + 1) * (i + 1);
+            sG2 += (long long)rs * rs;
+            lgl += (double)rs * ri2;
+            srl += ri2 * arj;
+            srh += i2 * arj;
+            lrl += ri2 * (double)bj2;
+            lrh += i2 * (double)bj2;
+        }
+    }
+    if (sN == 0) return 0;
+    long long sRJ = 0, sRJ2 = 0, sR2 = 0;
+    double sre = 0;
+    for (int j = 0; j < maxlen; j++) {
+        const int c = LMI(lm, j);
+        if (!c) continue;
+        sRJ += (long long)c * (j + 1);
+        sRJ2 += (long long)c * (j + 1) * (j + 1);
+        sR2 += (long long)c * c;
+        sre += (double)c * tab_inv2(tb, j + 1);
+    }
+    const double N = (double)sN, rN = radb_div(1.0, N);
+    o[0] = (double)sG2 * rN;
+    o[1] = (double)sG2 * rN * rN;
+    o[2] = (double)(sN * sGI2 - sGI * sGI) * rN * rN;
+    o[3] = (double)sGI2 * rN;
+    o[4] = (double)sRJ2 * rN;
+    o[5] = lrh * rN;
+    o[6] = lrl * rN;
+    o[7] = lgl * rN;
+    o[8] = radb_log2(N) - e1 * rN - RADB_EPS_LN2 * (double)nnz;
+    o[9] = (double)sR2 * rN;
+    o[10] = (double)sR2 * rN * rN;
+    o[11] = radb_div(N, (double)sRJ);
+    o[12] = (double)(sN * sRJ2 - sRJ * sRJ) * rN * rN;
+    o[13] = sre * rN;
+    o[14] = srh * rN;
+    o[15] = srl * rN;
+    return 1;
+}
+
+// ------------------------------------------------------------------ MCC, one thread
+// #eigenvalues of the tridiagonal (d, e2) below x (same recurrence as sturm_count, slot-major operands)
+__device__ __forceinline__ int sturm_lane(LaneMem lm, int oD, int oE, int m, double x)
+{
+    double p0 = 1.0, p1 = LMD(lm, oD) - x;
+    bool neg = p1 < 0.0;
+    int cnt = neg ? 1 : 0;
+    int i = 1;
+#pragma unroll 1
+    for (; i + 1 < m; i += 2) {
+        const double pa = (LMD(lm, oD + i) - x) * p1 - LMD(lm, oE + i - 1) * p0;
+        const bool na = (pa < 0.0) || (pa == 0.0 && neg);
+        const double pb = (LMD(lm, oD + i + 1) - x) * pa - LMD(lm, oE + i) * p1;
+        const bool nb = (pb < 0.0) || (pb == 0.0 && na);
+        cnt += (na != neg) + (nb != na);
+        neg = nb;
+        const double ap = fabs(pb);
+        const double sc = ap > 1e100 ? 1e-100 : (ap < 1e-100 ? 1e100 : 1.0);
+        p0 = pa * sc;
+        p1 = pb * sc;
+    }
+    if (i < m) {
+        const double pn = (LMD(lm, oD + i) - x) * p1 - LMD(lm, oE + i - 1) * p0;
+        const bool nneg = (pn < 0.0) || (pn == 0.0 && neg);
+        cnt += (nneg != neg) ? 1 : 0;
+    }
+    return cnt;
+}
+// k-th smallest eigenvalue by bisection; the spectrum of A = Dx^-1/2 P Dx^-1/2 lies in [-1, 1]
+__device__ double tridiag_kth_lane(LaneMem lm, int oD, int oE, int m, int k)
+{
+    double lo = -1.000001, hi = 1.000001;
+#pragma unroll 1
+    for (int it = 0; it < 40 && hi - lo > 1e-10; it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (sturm_lane(lm, oD, oE, m, mid) <= k) lo = mid; else hi = mid;  // count(x) <= k  <=>  x <= lambda_k
+    }
+    return 0.5 * (lo + hi);
+}
+
+// On entry: M = GLCM counts (packed lower triangle, n x n, as doubles), E[i] = N / px[i] (0: level absent).
+// Returns the second largest |eigenvalue| of A (= sqrt of the second largest eigenvalue of Q, A.6).
+__device__ double mcc_lane(LaneMem lm, int n, double rN)
+{
+    const int oD = n * (n + 1) / 2, oE = oD + n;
+    int m = 0;
+    for (int i = 0; i < n; i++) {
+        const double r = LMD(lm, oE + i);
+        LMD(lm, oD + i) = r > 0.0 ? radb_sqrt(r * rN) : 0.0;  // 1 / sqrt(px[i])
+        m += r > 0.0;
+    }
+    if (m < 2) return 0.0;
+    {   // compact the levels that occur and scale, in place (the write index never passes the read index)
+        int w = 0;
+        for (int i = 0; i < n; i++) {
+            const double ri = LMD(lm, oD + i);
+            if (ri == 0.0) continue;
+            const int rb = i * (i + 1) / 2;
+            for (int j = 0; j <= i; j++) {
+                const double rj = LMD(lm, oD + j);
+                if (rj == 0.0) continue;
+                LMD(lm, w) = LMD(lm, rb + j) * ri * rj;
+                w++;
+            }
+        }
+    }
+    // Householder tridiagonalisation of the m x m packed matrix; d -> D, e^2 -> E, v / w in their tails
+#pragma unroll 1
+    for (int k = 0; k < m - 2; k++) {
+        const int ck = (k + 1) * (k + 2) / 2 + k;  // tri(k+1, k)
+        double tail = 0;
+        {
+            int idx = ck + k + 2;  // tri(k+2, k)
+            for (int r = k + 2; r < m; r++) {
+                const double x = LMD(lm, idx);
+                tail += x * x;
+                LMD(lm, oD + r) = x;  // v[r]
+                LMD(lm, oE + r) = 0.0;
+                idx += r + 1;
+            }
+        }
+        const double x0 = LMD(lm, ck), dk = LMD(lm, k * (k + 1) / 2 + k);
+        if (tail == 0.0) {
+            LMD(lm, oD + k) = dk;
+            LMD(lm, oE + k) = x0 * x0;
+            continue;
+        }
+        const double nrm = radb_sqrt(tail + x0 * x0);
+        const double alpha = x0 > 0 ? -nrm : nrm;
+        const double v0 = x0 - alpha;
+        const double beta = radb_div(2.0, tail + v0 * v0);
+        LMD(lm, oD + k + 1) = v0;
+        LMD(lm, oE + k + 1) = 0.0;
+        // q = M22 v in one sweep over the lower triangle; vMv = v^T q
+        double vmv = 0;
+        for (int r = k + 1; r < m; r++) {
+            const int rb = r * (r + 1) / 2;
+            const double vr = LMD(lm, oD + r);
+            double acc = 0;
+            for (int c = k + 1; c < r; c++) {
+                const double mv = LMD(lm, rb + c);
+                acc += mv * LMD(lm, oD + c);
+                LMD(lm, oE + c) += mv * vr;
+            }
+            acc += LMD(lm, rb + r) * vr;
+            LMD(lm, oE + r) += acc;
+        }
+        for (int r = k + 1; r < m; r++) vmv += LMD(lm, oE + r) * LMD(lm, oD + r);
+        const double K = 0.5 * beta * beta * vmv;
+        for (int r = k + 1; r < m; r++) LMD(lm, oE + r) = beta * LMD(lm, oE + r) - K * LMD(lm, oD + r);  // w'
+        // M22 -= v w'^T + w' v^T
+        for (int r = k + 1; r < m; r++) {
+            const int rb = r * (r + 1) / 2;
+            const double vr = LMD(lm, oD + r), wr = LMD(lm, oE + r);
+            for (int c = k + 1; c <= r; c++) LMD(lm, rb + c) -= vr * LMD(lm, oE + c) + wr * LMD(lm, oD + c);
+        }
+        LMD(lm, oD + k) = dk;
+        LMD(lm, oE + k) = alpha * alpha;
+    }
+    {
+        const int a = (m - 2) * (m - 1) / 2 + (m - 2), b = (m - 1) * m / 2;
+        LMD(lm, oD + m - 2) = LMD(lm, a);
+        const double x = LMD(lm, b + m - 2);
+        LMD(lm, oE + m - 2) = x * x;
+        LMD(lm, oD + m - 1) = LMD(lm, b + m - 1);
+    }
+    const double t = fabs(tridiag_kth_lane(lm, oD, oE, m, m - 2));
+    // second largest |lambda(A)|: lambda_min matters only if it lies below -|lambda_2|
+    if (sturm_lane(lm, oD, oE, m, -t * (1.0 + 1e-9) - 1e-12) == 0) return t;
+    return fmax(t, fabs(tridiag_kth_lane(lm, oD, oE, m, 0)));
+}
+
+// ------------------------------------------------------------------ GLCM, one thread (symmetric matrices)
+// P = final integer counts of one angle [n][n] (already symmetrised: P[i][j] == P[j][i], diagonal doubled).
+__device__ int glcm_lane(const RadbTabs& tb, const int* P, int n, LaneMem lm, double* o)
+{
+    const int T = n * (n + 1) / 2;
+    const int iPX = 2 * T, iSUB = 2 * T + n, iADD = 2 * T + 2 * n;  // int views inside D | E
+    for (int k = 0; k < 4 * n; k++) LMI(lm, iPX + k) = 0;
+    long long sIJ = 0, sD2 = 0, sC2 = 0;
+    int nnz = 0, maxc = 0;
+    for (int i = 0; i < n; i++) {
+        const int* row = P + i * n;
+        const int rb = i * (i + 1) / 2;
+        int rs = 0;
+        for (int j = 0; j < i; j++) {  // cell (i, j) stands for (i, j) and (j, i)
+            const int c = row[j];
+            LMD(lm, rb + j) = (double)c;
+            if (c) {
+                rs += c;
+                LMI(lm, iPX + j) += c;
+                LMI(lm, iADD + i + j) += 2 * c;
+                LMI(lm, iSUB + i - j) += 2 * c;
+                sIJ += 2LL * c * (i + 1) * (j + 1);
+                sD2 += 2LL * c * (i - j) * (i - j);
+                sC2 += 2LL * c * c;
+                nnz += 2;
+                maxc = c > maxc ? c : maxc;
+            }
+        }
+        const int c = row[i];
+        LMD(lm, rb + i) = (double)c;
+        if (c) {
+            rs += c;
+            LMI(lm, iADD + 2 * i) += c;
+            LMI(lm, iSUB) += c;
+            sIJ += (long long)c * (i + 1) * (i + 1);
+            sC2 += (long long)c * c;
+            nnz++;
+            maxc = c > maxc ? c : maxc;
+        }
+        LMI(lm, iPX + i) += rs;
+    }
+    long long sN = 0, sI = 0;
+    for (int i = 0; i < n; i++) {
+        const int a = LMI(lm, iPX + i);
+        sN += a;
+        sI += (long long)a * (i + 1);
+    }
+    if (sN == 0) return 0;
+    const double N = (double)sN, rN = radb_div(1.0, N);
+    const double ux = (double)sI * rN;  // = uy
+    const double autoc = (double)sIJ * rN, contrast = (double)sD2 * rN, energy = (double)sC2 * rN * rN;
+    const double maxp = (double)maxc * rN;
+    const double log2N = tab_log2(tb, (int)sN);
+    // marginal entropies (same table for c, px and N: exact cancellation for a one-level ROI)
+    double hx0 = 0;
+    int nx = 0;
+    for (int i = 0; i < n; i++) {
+        const int a = LMI(lm, iPX + i);
+        if (a) { hx0 -= (double)a * rN * (tab_log2(tb, a) - log2N); nx++; }
+    }
+    const double hx = hx0 - RADB_EPS_LN2 * (double)nx;
+    // |i-j| marginal
+    double da = 0, de = 0, idv = 0, idm = 0, idmn = 0, idn = 0, iv = 0;
+    const double rdn = radb_div(1.0, (double)n);
+    for (int k = 0; k < n; k++) {
+        const int c = LMI(lm, iSUB + k);
+        if (!c) continue;
+        const double q = (double)c * rN, dk = (double)k;
+        da += dk * q;
+        de -= q * (tab_log2(tb, c) - log2N) + RADB_EPS_LN2;
+        idv += radb_div(q, 1.0 + dk);
+        idm += radb_div(q, 1.0 + dk * dk);
+        idmn += radb_div(q, 1.0 + (dk * dk) * rdn * rdn);
+        idn += radb_div(q, 1.0 + dk * rdn);
+        if (k > 0) iv += q * tab_inv2(tb, k);
+    }
+    double dvar = 0;
+    for (int k = 0; k < n; k++) {
+        const int c = LMI(lm, iSUB + k);
+        if (c) dvar += (double)c * rN * ((double)k - da) * ((double)k - da);
+    }
+    // i+j marginal (index k <-> i+j = k+2)
+    double sa = 0, se = 0;
+    for (int k = 0; k < 2 * n - 1; k++) {
+        const int c = LMI(lm, iADD + k);
+        if (!c) continue;
+        const double q = (double)c * rN;
+        sa += (double)(k + 2) * q;
+        se -= q * (tab_log2(tb, c) - log2N) + RADB_EPS_LN2;
+    }
+    // E[i] = N / px[i] (padd is dead; px lives in D and is consumed here)
+    const int oE = T + n;
+    for (int i = 0; i < n; i++) {
+        const int a = LMI(lm, iPX + i);
+        LMD(lm, oE + i) = a ? radb_div(N, (double)a) : 0.0;
+    }
+    // second pass over the stored counts: cluster moments, correlation, joint entropy
+    double ct = 0, cs = 0, cp = 0, ssq = 0, corm = 0, h1 = 0, sclog = 0;
+    for (int i = 0; i < n; i++) {
+        const int rb = i * (i + 1) / 2;
+        const double di = (double)(i + 1) - ux, rpxi = LMD(lm, oE + i);
+        for (int j = 0; j < i; j++) {
+            const double dc = LMD(lm, rb + j);
+            if (dc == 0.0) continue;
+            const double pij = dc * rN, dj = (double)(j + 1) - ux, s = di + dj, s2 = s * s;
+            const double p2 = pij + pij;
+            ct += p2 * s2;
+            cs += p2 * s2 * s;
+            cp += p2 * s2 * s2;
+            ssq += pij * (di * di + dj * dj);
+            corm += p2 * di * dj;
+            h1 += 2.0 * dc * rpxi * LMD(lm, oE + j);
+            sclog += 2.0 * dc * (tab_log2(tb, (int)dc) - log2N);
+        }
+        const double dc = LMD(lm, rb + i);
+        if (dc != 0.0) {
+            const double pij = dc * rN, s = di + di, s2 = s * s;
+            ct += pij * s2;
+            cs += pij * s2 * s;
+            cp += pij * s2 * s2;
+            ssq += pij * di * di;
+            corm += pij * di * di;
+            h1 += dc * rpxi * rpxi;
+            sclog += dc * (tab_log2(tb, (int)dc) - log2N);
+        }
+    }
+    const double h1corr = h1 * rN;  // sum p / (px * py)
+    const double hxy = -sclog * rN - RADB_EPS_LN2 * (double)nnz;
+    const double hxy1 = hx0 + hx0 - RADB_EPS_LN2 * h1corr;
+    const double hxy2 = hx0 + hx0 - RADB_EPS_LN2 * (double)nx * (double)nx;
+    const double mcc = mcc_lane(lm, n, rN);
+    double im2 = 1.0 - exp(-2.0 * (hxy2 - hxy));
+    im2 = im2 < 0.0 ? 0.0 : im2;
+    o[0] = autoc;
+    o[1] = cp;
+    o[2] = cs;
+    o[3] = ct;
+    o[4] = contrast;
+    {
+        const double sg = radb_sqrt(ssq);
+        o[5] = (sg * sg == 0.0) ? 1.0 : radb_div(corm, sg * sg + RADB_EPS);
+    }
+    o[6] = da;
+    o[7] = de;
+    o[8] = dvar;
+    o[9] = idv;
+    o[10] = idm;
+    o[11] = idmn;
+    o[12] = idn;
+    o[13] = (hx != 0.0) ? radb_div(hxy - hxy1, hx) : 0.0;
+    o[14] = radb_sqrt(im2);
+    o[15] = iv;
+    o[16] = ux;
+    o[17] = energy;
+    o[18] = hxy;
+    o[19] = mcc;
+    o[20] = maxp;
+    o[21] = sa;
+    o[22] = se;
+    o[23] = ssq;
+    return 1;
+}
+
+// ------------------------------------------------------------------ the kernel body
+// Thread g of the grid <-> (patch g / NAP, angle g % NAP), NAP = n_angles rounded up to a power of two,
+// so the angles of a patch are adjacent lanes of one warp and the nanmean over the non-empty angles
+// (A.6: upstream deletes empty angles before numpy.nanmean) is two xor shuffles.
+template <int NF>
+__device__ __forceinline__ void lane_mean(double (&f)[NF], int valid, int nap)
+{
+    int k = valid;
+    for (int m = 1; m < nap; m <<= 1) k += __shfl_xor_sync(FULLMASK, k, m);
+    const double rk = k == 4 ? 0.25 : k == 3 ? (1.0 / 3.0) : k == 2 ? 0.5 : 1.0;
+#pragma unroll
+    for (int i = 0; i < NF; i++) {
+        double s = valid ? f[i] : 0.0;
+        for (int m = 1; m < nap; m <<= 1) s += __shfl_xor_sync(FULLMASK, s, m);
+        f[i] = k ? s * rk : nan_f64();
+    }
+}
+template <int NF>
+__device__ __forceinline__ void lane_store(const double (&f)[NF], int nap, int a, double* out)
+{
+#pragma unroll
+    for (int i = 0; i < NF; i++)
+        if ((i & (nap - 1)) == a) out[i] = f[i];  // the lanes of a patch share the stores
+}
+
+__device__ void radb_angle_lane_cta(const RadbParams& p, long long cta, unsigned char* smem)
+{
+    const int t = threadIdx.x;
+    const int NA = p.n_angles, NAP = p.l_nap;
+    const long long g = cta * RADB_NTL + t;
+    const long long patch = g / NAP;
+    const int a = (int)(g - patch * NAP);
+    const bool patch_ok = patch < p.B && p.status[patch] == 0;  // status != 0: NaN row written by the build kernel
+    const bool live = patch_ok && a < NA;
+    LaneMem lm;
+    lm.d = (double*)smem + t;
+    lm.i = (int*)smem + 2 * t;
+    RadbTabs tb;
+    tb.inv2 = p.g_inv2;
+    tb.ninv = p.ninv;
+    tb.tlog = p.g_tlog;
+    tb.red = (double*)0;
+    const unsigned char* rec = p.ws + (patch_ok ? patch : 0) * (long long)p.rec_bytes;
+    const int* misc = (const int*)(rec + (p.o_misc - p.o_rec));
+    int ng = 0, nroi = 0;
+    if (patch_ok) { ng = misc[8]; nroi = misc[9]; }
+    double* out = p.out + (patch_ok ? patch : 0) * (long long)p.F;
+    if (p.off_glrlm >= 0) {
+        double f[RADB_GLRLM_NF];
+#pragma unroll
+        for (int i = 0; i < RADB_GLRLM_NF; i++) f[i] = 0.0;
+        int ok = 0;
+        if (live)
+            ok = glrlm_lane(tb, (const unsigned*)(rec + (p.o_glrlm - p.o_rec) + a * p.glrlm_stride), p.wide, ng, p.nr,
+                            misc[10 + a], lm, f);
+        lane_mean<RADB_GLRLM_NF>(f, ok, NAP);
+        if (patch_ok) lane_store<RADB_GLRLM_NF>(f, NAP, a, out + p.off_glrlm);
+    }
+    if (p.off_glcm >= 0) {
+        double f[RADB_GLCM_NF];
+#pragma unroll
+        for (int i = 0; i < RADB_GLCM_NF; i++) f[i] = 0.0;
+        int ok = 0;
+        if (live) ok = glcm_lane(tb, (const int*)(rec + (p.o_glcm - p.o_rec)) + a * ng * ng, ng, lm, f);
+        lane_mean<RADB_GLCM_NF>(f, ok, NAP);
+        if (nroi < 2) f[19] = 1.0;  // MCC of a one-level ROI (glcm.py: "flat region" special case)
+        if (patch_ok) lane_store<RADB_GLCM_NF>(f, NAP, a, out + p.off_glcm);
+    }
+}

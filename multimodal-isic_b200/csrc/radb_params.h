@@ -10,6 +10,7 @@
 #ifndef RADB_NTB_MINB
 #define RADB_NTB_MINB 5      // min resident build CTAs per SM (register cap: 48)
 #endif
+#define RADB_NTL 64          // threads per CTA of the lane kernel: one THREAD per (patch, angle)
 #define RADB_MAX_ANGLES 4    // unidirectional offsets at distance 1 in a plane
 #define RADB_GLCM_NF 24
 #define RADB_GLRLM_NF 16
@@ -63,6 +64,8 @@ struct RadbParams {
     // ---- misc kernel (GLSZM, GLDM, NGTDM, first-order: one warp each)
     int m_pg, m_ovf2, m_ngp, m_qv, m_red, m_smem_total;
     int s_smem_total;  // shape kernel
+    // ---- lane kernel (radb_lane.cuh): one thread per (patch, angle), l_doubles fp64 slots of shared memory each
+    int use_lane, l_nap, l_doubles, l_smem_total;
     // global workspace + tables (device pointers)
     unsigned char* ws;        // [B][rec_bytes]
     unsigned char* ws_scr;    // [B][scr_bytes] (wide mode)
@@ -151,6 +154,14 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->a_fsc = o; o += RADB_MAX_ANGLES * RADB_FSC_STRIDE * 8;
     p->a_valid = o; o += 16 * 4;
     p->a_smem_total = o;
+    // ---- lane kernel: replaces the angle kernel for symmetric GLCMs whose per-thread workspace fits
+    p->l_nap = na <= 1 ? 1 : (na <= 2 ? 2 : 4);
+    p->l_doubles = ng * (ng + 1) / 2 + 2 * ng;
+    if (p->l_doubles < (p->nr + 1) / 2 + 1) p->l_doubles = (p->nr + 1) / 2 + 1;
+    p->l_smem_total = p->l_doubles * 8 * RADB_NTL;
+    // (>= 3 resident CTAs per SM: with fewer the serial per-thread chains are latency-bound and the
+    // warp-per-angle kernel wins -- measured at Ng 26: 1.55 ms vs 1.16 ms per 8192 patches)
+    p->use_lane = (p->symmetric && p->l_smem_total <= 72 * 1024) ? 1 : 0;
     // ---- misc kernel
     o = 0;
     p->m_pg = o; o += radb_align(ng * 4, 16);

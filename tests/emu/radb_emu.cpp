@@ -72,6 +72,8 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
     int mx = p.smem_total > p.a_smem_total ? p.smem_total : p.a_smem_total;
     mx = mx > p.m_smem_total ? mx : p.m_smem_total;
     mx = mx > p.s_smem_total ? mx : p.s_smem_total;
+    if (getenv("RADB_NO_LANE")) p.use_lane = 0;
+    if (p.use_lane && p.l_smem_total > mx) mx = p.l_smem_total;
     std::vector<unsigned char> smem((size_t)mx + 64);
     unsigned char* sm = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
     // the same three launches radb_api.cu issues, CTA by CTA on host threads
@@ -87,7 +89,10 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
         case RADB_DTYPE_F64: EMU_BUILD(double) break;
         default: g_err = "unknown dtype"; return -1;
     }
-    emu::launch((unsigned)B, RADB_NT, [&]() { radb_angle_cta(p, (long long)blockIdx.x, sm); });
+    if (p.use_lane)
+        emu::launch((unsigned)((B * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, [&]() { radb_angle_lane_cta(p, (long long)blockIdx.x, sm); });
+    else
+        emu::launch((unsigned)B, RADB_NT, [&]() { radb_angle_cta(p, (long long)blockIdx.x, sm); });
     emu::launch((unsigned)B, RADB_NT, [&]() { radb_misc_cta(p, (long long)blockIdx.x, sm); });
     if (p.off_shape >= 0) emu::launch((unsigned)B, RADB_NT, [&]() { radb_shape_cta(p, (long long)blockIdx.x, sm); });
     return 0;

@@ -42,6 +42,22 @@ def test_emu_edge_cases(emu):
     assert list(r["status"][:3]) == [1, 2, 3]
 
 
+@pytest.mark.parametrize("bw,angles,force2d", [(25, INPLANE, False), (20, LITERAL, True), (32, INPLANE, False)])
+def test_emu_thread_per_angle_kernel(emu, monkeypatch, bw, angles, force2d):
+    """Few gray levels select radb_angle_lane_kernel (one thread per (patch, angle)); RADB_NO_LANE forces the
+    warp-per-angle kernel.  Both must match the oracle, edge cases included, and each other."""
+    a, am = synth.make_patches(5, 20, seed=11)
+    e, em_ = edge_case_batch(H=20, W=20)
+    imgs, masks = np.concatenate([a, e]), np.concatenate([am, em_])
+    r = emu.run(imgs, masks, bw, 255, angles)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=bw, force2D=force2d)) == 11
+    monkeypatch.setenv("RADB_NO_LANE", "1")
+    r2 = emu.run(imgs, masks, bw, 255, angles)
+    assert compare_with_oracle(r2, imgs, masks, dict(label=255, binWidth=bw, force2D=force2d), check_matrices=False) == 11
+    np.testing.assert_allclose(r["features"], r2["features"], rtol=1e-8, atol=1e-11, equal_nan=True)
+    assert not np.array_equal(r["features"], r2["features"], equal_nan=True)  # they really are different code paths
+
+
 def test_emu_large_zones_overflow_path(emu):
     # smooth image -> zones larger than the dense GLSZM columns (overflow list)
     H = W = 48

@@ -314,7 +314,9 @@ def test_other_pixel_types(gpu_pkg, dt):
     # the drop-in class sizes an engine from the data range
     ex = gpu_pkg.RadiomicsExtractor({"setting": {"label": 255, "binWidth": bw}})
     out, st = ex.extract_batch(tt, torch.as_tensor(masks).cuda())
-    np.testing.assert_allclose(out.cpu().numpy(), r["features"], rtol=1e-12, atol=0)
+    # the two engines are sized differently (max_ng 40 vs data range) and may take different reduction
+    # kernels (warp-per-angle vs thread-per-angle): same features well inside the 1e-6 contract
+    np.testing.assert_allclose(out.cpu().numpy(), r["features"], rtol=1e-8, atol=1e-12)
 
 
 def test_float_wide_mode(gpu_pkg):
