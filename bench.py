@@ -330,14 +330,14 @@ def gpu_arm(args):
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": workload_config(args, B, F),
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": traffic, "kernel": "radb_build_kernel + radb_angle_kernel + radb_misc_kernel "
-                                                       "(one pass of the hot path; chunks of 16384 patches)",
+                         "traffic": traffic, "kernel": "radb_build_kernel + radb_angle_lane_kernel + radb_misc_lane_kernel (+ warp-level "
+                                                       "radb_misc_kernel residual); one pass of the hot path, chunks of 65536 patches",
                          "kernel_ms": kms, "kernel_ms_parts": kparts, "dominant_kernel": "radb_%s_kernel" % dom,
                          "dominant_share": kparts[dom] / kms,
                          "dominant_achieved": B * bpp / (kparts[dom] / 1e3) / 1e9,
                          "bytes_per_patch": bpp, "peak_source": peak_src,
                          "note": "algorithmic bytes = H*W px + H*W mask + 8*F per patch over the summed duration of "
-                                 "the three kernels of a pass; dominant_achieved uses the dominant kernel's duration "
+                                 "the kernels of a pass (build / angle reductions / misc reductions); dominant_achieved uses the dominant kernel's duration "
                                  "alone. The pass is issue/latency bound (shared-memory atomics, fp64), not HBM "
                                  "bound (DESIGN.md, profiles/)"},
             "cpu_baseline": cpu,

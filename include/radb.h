@@ -133,8 +133,9 @@ int radb_debug_matrices(radb_handle* h, const void* img, int dtype, const uint8_
 
 int radb_max_ng(const radb_handle* h);
 
-/* Number of kernel launches this handle has issued (bench.py's gpu_launches evidence): three
- * kernels (build, angle, misc) per chunk of 16384 patches. */
+/* Number of kernel launches this handle has issued (bench.py's gpu_launches evidence): four
+ * kernels (build, angle-level reductions, misc thread-level, misc warp-level residual) per chunk of
+ * 65536 patches (+1 with shape2D, +1 for the BGR front-end). */
 int64_t radb_launch_count(const radb_handle* h);
 
 /* Per-kernel device timing for bench.py's roofline: with profiling on, every launch records CUDA

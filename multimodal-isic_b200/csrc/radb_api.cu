@@ -13,7 +13,7 @@
 static thread_local std::string g_err;
 
 #define RADB_TAB_NINV 4096   // entries of the device 1/k^2 table (beyond it the kernels divide)
-#define RADB_CHUNK_DEFAULT 16384  // patches per pass through the three kernels (bounds the workspace)
+#define RADB_CHUNK_DEFAULT 65536  // patches per pass through the kernels (bounds the workspace; the thread-level reduction kernels want >= 5 waves)
 static int64_t g_chunk = 0;
 static int64_t radb_chunk()
 {
@@ -216,6 +216,8 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     if (!rc) rc = p.use_lane ? set_smem(h, radb_angle_lane_kernel, 3, p.l_smem_total) : set_smem(h, radb_angle_kernel, 1, p.a_smem_total);
     if (!rc && p.off_shape >= 0) rc = set_smem(h, radb_shape_kernel, 8, p.s_smem_total);
     if (!rc) rc = set_smem(h, radb_misc_kernel, 2, p.m_smem_total);
+    p.only_big_ovf = (!no_lane && p.ml_smem_total <= 96 * 1024) ? 1 : 0;
+    if (!rc && p.only_big_ovf) rc = set_smem(h, radb_misc_lane_kernel, 4, p.ml_smem_total);
     unsigned char* wsp = nullptr;
     if (!rc) rc = ensure_ws(h, p, p.B, stream, &wsp);
     if (rc) return rc;
@@ -261,6 +263,10 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         else
             radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, st>>>(q);
         mark();
+        if (p.only_big_ovf) {
+            radb_misc_lane_kernel<<<(unsigned)((n + 31) / 32), RADB_NT, p.ml_smem_total, st>>>(q);
+            h->launches += 1;
+        }
         radb_misc_kernel<<<(unsigned)n, RADB_NT, p.m_smem_total, st>>>(q);
         if (p.off_shape >= 0) {
             radb_shape_kernel<<<(unsigned)n, RADB_NT, p.s_smem_total, st>>>(q);

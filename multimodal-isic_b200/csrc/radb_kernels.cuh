@@ -1100,7 +1100,8 @@ __device__ void radb_misc_cta(const RadbParams& p, long long patch, unsigned cha
     tb.ninv = p.ninv;
     tb.tlog = p.g_tlog;
     tb.red = (double*)(smem + p.m_red) + warp * RADB_RED_DOUBLES;
-    for (int t = warp; t < 4; t += RADB_NT / 32) {
+    if (p.only_big_ovf && (misc[5] <= RADB_LANE_MAX_OVF || p.off_glszm < 0)) return;  // done by radb_misc_lane_kernel
+    for (int t = warp; t < (p.only_big_ovf ? 1 : 4); t += RADB_NT / 32) {
         if (t == 0) {
             if (p.off_glszm < 0) continue;
             int* pg = (int*)(smem + p.m_pg);
@@ -1318,6 +1319,11 @@ __global__ void __launch_bounds__(RADB_NTL) radb_angle_lane_kernel(const RadbPar
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
     radb_angle_lane_cta(p, (long long)blockIdx.x, radb_smem);
+}
+__global__ void __launch_bounds__(RADB_NT) radb_misc_lane_kernel(const RadbParams p)
+{
+    extern __shared__ __align__(16) unsigned char radb_smem[];
+    radb_misc_lane_cta(p, (long long)blockIdx.x, radb_smem);
 }
 __global__ void __launch_bounds__(RADB_NT, 8) radb_misc_kernel(const RadbParams p)
 {

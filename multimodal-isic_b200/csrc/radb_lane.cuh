@@ -461,3 +461,295 @@ __device__ void radb_angle_lane_cta(const RadbParams& p, long long cta, unsigned
         if (patch_ok) lane_store<RADB_GLCM_NF>(f, NAP, a, out + p.off_glcm);
     }
 }
+
+// ==================================================================== misc classes, one thread per (patch, class)
+// CTA = 128 threads = 32 patches: warp w reduces class w (0 GLSZM, 1 GLDM, 2 NGTDM, 3 first-order) of the
+// CTA's 32 patches, lane <-> patch, so every warp runs one code path with all lanes busy.  Per-thread fp64
+// scratch (2 * max_ng + 16 slots) is slot-major per warp (slot k of lane l at base[k * 32 + l]).
+// Same closed forms as the warp-level tasks in radb_features.cuh.
+#define MLD(b, k) (b)[(k) * 32]
+#define MLU(b, k) (((unsigned*)&(b)[((k) >> 1) * 32])[(k) & 1])  // u32 view: two per fp64 slot of the same thread
+#define RADB_LANE_MAX_OVF 48  // GLSZM patches with more overflow zones than this go to the warp kernel
+
+// A.8 GLSZM: dense counters Z[n][s0] + overflow list (level << 24 | size) of the zones larger than s0
+__device__ void glszm_lane(const RadbParams& p, const RadbTabs& tb, const int* Z, const unsigned* ovf, int novf, int n,
+                           double* scr, double* o)
+{
+    const int s0 = p.s0;
+    ZoneSums z;
+    zs_init(z);
+    for (int i = 0; i < n; i++) {
+        int g = 0;
+        for (int j = 0; j < s0; j++) {
+            const int c = Z[i * s0 + j];
+            if (!c) continue;
+            g += c;
+            zs_cell(z, tb, i + 1, j + 1, c);
+        }
+        for (int e = 0; e < novf; e++) g += ((int)(ovf[e] >> 24) == i + 1);
+        if (g) zs_level(z, tb, i + 1, g);
+    }
+    for (int j = 0; j < s0; j++) {
+        int cs = 0;
+        for (int i = 0; i < n; i++) cs += Z[i * s0 + j];
+        z.PJ2 += (long long)cs * cs;
+    }
+    // overflow zones: the list was appended in atomic order, so it is first insertion-sorted by (size, level)
+    // into this thread's scratch -- every sum below then runs in an order that depends on the data only
+    // (bit-reproducible rows), equal cells are adjacent and so are equal sizes
+    for (int e = 0; e < novf; e++) {
+        const unsigned k0 = ovf[e], key = ((k0 & 0xffffffu) << 8) | (k0 >> 24);
+        int j = e;
+        while (j > 0 && MLU(scr, j - 1) > key) { MLU(scr, j) = MLU(scr, j - 1); j--; }
+        MLU(scr, j) = key;
+    }
+    for (int e = 0; e < novf;) {
+        const unsigned key = MLU(scr, e);
+        const int sz = (int)(key >> 8);
+        int same_size = 0;
+        while (e < novf && (int)(MLU(scr, e) >> 8) == sz) {  // all zones of this size
+            const unsigned k1 = MLU(scr, e);
+            int cnt = 0;
+            while (e < novf && MLU(scr, e) == k1) { cnt++; e++; }
+            zs_cell(z, tb, (int)(k1 & 0xffu), sz, cnt);
+            same_size += cnt;
+        }
+        z.PJ2 += (long long)same_size * same_size;
+    }
+    const double N = z.N ? (double)z.N : 1.0, rN = radb_div(1.0, N);
+    const double Np = z.J1 ? (double)z.J1 : 1.0;
+    o[0] = (double)z.G2 * rN;
+    o[1] = (double)z.G2 * rN * rN;
+    o[2] = (double)(z.N * z.GI2 - z.GI * z.GI) * rN * rN;
+    o[3] = (double)z.GI2 * rN;
+    o[4] = (double)z.J2 * rN;
+    o[5] = z.lh * rN;
+    o[6] = z.ll * rN;
+    o[7] = z.lgl * rN;
+    o[8] = (double)z.PJ2 * rN;
+    o[9] = (double)z.PJ2 * rN * rN;
+    o[10] = z.small * rN;
+    o[11] = z.sh * rN;
+    o[12] = z.sl * rN;
+    o[13] = z.N ? radb_log2(N) - z.e1 * rN - RADB_EPS_LN2 * (double)z.nnz : 0.0;
+    o[14] = radb_div(N, Np);
+    o[15] = (double)(z.N * z.J2 - z.J1 * z.J1) * rN * rN;
+}
+
+// A.9 GLDM: D[n][nd] counters, column = dependence count
+__device__ void gldm_lane(const RadbTabs& tb, const int* D, int n, int nd, double* o)
+{
+    ZoneSums z;
+    zs_init(z);
+    for (int i = 0; i < n; i++) {
+        int g = 0;
+        for (int j = 0; j < nd; j++) {
+            const int c = D[i * nd + j];
+            if (!c) continue;
+            g += c;
+            zs_cell(z, tb, i + 1, j + 1, c);
+        }
+        if (g) zs_level(z, tb, i + 1, g);
+    }
+    for (int j = 0; j < nd; j++) {
+        int cs = 0;
+        for (int i = 0; i < n; i++) cs += D[i * nd + j];
+        z.PJ2 += (long long)cs * cs;
+    }
+    const double N = z.N ? (double)z.N : 1.0, rN = radb_div(1.0, N);
+    o[0] = z.N ? radb_log2(N) - z.e1 * rN - RADB_EPS_LN2 * (double)z.nnz : 0.0;
+    o[1] = (double)z.PJ2 * rN;
+    o[2] = (double)z.PJ2 * rN * rN;
+    o[3] = (double)(z.N * z.J2 - z.J1 * z.J1) * rN * rN;
+    o[4] = (double)z.G2 * rN;
+    o[5] = (double)(z.N * z.GI2 - z.GI * z.GI) * rN * rN;
+    o[6] = (double)z.GI2 * rN;
+    o[7] = (double)z.J2 * rN;
+    o[8] = z.lh * rN;
+    o[9] = z.ll * rN;
+    o[10] = z.lgl * rN;
+    o[11] = z.small * rN;
+    o[12] = z.sh * rN;
+    o[13] = z.sl * rN;
+}
+
+// A.9 NGTDM: C[n][nb] voxel counts per neighbour count, S[n][nb] integer numerators (see ngtdm_task)
+__device__ void ngtdm_lane(const int* C, const int* S, int n, int nb, double* scr, double* o, int* dbg_n, double* dbg_s)
+{
+    long long nvp = 0;
+    for (int i = 0; i < n; i++) {
+        int ni = 0;
+        double s = 0;
+        for (int c = 0; c < nb; c++) {
+            const int cc = C[i * nb + c];
+            if (!cc) continue;
+            ni += cc;
+            s += radb_div((double)S[i * nb + c], (double)(c + 1));
+        }
+        MLD(scr, i) = (double)ni;
+        MLD(scr, n + i) = s;
+        nvp += ni;
+        if (dbg_n) { dbg_n[i] = ni; dbg_s[i] = s; }
+    }
+    if (nvp == 0) {
+        for (int f = 0; f < 5; f++) o[f] = nan_f64();
+        return;
+    }
+    const double Nvp = (double)nvp, rNvp = radb_div(1.0, Nvp);
+    for (int i = 0; i < n; i++) {
+        const double c = MLD(scr, i);
+        if (c != 0.0) MLD(scr, i) = radb_div(c, Nvp);  // true division, as upstream (Busyness tests a sum against 0)
+    }
+    double sum_ps = 0, sum_s = 0, absd = 0, cplx = 0, contr = 0, stren = 0;
+    int ngp = 0;
+    for (int i = 0; i < n; i++) {
+        const double p_i = MLD(scr, i);
+        if (p_i == 0.0) continue;
+        ngp++;
+        const double s_i = MLD(scr, n + i), di = (double)(i + 1), ip = __dmul_rn(di, p_i);
+        sum_ps += p_i * s_i;
+        sum_s += s_i;
+        for (int j = 0; j < i; j++) {  // the (i, j) and (j, i) terms are equal
+            const double p_j = MLD(scr, j);
+            if (p_j == 0.0) continue;
+            const double dj = (double)(j + 1), dd = di - dj, d2 = dd * dd;
+            absd += 2.0 * fabs(ip - __dmul_rn(dj, p_j));
+            cplx += 2.0 * radb_div(fabs(dd) * (p_i * s_i + p_j * MLD(scr, n + j)), p_i + p_j);
+            contr += 2.0 * p_i * p_j * d2;
+            stren += 2.0 * (p_i + p_j) * d2;
+        }
+    }
+    const double div = (double)ngp * (double)(ngp - 1);
+    o[0] = (absd != 0.0) ? radb_div(sum_ps, absd) : 0.0;
+    o[1] = (sum_ps != 0.0) ? radb_div(1.0, sum_ps) : 1e6;
+    o[2] = cplx * rNvp;
+    o[3] = (div != 0.0) ? radb_div(contr * sum_s * rNvp, div) : 0.0;
+    o[4] = (sum_s != 0.0) ? radb_div(stren, sum_s) : 0.0;
+}
+
+// A.5 first-order for uint8 pixels from the 256-bin raw histogram + the level histogram
+__device__ void fo_lane_u8(const RadbParams& p, const int* hist, const int* lhist, int ng, int N, double* scr, double* o)
+{
+    const double dN = (double)N, rN = radb_div(1.0, dN), shift = p.shift;
+    // ranks behind the 10/25/50/75/90 percentiles (numpy 'linear'): lo/hi order statistics, ascending
+    for (int q = 0; q < 5; q++) {
+        const double qq = q == 0 ? 0.1 : q == 1 ? 0.25 : q == 2 ? 0.5 : q == 3 ? 0.75 : 0.9;
+        const double pos = qq * (dN - 1.0), fl = floor(pos);
+        int lo = (int)fl;
+        lo = lo > N - 1 ? N - 1 : lo;
+        const int hi = lo + 1 > N - 1 ? N - 1 : lo + 1;
+        MLD(scr, 10 + q) = pos - fl;
+        MLD(scr, 2 * q) = (double)lo;      // rank now, order statistic after the pass
+        MLD(scr, 2 * q + 1) = (double)hi;
+    }
+    long long s1 = 0;
+    int vmin = 256, vmax = -1, cum = 0;
+    // the lo ranks (slots 0, 2, ..) and the hi ranks (slots 1, 3, ..) are each non-decreasing: one cursor per sequence
+    int tl = 0, th = 1;
+    int nextl = (int)MLD(scr, 0), nexth = (int)MLD(scr, 1);
+    for (int v = 0; v < 256; v++) {
+        const int hk = hist[v];
+        if (!hk) continue;
+        s1 += (long long)hk * v;
+        vmin = v < vmin ? v : vmin;
+        vmax = v;
+        cum += hk;
+        while (tl < 10 && nextl < cum) {
+            MLD(scr, tl) = (double)v;
+            tl += 2;
+            nextl = tl < 10 ? (int)MLD(scr, tl) : 0;
+        }
+        while (th < 10 && nexth < cum) {
+            MLD(scr, th) = (double)v;
+            th += 2;
+            nexth = th < 10 ? (int)MLD(scr, th) : 0;
+        }
+    }
+    const double mean = (double)s1 * rN;
+    double pc[5];
+#pragma unroll
+    for (int q = 0; q < 5; q++) pc[q] = MLD(scr, 2 * q) + (MLD(scr, 2 * q + 1) - MLD(scr, 2 * q)) * MLD(scr, 10 + q);
+    const double p10 = pc[0], p25 = pc[1], med = pc[2], p75 = pc[3], p90 = pc[4];
+    double m2 = 0, m3 = 0, m4 = 0, mad = 0, en = 0, in_s1 = 0;
+    int in_n = 0;
+    for (int v = vmin; v <= vmax; v++) {
+        const int hi_ = hist[v];
+        if (!hi_) continue;
+        const double dv = (double)v, hk = (double)hi_, d = dv - mean, d2 = d * d;
+        m2 += hk * d2;
+        m3 += hk * d2 * d;
+        m4 += hk * d2 * d2;
+        mad += hk * fabs(d);
+        en += hk * (dv + shift) * (dv + shift);
+        if (dv >= p10 && dv <= p90) { in_n += hi_; in_s1 += hk * dv; }
+    }
+    m2 *= rN; m3 *= rN; m4 *= rN; mad *= rN;
+    const double rin = radb_div(1.0, (double)in_n), in_mean = in_s1 * rin;
+    double rmad = 0;
+    for (int v = vmin; v <= vmax; v++) {
+        const double dv = (double)v;
+        if (dv >= p10 && dv <= p90) rmad += (double)hist[v] * fabs(dv - in_mean);
+    }
+    double ent = 0, uni = 0;
+    for (int i = 0; i < ng; i++) {
+        const int c = lhist[i];
+        if (!c) continue;
+        const double pi = (double)c * rN;
+        ent -= pi * radb_log2(pi + RADB_EPS);
+        uni += pi * pi;
+    }
+    o[0] = p10;
+    o[1] = p90;
+    o[2] = en;
+    o[3] = ent;
+    o[4] = p75 - p25;
+    o[5] = (m2 == 0.0) ? 0.0 : radb_div(m4, m2 * m2);
+    o[6] = (double)vmax;
+    o[7] = mad;
+    o[8] = mean;
+    o[9] = med;
+    o[10] = (double)vmin;
+    o[11] = (double)(vmax - vmin);
+    o[12] = rmad * rin;
+    o[13] = radb_sqrt(en * rN);
+    o[14] = (m2 == 0.0) ? 0.0 : radb_div(m3, m2 * radb_sqrt(m2));
+    o[15] = en;  // TotalEnergy: pixel spacing is (1, 1)
+    o[16] = uni;
+    o[17] = m2;
+}
+
+__device__ void radb_misc_lane_cta(const RadbParams& p, long long cta, unsigned char* smem)
+{
+    const int tid = threadIdx.x, lane = tid & 31, cls = tid >> 5;
+    const long long patch = cta * 32 + lane;
+    if (patch >= p.B || p.status[patch] != 0) return;  // no collectives below: early exit is safe
+    const unsigned char* rec = p.ws + patch * (long long)p.rec_bytes;
+    const int* misc = (const int*)(rec + (p.o_misc - p.o_rec));
+    const int ng = misc[8], NB = 2 * p.n_angles;
+    double* out = p.out + patch * (long long)p.F;
+    double* scr = (double*)smem + cls * (p.ml_doubles * 32) + lane;
+    RadbTabs tb;
+    tb.inv2 = p.g_inv2;
+    tb.ninv = p.ninv;
+    tb.tlog = p.g_tlog;
+    tb.red = (double*)0;
+    if (cls == 0) {
+        const int novf = misc[5];
+        if (p.off_glszm >= 0 && novf <= RADB_LANE_MAX_OVF)
+            glszm_lane(p, tb, (const int*)(rec + (p.o_szm - p.o_rec)), (const unsigned*)(rec + (p.o_ovf - p.o_rec)), novf, ng,
+                       scr, out + p.off_glszm);
+    } else if (cls == 1) {
+        if (p.off_gldm >= 0) gldm_lane(tb, (const int*)(rec + (p.o_gldm - p.o_rec)), ng, NB + 1, out + p.off_gldm);
+    } else if (cls == 2) {
+        if (p.off_ngtdm >= 0 || p.dbg_ngn) {
+            double dummy[5];
+            ngtdm_lane((const int*)(rec + (p.o_ngc - p.o_rec)), (const int*)(rec + (p.o_ngn - p.o_rec)), ng, NB, scr,
+                       p.off_ngtdm >= 0 ? out + p.off_ngtdm : dummy, p.dbg_ngn ? p.dbg_ngn + patch * p.max_ng : (int*)0,
+                       p.dbg_ngs ? p.dbg_ngs + patch * p.max_ng : (double*)0);
+        }
+    } else {
+        if (p.off_fo >= 0 && p.pix_bytes == 1)  // non-uint8: done by the build kernel
+            fo_lane_u8(p, (const int*)(rec + (p.o_hist - p.o_rec)), (const int*)(rec + (p.o_lhist - p.o_rec)), ng, misc[0],
+                       scr, out + p.off_fo);
+    }
+}

@@ -66,6 +66,9 @@ struct RadbParams {
     int s_smem_total;  // shape kernel
     // ---- lane kernel (radb_lane.cuh): one thread per (patch, angle), l_doubles fp64 slots of shared memory each
     int use_lane, l_nap, l_doubles, l_smem_total;
+    // ---- misc lane kernel: one thread per (patch, class); the warp-level misc kernel then only serves GLSZM
+    // patches with a long overflow list (only_big_ovf = 1)
+    int ml_doubles, ml_smem_total, only_big_ovf;
     // global workspace + tables (device pointers)
     unsigned char* ws;        // [B][rec_bytes]
     unsigned char* ws_scr;    // [B][scr_bytes] (wide mode)
@@ -162,6 +165,8 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     // (>= 3 resident CTAs per SM: with fewer the serial per-thread chains are latency-bound and the
     // warp-per-angle kernel wins -- measured at Ng 26: 1.55 ms vs 1.16 ms per 8192 patches)
     p->use_lane = (p->symmetric && p->l_smem_total <= 72 * 1024) ? 1 : 0;
+    p->ml_doubles = 2 * ng + 16 > 32 ? 2 * ng + 16 : 32;  // >= RADB_LANE_MAX_OVF / 2 slots for the sorted overflow list
+    p->ml_smem_total = 4 * p->ml_doubles * 32 * 8;
     // ---- misc kernel
     o = 0;
     p->m_pg = o; o += radb_align(ng * 4, 16);

@@ -74,6 +74,8 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
     mx = mx > p.s_smem_total ? mx : p.s_smem_total;
     if (getenv("RADB_NO_LANE")) p.use_lane = 0;
     if (p.use_lane && p.l_smem_total > mx) mx = p.l_smem_total;
+    p.only_big_ovf = (!getenv("RADB_NO_LANE") && p.ml_smem_total <= 96 * 1024) ? 1 : 0;
+    if (p.only_big_ovf && p.ml_smem_total > mx) mx = p.ml_smem_total;
     std::vector<unsigned char> smem((size_t)mx + 64);
     unsigned char* sm = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
     // the same three launches radb_api.cu issues, CTA by CTA on host threads
@@ -93,6 +95,8 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
         emu::launch((unsigned)((B * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, [&]() { radb_angle_lane_cta(p, (long long)blockIdx.x, sm); });
     else
         emu::launch((unsigned)B, RADB_NT, [&]() { radb_angle_cta(p, (long long)blockIdx.x, sm); });
+    if (p.only_big_ovf)
+        emu::launch((unsigned)((B + 31) / 32), RADB_NT, [&]() { radb_misc_lane_cta(p, (long long)blockIdx.x, sm); });
     emu::launch((unsigned)B, RADB_NT, [&]() { radb_misc_cta(p, (long long)blockIdx.x, sm); });
     if (p.off_shape >= 0) emu::launch((unsigned)B, RADB_NT, [&]() { radb_shape_cta(p, (long long)blockIdx.x, sm); });
     return 0;

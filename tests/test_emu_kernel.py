@@ -69,6 +69,20 @@ def test_emu_large_zones_overflow_path(emu):
     assert (r["glszm"][0].sum(0)[16:] > 0).any()
 
 
+def test_emu_many_large_zones_take_the_warp_level_glszm(emu):
+    # 1-pixel stripes of alternating levels: 60 zones of 60 pixels each -> longer overflow list than the
+    # thread-per-patch GLSZM task accepts (RADB_LANE_MAX_OVF = 48), so the warp-level task must take the patch;
+    # the second patch has 30 such zones and stays on the thread-level task
+    H = W = 60
+    img = np.zeros((2, H, W), np.uint8)
+    img[0] = np.where(np.arange(W) % 2 == 0, 40, 200)[None, :]
+    img[1] = np.where((np.arange(W) // 2) % 2 == 0, 40, 200)[None, :]
+    mask = np.full((2, H, W), 255, np.uint8)
+    r = emu.run(img, mask, 25, 255, INPLANE)
+    assert compare_with_oracle(r, img, mask, dict(label=255, binWidth=25, force2D=False)) == 2
+    assert r["glszm"][0].sum() == 60 and r["glszm"][1].sum() == 30
+
+
 def test_emu_golden_fixture(emu):
     z = np.load(os.path.join(GOLD, "oracle_features_seed0.npz"))
     r = emu.run(z["images"][:2], z["masks"][:2], 10, 255, INPLANE)
