@@ -103,6 +103,16 @@ int radb_smem_bytes(const radb_handle* h, int H, int W, int dtype);
 int radb_extract(radb_handle* h, const void* img, int dtype, const uint8_t* mask, int64_t B, int H, int W,
                  int64_t img_stride_b, int64_t mask_stride_b, double* out, int32_t* status, void* cuda_stream);
 
+/* Variable-size batches -- the reference's records are whole images of differing sizes, each with its own
+ * mask (RadiomicExtractor.py:29-36), fanned out one execute() per record (:58-65).  `img_pool` / `mask_pool`
+ * are DEVICE buffers holding n patches back to back in any order; the HOST arrays img_off[n] / mask_off[n]
+ * give each patch's byte offset into its pool and hw[n][2] its (H, W).  Patches of equal size are launched
+ * together; row i of out / status belongs to patch i whatever its size.  Offsets that are multiples of 16
+ * bytes keep the TMA staging path.  The index lists are copied to a grow-only device buffer of the handle. */
+int radb_extract_ragged(radb_handle* h, const void* img_pool, int dtype, const uint8_t* mask_pool, int64_t n,
+                        const int64_t* img_off, const int64_t* mask_off, const int32_t* hw, double* out,
+                        int32_t* status, void* cuda_stream);
+
 /* RadiomicsExtractor.extract_radiomics (RadiomicExtractor.py:23-55) for a batch of decoded records:
  * `bgr` = interleaved BGR uint8 images [n][H][W][3] exactly as cv2.imread returns them (:29), `mask`
  * = one uint8 mask per image [n][H][W] (:33-36).  A front-end kernel writes the gray (cv2 BGR2GRAY

@@ -32,7 +32,7 @@ struct radb_handle {
     int smem_optin;              // max dynamic shared memory per block the device allows
     int smem_set[32];             // configured MaxDynamicSharedMemorySize per kernel
     int64_t launches;
-    struct Ws { void* stream; unsigned char* p; size_t bytes; };
+    struct Ws { void* stream; unsigned char* p; size_t bytes; long long* meta; size_t meta_bytes; };
     std::vector<Ws> ws;          // per-patch records of one chunk, one workspace per CUDA stream
                                  // (launches on different streams may overlap; each owns its records)
     double* d_inv2;
@@ -98,8 +98,10 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
 extern "C" void radb_destroy(radb_handle* h)
 {
     if (!h) return;
-    for (auto& w : h->ws)
+    for (auto& w : h->ws) {
         if (w.p) cudaFree(w.p);
+        if (w.meta) cudaFree(w.meta);
+    }
     if (h->d_inv2) cudaFree(h->d_inv2);
     if (h->d_tlog) cudaFree(h->d_tlog);
     delete h;
@@ -125,7 +127,7 @@ static int ensure_ws(radb_handle* h, const RadbParams& p, int64_t B, void* strea
     for (auto& e : h->ws)
         if (e.stream == stream) w = &e;
     if (!w) {
-        h->ws.push_back({stream, nullptr, 0});
+        h->ws.push_back({stream, nullptr, 0, nullptr, 0});
         w = &h->ws.back();
     }
     if (need > w->bytes) {
@@ -232,10 +234,16 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     while (done < p.B) {
         const long long n = p.B - done < chunk ? p.B - done : chunk;
         RadbParams q = p;
-        q.img = (const unsigned char*)p.img + done * p.img_stride;
-        q.mask = p.mask + (done / p.mask_group) * p.mask_stride;  // chunks are multiples of mask_group
-        q.out = p.out + done * p.F;
-        q.status = p.status + done;
+        if (p.rows) {  // ragged group: the index lists advance, the pools and the output stay put
+            q.img_off = p.img_off + done;
+            q.mask_off = p.mask_off + done;
+            q.rows = p.rows + done;
+        } else {
+            q.img = (const unsigned char*)p.img + done * p.img_stride;
+            q.mask = p.mask + (done / p.mask_group) * p.mask_stride;  // chunks are multiples of mask_group
+            q.out = p.out + done * p.F;
+            q.status = p.status + done;
+        }
         q.B = n;
         if (done) {  // debug buffers (parity tests) advance with the chunk
             const long long HW = p.HW, NA = p.n_angles, NG = p.max_ng;
@@ -313,6 +321,81 @@ extern "C" int radb_extract(radb_handle* h, const void* img, int dtype, const ui
     if (rc) return rc;
     if (B == 0) return RADB_OK;
     return launch(h, p, dtype, cuda_stream);
+}
+
+// Variable-size batches: patches are grouped by (H, W) and every group runs the same kernels as radb_extract,
+// reading its patches through per-patch byte offsets and writing rows in input order.
+extern "C" int radb_extract_ragged(radb_handle* h, const void* img_pool, int dtype, const uint8_t* mask_pool, int64_t n,
+                                   const int64_t* img_off, const int64_t* mask_off, const int32_t* hw, double* out,
+                                   int32_t* status, void* cuda_stream)
+{
+    if (!h || !img_pool || !mask_pool || !out || !status) return fail(RADB_E_INVALID, "null argument");
+    if (n < 0) return fail(RADB_E_INVALID, "negative batch size");
+    if (n == 0) return RADB_OK;
+    if (!img_off || !mask_off || !hw) return fail(RADB_E_INVALID, "null argument");
+    std::vector<radb::RaggedGroup> groups;
+    std::string err;
+    int rc = radb::group_ragged(n, hw, groups, err);
+    if (rc) return fail(rc, err);
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != h->device) cudaSetDevice(h->device);
+    // device copy of the index lists: [img_off | mask_off | rows] per group, group after group
+    radb_handle::Ws* w = nullptr;
+    for (auto& e : h->ws)
+        if (e.stream == cuda_stream) w = &e;
+    if (!w) {
+        h->ws.push_back({cuda_stream, nullptr, 0, nullptr, 0});
+        w = &h->ws.back();
+    }
+    const size_t need = (size_t)n * 3 * sizeof(long long);
+    if (need > w->meta_bytes) {
+        if (w->meta) cudaFree(w->meta);
+        w->meta = nullptr;
+        w->meta_bytes = 0;
+        cudaError_t e = cudaMalloc(&w->meta, need);
+        if (e != cudaSuccess) return cuda_fail(e, "ragged index allocation");
+        w->meta_bytes = need;
+    }
+    std::vector<long long> host((size_t)n * 3);
+    {
+        size_t o = 0;
+        for (const auto& g : groups) {
+            const size_t k = g.idx.size();
+            for (size_t j = 0; j < k; j++) {
+                host[o + j] = img_off[g.idx[j]];
+                host[o + k + j] = mask_off[g.idx[j]];
+                host[o + 2 * k + j] = g.idx[j];
+            }
+            o += 3 * k;
+        }
+    }
+    long long* meta = w->meta;  // (ensure_ws below may reallocate h->ws entries, not this buffer)
+    cudaError_t e = cudaMemcpyAsync(meta, host.data(), need, cudaMemcpyHostToDevice, (cudaStream_t)cuda_stream);
+    if (e != cudaSuccess) return cuda_fail(e, "ragged index upload");
+    // pageable source: the call returns once `host` has been staged, so the vector may die with this scope
+    size_t o = 0;
+    for (const auto& g : groups) {
+        const long long k = (long long)g.idx.size();
+        RadbParams p;
+        const long long HWb = (long long)g.H * g.W;
+        rc = setup(h, img_pool, dtype, mask_pool, k, g.H, g.W, HWb * (dtype == RADB_DTYPE_U8 ? 1 : dtype == RADB_DTYPE_U16 ? 2 : dtype == RADB_DTYPE_F32 ? 4 : 8),
+                   HWb, out, status, p);
+        if (rc) return rc;
+        p.img_off = meta + o;
+        p.mask_off = meta + o + k;
+        p.rows = meta + o + 2 * k;
+        bool aligned = p.use_tma;
+        for (long long j = 0; j < k && aligned; j++)
+            aligned = (img_off[g.idx[j]] % 16 == 0) && (mask_off[g.idx[j]] % 16 == 0);
+        p.use_tma = aligned ? 1 : 0;
+        for (long long j = 0; j < k; j++)
+            if (img_off[g.idx[j]] % p.pix_bytes != 0) return fail(RADB_E_INVALID, "ragged batch: pixel offset not aligned to the pixel size");
+        rc = launch(h, p, dtype, cuda_stream);
+        if (rc) return rc;
+        o += 3 * k;
+    }
+    return RADB_OK;
 }
 
 extern "C" int radb_debug_matrices(radb_handle* h, const void* img, int dtype, const uint8_t* mask, int64_t B,

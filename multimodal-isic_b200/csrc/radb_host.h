@@ -179,6 +179,30 @@ static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParam
     return 0;
 }
 
+// radb_extract_ragged: patches of one (H, W) are launched together.  Groups keep the order in which their
+// size first appears and every group keeps its members in input order.
+struct RaggedGroup {
+    int H, W;
+    std::vector<long long> idx;  // input positions
+};
+static inline int group_ragged(long long n, const int32_t* hw, std::vector<RaggedGroup>& groups, std::string& err)
+{
+    groups.clear();
+    for (long long i = 0; i < n; i++) {
+        const int H = hw[2 * i], W = hw[2 * i + 1];
+        if (H < 1 || W < 1) { err = "ragged batch: non-positive patch size"; return RADB_E_INVALID; }
+        RaggedGroup* g = nullptr;
+        for (auto& e : groups)
+            if (e.H == H && e.W == W) { g = &e; break; }
+        if (!g) {
+            groups.push_back({H, W, {}});
+            g = &groups.back();
+        }
+        g->idx.push_back(i);
+    }
+    return 0;
+}
+
 // 1/k^2 and log2(k) tables read by the reduction kernels (device copies are made at radb_create)
 static inline void make_tables(int ninv, std::vector<double>& inv2, std::vector<double>& tlog)
 {

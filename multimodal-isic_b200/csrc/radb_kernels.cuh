@@ -270,6 +270,13 @@ __device__ __forceinline__ double py_mod(double a, double b)
     return r;
 }
 
+// dense batches: patch k is row k; ragged batches: the group-local patch k maps to output row rows[k]
+__device__ __forceinline__ long long radb_row(const RadbParams& p, long long patch) { return p.rows ? p.rows[patch] : patch; }
+__device__ __forceinline__ const unsigned char* radb_mask_ptr(const RadbParams& p, long long patch)
+{
+    return p.mask_off ? p.mask + p.mask_off[patch] : p.mask + (patch / p.mask_group) * p.mask_stride;
+}
+
 #include "radb_features.cuh"
 #include "radb_lane.cuh"
 
@@ -508,8 +515,9 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     const UW ULO = (((UW)1) << US) - 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, HW = p.HW, WP = p.WP, XO = p.xo, NA = p.n_angles, NB = 2 * p.n_angles;
-    const PT* g_img = (const PT*)((const unsigned char*)p.img + patch * p.img_stride);
-    const unsigned char* g_msk = p.mask + (patch / p.mask_group) * p.mask_stride;
+    const PT* g_img = (const PT*)((const unsigned char*)p.img + (p.img_off ? p.img_off[patch] : patch * p.img_stride));
+    const unsigned char* g_msk = radb_mask_ptr(p, patch);
+    const long long row = radb_row(p, patch);
     unsigned char* g_rec = p.ws + patch * (long long)p.rec_bytes;              // this patch's record (global)
     unsigned char* g_scr = WIDE ? p.ws_scr + patch * p.scr_bytes : (unsigned char*)0;  // wide-mode scratch (global)
     // narrow: the raw patch is staged in shared memory and the level image / union-find words live
@@ -529,7 +537,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     unsigned* ovf = WIDE ? (unsigned*)(g_rec + (p.o_ovf - p.o_rec)) : (unsigned*)(smem + p.o_ovf);
     unsigned char* glrlm_base = WIDE ? g_rec + (p.o_glrlm - p.o_rec) : smem + p.o_glrlm;
     int* misc = (int*)(smem + p.o_misc);
-    double* out = p.out + patch * (long long)p.F;
+    double* out = p.out + row * (long long)p.F;
 
     // ---- phase 0: stage the patch, zero the counters
 #ifndef RADB_EMU
@@ -697,12 +705,12 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         if (st) {
             for (int f = tid; f < p.F; f += RADB_NTB) out[f] = nan_f64();
             if (tid == 0) {
-                p.status[patch] = st;
+                p.status[row] = st;
                 if (DBG && p.dbg_ng) p.dbg_ng[patch] = 0;
             }
             return;
         }
-        if (tid == 0) { misc[8] = ng; p.status[patch] = 0; }
+        if (tid == 0) { misc[8] = ng; p.status[row] = 0; }
     }
     __syncthreads();
     const int ng = misc[8];
@@ -1037,13 +1045,14 @@ __device__ void radb_angle_cta(const RadbParams& p, long long patch, unsigned ch
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NA = p.n_angles;
-    if (p.status[patch] != 0) return;  // NaN row already written by the build kernel
+    const long long row = radb_row(p, patch);
+    if (p.status[row] != 0) return;  // NaN row already written by the build kernel
     const unsigned char* rec = p.ws + patch * (long long)p.rec_bytes;
     const int* misc = (const int*)(rec + (p.o_misc - p.o_rec));
     const int ng = misc[8], nroi = misc[9];
     double* fsc = (double*)(smem + p.a_fsc);
     int* valid = (int*)(smem + p.a_valid);
-    double* out = p.out + patch * (long long)p.F;
+    double* out = p.out + row * (long long)p.F;
     RadbTabs tb;
     tb.inv2 = p.g_inv2;
     tb.ninv = p.ninv;
@@ -1090,11 +1099,12 @@ __device__ void radb_misc_cta(const RadbParams& p, long long patch, unsigned cha
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int NB = 2 * p.n_angles;
-    if (p.status[patch] != 0) return;
+    const long long row = radb_row(p, patch);
+    if (p.status[row] != 0) return;
     const unsigned char* rec = p.ws + patch * (long long)p.rec_bytes;
     const int* misc = (const int*)(rec + (p.o_misc - p.o_rec));
     const int ng = misc[8];
-    double* out = p.out + patch * (long long)p.F;
+    double* out = p.out + row * (long long)p.F;
     RadbTabs tb;
     tb.inv2 = p.g_inv2;
     tb.ninv = p.ninv;
@@ -1189,9 +1199,10 @@ __device__ void radb_shape_cta(const RadbParams& p, long long patch, unsigned ch
 {
     const int tid = threadIdx.x, lane = tid & 31;
     const int H = p.H, W = p.W;
-    if (p.status[patch] != 0 || p.off_shape < 0) return;
-    const unsigned char* m = p.mask + (patch / p.mask_group) * p.mask_stride;
-    double* out = p.out + patch * (long long)p.F + p.off_shape;
+    const long long row = radb_row(p, patch);
+    if (p.status[row] != 0 || p.off_shape < 0) return;
+    const unsigned char* m = radb_mask_ptr(p, patch);
+    double* out = p.out + row * (long long)p.F + p.off_shape;
     const int nrow = 2 * H + 1;                     // doubled y coordinates 0..2H of contour vertices (shifted by +1)
     int* xmin = (int*)smem;                         // [nrow]
     int* xmax = xmin + nrow;                        // [nrow]

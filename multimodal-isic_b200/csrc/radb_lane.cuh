@@ -424,7 +424,8 @@ __device__ void radb_angle_lane_cta(const RadbParams& p, long long cta, unsigned
     const long long g = cta * RADB_NTL + t;
     const long long patch = g / NAP;
     const int a = (int)(g - patch * NAP);
-    const bool patch_ok = patch < p.B && p.status[patch] == 0;  // status != 0: NaN row written by the build kernel
+    const long long row = patch < p.B ? radb_row(p, patch) : 0;
+    const bool patch_ok = patch < p.B && p.status[row] == 0;  // status != 0: NaN row written by the build kernel
     const bool live = patch_ok && a < NA;
     LaneMem lm;
     lm.d = (double*)smem + t;
@@ -438,7 +439,7 @@ __device__ void radb_angle_lane_cta(const RadbParams& p, long long cta, unsigned
     const int* misc = (const int*)(rec + (p.o_misc - p.o_rec));
     int ng = 0, nroi = 0;
     if (patch_ok) { ng = misc[8]; nroi = misc[9]; }
-    double* out = p.out + (patch_ok ? patch : 0) * (long long)p.F;
+    double* out = p.out + row * (long long)p.F;
     if (p.off_glrlm >= 0) {
         double f[RADB_GLRLM_NF];
 #pragma unroll
@@ -722,11 +723,13 @@ __device__ void radb_misc_lane_cta(const RadbParams& p, long long cta, unsigned 
 {
     const int tid = threadIdx.x, lane = tid & 31, cls = tid >> 5;
     const long long patch = cta * 32 + lane;
-    if (patch >= p.B || p.status[patch] != 0) return;  // no collectives below: early exit is safe
+    if (patch >= p.B) return;  // no collectives below: early exit is safe
+    const long long row = radb_row(p, patch);
+    if (p.status[row] != 0) return;
     const unsigned char* rec = p.ws + patch * (long long)p.rec_bytes;
     const int* misc = (const int*)(rec + (p.o_misc - p.o_rec));
     const int ng = misc[8], NB = 2 * p.n_angles;
-    double* out = p.out + patch * (long long)p.F;
+    double* out = p.out + row * (long long)p.F;
     double* scr = (double*)smem + cls * (p.ml_doubles * 32) + lane;
     RadbTabs tb;
     tb.inv2 = p.g_inv2;

@@ -24,6 +24,11 @@ struct RadbParams {
     long long img_stride;   // bytes between patches
     long long mask_stride;  // bytes between masks
     int mask_group;         // consecutive patches sharing one mask (1; 4 for the gray/R/G/B planes of an image)
+    // ragged batches (radb_extract_ragged): patch k of a same-size group reads its pixels / mask at byte
+    // offsets img_off[k] / mask_off[k] from img / mask and writes row rows[k] of out / status (null: dense)
+    const long long* img_off;
+    const long long* mask_off;
+    const long long* rows;
     double* out;            // [B][F]
     int* status;            // [B]
     long long B;

@@ -97,6 +97,41 @@ class Engine:
             raise RadbError("radb_extract failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
         return out, status
 
+    def extract_ragged(self, img_pool, mask_pool, img_off, mask_off, hw, out=None, status=None, stream=None):
+        """Variable-size batch (radb_extract_ragged): ``img_pool`` / ``mask_pool`` are 1-D device tensors
+        holding the patches back to back, ``img_off`` / ``mask_off`` (int64, BYTES) and ``hw`` ([n, 2] int32)
+        are host arrays.  Row i of the result belongs to patch i."""
+        if not (img_pool.is_cuda and mask_pool.is_cuda and img_pool.is_contiguous() and mask_pool.is_contiguous()):
+            raise ValueError("pools must be contiguous CUDA tensors")
+        if img_pool.dtype not in self.DTYPES or mask_pool.dtype != torch.uint8:
+            raise TypeError("img_pool must be uint8/uint16/float32/float64 and mask_pool uint8")
+        import numpy as np
+
+        img_off = np.ascontiguousarray(img_off, dtype=np.int64)
+        mask_off = np.ascontiguousarray(mask_off, dtype=np.int64)
+        hw = np.ascontiguousarray(hw, dtype=np.int32).reshape(-1, 2)
+        n = len(hw)
+        if len(img_off) != n or len(mask_off) != n:
+            raise ValueError("img_off, mask_off and hw must have one entry per patch")
+        es = img_pool.element_size()
+        if n:
+            px = hw[:, 0].astype(np.int64) * hw[:, 1]
+            if (img_off < 0).any() or (mask_off < 0).any() or (img_off + px * es > img_pool.numel() * es).any() or \
+                    (mask_off + px > mask_pool.numel()).any():
+                raise ValueError("patch extends beyond its pool")
+        dev = img_pool.device
+        if out is None:
+            out = torch.empty((n, self.F), dtype=torch.float64, device=dev)
+        if status is None:
+            status = torch.empty((n,), dtype=torch.int32, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = self.lib.radb_extract_ragged(self._h, img_pool.data_ptr(), self.DTYPES[img_pool.dtype], mask_pool.data_ptr(),
+                                          n, img_off.ctypes.data, mask_off.ctypes.data, hw.ctypes.data, out.data_ptr(),
+                                          status.data_ptr(), st.cuda_stream)
+        if rc != 0:
+            raise RadbError("radb_extract_ragged failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+        return out, status
+
     def extract_bgr(self, bgr, masks, stream=None, return_planes=False):
         """Decoded records in, four feature rows per record out (gray, R, G, B): ``bgr`` [n, H, W, 3]
         uint8 (cv2.imread layout), ``masks`` [n, H, W] uint8, both on the device.  The gray/R/G/B planes
@@ -161,6 +196,39 @@ class Engine:
         res["features"] = out.cpu().numpy()
         res["status"] = status.cpu().numpy()
         return res
+
+
+def pack_ragged(images, masks, align=16):
+    """Host-side packing of variable-size (image [H, W], mask [H, W]) pairs into two flat pools with
+    ``align``-byte aligned patch starts (keeps the TMA staging path).  Returns NumPy
+    ``(img_pool, mask_pool, img_off, mask_off, hw)`` ready for ``Engine.extract_ragged``."""
+    import numpy as np
+
+    if len(images) != len(masks):
+        raise ValueError("one mask per image")
+    n = len(images)
+    if n == 0:
+        return np.zeros(0, np.uint8), np.zeros(0, np.uint8), np.zeros(0, np.int64), np.zeros(0, np.int64), np.zeros((0, 2), np.int32)
+    dt = np.asarray(images[0]).dtype
+    es = dt.itemsize
+    hw = np.zeros((n, 2), np.int32)
+    img_off, mask_off = np.zeros(n, np.int64), np.zeros(n, np.int64)
+    io = mo = 0
+    for i, (im, mk) in enumerate(zip(images, masks)):
+        im, mk = np.asarray(im), np.asarray(mk)
+        if im.ndim != 2 or im.shape != mk.shape or im.dtype != dt:
+            raise ValueError("every image must be 2-D, of one dtype, with a mask of its own shape")
+        hw[i] = im.shape
+        img_off[i], mask_off[i] = io, mo
+        io += (im.size * es + align - 1) // align * align
+        mo += (im.size + align - 1) // align * align
+    img_pool = np.zeros(io // es, dt)
+    mask_pool = np.zeros(mo, np.uint8)
+    for i, (im, mk) in enumerate(zip(images, masks)):
+        k = hw[i, 0] * hw[i, 1]
+        img_pool[img_off[i] // es: img_off[i] // es + k] = np.asarray(im).reshape(-1)
+        mask_pool[mask_off[i]: mask_off[i] + k] = np.asarray(mk, dtype=np.uint8).reshape(-1)
+    return img_pool, mask_pool, img_off, mask_off, hw
 
 
 class HostPipeline:

@@ -195,6 +195,44 @@ class RadiomicsExtractor:
         return out, status
 
 
+    def extract_list(self, images, masks, strict=False):
+        """Variable-size batch: ``images`` / ``masks`` are sequences of 2-D arrays (one dtype; each mask has
+        its image's shape) -- the shape the reference's records have after decoding (RadiomicExtractor.py:
+        29-36: whole images of differing sizes).  One call packs them into two pools, copies them to the
+        device and runs ``radb_extract_ragged`` (patches of equal size share a launch).  Returns NumPy
+        ``(features [n, F], status [n])`` in input order."""
+        if self.derived_types or not self._has_original:
+            raise NotImplementedError("extract_list handles the Original image type")
+        from .engine import pack_ragged
+
+        img_pool, mask_pool, img_off, mask_off, hw = pack_ragged(images, masks)
+        engine = self.engine
+        if img_pool.dtype != np.uint8:
+            engine, _ = self._engine_for_pool(images, masks)
+        dev = torch.device("cuda", self.device)
+        ip = torch.as_tensor(img_pool.view(np.int16) if img_pool.dtype == np.uint16 else img_pool).to(dev)
+        if img_pool.dtype == np.uint16:
+            ip = ip.view(torch.uint16)
+        out, status = engine.extract_ragged(ip, torch.as_tensor(mask_pool).to(dev), img_off, mask_off, hw)
+        out = self._permute(out).cpu().numpy()
+        status = status.cpu().numpy()
+        if strict and status.any():
+            raise _status_error(int(status[np.nonzero(status)[0][0]]), self.params.label)
+        return out, status
+
+    def _engine_for_pool(self, images, masks):
+        """Non-uint8 ragged batches: an engine sized for the largest ROI range of the batch (see _engine_for)."""
+        span = 0.0
+        for im, mk in zip(images, masks):
+            roi = np.asarray(im)[np.asarray(mk) == self.params.label]
+            if roi.size:
+                span = max(span, float(roi.max()) - float(roi.min()))
+        ng = min(255, (int(span / self.params.bin_width) + 3 + 7) // 8 * 8)
+        if ng not in self._engines_ng:
+            eng = Engine(*self._engine_args, max_ng=ng, device=self.device)
+            self._engines_ng[ng] = (eng, HostPipeline(eng, self.pipeline.chunk))
+        return self._engines_ng[ng]
+
     # ---- several image types ------------------------------------------------------------------
     def _device_blocks(self, images, masks, first=None):
         """[shape | block per image type] for uint8 device images; ``first`` = precomputed (out, status) of

@@ -33,33 +33,9 @@ extern "C" int radb_emu_max_ng(const radb_settings* s)
     return pl.max_ng;
 }
 
-// Host-pointer twin of radb_debug_matrices.
-extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dtype, const uint8_t* mask, int64_t B,
-                                int H, int W, int64_t img_stride_b, int64_t mask_stride_b, double* out,
-                                int32_t* status, int32_t* levels, int32_t* glcm, int32_t* glrlm, int32_t* glszm,
-                                int32_t* gldm, int32_t* ngtdm_n, double* ngtdm_s, int32_t* ng)
+// the launches radb_api.cu issues for one same-size batch, CTA by CTA on host threads
+static int emu_launch(RadbParams& p, int dtype, int64_t B)
 {
-    radb::Plan pl;
-    int rc = radb::make_plan(*s, pl, g_err);
-    if (rc) return rc;
-    RadbParams p;
-    rc = radb::fill_params(pl, H, W, dtype, p, g_err);
-    if (rc) return rc;
-    p.img = img;
-    p.mask = mask;
-    p.img_stride = img_stride_b;
-    p.mask_stride = mask_stride_b;
-    p.out = out;
-    p.status = status;
-    p.B = B;
-    p.dbg_levels = levels;
-    p.dbg_glcm = glcm;
-    p.dbg_glrlm = glrlm;
-    p.dbg_glszm = glszm;
-    p.dbg_gldm = gldm;
-    p.dbg_ngn = ngtdm_n;
-    p.dbg_ngs = ngtdm_s;
-    p.dbg_ng = ng;
     std::vector<double> inv2, tlog;
     radb::make_tables(p.ninv, inv2, tlog);
     if (getenv("RADB_EMU_PERTURB_TABLES"))  // host-libm vs device-libm: the tables may differ by an ulp
@@ -102,6 +78,36 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
     return 0;
 }
 
+// Host-pointer twin of radb_debug_matrices.
+extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dtype, const uint8_t* mask, int64_t B,
+                                int H, int W, int64_t img_stride_b, int64_t mask_stride_b, double* out,
+                                int32_t* status, int32_t* levels, int32_t* glcm, int32_t* glrlm, int32_t* glszm,
+                                int32_t* gldm, int32_t* ngtdm_n, double* ngtdm_s, int32_t* ng)
+{
+    radb::Plan pl;
+    int rc = radb::make_plan(*s, pl, g_err);
+    if (rc) return rc;
+    RadbParams p;
+    rc = radb::fill_params(pl, H, W, dtype, p, g_err);
+    if (rc) return rc;
+    p.img = img;
+    p.mask = mask;
+    p.img_stride = img_stride_b;
+    p.mask_stride = mask_stride_b;
+    p.out = out;
+    p.status = status;
+    p.B = B;
+    p.dbg_levels = levels;
+    p.dbg_glcm = glcm;
+    p.dbg_glrlm = glrlm;
+    p.dbg_glszm = glszm;
+    p.dbg_gldm = gldm;
+    p.dbg_ngn = ngtdm_n;
+    p.dbg_ngs = ngtdm_s;
+    p.dbg_ng = ng;
+    return emu_launch(p, dtype, B);
+}
+
 // Host twin of radb_bgr_planes_kernel (one "thread" per 4 pixels).
 extern "C" void radb_emu_bgr_planes(const uint8_t* bgr, uint8_t* planes, int64_t n_images, int64_t HW)
 {
@@ -117,4 +123,35 @@ extern "C" void radb_emu_derive(const uint8_t* img, int64_t n_images, int64_t HW
         for (int64_t k = 0; k < HW; k++) m = img[i * HW + k] > m ? img[i * HW + k] : m;
         for (int64_t k = 0; k < HW; k++) out[i * HW + k] = radb_derive_px(type, (double)img[i * HW + k], (double)m);
     }
+}
+
+// Host-pointer twin of radb_extract_ragged: same grouping (radb::group_ragged), same per-group launches.
+extern "C" int radb_emu_extract_ragged(const radb_settings* s, const void* img_pool, int dtype, const uint8_t* mask_pool,
+                                       int64_t n, const int64_t* img_off, const int64_t* mask_off, const int32_t* hw,
+                                       double* out, int32_t* status)
+{
+    radb::Plan pl;
+    int rc = radb::make_plan(*s, pl, g_err);
+    if (rc) return rc;
+    std::vector<radb::RaggedGroup> groups;
+    rc = radb::group_ragged(n, hw, groups, g_err);
+    if (rc) return rc;
+    for (const auto& g : groups) {
+        RadbParams p;
+        rc = radb::fill_params(pl, g.H, g.W, dtype, p, g_err);
+        if (rc) return rc;
+        std::vector<long long> io, mo, rows;
+        for (long long i : g.idx) { io.push_back(img_off[i]); mo.push_back(mask_off[i]); rows.push_back(i); }
+        p.img = img_pool;
+        p.mask = mask_pool;
+        p.img_off = io.data();
+        p.mask_off = mo.data();
+        p.rows = rows.data();
+        p.out = out;
+        p.status = status;
+        p.B = (long long)g.idx.size();
+        rc = emu_launch(p, dtype, p.B);
+        if (rc) return rc;
+    }
+    return 0;
 }

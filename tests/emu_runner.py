@@ -17,6 +17,23 @@ class EmuRunner:
         self.lib.radb_emu_extract.argtypes = [vp, vp, i32, vp, i64, i32, i32, i64, i64] + [vp] * 10
         self.lib.radb_emu_last_error.restype = ctypes.c_char_p
 
+    def run_ragged(self, images, masks, bin_width=10, label=255, angles=((0, 1),), classes=_abi.CLASS_ORDER, max_ng=0):
+        """Host twin of radb_extract_ragged on a list of variable-size (image, mask) pairs."""
+        from multimodal_isic_b200.engine import pack_ragged
+
+        ip, mp, io, mo, hw = pack_ragged(images, masks)
+        dtype = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3}[ip.dtype]
+        s = _abi.make_settings(bin_width, label, angles, classes=classes, max_ng=max_ng)
+        F = self.lib.radb_emu_feature_count(ctypes.byref(s))
+        n = len(hw)
+        out, status = np.zeros((n, F)), np.zeros(n, np.int32)
+        p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+        self.lib.radb_emu_extract_ragged.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                                     ctypes.c_int64] + [ctypes.c_void_p] * 5
+        rc = self.lib.radb_emu_extract_ragged(ctypes.byref(s), p(ip), dtype, p(mp), n, p(io), p(mo), p(hw), p(out), p(status))
+        assert rc == 0, self.lib.radb_emu_last_error()
+        return out, status
+
     def is_wide(self, H, W, bin_width=10, angles=((0, 1),)):
         s = _abi.make_settings(bin_width, 255, angles)
         return self.lib.radb_emu_is_wide(ctypes.byref(s), H, W)

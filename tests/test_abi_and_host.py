@@ -147,3 +147,24 @@ def test_settings_derived_image_types():
     assert names[:9] == ["original_shape2D_%s" % f for f in orc.SHAPE2D_NAMES]
     assert names[102] == "square_firstorder_10Percentile" and names[-1] == "exponential_ngtdm_Strength"
     assert s.engine_columns()[1] == list(range(len(names)))
+
+
+def test_pack_ragged_layout():
+    """Host packing for radb_extract_ragged: 16-byte aligned patch starts, (H, W) table, lossless pools."""
+    from multimodal_isic_b200 import pack_ragged
+
+    rng = np.random.default_rng(0)
+    shapes = [(5, 7), (16, 16), (3, 3), (16, 16)]
+    imgs = [rng.integers(0, 65535, s).astype(np.uint16) for s in shapes]
+    msks = [(rng.random(s) < 0.5).astype(np.uint8) * 255 for s in shapes]
+    ip, mp, io, mo, hw = pack_ragged(imgs, msks)
+    assert ip.dtype == np.uint16 and mp.dtype == np.uint8 and hw.tolist() == [list(s) for s in shapes]
+    assert (io % 16 == 0).all() and (mo % 16 == 0).all()
+    for i, s in enumerate(shapes):
+        k = s[0] * s[1]
+        assert np.array_equal(ip[io[i] // 2: io[i] // 2 + k].reshape(s), imgs[i])
+        assert np.array_equal(mp[mo[i]: mo[i] + k].reshape(s), msks[i])
+    with pytest.raises(ValueError):
+        pack_ragged(imgs, msks[:-1])
+    with pytest.raises(ValueError):
+        pack_ragged([imgs[0]], [msks[1]])

@@ -83,6 +83,33 @@ def test_emu_many_large_zones_take_the_warp_level_glszm(emu):
     assert r["glszm"][0].sum() == 60 and r["glszm"][1].sum() == 30
 
 
+def test_emu_ragged_mixed_sizes(emu):
+    """BASELINE.json configs[3] in miniature: patches of mixed size and mask coverage in ONE call; rows come
+    back in input order whatever the grouping, invalid ROIs keep their status, odd sizes lose the TMA path."""
+    rng = np.random.default_rng(5)
+    sizes = [(16, 16), (24, 20), (16, 16), (33, 17), (24, 20), (16, 16), (8, 40)]
+    images, masks = [], []
+    for i, (H, W) in enumerate(sizes):
+        g, m = synth.make_patches(1, H, W, seed=20 + i)
+        images.append(g[0])
+        masks.append(m[0])
+    masks[2] = np.zeros_like(masks[2])            # label absent
+    masks[5] = (rng.random((16, 16)) < 0.9).astype(np.uint8) * 255  # near-full coverage
+    out, status = emu.run_ragged(images, masks, 25, 255, INPLANE)
+    assert list(status) == [0, 0, 1, 0, 0, 0, 0]
+    s = orc.resolve_settings(dict(label=255, binWidth=25, force2D=False))
+    names = orc.feature_names(orc.CLASS_ORDER)
+    for i in range(len(sizes)):
+        if status[i]:
+            assert np.isnan(out[i]).all()
+            continue
+        f = orc.execute(images[i], masks[i], s)
+        np.testing.assert_allclose(out[i], [f[k] for k in names], rtol=1e-6, atol=1e-9)
+    # same rows as the dense entry point, group by group
+    dense = emu.run(np.stack([images[0], images[5]]), np.stack([masks[0], masks[5]]), 25, 255, INPLANE)["features"]
+    assert np.array_equal(dense, out[[0, 5]])
+
+
 def test_emu_golden_fixture(emu):
     z = np.load(os.path.join(GOLD, "oracle_features_seed0.npz"))
     r = emu.run(z["images"][:2], z["masks"][:2], 10, 255, INPLANE)

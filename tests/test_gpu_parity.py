@@ -406,3 +406,37 @@ def test_fuzz_random_shapes_patterns_masks(gpu_pkg):
         r = _dbg(_engine(gpu_pkg, bw, ang, classes=ALL_CLASSES), imgs, masks)
         total += compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=bw, force2D=literal), classes=ALL_CLASSES)
     assert total > 120
+
+
+def test_ragged_mixed_sizes_and_coverage(gpu_pkg):
+    """BASELINE.json configs[3]: patch sizes 32 / 64 / 224 mixed 1:1:1 with mask coverage 2-100 % in ONE
+    radb_extract_ragged call (narrow and wide kernels, TMA and non-TMA staging): rows in input order,
+    equal to the dense entry point size class by size class, and equal to the oracle."""
+    rng = np.random.default_rng(9)
+    images, masks = [], []
+    for i in range(18):
+        H = (32, 64, 224)[i % 3]
+        g, m = gpu_pkg.synth.make_patches(1, H, seed=100 + i)
+        if i % 5 == 4:  # variable coverage: a random sub-mask of the lesion, down to a few percent
+            m = np.where(rng.random(m.shape) < rng.uniform(0.02, 1.0), m, 0).astype(np.uint8)
+        images.append(g[0])
+        masks.append(m[0])
+    images.append(rng.integers(0, 256, (37, 29)).astype(np.uint8))  # odd size: no TMA path
+    masks.append(np.full((37, 29), 255, np.uint8))
+    images.append(images[0].copy())
+    masks.append(np.zeros((32, 32), np.uint8))                      # label absent
+    ex = gpu_pkg.RadiomicsExtractor({"setting": {"label": 255, "binWidth": 25}})
+    out, status = ex.extract_list(images, masks)
+    assert status[-1] == 1 and np.isnan(out[-1]).all() and not status[:-1].any()
+    for H in (32, 64, 224):
+        idx = [i for i in range(18) if images[i].shape[0] == H]
+        d, st = ex.extract_batch(torch.as_tensor(np.stack([images[i] for i in idx])).cuda(),
+                                 torch.as_tensor(np.stack([masks[i] for i in idx])).cuda())
+        assert np.array_equal(d.cpu().numpy(), out[idx])
+    s = orc.resolve_settings(dict(label=255, binWidth=25, force2D=False))
+    names = orc.feature_names(orc.CLASS_ORDER)
+    for i in (0, 1, 4, 9, 18):  # one per size class incl. a thinned mask and the odd size (the 224s are slow on the CPU)
+        f = orc.execute(images[i], masks[i], s, matrix_backend=cmatrices)
+        np.testing.assert_allclose(out[i], [f[k] for k in names], rtol=RTOL, atol=ATOL)
+    with pytest.raises(ValueError):
+        ex.extract_list(images, masks, strict=True)
