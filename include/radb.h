@@ -73,7 +73,7 @@ typedef struct radb_settings {
     double gldm_alpha;         /* gldm_a (0) */
     double voxel_array_shift;  /* voxelArrayShift (0) */
     uint32_t class_mask;       /* RADB_CLASS_* bits: params.yml:164-171 featureClass */
-    int32_t max_ng;            /* sizing bound on gray levels (<= 255); 0 = derive from bin_width for
+    int32_t max_ng;            /* sizing bound on gray levels (<= 256; <= 255 for uint8 pixels); 0 = derive from bin_width for
                                   uint8 pixels; required for the other pixel types */
     int32_t device;            /* CUDA device ordinal */
 } radb_settings;

@@ -30,7 +30,7 @@ struct radb_handle {
     radb::Plan plan;
     int device;
     int smem_optin;              // max dynamic shared memory per block the device allows
-    int smem_set[32];             // configured MaxDynamicSharedMemorySize per kernel
+    int smem_set[40];             // configured MaxDynamicSharedMemorySize per kernel
     int64_t launches;
     struct Ws { void* stream; unsigned char* p; size_t bytes; long long* meta; size_t meta_bytes; };
     std::vector<Ws> ws;          // per-patch records of one chunk, one workspace per CUDA stream
@@ -66,7 +66,7 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
     if (rc) { delete h; return fail(rc, err); }
     h->device = s->device;
     h->launches = 0;
-    for (int i = 0; i < 32; i++) h->smem_set[i] = 0;
+    for (int i = 0; i < 40; i++) h->smem_set[i] = 0;
     h->d_inv2 = h->d_tlog = nullptr;
     h->profiling = false;
     int ndev = 0;
@@ -204,15 +204,18 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     build_fn build = nullptr;
 #define RADB_PICK(PT) (p.wide ? (dbg ? radb_build_kernel<PT, true, true> : radb_build_kernel<PT, false, true>) \
                               : (dbg ? radb_build_kernel<PT, true, false> : radb_build_kernel<PT, false, false>))
+#define RADB_PICK16(PT) (dbg ? radb_build_kernel<PT, true, true, true> : radb_build_kernel<PT, false, true, true>)
+    const bool l16 = p.lev_bytes == 2;  // > 255 gray levels: u16 level image (big mode, never uint8 pixels)
     switch (dtype) {
         case RADB_DTYPE_U8: build = RADB_PICK(unsigned char); break;
-        case RADB_DTYPE_U16: build = RADB_PICK(unsigned short); break;
-        case RADB_DTYPE_F32: build = RADB_PICK(float); break;
-        case RADB_DTYPE_F64: build = RADB_PICK(double); break;
+        case RADB_DTYPE_U16: build = l16 ? RADB_PICK16(unsigned short) : RADB_PICK(unsigned short); break;
+        case RADB_DTYPE_F32: build = l16 ? RADB_PICK16(float) : RADB_PICK(float); break;
+        case RADB_DTYPE_F64: build = l16 ? RADB_PICK16(double) : RADB_PICK(double); break;
         default: return fail(RADB_E_INVALID, "unknown pixel dtype");
     }
 #undef RADB_PICK
-    int rc = set_smem(h, build, 9 + dtype * 4 + (p.wide ? 2 : 0) + (dbg ? 1 : 0), p.smem_total);
+#undef RADB_PICK16
+    int rc = set_smem(h, build, l16 ? 25 + dtype * 2 + (dbg ? 1 : 0) : 9 + dtype * 4 + (p.wide ? 2 : 0) + (dbg ? 1 : 0), p.smem_total);
     static const bool no_lane = getenv("RADB_NO_LANE") != nullptr;  // A/B switch: force the warp-per-angle kernel
     if (no_lane) p.use_lane = 0;
     if (!rc) rc = p.use_lane ? set_smem(h, radb_angle_lane_kernel, 3, p.l_smem_total) : set_smem(h, radb_angle_kernel, 1, p.a_smem_total);

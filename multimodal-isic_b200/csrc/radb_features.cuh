@@ -665,7 +665,7 @@ __device__ __forceinline__ void zs_reduce(ZoneSums& z, const RadbTabs& tb, int l
     z.nnz = warp_sum_i(z.nnz);
 }
 
-// A.8.  Dense counters Z[n][s0] (sizes 1..s0) + overflow list of (level << 24 | size) zones with
+// A.8.  Dense counters Z[n][s0] (sizes 1..s0) + overflow list of ((level - 1) << 24 | size) zones with
 // size > s0.  pg = int scratch [n] (zeroed), sorted = scratch for the rank-sorted overflow list.
 __device__ void glszm_task(const RadbParams& p, const RadbTabs& tb, const int* Z, const unsigned* ovf,
                            unsigned* sorted, int novf, int n, int* pg, double* o, int lane)
@@ -701,7 +701,7 @@ __device__ void glszm_task(const RadbParams& p, const RadbTabs& tb, const int* Z
     __syncwarp();
     for (int e = lane; e < novf; e += 32) {
         unsigned key = sorted[e];
-        int sz = (int)(key & 0xffffffu), lv = (int)(key >> 24);
+        int sz = (int)(key & 0xffffffu), lv = (int)(key >> 24) + 1;
         atomicAdd(&pg[lv - 1], 1);
         if (e == 0 || sorted[e - 1] != key) {  // first of its (level, size) cell
             int cnt = 1;

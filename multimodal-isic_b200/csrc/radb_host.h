@@ -100,7 +100,7 @@ static inline int make_plan(const radb_settings& s, Plan& pl, std::string& err)
     }
     int ng = s.max_ng;
     if (ng <= 0) ng = (int)floor(255.0 / s.bin_width) + 1;  // uint8 pixels: levels 1..floor(255/bw)+1
-    if (ng > 255) { err = "more than 255 gray levels (binWidth too small for the u8 level image)"; return RADB_E_UNSUPPORTED; }
+    if (ng > 256) { err = "more than 256 gray levels"; return RADB_E_UNSUPPORTED; }
     pl.max_ng = ng;
     pl.F = 0;
     pl.names.clear();
@@ -166,12 +166,20 @@ static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParam
     p.off_shape = pl.off_shape;
     // narrow mode (everything in shared memory) when the patch fits with >= 2 CTAs per SM,
     // otherwise wide mode (level image, union-find words, GLRLM, overflow list in global memory)
+    // and big mode (GLCM counters + MCC workspace in global memory as well) when the gray-level count makes
+    // even that too large (Ng >~ 90 with 4 angles: the binWidth sweep of BASELINE.json configs[4])
     p.wide = 0;
+    p.big = 0;
     radb_layout(&p, pix_bytes);
-    if ((long long)H * W > 65535 || p.smem_total > 110 * 1024) {
+    if ((long long)H * W > 65535 || p.smem_total > 110 * 1024 || pl.max_ng > 255) {
         p.wide = 1;
         radb_layout(&p, pix_bytes);
+        if (p.smem_total > 200 * 1024 || p.a_smem_total > 200 * 1024 || pl.max_ng > 255) {
+            p.big = 1;
+            radb_layout(&p, pix_bytes);
+        }
     }
+    if (p.lev_bytes == 2 && pix_bytes == 1) { err = "uint8 pixels cannot have more than 255 gray levels"; return RADB_E_INVALID; }
     if (p.smem_total > 227 * 1024 || p.a_smem_total > 227 * 1024 || p.m_smem_total > 227 * 1024 || p.s_smem_total > 227 * 1024) {
         err = "image size x gray levels need more than 227 KB of shared memory";
         return RADB_E_SMEM;

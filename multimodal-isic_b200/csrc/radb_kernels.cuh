@@ -506,10 +506,15 @@ template <> struct fo_dispatch<unsigned char> {
                                                double, double, const int*, int, unsigned char*, double*, int) {}
 };
 
+// level image element: u8, or u16 when the extractor is sized for more than 255 gray levels (big mode)
+template <bool L16> struct LevT { typedef unsigned char T; };
+template <> struct LevT<true> { typedef unsigned short T; };
+
 // ------------------------------------------------------------------ build kernel: one CTA per patch
-template <typename PT, bool DBG, bool WIDE>
+template <typename PT, bool DBG, bool WIDE, bool L16 = false>
 __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned char* smem)
 {
+    typedef typename LevT<L16>::T LT;
     typedef typename UF<WIDE>::W UW;  // union-find word
     const int US = UF<WIDE>::S;
     const UW ULO = (((UW)1) << US) - 1;
@@ -525,11 +530,11 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     const PT* s_img = WIDE ? g_img : (const PT*)(smem + p.o_stage);
     const unsigned char* s_msk = WIDE ? g_msk : smem + p.o_mask;
     UW* lab = WIDE ? (UW*)(g_scr + p.g_lab) : (UW*)(smem + p.o_stage);
-    unsigned char* lev = WIDE ? g_scr + p.g_lev : smem + p.o_lev;
+    LT* lev = (LT*)(WIDE ? g_scr + p.g_lev : smem + p.o_lev);
     int* hist = (int*)(smem + p.o_hist);
     unsigned char* lut = smem + p.o_lut;
     int* lhist = (int*)(smem + p.o_lhist);
-    int* glcm = (int*)(smem + p.o_glcm);
+    int* glcm = (WIDE && p.big) ? (int*)(g_rec + (p.o_glcm - p.o_rec)) : (int*)(smem + p.o_glcm);
     int* gldm = (int*)(smem + p.o_gldm);
     int* ngc = (int*)(smem + p.o_ngc);
     int* ngn = (int*)(smem + p.o_ngn);
@@ -565,6 +570,11 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             uint4* zr = (uint4*)glrlm_base;
             const int nrr = NA * p.glrlm_stride / 16;
             for (int i = tid; i < nrr; i += RADB_NTB) zr[i] = zero;
+            if (p.big) {  // GLCM counters in the global record
+                uint4* zg = (uint4*)glcm;
+                const int ngc = (NA * p.max_ng * p.max_ng * 4 + 15) / 16;
+                for (int i = tid; i < ngc; i += RADB_NTB) zg[i] = zero;
+            }
         }
     }
     if (!WIDE) {
@@ -732,18 +742,18 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
 #pragma unroll
                 for (int k = 0; k < 4; k++)
                     if (eq & (0x80u << (8 * k))) w |= (unsigned)lut[(v4 >> (8 * k)) & 0xffu] << (8 * k);
-                ((unsigned*)(lev + (y + 1) * WP + XO))[xq] = w;  // XO = 4 and WP % 4 == 0: aligned
+                ((unsigned*)((unsigned char*)lev + (y + 1) * WP + XO))[xq] = w;  // u8 levels; XO = 4 and WP % 4 == 0: aligned
             }
     } else
     for (int y = warp; y < H; y += RADB_NTB / 32)
         for (int x = lane; x < W; x += 32) {
             int i = y * W + x;
-            unsigned char L = 0;
+            LT L = 0;
             if ((int)s_msk[i] == p.label) {
                 if (U8) {
                     L = lut[(int)s_img[i]];
                 } else {
-                    L = (unsigned char)radb_level((double)s_img[i], low, p.bin_width);
+                    L = (LT)radb_level((double)s_img[i], low, p.bin_width);
                     atomicAdd(&lhist[L - 1], 1);
                 }
             }
@@ -999,7 +1009,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             atomicAdd(&szm[(c - 1) * p.s0 + s - 1], 1);
         } else {
             int k = atomicAdd(&misc[5], 1);
-            if (k < p.ovf_cap) ovf[k] = ((unsigned)c << 24) | (unsigned)s;  // sizes < 2^24
+            if (k < p.ovf_cap) ovf[k] = ((unsigned)(c - 1) << 24) | (unsigned)s;  // level - 1 (<= 255) | size (< 2^24)
         }
         if (DBG && p.dbg_glszm) atomicAdd(&p.dbg_glszm[(patch * p.max_ng + (c - 1)) * (long long)HW + s - 1], 1);
     }
@@ -1067,9 +1077,10 @@ __device__ void radb_angle_cta(const RadbParams& p, long long patch, unsigned ch
         int ok = glrlm_task(tb, R, p.wide, ng, p.nr, misc[10 + a], (int*)(ws + p.a_pr), fsc + a * RADB_FSC_STRIDE + RADB_GLCM_NF, lane);
         if (lane == 0) valid[4 + a] = ok;
         const int* P = (const int*)(rec + (p.o_glcm - p.o_rec)) + a * ng * ng;
+        double* mccws = p.big ? (double*)(p.ws_scr + patch * p.scr_bytes + p.g_mcc) + (long long)a * p.mcc_stride
+                              : (double*)(ws + p.a_mcc);
         ok = glcm_task(p, tb, P, ng, (int*)(ws + p.a_px), (int*)(ws + p.a_py), (int*)(ws + p.a_padd),
-                       (int*)(ws + p.a_psub), (double*)(ws + p.a_mcc), ws + p.a_idx, fsc + a * RADB_FSC_STRIDE,
-                       lane);
+                       (int*)(ws + p.a_psub), mccws, ws + p.a_idx, fsc + a * RADB_FSC_STRIDE, lane);
         if (lane == 0) valid[a] = ok;
     }
     __syncthreads();
@@ -1312,11 +1323,11 @@ __device__ void radb_shape_cta(const RadbParams& p, long long patch, unsigned ch
 }
 
 #ifndef RADB_EMU
-template <typename PT, bool DBG, bool WIDE>
+template <typename PT, bool DBG, bool WIDE, bool L16 = false>
 __global__ void __launch_bounds__(RADB_NTB, RADB_NTB_MINB) radb_build_kernel(const RadbParams p)
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
-    radb_build_cta<PT, DBG, WIDE>(p, (long long)blockIdx.x, radb_smem);
+    radb_build_cta<PT, DBG, WIDE, L16>(p, (long long)blockIdx.x, radb_smem);
 }
 #ifndef RADB_ANGLE_MINB
 #define RADB_ANGLE_MINB 6

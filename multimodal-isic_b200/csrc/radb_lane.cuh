@@ -472,7 +472,7 @@ __device__ void radb_angle_lane_cta(const RadbParams& p, long long cta, unsigned
 #define MLU(b, k) (((unsigned*)&(b)[((k) >> 1) * 32])[(k) & 1])  // u32 view: two per fp64 slot of the same thread
 #define RADB_LANE_MAX_OVF 48  // GLSZM patches with more overflow zones than this go to the warp kernel
 
-// A.8 GLSZM: dense counters Z[n][s0] + overflow list (level << 24 | size) of the zones larger than s0
+// A.8 GLSZM: dense counters Z[n][s0] + overflow list ((level - 1) << 24 | size) of the zones larger than s0
 __device__ void glszm_lane(const RadbParams& p, const RadbTabs& tb, const int* Z, const unsigned* ovf, int novf, int n,
                            double* scr, double* o)
 {
@@ -487,7 +487,7 @@ __device__ void glszm_lane(const RadbParams& p, const RadbTabs& tb, const int* Z
             g += c;
             zs_cell(z, tb, i + 1, j + 1, c);
         }
-        for (int e = 0; e < novf; e++) g += ((int)(ovf[e] >> 24) == i + 1);
+        for (int e = 0; e < novf; e++) g += ((int)(ovf[e] >> 24) == i);
         if (g) zs_level(z, tb, i + 1, g);
     }
     for (int j = 0; j < s0; j++) {
@@ -512,7 +512,7 @@ __device__ void glszm_lane(const RadbParams& p, const RadbTabs& tb, const int* Z
             const unsigned k1 = MLU(scr, e);
             int cnt = 0;
             while (e < novf && MLU(scr, e) == k1) { cnt++; e++; }
-            zs_cell(z, tb, (int)(k1 & 0xffu), sz, cnt);
+            zs_cell(z, tb, (int)(k1 & 0xffu) + 1, sz, cnt);
             same_size += cnt;
         }
         z.PJ2 += (long long)same_size * same_size;

@@ -52,6 +52,9 @@ struct RadbParams {
     int use_tma;
     int pix_bytes; // 1 uint8, 2 uint16, 4 float32, 8 float64
     int wide;      // 1: whole-image mode (level image, union-find words, GLRLM and overflow list in global memory)
+    int big;       // 1 (implies wide): many gray levels -- the GLCM counters and the MCC workspace live in global memory too
+    int lev_bytes; // bytes per pixel of the level image: 1, or 2 when max_ng > 255
+    long long g_mcc;  // big mode: byte offset of the per-angle MCC workspaces inside the per-patch global scratch
     // ---- build kernel: shared-memory byte offsets.  [o_rec, o_rec + rec_bytes) is the per-patch
     // RECORD (header + every integer matrix); the build kernel copies it to the global workspace
     // and the reduction kernels read it from there at the same relative offsets.
@@ -96,7 +99,8 @@ static inline int radb_align(int v, int a) { return (v + a - 1) / a * a; }
 // and p->wide.  Record layout (both modes): header, hist, lhist, glcm, gldm, ngc, ngn, szm | glrlm, ovf.
 static inline void radb_layout(RadbParams* p, int pix_bytes)
 {
-    const int H = p->H, W = p->W, ng = p->max_ng, na = p->n_angles, wide = p->wide;
+    const int H = p->H, W = p->W, ng = p->max_ng, na = p->n_angles, wide = p->wide, big = p->big;
+    p->lev_bytes = ng > 255 ? 2 : 1;
     p->pix_bytes = pix_bytes;
     p->HW = H * W;
     p->vec4 = (!wide && pix_bytes == 1 && W % 4 == 0) ? 1 : 0;
@@ -124,7 +128,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->o_mbar = o; o += 16;
     p->o_zero = o;                        // everything from here on is zeroed at CTA start
     p->o_lev = o;
-    if (!wide) o += radb_align((H + 2) * p->WP, 16);
+    if (!wide) o += radb_align((H + 2) * p->WP * p->lev_bytes, 16);
     p->o_uq = o; o += (RADB_NTB / 32) * 64 * (wide ? 8 : 4);   // per-warp union request queues
     p->o_lut = o; o += 256;
     p->o_fo = o; o += pix_bytes == 1 ? 16 : radb_align(64 * 8 + 16 * 8 + 10 * 8 + 10 * 8 + 10 * 4 + 10 * 4 + 8 + 10 * 256 * 4 + 64, 16);  // RADB_FO_SCRATCH
@@ -132,7 +136,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->o_misc = o; o += 32 * 4;           // record header: [0] Np, [5] #overflow zones, [8] Ng, [9] #levels present, [10+a] longest run of angle a
     p->o_hist = o; o += 256 * 4;
     p->o_lhist = o; o += radb_align(ng * 4, 16);
-    p->o_glcm = o; o += radb_align(na * ng * ng * 4, 16);
+    p->o_glcm = o; if (!big) o += radb_align(na * ng * ng * 4, 16);
     p->o_gldm = o; o += radb_align(ng * (2 * na + 1) * 4, 16);
     p->o_ngc = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] voxel counts per neighbour count
     p->o_ngn = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] sum |cnt*i - sum(neigh)|
@@ -141,12 +145,15 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->glrlm_stride = radb_align(ng * p->nr * (wide ? 4 : 2), 16);
     p->o_glrlm = o; o += na * p->glrlm_stride;             // wide: lives in the global record only
     p->o_ovf = o; o += radb_align(p->ovf_cap * 4, 16);     // wide: lives in the global record only
+    if (big) { p->o_glcm = o; o += radb_align(na * ng * ng * 4, 16); }  // big: GLCM in the global record only
     p->rec_bytes = o - p->o_rec;
     p->smem_total = wide ? p->o_rec + p->rec_copy_bytes : o;
     if (!wide) p->rec_copy_bytes = p->rec_bytes;
     p->g_lev = 0;
-    p->g_lab = radb_align((H + 2) * p->WP, 16);
+    p->g_lab = radb_align((H + 2) * p->WP * p->lev_bytes, 16);
     p->scr_bytes = wide ? (p->g_lab + (long long)p->HW * 8 + 15) / 16 * 16 : 0;  // 16-byte multiple: uint4 stores
+    p->g_mcc = 0;  // big: the MCC workspaces re-use the scratch once the build kernel is done with it
+    if (big && p->scr_bytes < (long long)na * p->mcc_stride * 8) p->scr_bytes = (long long)na * p->mcc_stride * 8;
     // ---- angle kernel
     o = 0;
     p->a_px = o; o += radb_align(ng * 4, 16);
@@ -155,7 +162,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->a_psub = o; o += radb_align(ng * 4, 16);
     p->a_pr = o; o += radb_align(p->nr * 4, 16);
     p->a_idx = o; o += radb_align(ng, 16);
-    p->a_mcc = o; o += radb_align(p->mcc_stride * 8, 16);
+    p->a_mcc = o; if (!big) o += radb_align(p->mcc_stride * 8, 16);
     p->a_red = o; o += 14 * 33 * 8;       // RADB_RED_DOUBLES
     p->a_warp_bytes = o;
     o = (RADB_NT / 32) * p->a_warp_bytes;

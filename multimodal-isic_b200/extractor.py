@@ -163,7 +163,7 @@ class RadiomicsExtractor:
         hi = torch.where(m, f, torch.full_like(f, -big)).flatten(1).amax(1)
         ok = hi >= lo
         span = float(((hi - lo)[ok] / self.params.bin_width).max().item()) if bool(ok.any()) else 0.0
-        ng = min(255, (int(span) + 3 + 7) // 8 * 8)
+        ng = min(256, (int(span) + 3 + 7) // 8 * 8)
         if ng not in self._engines_ng:
             eng = Engine(*self._engine_args, max_ng=ng, device=self.device)
             self._engines_ng[ng] = (eng, HostPipeline(eng, self.pipeline.chunk))
@@ -227,7 +227,7 @@ class RadiomicsExtractor:
             roi = np.asarray(im)[np.asarray(mk) == self.params.label]
             if roi.size:
                 span = max(span, float(roi.max()) - float(roi.min()))
-        ng = min(255, (int(span / self.params.bin_width) + 3 + 7) // 8 * 8)
+        ng = min(256, (int(span / self.params.bin_width) + 3 + 7) // 8 * 8)
         if ng not in self._engines_ng:
             eng = Engine(*self._engine_args, max_ng=ng, device=self.device)
             self._engines_ng[ng] = (eng, HostPipeline(eng, self.pipeline.chunk))

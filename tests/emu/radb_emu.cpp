@@ -56,7 +56,9 @@ static int emu_launch(RadbParams& p, int dtype, int64_t B)
     unsigned char* sm = (unsigned char*)(((uintptr_t)smem.data() + 15) & ~(uintptr_t)15);
     // the same three launches radb_api.cu issues, CTA by CTA on host threads
 #define EMU_BUILD(PT)                                                                                             \
-    if (p.wide)                                                                                                   \
+    if (p.lev_bytes == 2)                                                                                         \
+        emu::launch((unsigned)B, RADB_NTB, [&]() { radb_build_cta<PT, true, true, true>(p, (long long)blockIdx.x, sm); }); \
+    else if (p.wide)                                                                                                   \
         emu::launch((unsigned)B, RADB_NTB, [&]() { radb_build_cta<PT, true, true>(p, (long long)blockIdx.x, sm); }); \
     else                                                                                                          \
         emu::launch((unsigned)B, RADB_NTB, [&]() { radb_build_cta<PT, true, false>(p, (long long)blockIdx.x, sm); });

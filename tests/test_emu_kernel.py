@@ -110,6 +110,19 @@ def test_emu_ragged_mixed_sizes(emu):
     assert np.array_equal(dense, out[[0, 5]])
 
 
+@pytest.mark.parametrize("ng_cap,bw", [(256, 8), (128, 16)])
+def test_emu_many_gray_levels_big_mode(emu, ng_cap, bw):
+    """BASELINE.json configs[4] (binWidth sweep on uint16 intensities in [0, 2048)): 128 and 256 gray levels.
+    The GLCM counters and the MCC workspace no longer fit shared memory (big mode: global memory), and 256
+    levels need the u16 level image."""
+    g, masks = synth.make_patches(2, 20, seed=31, dtype=np.uint16, vmax=2047)
+    g[1] = (np.arange(400).reshape(20, 20) * 5 % 2048).astype(np.uint16)  # every pixel its own level: Ng = 256 exactly
+    masks[1] = 255
+    r = emu.run(g, masks, bw, 255, INPLANE, max_ng=ng_cap)
+    assert compare_with_oracle(r, g, masks, dict(label=255, binWidth=bw, force2D=False)) == 2
+    assert r["ng"].max() > (200 if bw == 8 else 100)
+
+
 def test_emu_golden_fixture(emu):
     z = np.load(os.path.join(GOLD, "oracle_features_seed0.npz"))
     r = emu.run(z["images"][:2], z["masks"][:2], 10, 255, INPLANE)

@@ -440,3 +440,20 @@ def test_ragged_mixed_sizes_and_coverage(gpu_pkg):
         np.testing.assert_allclose(out[i], [f[k] for k in names], rtol=RTOL, atol=ATOL)
     with pytest.raises(ValueError):
         ex.extract_list(images, masks, strict=True)
+
+
+@pytest.mark.parametrize("bw", [8, 16, 32, 64])
+def test_binwidth_sweep_uint16_up_to_256_levels(gpu_pkg, bw):
+    """BASELINE.json configs[4]: binWidth 8..64 on uint16 intensities in [0, 2048) -> 256..32 gray levels.
+    64 levels still fit shared memory; 128 and 256 run in big mode (GLCM + MCC workspace in global memory,
+    u16 level image for 256)."""
+    g, masks = gpu_pkg.synth.make_patches(3, 64, seed=41, dtype=np.uint16, vmax=2047)
+    ng_cap = 2048 // bw
+    eng = gpu_pkg.Engine(bw, 255, INPLANE, max_ng=ng_cap)
+    tt = torch.as_tensor(g.view(np.int16)).cuda().view(torch.uint16)
+    r = eng.debug_matrices(tt, torch.as_tensor(masks).cuda())
+    assert compare_with_oracle(r, g, masks, dict(label=255, binWidth=bw, force2D=False)) == 3
+    assert r["ng"].max() > ng_cap // 2
+    ex = gpu_pkg.RadiomicsExtractor({"setting": {"label": 255, "binWidth": bw}})
+    out, st = ex.extract_batch(tt, torch.as_tensor(masks).cuda())
+    np.testing.assert_allclose(out.cpu().numpy(), r["features"], rtol=1e-8, atol=1e-12)
