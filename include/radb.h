@@ -94,6 +94,11 @@ const char* radb_feature_name(const radb_handle* h, int i);
  * issued on different streams may overlap. */
 int radb_reserve(radb_handle* h, int H, int W, int dtype, int64_t max_batch, void* cuda_stream);
 
+/* Patches per chunk (rounded up to a multiple of 4; 0 restores the default: RADB_CHUNK in the environment, else
+ * 65536).  A batch larger than one chunk is cut into equal chunks and pipelined over two streams: the build
+ * kernel of chunk i+1 overlaps the reduction kernels of chunk i.  The workspace holds two chunks of records. */
+int radb_set_chunk(radb_handle* h, int64_t patches);
+
 /* Dynamic shared memory (bytes) one CTA of the build kernel needs for HxW patches of `dtype`; < 0 if it cannot fit. */
 int radb_smem_bytes(const radb_handle* h, int H, int W, int dtype);
 

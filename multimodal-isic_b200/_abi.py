@@ -100,6 +100,8 @@ def load_library(path=None):
     lib.radb_max_ng.restype = i32
     lib.radb_launch_count.argtypes = [vp]
     lib.radb_launch_count.restype = i64
+    lib.radb_set_chunk.argtypes = [vp, i64]
+    lib.radb_set_chunk.restype = i32
     lib.radb_set_profiling.argtypes = [vp, i32]
     lib.radb_set_profiling.restype = i32
     lib.radb_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double * 3)]
@@ -115,7 +117,7 @@ def load_library(path=None):
 
 EXPORTED_SYMBOLS = (
     "radb_create", "radb_destroy", "radb_feature_count", "radb_feature_name", "radb_reserve", "radb_smem_bytes",
-    "radb_extract", "radb_extract_ragged", "radb_extract_bgr", "radb_derive_image", "radb_debug_matrices", "radb_max_ng", "radb_launch_count", "radb_set_profiling",
+    "radb_extract", "radb_extract_ragged", "radb_extract_bgr", "radb_derive_image", "radb_debug_matrices", "radb_max_ng", "radb_launch_count", "radb_set_chunk", "radb_set_profiling",
     "radb_kernel_ms", "radb_last_error",
     "radb_version",
 )

@@ -37,6 +37,9 @@ struct radb_handle {
                                  // (launches on different streams may overlap; each owns its records)
     double* d_inv2;
     double* d_tlog;
+    int64_t chunk;               // patches per chunk (0: RADB_CHUNK env / default); radb_set_chunk
+    cudaStream_t red_stream;     // high-priority stream of the reduction kernels (multi-chunk batches only)
+    std::vector<cudaEvent_t> sync_events;  // build-done / reduce-done events of the two-stream pipeline (re-used)
     bool profiling;              // record CUDA events around every kernel (radb_set_profiling)
     std::vector<cudaEvent_t> events;  // 4 per chunk: start, after build, after angle, after misc
 };
@@ -69,6 +72,8 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
     for (int i = 0; i < 40; i++) h->smem_set[i] = 0;
     h->d_inv2 = h->d_tlog = nullptr;
     h->profiling = false;
+    h->red_stream = nullptr;
+    h->chunk = 0;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -104,25 +109,36 @@ extern "C" void radb_destroy(radb_handle* h)
     }
     if (h->d_inv2) cudaFree(h->d_inv2);
     if (h->d_tlog) cudaFree(h->d_tlog);
+    for (auto ev : h->sync_events) cudaEventDestroy(ev);
+    for (auto ev : h->events) cudaEventDestroy(ev);
+    if (h->red_stream) cudaStreamDestroy(h->red_stream);
     delete h;
 }
 
-// Patches per pass through the three kernels: bounds the workspace (records + wide-mode scratch).
-static int64_t chunk_for(const RadbParams& p, int64_t B)
+// Patches per pass through the kernels: bounds the workspace (records + wide-mode scratch).  Batches larger
+// than one chunk are cut into equal chunks so that the two-stream pipeline below has balanced stages.
+static int64_t chunk_for(const radb_handle* h, const RadbParams& p, int64_t B)
 {
     const size_t per = (size_t)p.rec_bytes + (size_t)p.scr_bytes;
     int64_t n = (int64_t)(((size_t)1 << 30) / per);  // <= 1 GiB
-    if (n > RADB_CHUNK) n = RADB_CHUNK;
+    const int64_t want = h->chunk > 0 ? h->chunk : RADB_CHUNK;
+    if (n > want) n = want;
     n -= n % 4;  // keeps the 4 planes of an image (shared mask) in one chunk
     if (n < 4) n = 4;
-    return B < n ? B : n;
+    if (B <= n) return B;
+    const int64_t k = (B + n - 1) / n;        // number of chunks
+    int64_t eq = (B + k - 1) / k;             // equalised
+    eq = (eq + 3) / 4 * 4;
+    return eq < n ? eq : n;
 }
 
 // Grow-only workspace: one record (+ scratch) per patch of a chunk, keyed by the stream the kernels run on.
+// Batches of several chunks get two such slots: chunk i+1 is built while chunk i is being reduced.
 static int ensure_ws(radb_handle* h, const RadbParams& p, int64_t B, void* stream, unsigned char** out)
 {
-    const int64_t n = chunk_for(p, B);
-    const size_t need = (size_t)n * ((size_t)p.rec_bytes + (size_t)p.scr_bytes);
+    const int64_t n = chunk_for(h, p, B);
+    const size_t slots = B > n ? 2 : 1;
+    const size_t need = slots * (size_t)n * ((size_t)p.rec_bytes + (size_t)p.scr_bytes);
     radb_handle::Ws* w = nullptr;
     for (auto& e : h->ws)
         if (e.stream == stream) w = &e;
@@ -226,17 +242,42 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     unsigned char* wsp = nullptr;
     if (!rc) rc = ensure_ws(h, p, p.B, stream, &wsp);
     if (rc) return rc;
-    const long long chunk = chunk_for(p, p.B);
-    p.ws = wsp;
-    p.ws_scr = wsp + (size_t)chunk * (size_t)p.rec_bytes;
+    const long long chunk = chunk_for(h, p, p.B);
+    const size_t slot_bytes = (size_t)chunk * ((size_t)p.rec_bytes + (size_t)p.scr_bytes);
     p.g_inv2 = h->d_inv2;
     p.g_tlog = h->d_tlog;
     if (p.ninv > RADB_TAB_NINV) p.ninv = RADB_TAB_NINV;
     cudaStream_t st = (cudaStream_t)stream;
+    // Two-stream pipeline for batches of several chunks: the build kernel of chunk i+1 (issue-bound) runs on
+    // the caller's stream while the reduction kernels of chunk i (latency-bound, few warps) run on a
+    // high-priority side stream and fill the SMs' idle issue slots.  Records alternate between two workspace
+    // slots; events order build -> reduce per chunk and reduce(i) -> build(i+2) per slot; the caller's stream
+    // waits for the last reduction, so the call stays stream-ordered for the caller.  Per-kernel timing
+    // (radb_set_profiling) needs the kernels back to back: profiling runs serialise on the caller's stream.
+    static const bool no_overlap = getenv("RADB_NO_OVERLAP") != nullptr;
+    const long long nchunks = (p.B + chunk - 1) / chunk;
+    const bool piped = nchunks > 1 && !h->profiling && !no_overlap;
+    if (piped) {
+        if (!h->red_stream) {
+            int lo = 0, hi = 0;
+            cudaDeviceGetStreamPriorityRange(&lo, &hi);
+            e = cudaStreamCreateWithPriority(&h->red_stream, cudaStreamNonBlocking, hi);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreateWithPriority");
+        }
+        while ((long long)h->sync_events.size() < 2 * nchunks) {
+            cudaEvent_t ev;
+            e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
+            if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
+            h->sync_events.push_back(ev);
+        }
+    }
+    cudaStream_t rs = piped ? h->red_stream : st;
     long long done = 0;
-    while (done < p.B) {
+    for (long long c = 0; done < p.B; c++) {
         const long long n = p.B - done < chunk ? p.B - done : chunk;
         RadbParams q = p;
+        q.ws = wsp + (size_t)(c & 1) * (nchunks > 1 ? slot_bytes : 0);
+        q.ws_scr = q.ws + (size_t)chunk * (size_t)p.rec_bytes;
         if (p.rows) {  // ragged group: the index lists advance, the pools and the output stay put
             q.img_off = p.img_off + done;
             q.mask_off = p.mask_off + done;
@@ -266,27 +307,34 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
             cudaEventRecord(ev, st);
             h->events.push_back(ev);
         };
+        if (piped && c >= 2) cudaStreamWaitEvent(st, h->sync_events[2 * (c - 2) + 1], 0);  // slot free again
         mark();
         build<<<(unsigned)n, RADB_NTB, p.smem_total, st>>>(q);
         mark();
+        if (piped) {
+            cudaEventRecord(h->sync_events[2 * c], st);
+            cudaStreamWaitEvent(rs, h->sync_events[2 * c], 0);
+        }
         if (p.use_lane)
-            radb_angle_lane_kernel<<<(unsigned)((n * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, p.l_smem_total, st>>>(q);
+            radb_angle_lane_kernel<<<(unsigned)((n * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, p.l_smem_total, rs>>>(q);
         else
-            radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, st>>>(q);
+            radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, rs>>>(q);
         mark();
         if (p.only_big_ovf) {
-            radb_misc_lane_kernel<<<(unsigned)((n + 31) / 32), RADB_NT, p.ml_smem_total, st>>>(q);
+            radb_misc_lane_kernel<<<(unsigned)((n + RADB_NT - 1) / RADB_NT), RADB_NT, p.ml_smem_total, rs>>>(q);
             h->launches += 1;
         }
-        radb_misc_kernel<<<(unsigned)n, RADB_NT, p.m_smem_total, st>>>(q);
+        radb_misc_kernel<<<(unsigned)n, RADB_NT, p.m_smem_total, rs>>>(q);
         if (p.off_shape >= 0) {
-            radb_shape_kernel<<<(unsigned)n, RADB_NT, p.s_smem_total, st>>>(q);
+            radb_shape_kernel<<<(unsigned)n, RADB_NT, p.s_smem_total, rs>>>(q);
             h->launches += 1;
         }
         mark();
+        if (piped) cudaEventRecord(h->sync_events[2 * c + 1], rs);
         h->launches += 3;
         done += n;
     }
+    if (piped) cudaStreamWaitEvent(st, h->sync_events[2 * (nchunks - 1) + 1], 0);  // the side stream is in order
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "radb kernel launch");
     return RADB_OK;
@@ -420,6 +468,13 @@ extern "C" int radb_debug_matrices(radb_handle* h, const void* img, int dtype, c
     p.dbg_ngs = ngtdm_s;
     p.dbg_ng = ng;
     return launch(h, p, dtype, cuda_stream);
+}
+
+extern "C" int radb_set_chunk(radb_handle* h, int64_t patches)
+{
+    if (!h || patches < 0) return fail(RADB_E_INVALID, "bad argument");
+    h->chunk = patches ? (patches + 3) / 4 * 4 : 0;
+    return RADB_OK;
 }
 
 extern "C" int radb_set_profiling(radb_handle* h, int on)

@@ -10,7 +10,7 @@
 // independent matrices per warp keep every lane busy and the per-patch instruction count drops ~20x.
 //
 // Storage: every thread owns `l_doubles` fp64 slots of shared memory, slot-major (slot k of thread t at
-// smem[k * RADB_NTL + t]: consecutive lanes -> consecutive banks, conflict-free).  Integer scratch is
+// smem[k * RADB_LSTRIDE + t]: consecutive lanes -> consecutive banks, conflict-free).  Integer scratch is
 // packed two-per-slot inside the thread's own slots (never aliases another thread's data, so no CTA
 // barriers are needed).  Layout for a patch with n gray levels (T = n(n+1)/2):
 //   M [0, T)        packed lower triangle: GLCM counts as doubles, later A = Dx^-1/2 P Dx^-1/2 (compacted)
@@ -26,8 +26,8 @@ struct LaneMem {
     double* d;  // this thread's slot 0 (fp64 view)
     int* i;     // this thread's slot 0 (int view)
 };
-#define LMD(m, k) (m).d[(k) * RADB_NTL]
-#define LMI(m, k) (m).i[((k) >> 1) * (2 * RADB_NTL) + ((k) & 1)]
+#define LMD(m, k) (m).d[(k) * RADB_LSTRIDE]
+#define LMI(m, k) (m).i[((k) >> 1) * (2 * RADB_LSTRIDE) + ((k) & 1)]
 
 // ------------------------------------------------------------------ GLRLM, one thread
 // R = run counters [n][nr] of one angle (packed u16, or u32 in wide mode); returns 0 for an empty angle.
@@ -231,6 +231,8 @@ __device__ double mcc_lane(LaneMem lm, int n, double rN)
 
 // ------------------------------------------------------------------ GLCM, one thread (symmetric matrices)
 // P = final integer counts of one angle [n][n] (already symmetrised: P[i][j] == P[j][i], diagonal doubled).
+// (Staging the matrices cooperatively through shared memory instead of reading them per thread was tried:
+// the odd slot stride it needs costs one resident CTA per SM and the kernel got 25 % slower.)
 __device__ int glcm_lane(const RadbTabs& tb, const int* P, int n, LaneMem lm, double* o)
 {
     const int T = n * (n + 1) / 2;
@@ -464,8 +466,8 @@ __device__ void radb_angle_lane_cta(const RadbParams& p, long long cta, unsigned
 }
 
 // ==================================================================== misc classes, one thread per (patch, class)
-// CTA = 128 threads = 32 patches: warp w reduces class w (0 GLSZM, 1 GLDM, 2 NGTDM, 3 first-order) of the
-// CTA's 32 patches, lane <-> patch, so every warp runs one code path with all lanes busy.  Per-thread fp64
+// CTA = 128 threads = 128 patches, thread <-> patch: a warp reduces first-order, GLDM, NGTDM and GLSZM one after
+// the other for its 32 patches, so it runs one code path at a time with all lanes busy.  Per-thread fp64
 // scratch (2 * max_ng + 16 slots) is slot-major per warp (slot k of lane l at base[k * 32 + l]).
 // Same closed forms as the warp-level tasks in radb_features.cuh.
 #define MLD(b, k) (b)[(k) * 32]
@@ -721,8 +723,10 @@ __device__ void fo_lane_u8(const RadbParams& p, const int* hist, const int* lhis
 
 __device__ void radb_misc_lane_cta(const RadbParams& p, long long cta, unsigned char* smem)
 {
-    const int tid = threadIdx.x, lane = tid & 31, cls = tid >> 5;
-    const long long patch = cta * 32 + lane;
+    // thread <-> patch; a warp runs the four classes one after the other for its 32 patches (one code path per
+    // warp at any time, and no warp waits for a slower class of another warp)
+    const int tid = threadIdx.x;
+    const long long patch = cta * RADB_NT + tid;
     if (patch >= p.B) return;  // no collectives below: early exit is safe
     const long long row = radb_row(p, patch);
     if (p.status[row] != 0) return;
@@ -730,29 +734,24 @@ __device__ void radb_misc_lane_cta(const RadbParams& p, long long cta, unsigned 
     const int* misc = (const int*)(rec + (p.o_misc - p.o_rec));
     const int ng = misc[8], NB = 2 * p.n_angles;
     double* out = p.out + row * (long long)p.F;
-    double* scr = (double*)smem + cls * (p.ml_doubles * 32) + lane;
+    double* scr = (double*)smem + (tid >> 5) * (p.ml_doubles * 32) + (tid & 31);
     RadbTabs tb;
     tb.inv2 = p.g_inv2;
     tb.ninv = p.ninv;
     tb.tlog = p.g_tlog;
     tb.red = (double*)0;
-    if (cls == 0) {
-        const int novf = misc[5];
-        if (p.off_glszm >= 0 && novf <= RADB_LANE_MAX_OVF)
-            glszm_lane(p, tb, (const int*)(rec + (p.o_szm - p.o_rec)), (const unsigned*)(rec + (p.o_ovf - p.o_rec)), novf, ng,
-                       scr, out + p.off_glszm);
-    } else if (cls == 1) {
-        if (p.off_gldm >= 0) gldm_lane(tb, (const int*)(rec + (p.o_gldm - p.o_rec)), ng, NB + 1, out + p.off_gldm);
-    } else if (cls == 2) {
-        if (p.off_ngtdm >= 0 || p.dbg_ngn) {
-            double dummy[5];
-            ngtdm_lane((const int*)(rec + (p.o_ngc - p.o_rec)), (const int*)(rec + (p.o_ngn - p.o_rec)), ng, NB, scr,
-                       p.off_ngtdm >= 0 ? out + p.off_ngtdm : dummy, p.dbg_ngn ? p.dbg_ngn + patch * p.max_ng : (int*)0,
-                       p.dbg_ngs ? p.dbg_ngs + patch * p.max_ng : (double*)0);
-        }
-    } else {
-        if (p.off_fo >= 0 && p.pix_bytes == 1)  // non-uint8: done by the build kernel
-            fo_lane_u8(p, (const int*)(rec + (p.o_hist - p.o_rec)), (const int*)(rec + (p.o_lhist - p.o_rec)), ng, misc[0],
-                       scr, out + p.off_fo);
+    if (p.off_fo >= 0 && p.pix_bytes == 1)  // non-uint8: done by the build kernel
+        fo_lane_u8(p, (const int*)(rec + (p.o_hist - p.o_rec)), (const int*)(rec + (p.o_lhist - p.o_rec)), ng, misc[0], scr,
+                   out + p.off_fo);
+    if (p.off_gldm >= 0) gldm_lane(tb, (const int*)(rec + (p.o_gldm - p.o_rec)), ng, NB + 1, out + p.off_gldm);
+    if (p.off_ngtdm >= 0 || p.dbg_ngn) {
+        double dummy[5];
+        ngtdm_lane((const int*)(rec + (p.o_ngc - p.o_rec)), (const int*)(rec + (p.o_ngn - p.o_rec)), ng, NB, scr,
+                   p.off_ngtdm >= 0 ? out + p.off_ngtdm : dummy, p.dbg_ngn ? p.dbg_ngn + patch * p.max_ng : (int*)0,
+                   p.dbg_ngs ? p.dbg_ngs + patch * p.max_ng : (double*)0);
     }
+    const int novf = misc[5];
+    if (p.off_glszm >= 0 && novf <= RADB_LANE_MAX_OVF)
+        glszm_lane(p, tb, (const int*)(rec + (p.o_szm - p.o_rec)), (const unsigned*)(rec + (p.o_ovf - p.o_rec)), novf, ng, scr,
+                   out + p.off_glszm);
 }

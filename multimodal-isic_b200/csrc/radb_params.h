@@ -11,6 +11,7 @@
 #define RADB_NTB_MINB 5      // min resident build CTAs per SM (register cap: 48)
 #endif
 #define RADB_NTL 64          // threads per CTA of the lane kernel: one THREAD per (patch, angle)
+#define RADB_LSTRIDE RADB_NTL   // fp64 slot stride of its per-thread scratch (slot-major)
 #define RADB_MAX_ANGLES 4    // unidirectional offsets at distance 1 in a plane
 #define RADB_GLCM_NF 24
 #define RADB_GLRLM_NF 16
@@ -173,7 +174,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->l_nap = na <= 1 ? 1 : (na <= 2 ? 2 : 4);
     p->l_doubles = ng * (ng + 1) / 2 + 2 * ng;
     if (p->l_doubles < (p->nr + 1) / 2 + 1) p->l_doubles = (p->nr + 1) / 2 + 1;
-    p->l_smem_total = p->l_doubles * 8 * RADB_NTL;
+    p->l_smem_total = p->l_doubles * 8 * RADB_LSTRIDE;
     // (>= 3 resident CTAs per SM: with fewer the serial per-thread chains are latency-bound and the
     // warp-per-angle kernel wins -- measured at Ng 26: 1.55 ms vs 1.16 ms per 8192 patches)
     p->use_lane = (p->symmetric && p->l_smem_total <= 72 * 1024) ? 1 : 0;

@@ -49,6 +49,12 @@ class Engine:
     def launches(self):
         return int(self.lib.radb_launch_count(self._h))
 
+    def set_chunk(self, patches):
+        """Patches per chunk of the device pipeline (0 = default); see radb_set_chunk."""
+        rc = self.lib.radb_set_chunk(self._h, int(patches))
+        if rc != 0:
+            raise RadbError("radb_set_chunk failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+
     def set_profiling(self, on):
         self.lib.radb_set_profiling(self._h, int(bool(on)))
 

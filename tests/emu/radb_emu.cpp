@@ -74,7 +74,7 @@ static int emu_launch(RadbParams& p, int dtype, int64_t B)
     else
         emu::launch((unsigned)B, RADB_NT, [&]() { radb_angle_cta(p, (long long)blockIdx.x, sm); });
     if (p.only_big_ovf)
-        emu::launch((unsigned)((B + 31) / 32), RADB_NT, [&]() { radb_misc_lane_cta(p, (long long)blockIdx.x, sm); });
+        emu::launch((unsigned)((B + RADB_NT - 1) / RADB_NT), RADB_NT, [&]() { radb_misc_lane_cta(p, (long long)blockIdx.x, sm); });
     emu::launch((unsigned)B, RADB_NT, [&]() { radb_misc_cta(p, (long long)blockIdx.x, sm); });
     if (p.off_shape >= 0) emu::launch((unsigned)B, RADB_NT, [&]() { radb_shape_cta(p, (long long)blockIdx.x, sm); });
     return 0;

@@ -457,3 +457,39 @@ def test_binwidth_sweep_uint16_up_to_256_levels(gpu_pkg, bw):
     ex = gpu_pkg.RadiomicsExtractor({"setting": {"label": 255, "binWidth": bw}})
     out, st = ex.extract_batch(tt, torch.as_tensor(masks).cuda())
     np.testing.assert_allclose(out.cpu().numpy(), r["features"], rtol=1e-8, atol=1e-12)
+
+
+def test_multi_chunk_two_stream_pipeline_is_bit_identical(gpu_pkg):
+    """Batches larger than one chunk are cut into equal chunks and pipelined over two streams (build of chunk
+    i+1 overlaps the reductions of chunk i, two workspace slots).  Same rows, bit for bit, as one chunk --
+    dense, ragged, with shape2D, and with invalid ROIs in the batch."""
+    imgs, masks = gpu_pkg.synth.make_patches(61, 32, seed=77)
+    masks[7] = 0
+    masks[40] = 0
+    masks[40, 5, 5] = 255
+    ti, tm = torch.as_tensor(imgs).cuda(), torch.as_tensor(masks).cuda()
+    eng = gpu_pkg.Engine(25, 255, INPLANE, classes=gpu_pkg.CLASS_ORDER + ("shape2D",))
+    ref, rst = eng.extract_device(ti, tm)
+    torch.cuda.synchronize()
+    l0 = eng.launches
+    for chunk in (4, 8, 20, 60):
+        eng.set_chunk(chunk)
+        for _ in range(2):
+            out, st = eng.extract_device(ti, tm)
+            assert torch.equal(st, rst)
+            assert np.array_equal(out.cpu().numpy(), ref.cpu().numpy(), equal_nan=True)
+    assert eng.launches >= l0 + 2 * 5 * (16 + 8 + 4 + 2)
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):  # a caller stream other than the default one
+        out, st = eng.extract_device(ti, tm, stream=side)
+    side.synchronize()
+    assert np.array_equal(out.cpu().numpy(), ref.cpu().numpy(), equal_nan=True)
+    lst_i = [imgs[i] for i in range(61)] + [np.ascontiguousarray(imgs[3][:24, :20])] * 9
+    lst_m = [masks[i] for i in range(61)] + [np.ascontiguousarray(masks[3][:24, :20])] * 9
+    ip, mp, io, mo, hw = gpu_pkg.pack_ragged(lst_i, lst_m)
+    eng.set_chunk(0)
+    r0, s0 = eng.extract_ragged(torch.as_tensor(ip).cuda(), torch.as_tensor(mp).cuda(), io, mo, hw)
+    eng.set_chunk(8)
+    r1, s1 = eng.extract_ragged(torch.as_tensor(ip).cuda(), torch.as_tensor(mp).cuda(), io, mo, hw)
+    assert torch.equal(s0, s1) and np.array_equal(r0.cpu().numpy(), r1.cpu().numpy(), equal_nan=True)
+    assert np.array_equal(r0[:61].cpu().numpy(), ref.cpu().numpy(), equal_nan=True)
