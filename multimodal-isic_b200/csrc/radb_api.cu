@@ -235,6 +235,7 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     static const bool no_lane = getenv("RADB_NO_LANE") != nullptr;  // A/B switch: force the warp-per-angle kernel
     if (no_lane) p.use_lane = 0;
     if (!rc) rc = p.use_lane ? set_smem(h, radb_angle_lane_kernel, 3, p.l_smem_total) : set_smem(h, radb_angle_kernel, 1, p.a_smem_total);
+    if (!rc && p.use_lane == 2) rc = set_smem(h, radb_mcc_g8_kernel, 5, p.g8_smem_total);
     if (!rc && p.off_shape >= 0) rc = set_smem(h, radb_shape_kernel, 8, p.s_smem_total);
     if (!rc) rc = set_smem(h, radb_misc_kernel, 2, p.m_smem_total);
     p.only_big_ovf = (!no_lane && p.ml_smem_total <= 96 * 1024) ? 1 : 0;
@@ -314,6 +315,10 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         if (piped) {
             cudaEventRecord(h->sync_events[2 * c], st);
             cudaStreamWaitEvent(rs, h->sync_events[2 * c], 0);
+        }
+        if (p.use_lane == 2 && p.off_glcm >= 0) {
+            radb_mcc_g8_kernel<<<(unsigned)((n + RADB_NTM / 32 - 1) / (RADB_NTM / 32)), RADB_NTM, p.g8_smem_total, rs>>>(q);
+            h->launches += 1;
         }
         if (p.use_lane)
             radb_angle_lane_kernel<<<(unsigned)((n * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, p.l_smem_total, rs>>>(q);

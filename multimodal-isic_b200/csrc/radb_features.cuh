@@ -21,6 +21,14 @@ __device__ __noinline__ double radb_sqrt(double a) { return sqrt(a); }
 
 #define RADB_TLOG_N 2048  // entries of the log2(count) table
 
+// Read-only global loads (ld.global.nc): records and tables are written by earlier kernels / the host, so the
+// compiler may hoist and batch these loads across the shared-memory stores in between.
+#ifdef RADB_EMU
+#define RADB_LDG(ptr) (*(ptr))
+#else
+#define RADB_LDG(ptr) __ldg(ptr)
+#endif
+
 struct RadbTabs {
     const double* inv2;  // inv2[k-1] = 1/k^2, k = 1..ninv
     int ninv;
@@ -29,11 +37,11 @@ struct RadbTabs {
 };
 __device__ __forceinline__ double tab_inv2(const RadbTabs& t, int k)
 {
-    return k <= t.ninv ? t.inv2[k - 1] : radb_inv_sq(k);
+    return k <= t.ninv ? RADB_LDG(&t.inv2[k - 1]) : radb_inv_sq(k);
 }
 __device__ __forceinline__ double tab_log2(const RadbTabs& t, int c)
 {
-    return c < RADB_TLOG_N ? t.tlog[c] : radb_log2((double)c);
+    return c < RADB_TLOG_N ? RADB_LDG(&t.tlog[c]) : radb_log2((double)c);
 }
 __device__ __forceinline__ double tab_clog(const RadbTabs& t, int c) { return (double)c * tab_log2(t, c); }
 
@@ -343,6 +351,144 @@ __device__ double mcc_task(const int* P, const int* px, const int* py, int n, in
         const double t = fabs(l2);
         if (sturm_count(d, e2, m, -t * (1.0 + 1e-9) - 1e-12) == 0) return t;
         const double l1 = tridiag_kth(d, e2, m, 0, glo, ghi, lane);
+        return fmax(t, fabs(l1));
+    }
+    return radb_sqrt(fmax(l2, 0.0));
+}
+
+// ------------------------------------------------------------------ MCC, four angles per warp
+// With one warp per matrix most of mcc_task is per-step overhead (two warp reductions, a square root, a
+// division and three warp barriers per Householder step, 7 rounds of Sturm counts) paid for by 32 lanes of
+// which m - k - 1 <= 25 have a row to work on.  Here ONE warp solves the eigenproblems of all four angles at
+// once (radb_mcc_g8_kernel): the aligned 8-lane group g owns angle g, rows are dealt to its 8 lanes, and every
+// collective runs on the group's own mask, so the per-step overhead is shared by four matrices (ncu: 2.4x
+// fewer warp instructions at Ng 26).  Same mathematics as mcc_task.
+__device__ __forceinline__ double grp8_sum(double v, unsigned gm)
+{
+#pragma unroll
+    for (int m = 4; m >= 1; m >>= 1) v += __shfl_xor_sync(gm, v, m);
+    return v;
+}
+__device__ double tridiag_kth_g8(const double* d, const double* e2, int m, int k, double lo, double hi, int gl, unsigned gm,
+                                 int gshift)
+{
+    for (int it = 0; it < 12; it++) {  // 9-section: 9^11 = 3e10 shrink
+        const double w = (hi - lo) * (1.0 / 9.0);
+        const double x = lo + w * (double)(gl + 1);
+        const int c = sturm_count(d, e2, m, x);
+        const unsigned left = (__ballot_sync(gm, c <= k) >> gshift) & 0xffu;  // a prefix of the group
+        const int nl = __popc(left);
+        const double nlo = lo + w * (double)nl;
+        const double nhi = (nl == 8) ? hi : lo + w * (double)(nl + 1);
+        lo = nlo;
+        hi = nhi;
+        if (hi - lo <= 1e-10) break;
+    }
+    return 0.5 * (lo + hi);
+}
+__device__ double mcc_task_g8(const int* P, const int* px, const int* py, int n, int symmetric, double* ws,
+                              unsigned char* idx, int gl, unsigned gm, int gshift)
+{
+    int m = 0;
+    for (int base = 0; base < n; base += 8) {
+        const int i = base + gl;
+        const int present = (i < n) && (px[i] > 0);
+        const unsigned b = (__ballot_sync(gm, present) >> gshift) & 0xffu;
+        if (present) idx[m + __popc(b & ((1u << gl) - 1u))] = (unsigned char)i;
+        m += __popc(b);
+    }
+    __syncwarp(gm);
+    if (m < 2) return 0.0;
+    double* M = ws;
+    double* v = ws + m * (m + 1) / 2;
+    double* w = v + m;
+    double* d = w + m;
+    double* e2 = d + m;
+    for (int r = gl; r < m; r += 8) d[r] = radb_div(1.0, radb_sqrt((double)px[idx[r]]));
+    __syncwarp(gm);
+    for (int r = gl; r < m; r += 8) {
+        const int ir = idx[r];
+        const double rr = d[r];
+        for (int c = 0; c <= r; c++) {
+            const int ic = idx[c];
+            double val;
+            if (symmetric) {
+                val = (double)P[ir * n + ic];
+            } else {
+                val = 0;
+                for (int k = 0; k < n; k++)
+                    if (py[k] > 0) val += radb_div((double)P[ir * n + k] * (double)P[ic * n + k], (double)py[k]);
+            }
+            M[tri(r, c)] = val * rr * d[c];
+        }
+    }
+    __syncwarp(gm);
+    for (int k = 0; k < m - 2; k++) {
+        double part = 0;
+        for (int r = k + 2 + gl; r < m; r += 8) { const double x = M[tri(r, k)]; part += x * x; }
+        const double tail = grp8_sum(part, gm);
+        const double x0 = M[tri(k + 1, k)];
+        if (tail == 0.0) {
+            if (gl == 0) { d[k] = M[tri(k, k)]; e2[k] = x0 * x0; }
+            __syncwarp(gm);
+            continue;
+        }
+        const double nrm = radb_sqrt(tail + x0 * x0);
+        const double alpha = x0 > 0 ? -nrm : nrm;
+        const double vtv = tail + (x0 - alpha) * (x0 - alpha);
+        const double beta = radb_div(2.0, vtv);
+        for (int r = k + 1 + gl; r < m; r += 8) v[r] = (r == k + 1) ? x0 - alpha : M[tri(r, k)];
+        __syncwarp(gm);
+        double kpart = 0;
+        for (int r = k + 1 + gl; r < m; r += 8) {
+            const int rb = tri(r, 0);
+            double s = 0;
+            for (int c = k + 1; c <= r; c++) s += M[rb + c] * v[c];
+            for (int c = r + 1; c < m; c++) s += M[tri(c, r)] * v[c];
+            s *= beta;
+            w[r] = s;
+            kpart += s * v[r];
+        }
+        const double K = 0.5 * beta * grp8_sum(kpart, gm);
+        __syncwarp(gm);
+        for (int r = k + 1 + gl; r < m; r += 8) {
+            const double vr = v[r], wr = w[r] - K * vr;
+            const int rb = tri(r, 0);
+            for (int c = k + 1; c <= r; c++) {
+                const double vc = v[c];
+                M[rb + c] -= vr * (w[c] - K * vc) + wr * vc;
+            }
+        }
+        __syncwarp(gm);
+        if (gl == 0) { d[k] = M[tri(k, k)]; e2[k] = alpha * alpha; }
+        __syncwarp(gm);
+    }
+    if (gl == 0) {
+        d[m - 2] = M[tri(m - 2, m - 2)];
+        const double x = M[tri(m - 1, m - 2)];
+        e2[m - 2] = x * x;
+        d[m - 1] = M[tri(m - 1, m - 1)];
+    }
+    __syncwarp(gm);
+    double glo = 1e300, ghi = -1e300;
+    for (int i = gl; i < m; i += 8) {
+        const double r = (i > 0 ? radb_sqrt(e2[i - 1]) : 0.0) + (i < m - 1 ? radb_sqrt(e2[i]) : 0.0);
+        glo = fmin(glo, d[i] - r);
+        ghi = fmax(ghi, d[i] + r);
+    }
+#pragma unroll
+    for (int s = 4; s >= 1; s >>= 1) {
+        glo = fmin(glo, __shfl_xor_sync(gm, glo, s));
+        ghi = fmax(ghi, __shfl_xor_sync(gm, ghi, s));
+    }
+    const double span = ghi - glo;
+    glo -= 1e-12 * (span + 1.0);
+    ghi += 1e-12 * (span + 1.0);
+    const double l2 = tridiag_kth_g8(d, e2, m, m - 2, glo, ghi, gl, gm, gshift);
+    if (symmetric) {
+        const double t = fabs(l2);
+        if (sturm_count(d, e2, m, -t * (1.0 + 1e-9) - 1e-12) == 0) return t;
+        const double l1 = tridiag_kth_g8(d, e2, m, 0, glo, ghi, gl, gm, gshift);
         return fmax(t, fabs(l1));
     }
     return radb_sqrt(fmax(l2, 0.0));

@@ -1342,6 +1342,11 @@ __global__ void __launch_bounds__(RADB_NTL) radb_angle_lane_kernel(const RadbPar
     extern __shared__ __align__(16) unsigned char radb_smem[];
     radb_angle_lane_cta(p, (long long)blockIdx.x, radb_smem);
 }
+__global__ void __launch_bounds__(RADB_NTM) radb_mcc_g8_kernel(const RadbParams p)
+{
+    extern __shared__ __align__(16) unsigned char radb_smem[];
+    radb_mcc_g8_cta(p, (long long)blockIdx.x, radb_smem);
+}
 __global__ void __launch_bounds__(RADB_NT) radb_misc_lane_kernel(const RadbParams p)
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];

@@ -43,15 +43,34 @@ __device__ int glrlm_lane(const RadbTabs& tb, const unsigned* R, int wide, int n
         long long bj2 = 0;  // sum_j c * j^2 (exact)
         double arj = 0;     // sum_j c / j^2
         const int c0 = i * nr;
-        for (int j = 0; j < maxlen; j++) {
-            const int c = get_run(R, c0 + j, wide);
-            if (!c) continue;
+        auto cell = [&](int j, int c) {
             rs += c;
             LMI(lm, j) += c;
             e1 += tab_clog(tb, c);
             nnz++;
             arj += (double)c * tab_inv2(tb, j + 1);
             bj2 += (long long)c * (j + 1) * (j + 1);
+        };
+        if (!wide && !(nr & 1)) {  // packed u16 pairs, rows start on a word: four independent word loads per step
+            const unsigned* Rw = R + (c0 >> 1);
+            const int nw = (maxlen + 1) >> 1;
+            for (int w0 = 0; w0 < nw; w0 += 4) {
+                unsigned ww[4];
+#pragma unroll
+                for (int u = 0; u < 4; u++) ww[u] = (w0 + u < nw) ? RADB_LDG(Rw + w0 + u) : 0u;
+#pragma unroll
+                for (int u = 0; u < 4; u++) {
+                    if (!ww[u]) continue;
+                    const int lo = (int)(ww[u] & 0xffffu), hi = (int)(ww[u] >> 16), j = 2 * (w0 + u);
+                    if (lo) cell(j, lo);
+                    if (hi) cell(j + 1, hi);
+                }
+            }
+        } else {
+            for (int j = 0; j < maxlen; j++) {
+                const int c = get_run(R, c0 + j, wide);
+                if (c) cell(j, c);
+            }
         }
         if (rs) {
             const double i2 = (double)(i + 1) * (double)(i + 1), ri2 = tab_inv2(tb, i + 1);
@@ -233,9 +252,13 @@ __device__ double mcc_lane(LaneMem lm, int n, double rN)
 // P = final integer counts of one angle [n][n] (already symmetrised: P[i][j] == P[j][i], diagonal doubled).
 // (Staging the matrices cooperatively through shared memory instead of reading them per thread was tried:
 // the odd slot stride it needs costs one resident CTA per SM and the kernel got 25 % slower.)
+// MCC = false: mid-size matrices whose packed fp64 copy would not leave enough resident threads -- nothing is
+// stored (T = 0: the region is just D | E), the second pass re-reads P, and the eigenproblem is solved by
+// radb_mcc_g8_kernel (o[19] is filled in by the caller from the record).
+template <bool MCC>
 __device__ int glcm_lane(const RadbTabs& tb, const int* P, int n, LaneMem lm, double* o)
 {
-    const int T = n * (n + 1) / 2;
+    const int T = MCC ? n * (n + 1) / 2 : 0;
     const int iPX = 2 * T, iSUB = 2 * T + n, iADD = 2 * T + 2 * n;  // int views inside D | E
     for (int k = 0; k < 4 * n; k++) LMI(lm, iPX + k) = 0;
     long long sIJ = 0, sD2 = 0, sC2 = 0;
@@ -244,23 +267,29 @@ __device__ int glcm_lane(const RadbTabs& tb, const int* P, int n, LaneMem lm, do
         const int* row = P + i * n;
         const int rb = i * (i + 1) / 2;
         int rs = 0;
-        for (int j = 0; j < i; j++) {  // cell (i, j) stands for (i, j) and (j, i)
-            const int c = row[j];
-            LMD(lm, rb + j) = (double)c;
-            if (c) {
-                rs += c;
-                LMI(lm, iPX + j) += c;
-                LMI(lm, iADD + i + j) += 2 * c;
-                LMI(lm, iSUB + i - j) += 2 * c;
-                sIJ += 2LL * c * (i + 1) * (j + 1);
-                sD2 += 2LL * c * (i - j) * (i - j);
-                sC2 += 2LL * c * c;
-                nnz += 2;
-                maxc = c > maxc ? c : maxc;
+        for (int j0 = 0; j0 < i; j0 += 4) {  // cell (i, j) stands for (i, j) and (j, i); four loads in flight
+            int cc[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) cc[u] = (j0 + u < i) ? RADB_LDG(row + j0 + u) : 0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int j = j0 + u, c = cc[u];
+                if (MCC && j < i) LMD(lm, rb + j) = (double)c;
+                if (c) {
+                    rs += c;
+                    LMI(lm, iPX + j) += c;
+                    LMI(lm, iADD + i + j) += 2 * c;
+                    LMI(lm, iSUB + i - j) += 2 * c;
+                    sIJ += 2LL * c * (i + 1) * (j + 1);
+                    sD2 += 2LL * c * (i - j) * (i - j);
+                    sC2 += 2LL * c * c;
+                    nnz += 2;
+                    maxc = c > maxc ? c : maxc;
+                }
             }
         }
-        const int c = row[i];
-        LMD(lm, rb + i) = (double)c;
+        const int c = RADB_LDG(row + i);
+        if (MCC) LMD(lm, rb + i) = (double)c;
         if (c) {
             rs += c;
             LMI(lm, iADD + 2 * i) += c;
@@ -331,21 +360,30 @@ __device__ int glcm_lane(const RadbTabs& tb, const int* P, int n, LaneMem lm, do
     double ct = 0, cs = 0, cp = 0, ssq = 0, corm = 0, h1 = 0, sclog = 0;
     for (int i = 0; i < n; i++) {
         const int rb = i * (i + 1) / 2;
+        const int* row = P + i * n;
         const double di = (double)(i + 1) - ux, rpxi = LMD(lm, oE + i);
-        for (int j = 0; j < i; j++) {
-            const double dc = LMD(lm, rb + j);
-            if (dc == 0.0) continue;
-            const double pij = dc * rN, dj = (double)(j + 1) - ux, s = di + dj, s2 = s * s;
-            const double p2 = pij + pij;
-            ct += p2 * s2;
-            cs += p2 * s2 * s;
-            cp += p2 * s2 * s2;
-            ssq += pij * (di * di + dj * dj);
-            corm += p2 * di * dj;
-            h1 += 2.0 * dc * rpxi * LMD(lm, oE + j);
-            sclog += 2.0 * dc * (tab_log2(tb, (int)dc) - log2N);
+        for (int j0 = 0; j0 < i; j0 += 4) {
+            double dd[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++)
+                dd[u] = (j0 + u < i) ? (MCC ? LMD(lm, rb + j0 + u) : (double)RADB_LDG(row + j0 + u)) : 0.0;
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const double dc = dd[u];
+                if (dc == 0.0) continue;
+                const int j = j0 + u;
+                const double pij = dc * rN, dj = (double)(j + 1) - ux, s = di + dj, s2 = s * s;
+                const double p2 = pij + pij;
+                ct += p2 * s2;
+                cs += p2 * s2 * s;
+                cp += p2 * s2 * s2;
+                ssq += pij * (di * di + dj * dj);
+                corm += p2 * di * dj;
+                h1 += 2.0 * dc * rpxi * LMD(lm, oE + j);
+                sclog += 2.0 * dc * (tab_log2(tb, (int)dc) - log2N);
+            }
         }
-        const double dc = LMD(lm, rb + i);
+        const double dc = MCC ? LMD(lm, rb + i) : (double)RADB_LDG(row + i);
         if (dc != 0.0) {
             const double pij = dc * rN, s = di + di, s2 = s * s;
             ct += pij * s2;
@@ -361,7 +399,7 @@ __device__ int glcm_lane(const RadbTabs& tb, const int* P, int n, LaneMem lm, do
     const double hxy = -sclog * rN - RADB_EPS_LN2 * (double)nnz;
     const double hxy1 = hx0 + hx0 - RADB_EPS_LN2 * h1corr;
     const double hxy2 = hx0 + hx0 - RADB_EPS_LN2 * (double)nx * (double)nx;
-    const double mcc = mcc_lane(lm, n, rN);
+    const double mcc = MCC ? mcc_lane(lm, n, rN) : 0.0;
     double im2 = 1.0 - exp(-2.0 * (hxy2 - hxy));
     im2 = im2 < 0.0 ? 0.0 : im2;
     o[0] = autoc;
@@ -458,7 +496,15 @@ __device__ void radb_angle_lane_cta(const RadbParams& p, long long cta, unsigned
 #pragma unroll
         for (int i = 0; i < RADB_GLCM_NF; i++) f[i] = 0.0;
         int ok = 0;
-        if (live) ok = glcm_lane(tb, (const int*)(rec + (p.o_glcm - p.o_rec)) + a * ng * ng, ng, lm, f);
+        if (live) {
+            const int* P = (const int*)(rec + (p.o_glcm - p.o_rec)) + a * ng * ng;
+            if (p.use_lane == 1) {
+                ok = glcm_lane<true>(tb, P, ng, lm, f);
+            } else {
+                ok = glcm_lane<false>(tb, P, ng, lm, f);
+                f[19] = ((const double*)(misc + RADB_REC_MCC_INT))[a];  // written by radb_mcc_g8_kernel
+            }
+        }
         lane_mean<RADB_GLCM_NF>(f, ok, NAP);
         if (nroi < 2) f[19] = 1.0;  // MCC of a one-level ROI (glcm.py: "flat region" special case)
         if (patch_ok) lane_store<RADB_GLCM_NF>(f, NAP, a, out + p.off_glcm);
@@ -481,27 +527,54 @@ __device__ void glszm_lane(const RadbParams& p, const RadbTabs& tb, const int* Z
     const int s0 = p.s0;
     ZoneSums z;
     zs_init(z);
+    int col[16];  // column sums when s0 == 16 (narrow mode); the wide layout (s0 = 64) takes a second pass
+#pragma unroll
+    for (int j = 0; j < 16; j++) col[j] = 0;
     for (int i = 0; i < n; i++) {
         int g = 0;
-        for (int j = 0; j < s0; j++) {
-            const int c = Z[i * s0 + j];
-            if (!c) continue;
-            g += c;
-            zs_cell(z, tb, i + 1, j + 1, c);
+        if (s0 == 16) {
+            const int4* Zr = (const int4*)(Z + i * 16);  // 64-byte rows of a 16-byte aligned matrix
+            int4 q[4];
+#pragma unroll
+            for (int u = 0; u < 4; u++) q[u] = RADB_LDG(Zr + u);
+#pragma unroll
+            for (int u = 0; u < 4; u++) {
+                const int c4[4] = {q[u].x, q[u].y, q[u].z, q[u].w};
+#pragma unroll
+                for (int k = 0; k < 4; k++) {
+                    const int c = c4[k];
+                    if (!c) continue;
+                    g += c;
+                    col[4 * u + k] += c;
+                    zs_cell(z, tb, i + 1, 4 * u + k + 1, c);
+                }
+            }
+        } else {
+            for (int j = 0; j < s0; j++) {
+                const int c = RADB_LDG(Z + i * s0 + j);
+                if (!c) continue;
+                g += c;
+                zs_cell(z, tb, i + 1, j + 1, c);
+            }
         }
-        for (int e = 0; e < novf; e++) g += ((int)(ovf[e] >> 24) == i);
+        for (int e = 0; e < novf; e++) g += ((int)(RADB_LDG(ovf + e) >> 24) == i);
         if (g) zs_level(z, tb, i + 1, g);
     }
-    for (int j = 0; j < s0; j++) {
-        int cs = 0;
-        for (int i = 0; i < n; i++) cs += Z[i * s0 + j];
-        z.PJ2 += (long long)cs * cs;
+    if (s0 == 16) {
+#pragma unroll
+        for (int j = 0; j < 16; j++) z.PJ2 += (long long)col[j] * col[j];
+    } else {
+        for (int j = 0; j < s0; j++) {
+            int cs = 0;
+            for (int i = 0; i < n; i++) cs += RADB_LDG(Z + i * s0 + j);
+            z.PJ2 += (long long)cs * cs;
+        }
     }
     // overflow zones: the list was appended in atomic order, so it is first insertion-sorted by (size, level)
     // into this thread's scratch -- every sum below then runs in an order that depends on the data only
     // (bit-reproducible rows), equal cells are adjacent and so are equal sizes
     for (int e = 0; e < novf; e++) {
-        const unsigned k0 = ovf[e], key = ((k0 & 0xffffffu) << 8) | (k0 >> 24);
+        const unsigned k0 = RADB_LDG(ovf + e), key = ((k0 & 0xffffffu) << 8) | (k0 >> 24);
         int j = e;
         while (j > 0 && MLU(scr, j - 1) > key) { MLU(scr, j) = MLU(scr, j - 1); j--; }
         MLU(scr, j) = key;
@@ -544,21 +617,25 @@ __device__ void gldm_lane(const RadbTabs& tb, const int* D, int n, int nd, doubl
 {
     ZoneSums z;
     zs_init(z);
+    int col[9];  // nd <= 2 * RADB_MAX_ANGLES + 1
+#pragma unroll
+    for (int j = 0; j < 9; j++) col[j] = 0;
     for (int i = 0; i < n; i++) {
-        int g = 0;
-        for (int j = 0; j < nd; j++) {
-            const int c = D[i * nd + j];
+        int g = 0, cc[9];
+#pragma unroll
+        for (int j = 0; j < 9; j++) cc[j] = j < nd ? RADB_LDG(D + i * nd + j) : 0;
+#pragma unroll
+        for (int j = 0; j < 9; j++) {
+            const int c = cc[j];
             if (!c) continue;
             g += c;
+            col[j] += c;
             zs_cell(z, tb, i + 1, j + 1, c);
         }
         if (g) zs_level(z, tb, i + 1, g);
     }
-    for (int j = 0; j < nd; j++) {
-        int cs = 0;
-        for (int i = 0; i < n; i++) cs += D[i * nd + j];
-        z.PJ2 += (long long)cs * cs;
-    }
+#pragma unroll
+    for (int j = 0; j < 9; j++) z.PJ2 += (long long)col[j] * col[j];
     const double N = z.N ? (double)z.N : 1.0, rN = radb_div(1.0, N);
     o[0] = z.N ? radb_log2(N) - z.e1 * rN - RADB_EPS_LN2 * (double)z.nnz : 0.0;
     o[1] = (double)z.PJ2 * rN;
@@ -583,11 +660,17 @@ __device__ void ngtdm_lane(const int* C, const int* S, int n, int nb, double* sc
     for (int i = 0; i < n; i++) {
         int ni = 0;
         double s = 0;
-        for (int c = 0; c < nb; c++) {
-            const int cc = C[i * nb + c];
-            if (!cc) continue;
-            ni += cc;
-            s += radb_div((double)S[i * nb + c], (double)(c + 1));
+        int cc[8], ss[8];  // nb <= 2 * RADB_MAX_ANGLES
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            cc[c] = c < nb ? RADB_LDG(C + i * nb + c) : 0;
+            ss[c] = c < nb ? RADB_LDG(S + i * nb + c) : 0;
+        }
+#pragma unroll
+        for (int c = 0; c < 8; c++) {
+            if (!cc[c]) continue;
+            ni += cc[c];
+            s += radb_div((double)ss[c], (double)(c + 1));
         }
         MLD(scr, i) = (double)ni;
         MLD(scr, n + i) = s;
@@ -650,8 +733,12 @@ __device__ void fo_lane_u8(const RadbParams& p, const int* hist, const int* lhis
     // the lo ranks (slots 0, 2, ..) and the hi ranks (slots 1, 3, ..) are each non-decreasing: one cursor per sequence
     int tl = 0, th = 1;
     int nextl = (int)MLD(scr, 0), nexth = (int)MLD(scr, 1);
-    for (int v = 0; v < 256; v++) {
-        const int hk = hist[v];
+    for (int v0 = 0; v0 < 256; v0 += 4) {
+      const int4 h4 = RADB_LDG((const int4*)(hist + v0));  // 16-byte aligned histogram, four bins per load
+      const int hq[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int v = v0 + u, hk = hq[u];
         if (!hk) continue;
         s1 += (long long)hk * v;
         vmin = v < vmin ? v : vmin;
@@ -667,6 +754,7 @@ __device__ void fo_lane_u8(const RadbParams& p, const int* hist, const int* lhis
             th += 2;
             nexth = th < 10 ? (int)MLD(scr, th) : 0;
         }
+      }
     }
     const double mean = (double)s1 * rN;
     double pc[5];
@@ -675,8 +763,12 @@ __device__ void fo_lane_u8(const RadbParams& p, const int* hist, const int* lhis
     const double p10 = pc[0], p25 = pc[1], med = pc[2], p75 = pc[3], p90 = pc[4];
     double m2 = 0, m3 = 0, m4 = 0, mad = 0, en = 0, in_s1 = 0;
     int in_n = 0;
-    for (int v = vmin; v <= vmax; v++) {
-        const int hi_ = hist[v];
+    for (int v0 = vmin & ~3; v0 <= vmax; v0 += 4) {  // bins outside [vmin, vmax] are empty
+      const int4 h4 = RADB_LDG((const int4*)(hist + v0));
+      const int hq[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const int v = v0 + u, hi_ = hq[u];
         if (!hi_) continue;
         const double dv = (double)v, hk = (double)hi_, d = dv - mean, d2 = d * d;
         m2 += hk * d2;
@@ -685,17 +777,23 @@ __device__ void fo_lane_u8(const RadbParams& p, const int* hist, const int* lhis
         mad += hk * fabs(d);
         en += hk * (dv + shift) * (dv + shift);
         if (dv >= p10 && dv <= p90) { in_n += hi_; in_s1 += hk * dv; }
+      }
     }
     m2 *= rN; m3 *= rN; m4 *= rN; mad *= rN;
     const double rin = radb_div(1.0, (double)in_n), in_mean = in_s1 * rin;
     double rmad = 0;
-    for (int v = vmin; v <= vmax; v++) {
-        const double dv = (double)v;
-        if (dv >= p10 && dv <= p90) rmad += (double)hist[v] * fabs(dv - in_mean);
+    for (int v0 = vmin & ~3; v0 <= vmax; v0 += 4) {
+      const int4 h4 = RADB_LDG((const int4*)(hist + v0));
+      const int hq[4] = {h4.x, h4.y, h4.z, h4.w};
+#pragma unroll
+      for (int u = 0; u < 4; u++) {
+        const double dv = (double)(v0 + u);
+        if (hq[u] && dv >= p10 && dv <= p90) rmad += (double)hq[u] * fabs(dv - in_mean);
+      }
     }
     double ent = 0, uni = 0;
     for (int i = 0; i < ng; i++) {
-        const int c = lhist[i];
+        const int c = RADB_LDG(lhist + i);
         if (!c) continue;
         const double pi = (double)c * rN;
         ent -= pi * radb_log2(pi + RADB_EPS);
@@ -754,4 +852,32 @@ __device__ void radb_misc_lane_cta(const RadbParams& p, long long cta, unsigned 
     if (p.off_glszm >= 0 && novf <= RADB_LANE_MAX_OVF)
         glszm_lane(p, tb, (const int*)(rec + (p.o_szm - p.o_rec)), (const unsigned*)(rec + (p.o_ovf - p.o_rec)), novf, ng, scr,
                    out + p.off_glszm);
+}
+
+// ==================================================================== MCC kernel: one warp per patch
+// The aligned 8-lane group g of the warp owns angle g: row sums of its matrix (p_x), then mcc_task_g8.  The
+// four values go to the record header (RADB_REC_MCC_INT) for the thread-per-angle kernel's nanmean.
+__device__ void radb_mcc_g8_cta(const RadbParams& p, long long cta, unsigned char* smem)
+{
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long patch = cta * (RADB_NTM / 32) + warp;
+    if (patch >= p.B || p.off_glcm < 0) return;
+    if (p.status[radb_row(p, patch)] != 0) return;
+    const int g = lane >> 3, gl = lane & 7;
+    if (g >= p.n_angles) return;  // every collective below runs on the group's own mask
+    const unsigned gm = 0xffu << (8 * g);
+    unsigned char* rec = p.ws + patch * (long long)p.rec_bytes;
+    int* misc = (int*)(rec + (p.o_misc - p.o_rec));
+    const int n = misc[8];
+    const int* P = (const int*)(rec + (p.o_glcm - p.o_rec)) + g * n * n;
+    unsigned char* ws = smem + (warp * 4 + g) * p.g8_group_bytes;
+    int* px = (int*)(ws + p.g8_px);
+    for (int i = gl; i < n; i += 8) {
+        int rs = 0;
+        for (int j = 0; j < n; j++) rs += P[i * n + j];
+        px[i] = rs;
+    }
+    __syncwarp(gm);
+    const double mcc = mcc_task_g8(P, px, px, n, 1, (double*)(ws + p.g8_mcc), ws + p.g8_idx, gl, gm, 8 * g);
+    if (gl == 0) ((double*)(misc + RADB_REC_MCC_INT))[g] = mcc;
 }

@@ -12,10 +12,12 @@
 #endif
 #define RADB_NTL 64          // threads per CTA of the lane kernel: one THREAD per (patch, angle)
 #define RADB_LSTRIDE RADB_NTL   // fp64 slot stride of its per-thread scratch (slot-major)
+#define RADB_NTM 64          // threads per CTA of the MCC kernel: one WARP per patch, 8 lanes per angle
 #define RADB_MAX_ANGLES 4    // unidirectional offsets at distance 1 in a plane
 #define RADB_GLCM_NF 24
 #define RADB_GLRLM_NF 16
 #define RADB_FSC_STRIDE 40   // per-angle scratch: 24 GLCM + 16 GLRLM features
+#define RADB_REC_MCC_INT 16  // record header ints [16, 24): the per-angle MCC values (4 doubles) of radb_mcc_g8_kernel
 
 enum { RADB_U8 = 0, RADB_U16 = 1, RADB_F32 = 2, RADB_F64 = 3 };
 
@@ -75,6 +77,9 @@ struct RadbParams {
     int s_smem_total;  // shape kernel
     // ---- lane kernel (radb_lane.cuh): one thread per (patch, angle), l_doubles fp64 slots of shared memory each
     int use_lane, l_nap, l_doubles, l_smem_total;
+    // use_lane: 0 warp-per-angle kernel | 1 thread-per-angle kernel incl. MCC (Ng <= 14) | 2 thread-per-angle kernel
+    // without the matrix storage + radb_mcc_g8_kernel for the eigenproblems (Ng <= 40)
+    int g8_px, g8_idx, g8_mcc, g8_group_bytes, g8_smem_total;  // MCC kernel: per-group shared-memory layout
     // ---- misc lane kernel: one thread per (patch, class); the warp-level misc kernel then only serves GLSZM
     // patches with a long overflow list (only_big_ovf = 1)
     int ml_doubles, ml_smem_total, only_big_ovf;
@@ -178,6 +183,21 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     // (>= 3 resident CTAs per SM: with fewer the serial per-thread chains are latency-bound and the
     // warp-per-angle kernel wins -- measured at Ng 26: 1.55 ms vs 1.16 ms per 8192 patches)
     p->use_lane = (p->symmetric && p->l_smem_total <= 72 * 1024) ? 1 : 0;
+    if (!p->use_lane && p->symmetric && !big && ng <= 40) {
+        // mid-size matrices: the per-thread scratch only holds the marginals (2 * ng slots); the eigenproblems go
+        // to the MCC kernel, one warp per patch
+        p->use_lane = 2;
+        p->l_doubles = 2 * ng;
+        if (p->l_doubles < (p->nr + 1) / 2 + 1) p->l_doubles = (p->nr + 1) / 2 + 1;
+        p->l_smem_total = p->l_doubles * 8 * RADB_LSTRIDE;
+        if (p->l_smem_total > 72 * 1024) p->use_lane = 0;
+    }
+    o = 0;
+    p->g8_px = o; o += radb_align(ng * 4, 16);
+    p->g8_idx = o; o += radb_align(ng, 16);
+    p->g8_mcc = o; o += radb_align(p->mcc_stride * 8, 16);
+    p->g8_group_bytes = o;
+    p->g8_smem_total = (RADB_NTM / 32) * 4 * p->g8_group_bytes;
     p->ml_doubles = 2 * ng + 16 > 32 ? 2 * ng + 16 : 32;  // >= RADB_LANE_MAX_OVF / 2 slots for the sorted overflow list
     p->ml_smem_total = 4 * p->ml_doubles * 32 * 8;
     // ---- misc kernel

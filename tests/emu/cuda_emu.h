@@ -30,11 +30,23 @@
 struct alignas(16) uint4 {
     unsigned x, y, z, w;
 };
+struct alignas(16) int4 {
+    int x, y, z, w;
+};
 
 namespace emu {
 struct Warp {
     std::barrier<> bar{32};
+    std::barrier<> gbar[4] = {std::barrier<>(8), std::barrier<>(8), std::barrier<>(8), std::barrier<>(8)};
     uint64_t slot[32];
+    // full mask -> the warp barrier; 0xff << 8g -> the barrier of the aligned 8-lane group g (sub-warp collectives)
+    std::barrier<>& pick(unsigned mask) {
+        if (mask == 0xffffffffu) return bar;
+        for (int g = 0; g < 4; g++)
+            if (mask == (0xffu << (8 * g))) return gbar[g];
+        std::fprintf(stderr, "cuda_emu: unsupported collective mask %08x\n", mask);
+        std::abort();
+    }
 };
 struct Ctx {
     unsigned tid = 0, bid = 0, nthreads = 0;
@@ -64,24 +76,26 @@ inline T unbits(uint64_t b) {
 }
 // every lane publishes v, then reads the value of lane `src`
 template <class T>
-inline T exchange(T v, int src) {
+inline T exchange(T v, int src, unsigned mask = 0xffffffffu) {
     Warp* w = ctx.warp;
     int lane = ctx.tid & 31;
+    std::barrier<>& b = w->pick(mask);
     w->slot[lane] = bits(v);
-    w->bar.arrive_and_wait();
+    b.arrive_and_wait();
     T r = unbits<T>(w->slot[src & 31]);
-    w->bar.arrive_and_wait();
+    b.arrive_and_wait();
     return r;
 }
 // every lane publishes v and gets all 32 values
 template <class T>
-inline void gather(T v, T out[32]) {
+inline void gather(T v, T out[32], unsigned mask = 0xffffffffu) {
     Warp* w = ctx.warp;
     int lane = ctx.tid & 31;
+    std::barrier<>& b = w->pick(mask);
     w->slot[lane] = bits(v);
-    w->bar.arrive_and_wait();
-    for (int i = 0; i < 32; i++) out[i] = unbits<T>(w->slot[i]);
-    w->bar.arrive_and_wait();
+    b.arrive_and_wait();
+    for (int i = 0; i < 32; i++) out[i] = unbits<T>(w->slot[i]);  // only the lanes in `mask` are meaningful
+    b.arrive_and_wait();
 }
 
 // launch: grid CTAs run one after another, `nthreads` OS threads each
@@ -112,12 +126,12 @@ void launch(unsigned grid, unsigned nthreads, F body) {
 #define blockDim (emu::bdim())
 
 inline void __syncthreads() { emu::ctx.cta->arrive_and_wait(); }
-inline void __syncwarp(unsigned = 0xffffffffu) { emu::ctx.warp->bar.arrive_and_wait(); }
+inline void __syncwarp(unsigned mask = 0xffffffffu) { emu::ctx.warp->pick(mask).arrive_and_wait(); }
 
 template <class T>
-inline T __shfl_sync(unsigned, T v, int src) { return emu::exchange(v, src); }
+inline T __shfl_sync(unsigned m, T v, int src) { return emu::exchange(v, src, m); }
 template <class T>
-inline T __shfl_xor_sync(unsigned, T v, int m) { return emu::exchange(v, (emu::ctx.tid & 31) ^ m); }
+inline T __shfl_xor_sync(unsigned mask, T v, int m) { return emu::exchange(v, (emu::ctx.tid & 31) ^ m, mask); }
 template <class T>
 inline T __shfl_up_sync(unsigned, T v, unsigned d) {
     int lane = emu::ctx.tid & 31;
@@ -129,11 +143,12 @@ inline T __shfl_down_sync(unsigned, T v, unsigned d) {
     int lane = emu::ctx.tid & 31;
     return emu::exchange(v, lane + (int)d > 31 ? lane : lane + (int)d);
 }
-inline unsigned __ballot_sync(unsigned, int pred) {
+inline unsigned __ballot_sync(unsigned mask, int pred) {
     int all[32];
-    emu::gather<int>(pred ? 1 : 0, all);
+    emu::gather<int>(pred ? 1 : 0, all, mask);
     unsigned r = 0;
-    for (int i = 0; i < 32; i++) r |= (all[i] ? 1u : 0u) << i;
+    for (int i = 0; i < 32; i++)
+        if ((mask >> i) & 1u) r |= (all[i] ? 1u : 0u) << i;
     return r;
 }
 inline int __any_sync(unsigned m, int pred) { return __ballot_sync(m, pred) != 0; }

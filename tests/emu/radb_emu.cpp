@@ -50,6 +50,7 @@ static int emu_launch(RadbParams& p, int dtype, int64_t B)
     mx = mx > p.s_smem_total ? mx : p.s_smem_total;
     if (getenv("RADB_NO_LANE")) p.use_lane = 0;
     if (p.use_lane && p.l_smem_total > mx) mx = p.l_smem_total;
+    if (p.use_lane == 2 && p.g8_smem_total > mx) mx = p.g8_smem_total;
     p.only_big_ovf = (!getenv("RADB_NO_LANE") && p.ml_smem_total <= 96 * 1024) ? 1 : 0;
     if (p.only_big_ovf && p.ml_smem_total > mx) mx = p.ml_smem_total;
     std::vector<unsigned char> smem((size_t)mx + 64);
@@ -69,6 +70,8 @@ static int emu_launch(RadbParams& p, int dtype, int64_t B)
         case RADB_DTYPE_F64: EMU_BUILD(double) break;
         default: g_err = "unknown dtype"; return -1;
     }
+    if (p.use_lane == 2 && p.off_glcm >= 0)
+        emu::launch((unsigned)((B + RADB_NTM / 32 - 1) / (RADB_NTM / 32)), RADB_NTM, [&]() { radb_mcc_g8_cta(p, (long long)blockIdx.x, sm); });
     if (p.use_lane)
         emu::launch((unsigned)((B * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, [&]() { radb_angle_lane_cta(p, (long long)blockIdx.x, sm); });
     else

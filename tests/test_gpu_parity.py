@@ -36,7 +36,7 @@ def test_synthetic_inplane_bw10(gpu_pkg):
     eng = _engine(gpu_pkg)
     l0 = eng.launches
     r = _dbg(eng, imgs, masks)
-    assert eng.launches == l0 + 4  # build, angle, misc (thread-level), misc (warp-level residual) for one chunk
+    assert eng.launches == l0 + 5  # build, MCC (8 lanes per angle), angle + misc (thread-level), misc residual: one chunk
     assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=False)) == 24
 
 
