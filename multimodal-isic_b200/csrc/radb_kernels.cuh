@@ -789,6 +789,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     {
         const int nr = p.nr;
         int t0 = 0;
+        // when all the lines of all angles fit one round of the CTA, every angle starts on a warp boundary:
+        // a warp then walks one kind of line (row / column / diagonal) instead of diverging over two kinds
+        const int lines_max = bh > bw ? bh : bw;
+        const bool warp_aligned = NA * ((lines_max + 31) & ~31) <= RADB_NTB;
         for (int a = 0; a < NA; a++) {
             const int dy = p.ang_y[a], dx = p.ang_x[a];
             const int nlines = (dy == 0) ? bh : bw;
@@ -844,7 +848,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 }
             }
             if (mylen) atomicMax(&misc[10 + a], mylen);  // record header: longest run of angle a
-            t0 += nlines;
+            t0 += warp_aligned ? ((nlines + 31) & ~31) : nlines;
         }
     }
     __syncthreads();
