@@ -149,7 +149,7 @@ def workload_config(args, patches_per_step, F):
         "binWidth": args.bin_width,
         "angles": "literal force2D on 2-D input (1 angle, 2 neighbours)" if args.literal_force2d
         else "in-plane (4 angles, 8 neighbours)",
-        "label": 255, "parallelism": "patch-sharded, one process per GPU, all-gather of the feature block",
+        "label": 255, "parallelism": "patch-sharded, one process per GPU, all-gather of the feature block (sliced, overlapped with the extraction)",
         "l2_policy": "inputs (%.0f MB per step) larger than the 126 MB L2" % (patches_per_step * args.size * args.size * 2 / 1e6),
     }
 
@@ -210,11 +210,18 @@ def gpu_arm(args):
     out = torch.empty((B, F), dtype=torch.float64, device=dev)
     status = torch.empty((B,), dtype=torch.int32, device=dev)
     gathered = torch.empty((world * B, F), dtype=torch.float64, device=dev) if world > 1 else None
+    # N > 1: the shard is extracted in two slices and the all-gather of the first (NCCL on a side stream)
+    # overlaps the extraction of the second; the step ends when the full [world * B, F] matrix is on every rank
+    og = pkg.OverlappedGather(B, F, world, dev, pieces=2) if world > 1 else None
+
+    def extract_slice(lo, hi, o, s):
+        ex.engine.extract_device(imgs[lo:hi], masks[lo:hi], o, s)
 
     def step():
-        ex.engine.extract_device(imgs, masks, out, status)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)
+            og.run(extract_slice, out, status, gathered)
+        else:
+            ex.engine.extract_device(imgs, masks, out, status)
 
     def barrier():
         if world > 1:

@@ -1,16 +1,21 @@
-// radb -- B200-native radiomic feature kernels (sm_100a).  Three kernels per batch, one CTA
-// (128 threads) per patch in each, so that every kernel's code stays small enough for the SM
+// radb -- B200-native radiomic feature kernels (sm_100a).  A pass over a chunk of patches is a build
+// kernel followed by small reduction kernels, so that every kernel's code stays small enough for the SM
 // instruction caches (a fused single kernel measured 55 % "no instruction" stalls, profiles/):
-//   radb_build_kernel : TMA bulk copy (cp.async.bulk + mbarrier) of the raw patch + mask into
-//                       shared memory -> ROI histogram / bbox -> value->level LUT -> padded level
-//                       image -> line walks (GLRLM runs + row-run labels) -> one neighbourhood
-//                       pass (GLCM, GLDM, NGTDM, run-adjacency unions for GLSZM) -> zone sizes.
-//                       Every matrix is a shared-memory privatised integer counter array; the
-//                       finished RECORD (header + matrices) is copied to a global workspace.
-//   radb_angle_kernel : warp a reduces GLRLM angle a (16 features) and GLCM angle a (24 features,
-//                       MCC through Householder tridiagonalisation + Sturm multisection), fp64,
-//                       then the CTA forms the nanmean over angles.
-//   radb_misc_kernel  : one warp each for GLSZM, GLDM, NGTDM and first-order features.
+//   radb_build_kernel : one CTA per patch.  TMA bulk copy (cp.async.bulk + mbarrier) of the raw patch + mask
+//                       into shared memory -> ROI histogram / bbox -> value->level LUT -> padded level image
+//                       -> line walks (GLRLM runs + row-run labels) -> one neighbourhood pass (GLCM, GLDM,
+//                       NGTDM, run-adjacency unions for GLSZM) -> zone sizes.  Every matrix is a
+//                       shared-memory privatised integer counter array; the finished RECORD (header +
+//                       matrices) is copied to a global workspace.
+//   radb_angle_lane_kernel / radb_mcc_g8_kernel / radb_misc_lane_kernel (radb_lane.cuh): thread-level fp64
+//                       reductions of the records -- one thread per (patch, angle) for GLCM / GLRLM / MCC, one
+//                       thread per patch for first-order / GLDM / NGTDM / GLSZM; the eigenproblems of 15-40
+//                       gray levels on one warp per patch, 8 lanes per angle.
+//   radb_angle_kernel : warp a reduces GLRLM angle a (16 features) and GLCM angle a (24 features, MCC through
+//                       Householder tridiagonalisation + Sturm multisection), then the CTA forms the nanmean
+//                       over angles.  Kept for asymmetric GLCMs and more than 40 gray levels.
+//   radb_misc_kernel  : one warp each for GLSZM, GLDM, NGTDM and first-order features.  Kept for long GLSZM
+//                       overflow lists and many gray levels.
 // Semantics follow pyradiomics 3.1.0 as called from /root/reference/RadiomicExtractor.py:38-48
 // (settings /root/reference/params.yml:93-119); the algorithm restated is SURVEY.md Appendix A.
 // This header also compiles as plain C++ under tests/emu/cuda_emu.h (RADB_EMU) so that the same

@@ -67,3 +67,52 @@ def sharded_extract(extract_fn, n_patches, costs=None, group=None, F=None):
     full = all_gather_rows(feats, rows, group)
     st = all_gather_rows(status.view(-1, 1).to(torch.int32), rows, group).view(-1)
     return full, st, b
+
+
+class OverlappedGather:
+    """Equal shards (weak scaling: every rank owns ``rows`` patches): the local shard is extracted in
+    ``pieces`` slices, and the all-gather of slice k (NCCL over NVLink, on a side stream) overlaps the
+    extraction of slice k+1, so only the last slice's collective is exposed.  ``gathered`` is the full
+    ``[world * rows, F]`` matrix in rank-major (= original) order on every rank.
+
+    ``extract_fn(lo, hi, out, status)`` writes the rows of local patches ``[lo, hi)`` into the given
+    slices, asynchronously on the current stream (``Engine.extract_device`` does).  On CPU tensors
+    (gloo tests) the same slicing runs without streams."""
+
+    def __init__(self, rows, F, world, device, pieces=2, group=None):
+        self.rows, self.F, self.world, self.group = int(rows), int(F), int(world), group
+        self.pieces = max(1, min(int(pieces), self.rows or 1))
+        self.bounds = [self.rows * k // self.pieces for k in range(self.pieces + 1)]
+        self.cuda = torch.device(device).type == "cuda"
+        mx = max((self.bounds[k + 1] - self.bounds[k] for k in range(self.pieces)), default=0)
+        # one staging buffer per slice: slice k's collective may still be running when slice k+1 is extracted
+        self.tmp = [torch.empty((self.world, mx, self.F), dtype=torch.float64, device=device) for _ in range(self.pieces)]
+        self.comm = torch.cuda.Stream(device=device) if self.cuda and self.world > 1 else None
+
+    def run(self, extract_fn, out, status, gathered):
+        g = gathered.view(self.world, self.rows, self.F)
+        cur = torch.cuda.current_stream(out.device) if self.comm is not None else None
+        if self.comm is not None:
+            self.comm.wait_stream(cur)  # the previous step's consumers of `gathered` / tmp are done
+        for k in range(self.pieces):
+            lo, hi = self.bounds[k], self.bounds[k + 1]
+            extract_fn(lo, hi, out[lo:hi], status[lo:hi])
+            if self.world == 1:
+                g[0, lo:hi].copy_(out[lo:hi])
+                continue
+            if self.comm is not None:
+                ev = torch.cuda.Event()
+                ev.record(cur)
+                self.comm.wait_event(ev)
+                with torch.cuda.stream(self.comm):
+                    flat = self.tmp[k].view(-1, self.F)[: self.world * (hi - lo)].view(self.world, hi - lo, self.F)
+                    dist.all_gather_into_tensor(flat, out[lo:hi], group=self.group)
+                    g[:, lo:hi].copy_(flat)
+            else:
+                parts = [torch.empty((hi - lo, self.F), dtype=out.dtype) for _ in range(self.world)]
+                dist.all_gather(parts, out[lo:hi].contiguous(), group=self.group)
+                for r in range(self.world):
+                    g[r, lo:hi].copy_(parts[r])
+        if self.comm is not None:
+            cur.wait_stream(self.comm)
+        return gathered

@@ -49,3 +49,40 @@ def test_sharded_extract_world2():
     assert all(ok for _, ok, _ in res)
     b = res[0][2]
     assert b == res[1][2] and b[0] == 0 and b[-1] == n and b[1] > n // 2  # cost-balanced, not count-balanced
+
+
+def _worker_overlapped(rank, world, port, rows, F, q):
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    def fake_extract(lo, hi, out, status):  # stands in for Engine.extract_device on this rank's slice
+        idx = torch.arange(rank * rows + lo, rank * rows + hi, dtype=torch.float64)
+        out.copy_(idx[:, None] * 10 + torch.arange(F, dtype=torch.float64)[None, :])
+        status.copy_((idx % 3 == 0).to(torch.int32))
+
+    ok = True
+    for pieces in (1, 2, 3, rows + 5):
+        og = pkg.OverlappedGather(rows, F, world, "cpu", pieces=pieces)
+        out, status = torch.zeros((rows, F), dtype=torch.float64), torch.zeros(rows, dtype=torch.int32)
+        gathered = torch.zeros((world * rows, F), dtype=torch.float64)
+        og.run(fake_extract, out, status, gathered)
+        want = torch.arange(world * rows, dtype=torch.float64)[:, None] * 10 + torch.arange(F, dtype=torch.float64)
+        ok = ok and torch.equal(gathered, want) and og.bounds[0] == 0 and og.bounds[-1] == rows
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_overlapped_gather_world2():
+    """The sliced extract + all-gather pipeline bench.py uses for N > 1 (side stream on GPUs; same slicing on gloo)."""
+    world, rows, F = 2, 11, 4
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker_overlapped, args=(r, world, port, rows, F, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in range(world)]
+    for p in procs:
+        p.join(60)
+    assert all(ok for _, ok in res)
