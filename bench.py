@@ -348,8 +348,10 @@ def gpu_arm(args):
                                  "alone. The pass is issue/latency bound (shared-memory atomics, fp64), not HBM "
                                  "bound (DESIGN.md, profiles/)"},
             "cpu_baseline": cpu,
-            "e2e": {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(world * B * H * H * 2),
-                    "d2h_bytes_per_step": int(world * B * (F * 8 + 4)), "matches_device_path": same},
+            "e2e": {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(world * ex.pipeline.h2d_bytes),
+                    "d2h_bytes_per_step": int(world * B * (F * 8 + 4)), "matches_device_path": same,
+                    "masks": ("packed to 1 bit per pixel by %d host threads (radb_pack_mask_host), expanded on the device"
+                              % ex.pipeline.pack_threads) if ex.pipeline.pack_masks else "uint8, as handed over"},
             "gpu_launches": int(launches),
             "clocks": sampler.summary(),
             "invalid_rows": bad,

@@ -127,6 +127,15 @@ int radb_extract_ragged(radb_handle* h, const void* img_pool, int dtype, const u
 int radb_extract_bgr(radb_handle* h, const uint8_t* bgr, const uint8_t* mask, int64_t n_images, int H, int W,
                      uint8_t* planes, double* out, int32_t* status, void* cuda_stream);
 
+/* Packed-mask transfer path.  The reference hands over uint8 masks (RadiomicExtractor.py:33-36) of which only
+ * `mask == label` matters (params.yml:93): one bit per pixel.  End to end the extraction is bound by the
+ * host-to-device link, so the host may pack a mask buffer to 1 bit per pixel (bit i of the byte stream <->
+ * byte i of `mask`; HOST pointers; AVX2 over `threads` host threads, memory bound), copy n_bytes / 8 bytes
+ * instead of n_bytes, and expand it on the device with radb_unpack_mask (DEVICE pointers, stream-ordered;
+ * `mask` gets `label` where the bit is set and a different value elsewhere) before radb_extract. */
+int radb_pack_mask_host(const uint8_t* mask, int64_t n_bytes, int label, uint8_t* packed, int threads);
+int radb_unpack_mask(radb_handle* h, const uint8_t* packed, int64_t n_bytes, uint8_t* mask, void* cuda_stream);
+
 /* imageType filters of the parameter file (params.yml:141-144; pyradiomics imageoperations.getSquareImage,
  * getSquareRootImage, getLogarithmImage, getExponentialImage) for uint8 images, computed in float64:
  * type 1 Square, 2 SquareRoot, 3 Logarithm, 4 Exponential.  img [n][H*W] uint8 -> out [n][H*W] float64

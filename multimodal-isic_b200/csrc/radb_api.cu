@@ -532,6 +532,22 @@ extern "C" int radb_extract_bgr(radb_handle* h, const uint8_t* bgr, const uint8_
     return launch(h, p, RADB_DTYPE_U8, cuda_stream);
 }
 
+// Device half of the packed-mask transfer path (host half: radb_hostpack.cpp).
+extern "C" int radb_unpack_mask(radb_handle* h, const uint8_t* packed, int64_t n_bytes, uint8_t* mask, void* cuda_stream)
+{
+    if (!h || !packed || !mask || n_bytes < 0) return fail(RADB_E_INVALID, "bad argument");
+    if (n_bytes == 0) return RADB_OK;
+    int cur = -1;
+    cudaGetDevice(&cur);
+    if (cur != h->device) cudaSetDevice(h->device);
+    const long long threads = (n_bytes + 15) / 16;
+    radb_unpack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(packed, n_bytes, h->plan.s.label, mask);
+    h->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "radb_unpack_mask launch");
+    return RADB_OK;
+}
+
 // imageType filters of the pyradiomics parameter file (params.yml:141-144) for uint8 images:
 // type 1 Square, 2 SquareRoot, 3 Logarithm, 4 Exponential.  img [n][H*W] uint8 -> out [n][H*W] float64;
 // `mx` is an int32 [n] device scratch (per-image maximum).

@@ -1,0 +1,69 @@
+// Host side of the packed-mask transfer path (include/radb.h: radb_pack_mask_host).  The end-to-end rate of
+// the extraction is bound by the host-to-device link (4096 pixel bytes + 4096 mask bytes per 64x64 patch at
+// ~50 GB/s), and a mask carries one bit of information per pixel (ROI = mask == label,
+// RadiomicExtractor.py:33-38 / params.yml:93).  Packing it on the host -- AVX2 compare + movemask over a few
+// threads, memory bound -- and unpacking it on the device (radb_unpack_mask) takes 7/16 of the bytes off the
+// link.  Plain host C++ (compiled by the host compiler, no CUDA), no CPU path of the engine itself.
+#include <stdint.h>
+#include <string.h>
+#include <thread>
+#include <vector>
+#if defined(__x86_64__) || defined(__i386__)
+#include <immintrin.h>
+#define RADB_X86 1
+#endif
+
+static void pack_scalar(const uint8_t* m, int64_t n, uint8_t lab, uint8_t* out)
+{
+    // n is a multiple of 8 except possibly for the last call (tail bits are zero)
+    for (int64_t i = 0; i < n; i += 8) {
+        unsigned b = 0;
+        const int64_t e = n - i < 8 ? n - i : 8;
+        for (int64_t k = 0; k < e; k++) b |= (unsigned)(m[i + k] == lab) << k;
+        out[i >> 3] = (uint8_t)b;
+    }
+}
+#ifdef RADB_X86
+__attribute__((target("avx2"))) static void pack_avx2(const uint8_t* m, int64_t n, uint8_t lab, uint8_t* out)
+{
+    const __m256i l = _mm256_set1_epi8((char)lab);
+    int64_t i = 0;
+    for (; i + 32 <= n; i += 32) {
+        const __m256i v = _mm256_loadu_si256((const __m256i*)(m + i));
+        const uint32_t bits = (uint32_t)_mm256_movemask_epi8(_mm256_cmpeq_epi8(v, l));  // bit j <-> byte i + j
+        memcpy(out + (i >> 3), &bits, 4);
+    }
+    if (i < n) pack_scalar(m + i, n - i, lab, out + (i >> 3));
+}
+#endif
+
+extern "C" int radb_pack_mask_host(const uint8_t* mask, int64_t n_bytes, int label, uint8_t* packed, int threads)
+{
+    if (!mask || !packed || n_bytes < 0) return -1;
+    if (label < 0 || label > 255) {  // no uint8 value can match: empty ROI everywhere
+        memset(packed, 0, (size_t)((n_bytes + 7) / 8));
+        return 0;
+    }
+    void (*fn)(const uint8_t*, int64_t, uint8_t, uint8_t*) = pack_scalar;
+#ifdef RADB_X86
+    if (__builtin_cpu_supports("avx2")) fn = pack_avx2;
+#endif
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    const int64_t block = 1 << 20;  // bytes per work item (a multiple of 32)
+    if (threads == 1 || n_bytes <= block) {
+        fn(mask, n_bytes, (uint8_t)label, packed);
+        return 0;
+    }
+    const int64_t nblocks = (n_bytes + block - 1) / block;
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++)
+        pool.emplace_back([=]() {
+            for (int64_t b = t; b < nblocks; b += threads) {
+                const int64_t lo = b * block, len = (n_bytes - lo < block) ? n_bytes - lo : block;
+                fn(mask + lo, len, (uint8_t)label, packed + (lo >> 3));
+            }
+        });
+    for (auto& th : pool) th.join();
+    return 0;
+}

@@ -1391,6 +1391,30 @@ __global__ void radb_derive_kernel(const unsigned char* img, long long n_images,
     const long long image = t / HW;
     out[t] = radb_derive_px(type, (double)img[t], (double)mx[image]);
 }
+// packed mask (bit i of the stream <-> pixel i, radb_pack_mask_host) -> uint8 mask: `label` where the bit is set,
+// another value elsewhere.  One thread expands 16 bits into one 128-bit store.
+__global__ void radb_unpack_mask_kernel(const unsigned char* packed, long long n_bytes, int label, unsigned char* mask)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long p0 = t * 16;
+    if (p0 >= n_bytes) return;
+    const unsigned on = (unsigned)(label & 0xff), off = on ? 0u : 255u;
+    unsigned bits = packed[p0 >> 3];
+    if (p0 + 8 < n_bytes) bits |= (unsigned)packed[(p0 >> 3) + 1] << 8;
+    if (p0 + 16 <= n_bytes && (((unsigned long long)(mask + p0)) & 15ull) == 0) {
+        unsigned w[4];
+#pragma unroll
+        for (int q = 0; q < 4; q++) {
+            unsigned v = 0;
+#pragma unroll
+            for (int k = 0; k < 4; k++) v |= (((bits >> (4 * q + k)) & 1u) ? on : off) << (8 * k);
+            w[q] = v;
+        }
+        *(uint4*)(mask + p0) = make_uint4(w[0], w[1], w[2], w[3]);
+    } else {
+        for (int k = 0; k < 16 && p0 + k < n_bytes; k++) mask[p0 + k] = (unsigned char)(((bits >> k) & 1u) ? on : off);
+    }
+}
 __global__ void radb_bgr_planes_kernel(const unsigned char* bgr, unsigned char* planes, long long n_images, long long HW)
 {
     radb_bgr_planes_thread(bgr, planes, n_images, HW, (long long)blockIdx.x * blockDim.x + threadIdx.x);

@@ -22,6 +22,7 @@ class Engine:
             raise RadbError("radb: no CUDA device visible -- the radiomic engine has no CPU fallback")
         self.lib = _abi.load_library()
         self.device = int(device)
+        self.label = int(label)
         self.n_angles = len(angles)
         self._settings = _abi.make_settings(bin_width, label, angles, symmetrical_glcm, gldm_alpha,
                                             voxel_array_shift, classes, max_ng, device)
@@ -162,6 +163,26 @@ class Engine:
             return out, status, planes
         return out, status
 
+    def pack_mask_host(self, masks, packed, threads):
+        """Host half of the packed-mask transfer (radb_pack_mask_host): contiguous uint8 host tensor ``masks``
+        -> 1 bit per pixel in the host tensor ``packed`` (numel >= ceil(masks.numel() / 8))."""
+        if masks.is_cuda or packed.is_cuda or masks.dtype != torch.uint8 or packed.dtype != torch.uint8:
+            raise TypeError("pack_mask_host takes uint8 host tensors")
+        if not (masks.is_contiguous() and packed.is_contiguous()) or packed.numel() * 8 < masks.numel():
+            raise ValueError("masks / packed must be contiguous and packed large enough")
+        rc = self.lib.radb_pack_mask_host(masks.data_ptr(), masks.numel(), self.label, packed.data_ptr(), int(threads))
+        if rc != 0:
+            raise RadbError("radb_pack_mask_host failed (%d)" % rc)
+
+    def unpack_mask(self, packed, masks, stream=None):
+        """Device half (radb_unpack_mask): ``packed`` device bytes -> ``masks`` uint8 device tensor (label where set)."""
+        if not (packed.is_cuda and masks.is_cuda) or masks.dtype != torch.uint8 or not masks.is_contiguous():
+            raise ValueError("unpack_mask takes contiguous CUDA tensors")
+        st = stream if stream is not None else torch.cuda.current_stream(masks.device)
+        rc = self.lib.radb_unpack_mask(self._h, packed.data_ptr(), masks.numel(), masks.data_ptr(), st.cuda_stream)
+        if rc != 0:
+            raise RadbError("radb_unpack_mask failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+
     def derive_image(self, images, type_code, stream=None):
         """Point-wise derived image type (1 Square, 2 SquareRoot, 3 Logarithm, 4 Exponential) of uint8
         device images [B, H, W] -> float64 [B, H, W] (pyradiomics imageoperations.get*Image)."""
@@ -239,13 +260,29 @@ def pack_ragged(images, masks, align=16):
 
 class HostPipeline:
     """Host-buffer entry point: streams host (NumPy) patches through the engine in chunks with
-    double-buffered pinned staging so H2D copies, kernels and D2H copies overlap."""
+    double-buffered pinned staging so H2D copies, kernels and D2H copies overlap.
 
-    def __init__(self, engine, chunk=16384):
+    The path is bound by the host-to-device link (pixels + masks, ~50 GB/s), and of a mask only
+    ``mask == label`` matters, so with ``pack_masks`` the masks cross the link at 1 bit per pixel: packed on
+    the host by ``pack_threads`` threads (AVX2, memory bound: ~100 GB/s on 16 cores) while the device works on
+    the previous chunks (a helper thread runs one chunk ahead of the enqueue loop, ``slots`` chunks are in
+    flight), expanded on the device by ``radb_unpack_mask``: 16.0 -> 10.9 ms per 100 k 64x64 patches.  ``pack_masks=None`` (default)
+    enables it when this process has at least 8 host cores to itself (``os.cpu_count() // LOCAL_WORLD_SIZE``):
+    with eight ranks on one host the packing threads would only compete for the same memory bandwidth."""
+
+    def __init__(self, engine, chunk=8192, pack_masks=None, pack_threads=None, slots=6):
+        import os
+
         self.engine = engine
         self.chunk = int(chunk)
+        self.slots = max(2, int(slots))  # chunks in flight: the host packs / enqueues ahead of the device
         self._bufs = None
         self._key = None
+        self._pool = None
+        cores = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
+        self.pack_threads = int(pack_threads) if pack_threads else min(cores, 8)  # memory bound beyond ~8 threads
+        self.pack_masks = bool(pack_masks) if pack_masks is not None else cores >= 8
+        self.h2d_bytes = 0  # bytes copied host -> device by the last run()
 
     def _ensure(self, H, W, dtype=torch.uint8):
         key = (H, W, dtype)
@@ -254,12 +291,14 @@ class HostPipeline:
         dev = torch.device("cuda", self.engine.device)
         n, F = self.chunk, self.engine.F
         self._bufs = []
-        for _ in range(2):
+        for _ in range(self.slots):
             self._bufs.append(dict(
                 h_img=torch.empty((n, H, W), dtype=dtype).pin_memory(),
                 h_msk=torch.empty((n, H, W), dtype=torch.uint8).pin_memory(),
                 d_img=torch.empty((n, H, W), dtype=dtype, device=dev),
                 d_msk=torch.empty((n, H, W), dtype=torch.uint8, device=dev),
+                h_pk=torch.empty(((n * H * W + 7) // 8,), dtype=torch.uint8).pin_memory(),
+                d_pk=torch.empty(((n * H * W + 7) // 8,), dtype=torch.uint8, device=dev),
                 d_out=torch.empty((n, F), dtype=torch.float64, device=dev),
                 d_st=torch.empty((n,), dtype=torch.int32, device=dev),
                 stream=torch.cuda.Stream(dev), done=torch.cuda.Event()))
@@ -280,26 +319,52 @@ class HostPipeline:
         if status is None:
             status = torch.empty((B,), dtype=torch.int32).pin_memory()
         pinned_in = images.is_pinned() and masks.is_pinned()
-        k = 0
-        for s in range(0, B, self.chunk):
+        pack = self.pack_masks and masks.dtype == torch.uint8 and masks.is_contiguous()
+        self.h2d_bytes = 0
+        starts = list(range(0, B, self.chunk))
+
+        def prepare(k):
+            """Host work of chunk k, one chunk ahead of the enqueue loop on a helper thread: wait until the
+            slot has drained, then pack the masks (the C call releases the GIL and fans out to pack_threads)."""
+            s0 = starts[k]
+            n0 = min(self.chunk, B - s0)
+            bk = self._bufs[k % self.slots]
+            bk["done"].synchronize()
+            if pack:
+                self.engine.pack_mask_host(masks[s0:s0 + n0], bk["h_pk"], self.pack_threads)
+
+        if self._pool is None:
+            from concurrent.futures import ThreadPoolExecutor
+
+            self._pool = ThreadPoolExecutor(1)
+        fut = self._pool.submit(prepare, 0) if starts else None
+        for k, s in enumerate(starts):
             n = min(self.chunk, B - s)
-            b = self._bufs[k % 2]
-            b["done"].synchronize()  # previous use of this slot has drained
+            b = self._bufs[k % self.slots]
+            fut.result()
+            if k + 1 < len(starts):
+                fut = self._pool.submit(prepare, k + 1)
+            nb = (n * H * W + 7) // 8
             with torch.cuda.stream(b["stream"]):
                 if pinned_in:
                     b["d_img"][:n].copy_(images[s:s + n], non_blocking=True)
-                    b["d_msk"][:n].copy_(masks[s:s + n], non_blocking=True)
                 else:
                     b["h_img"][:n].copy_(images[s:s + n])
-                    b["h_msk"][:n].copy_(masks[s:s + n])
                     b["d_img"][:n].copy_(b["h_img"][:n], non_blocking=True)
+                if pack:
+                    b["d_pk"][:nb].copy_(b["h_pk"][:nb], non_blocking=True)
+                    self.engine.unpack_mask(b["d_pk"], b["d_msk"][:n], stream=b["stream"])
+                elif pinned_in:
+                    b["d_msk"][:n].copy_(masks[s:s + n], non_blocking=True)
+                else:
+                    b["h_msk"][:n].copy_(masks[s:s + n])
                     b["d_msk"][:n].copy_(b["h_msk"][:n], non_blocking=True)
+                self.h2d_bytes += n * H * W * images.element_size() + (nb if pack else n * H * W)
                 self.engine.extract_device(b["d_img"][:n], b["d_msk"][:n], b["d_out"][:n], b["d_st"][:n],
                                            stream=b["stream"])
                 out[s:s + n].copy_(b["d_out"][:n], non_blocking=True)
                 status[s:s + n].copy_(b["d_st"][:n], non_blocking=True)
                 b["done"].record(b["stream"])
-            k += 1
         for b in self._bufs:
             b["done"].synchronize()
         return out, status

@@ -38,7 +38,7 @@ class RadiomicsExtractor:
     ordinal), ``strict`` (raise instead of warn for enabled-but-unimplemented image types /
     classes), ``chunk`` (patches per pipelined H2D chunk), ``max_ng``."""
 
-    def __init__(self, param_file, *, device=0, strict=False, chunk=16384, max_ng=0, **setting_overrides):
+    def __init__(self, param_file, *, device=0, strict=False, chunk=8192, max_ng=0, **setting_overrides):
         self.params = Settings(param_file, strict=strict, **setting_overrides)
         self.device = int(device)
         eng_classes, self._perm = self.params.engine_columns()

@@ -168,3 +168,23 @@ def test_pack_ragged_layout():
         pack_ragged(imgs, msks[:-1])
     with pytest.raises(ValueError):
         pack_ragged([imgs[0]], [msks[1]])
+
+
+def test_pack_mask_host_matches_packbits():
+    """radb_pack_mask_host (host half of the packed-mask transfer path): bit i <-> mask[i] == label, any length,
+    any thread count, labels outside uint8 give an empty ROI.  Pure host code: runs without a GPU."""
+    import ctypes
+
+    lib = pkg.load_library()
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 7, 8, 31, 32, 33, 100003, 3_000_001):
+        m = rng.choice(np.array([0, 255, 128, 1], np.uint8), size=n, p=[0.5, 0.4, 0.05, 0.05])
+        for label in (255, 1, 0):
+            want = np.packbits(m == label, bitorder="little")
+            for th in (1, 3, 8):
+                out = np.full((n + 7) // 8, 0xAA, np.uint8)
+                assert lib.radb_pack_mask_host(m.ctypes.data, n, label, out.ctypes.data, th) == 0
+                assert np.array_equal(out, want), (n, label, th)
+        out = np.full((n + 7) // 8, 0xAA, np.uint8)
+        assert lib.radb_pack_mask_host(m.ctypes.data, n, 256, out.ctypes.data, 2) == 0 and not out.any()
+    assert lib.radb_pack_mask_host(None, 8, 255, None, 1) != 0

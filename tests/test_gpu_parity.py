@@ -495,3 +495,23 @@ def test_multi_chunk_two_stream_pipeline_is_bit_identical(gpu_pkg):
     r1, s1 = eng.extract_ragged(torch.as_tensor(ip).cuda(), torch.as_tensor(mp).cuda(), io, mo, hw)
     assert torch.equal(s0, s1) and np.array_equal(r0.cpu().numpy(), r1.cpu().numpy(), equal_nan=True)
     assert np.array_equal(r0[:61].cpu().numpy(), ref.cpu().numpy(), equal_nan=True)
+
+
+def test_packed_mask_transfer_path(gpu_pkg):
+    """Host pipeline with masks packed to 1 bit per pixel on the host and expanded on the device: same rows, bit
+    for bit, as the plain uint8 transfer; masks with other labels and odd sizes included."""
+    imgs, masks = gpu_pkg.synth.make_patches(37, 33, 29, seed=5)   # 957 pixels per patch: not a multiple of 8 / 16
+    masks[3][masks[3] == 255] = 7          # another label only: ROI absent
+    masks[4, :5] = 128                      # foreign label next to the ROI
+    eng = gpu_pkg.Engine(25, 255, INPLANE)
+    plain = gpu_pkg.HostPipeline(eng, chunk=10, pack_masks=False)
+    packed = gpu_pkg.HostPipeline(eng, chunk=10, pack_masks=True, pack_threads=3)
+    o0, s0 = plain.run(imgs, masks)
+    o1, s1 = packed.run(imgs, masks)
+    assert torch.equal(s0, s1) and s0[3] == 1
+    assert np.array_equal(o0.numpy(), o1.numpy(), equal_nan=True)
+    assert packed.h2d_bytes < plain.h2d_bytes * 0.6
+    d = torch.empty((37, 33, 29), dtype=torch.uint8, device="cuda")
+    pk = torch.as_tensor(np.packbits(masks.reshape(-1) == 255, bitorder="little")).cuda()
+    eng.unpack_mask(pk, d)
+    assert torch.equal(d.cpu() == 255, torch.as_tensor(masks == 255)) and set(d.unique().tolist()) <= {0, 255}
