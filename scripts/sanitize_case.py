@@ -35,3 +35,25 @@ eng = pkg.Engine(10, 255, [(0, 1)], classes=classes)
 out, st = eng.extract_bgr(bgr, torch.as_tensor(pkg.synth.make_patches(2, 40, 44, seed=3)[1]).cuda())
 torch.cuda.synchronize()
 print("bgr ok", int(st.sum()))
+# thread-level reduction kernels (binWidth 25: Ng <= 11, MCC in the thread), multi-chunk two-stream pipeline
+imgs, masks = pkg.synth.make_patches(45, 64, 64, seed=4)
+eng = pkg.Engine(25, 255, ang4, classes=classes)
+eng.set_chunk(12)
+out, st = eng.extract_device(torch.as_tensor(imgs).cuda(), torch.as_tensor(masks).cuda())
+torch.cuda.synchronize()
+print("lane + pipeline ok", int(st.sum()))
+# ragged batch (mixed sizes, odd offsets), packed-mask transfer
+lst_i = [imgs[0], imgs[1][:33, :29].copy(), imgs[2], pkg.synth.make_patches(1, 128, 128, seed=5)[0][0]]
+lst_m = [masks[0], masks[1][:33, :29].copy(), masks[2], pkg.synth.make_patches(1, 128, 128, seed=5)[1][0]]
+ip, mp, io, mo, hw = pkg.pack_ragged(lst_i, lst_m)
+out, st = eng.extract_ragged(torch.as_tensor(ip).cuda(), torch.as_tensor(mp).cuda(), io, mo, hw)
+torch.cuda.synchronize()
+print("ragged ok", st.tolist())
+o2, s2 = pkg.HostPipeline(eng, chunk=16, pack_masks=True, pack_threads=2).run(imgs, masks)
+print("packed masks ok", int(s2.sum()))
+# 256 gray levels: big mode (GLCM + MCC workspace in global memory, u16 level image)
+g, m = pkg.synth.make_patches(2, 32, 32, seed=6, dtype=np.uint16, vmax=2047)
+eng = pkg.Engine(8, 255, ang4, max_ng=256)
+out, st = eng.extract_device(torch.as_tensor(g.view(np.int16)).cuda().view(torch.uint16), torch.as_tensor(m).cuda())
+torch.cuda.synchronize()
+print("big mode ok", int(st.sum()))

@@ -16,3 +16,8 @@ g,mk=synth.make_patches(2,40,36,seed=6); f=(np.sqrt(g.astype(np.float64))*11.3-4
 r=emu.run(f,mk,7.5,255,INPLANE,max_ng=40); print('f64',r['status'])
 r=emu.run(f.astype(np.float32),mk,7.5,255,INPLANE,max_ng=40); print('f32',r['status'])
 r=emu.run((g.astype(np.uint16)*7),mk,64,255,INPLANE,max_ng=40); print('u16',r['status'])
+# thread-level reduction kernels with the in-thread MCC (binWidth 25 -> Ng <= 11), ragged batch, 256 gray levels (big mode)
+im,mk=synth.make_patches(5,40,44,seed=7); r=emu.run(im,mk,25,255,INPLANE,classes=ALL); print('lane',r['status'])
+imgs=[im[0],im[1][:33,:29].copy(),im[2],synth.make_patches(1,20,20,seed=8)[0][0]]; mks=[mk[0],mk[1][:33,:29].copy(),mk[2],synth.make_patches(1,20,20,seed=8)[1][0]]
+out,st=emu.run_ragged(imgs,mks,25,255,INPLANE); print('ragged',st)
+g16,m16=synth.make_patches(1,20,20,seed=9,dtype=np.uint16,vmax=2047); r=emu.run(g16,m16,8,255,INPLANE,max_ng=256); print('big',r['status'])
