@@ -118,13 +118,28 @@ class RadiomicsExtractor:
     def extract_radiomics(self, list_of_dicts):  # RadiomicExtractor.py:23-55 (one record)
         return self._extract_records([self._load_record(list_of_dicts)])[0]
 
+    @staticmethod
+    def _load_records(list_of_dicts, n_workers=None):
+        """Decode all records, in input order.  The reference fans whole records over ``cpu_count() - 1``
+        processes (RadiomicExtractor.py:60-65); here only the JPEG/PNG decode is host work, and cv2 releases
+        the GIL, so a thread pool of the same width does it."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
+        if n_workers is None:
+            n_workers = max(1, (os.cpu_count() or 2) - 1)
+        if n_workers <= 1 or len(list_of_dicts) <= 1:
+            return [RadiomicsExtractor._load_record(r) for r in list_of_dicts]
+        with ThreadPoolExecutor(int(n_workers)) as pool:
+            return list(pool.map(RadiomicsExtractor._load_record, list_of_dicts))  # map() keeps the input order
+
     def parallell_extraction(self, list_of_dicts, n_processes=None):  # RadiomicExtractor.py:58-71
-        """Order-preserving extraction of all records.  ``n_processes`` is accepted for
-        signature compatibility; the fan-out is over GPU CTAs, not host processes.  Records of
+        """Order-preserving extraction of all records.  ``n_processes`` (default ``cpu_count() - 1``, as in the
+        reference) is the width of the host decode pool; the feature fan-out is over GPU CTAs.  Records of
         equal image size are batched into one launch sequence."""
         logger.info("Extraction mode: parallel")
         t0 = time.time()
-        results = self._extract_records([self._load_record(r) for r in list_of_dicts])
+        results = self._extract_records(self._load_records(list_of_dicts, n_processes))
         h, m, s = self._convert_time(t0, time.time())
         logger.info(f" Time taken: {h}h:{m}m:{s}s")
         return results

@@ -188,3 +188,32 @@ def test_pack_mask_host_matches_packbits():
         out = np.full((n + 7) // 8, 0xAA, np.uint8)
         assert lib.radb_pack_mask_host(m.ctypes.data, n, 256, out.ctypes.data, 2) == 0 and not out.any()
     assert lib.radb_pack_mask_host(None, 8, 255, None, 1) != 0
+
+
+def test_record_decode_pool_keeps_order(tmp_path):
+    """parallell_extraction's host side (RadiomicExtractor.py:29-36,58-65): cv2 decode of image + mask on a thread
+    pool, input order kept, masks nearest-resized to their image, missing files raise."""
+    import cv2
+
+    from multimodal_isic_b200.extractor import RadiomicsExtractor
+
+    rng = np.random.default_rng(1)
+    recs, want = [], []
+    for k in range(9):
+        H, W = 20 + k, 31 - k
+        bgr = rng.integers(0, 256, (H, W, 3)).astype(np.uint8)
+        m = (rng.random((H, W)) < 0.5).astype(np.uint8) * 255
+        ip, sp = str(tmp_path / ("i%d.png" % k)), str(tmp_path / ("s%d.png" % k))
+        cv2.imwrite(ip, bgr)
+        cv2.imwrite(sp, m if k != 4 else cv2.resize(m, (W // 2, H // 2), interpolation=cv2.INTER_NEAREST))
+        recs.append({"image_path": ip, "segmentation_path": sp, "other": k})
+        want.append((bgr, m))
+    for workers in (None, 1, 4):
+        got = RadiomicsExtractor._load_records(recs, workers)
+        assert len(got) == 9
+        for k, ((im, sg), (bgr, m)) in enumerate(zip(got, want)):
+            assert np.array_equal(im, bgr) and sg.shape == m.shape
+            if k != 4:
+                assert np.array_equal(sg, m)
+    with pytest.raises(FileNotFoundError):
+        RadiomicsExtractor._load_records(recs + [{"image_path": str(tmp_path / "nope.png"), "segmentation_path": recs[0]["segmentation_path"]}], 3)
