@@ -158,3 +158,64 @@ def test_shape2d_oracle_against_independent_area_and_known_shapes():
         assert np.isclose(orc.shape2d_coefficients(m)[1], area_indep(m))
     f = orc.shape2d_features(np.ones((4, 10), bool))
     assert np.isclose(f["Elongation"], np.sqrt((4 ** 2 - 1) / (10 ** 2 - 1))) and f["PixelSurface"] == 40
+
+
+@settings(max_examples=25, deadline=None)
+@given(arrays, st.integers(0, 2 ** 31 - 1), st.sampled_from([10, 25, 64]))
+def test_oracle_against_independent_scipy_implementations(hw, seed, bw):
+    """Third-party cross-checks of the restated algorithm (pyradiomics itself is not installable here): GLSZM
+    zones = scipy.ndimage 8-connected components per gray level; GLCM = shifted-array pair counts; GLRLM rows =
+    run-length encoding of each row; first-order moments / entropy = scipy.stats on the ROI values."""
+    from scipy import ndimage, stats
+
+    H, W = hw
+    rng = np.random.default_rng(seed)
+    img = (rng.integers(0, 256, (H, W)) // 32 * 32).astype(np.uint8)  # few levels: real zones and runs
+    mask = np.where(rng.random((H, W)) < 0.8, 255, 0).astype(np.uint8)
+    s = dict(label=255, binWidth=bw, force2D=False)
+    try:
+        m = orc.matrices(img, mask, s)
+    except ValueError:
+        return
+    lev, roi, Ng = m["levels"], m["mask"], m["Ng"]
+    # GLSZM: connected components (8-connectivity) of every level inside the ROI
+    want = {}
+    for g in range(1, Ng + 1):
+        lab, n = ndimage.label((lev == g) & roi, structure=np.ones((3, 3), int))
+        for size in ndimage.sum_labels(np.ones_like(lab), lab, index=np.arange(1, n + 1)).astype(int) if n else []:
+            want[(g, size)] = want.get((g, size), 0) + 1
+    got = {(i + 1, j + 1): int(c) for (i, j), c in np.ndenumerate(m["glszm"]) if c}
+    assert got == want
+    # GLCM, angle by angle: pairs (p, p + offset) with both pixels in the ROI, symmetrised
+    offs = orc.angles(2)[0]
+    for a, (dy, dx) in enumerate(offs):
+        P = np.zeros((Ng, Ng), int)
+        for y in range(H):
+            for x in range(W):
+                yy, xx = y + dy, x + dx
+                if 0 <= yy < H and 0 <= xx < W and roi[y, x] and roi[yy, xx]:
+                    P[lev[y, x] - 1, lev[yy, xx] - 1] += 1
+        np.testing.assert_array_equal(m["glcm"][:, :, a], P + P.T)
+    # GLRLM along rows (the (0, 1) angle): itertools-style run-length encoding
+    a_row = [i for i, o in enumerate(offs) if tuple(o) == (0, 1)][0]
+    R = np.zeros_like(m["glrlm"][:, :, a_row])
+    for y in range(H):
+        x = 0
+        while x < W:
+            g = lev[y, x] if roi[y, x] else 0
+            e = x
+            while e + 1 < W and (lev[y, e + 1] if roi[y, e + 1] else 0) == g:
+                e += 1
+            if g:
+                R[g - 1, e - x] += 1
+            x = e + 1
+    np.testing.assert_array_equal(m["glrlm"][:, :, a_row], R)
+    # first-order statistics on the raw ROI values
+    f = orc.execute(img, mask, s, classes=("firstorder",))
+    x = img[roi].astype(np.float64)
+    np.testing.assert_allclose(f["original_firstorder_Skewness"], stats.skew(x) if x.std() > 0 else 0.0, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(f["original_firstorder_Kurtosis"], stats.kurtosis(x, fisher=False) if x.std() > 0 else 0.0, rtol=1e-9, atol=1e-12)
+    np.testing.assert_allclose(f["original_firstorder_Variance"], x.var(), rtol=1e-12, atol=1e-12)
+    np.testing.assert_allclose(f["original_firstorder_InterquartileRange"], stats.iqr(x), rtol=1e-12, atol=1e-12)
+    p = np.bincount(lev[roi])[1:] / roi.sum()
+    np.testing.assert_allclose(f["original_firstorder_Entropy"], stats.entropy(p[p > 0], base=2), rtol=1e-9, atol=1e-9)
