@@ -547,6 +547,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     unsigned* ovf = WIDE ? (unsigned*)(g_rec + (p.o_ovf - p.o_rec)) : (unsigned*)(smem + p.o_ovf);
     unsigned char* glrlm_base = WIDE ? g_rec + (p.o_glrlm - p.o_rec) : smem + p.o_glrlm;
     int* misc = (int*)(smem + p.o_misc);
+    unsigned short* runs = (unsigned short*)(smem + (p.o_runs >= 0 ? p.o_runs : 0));  // row-run start pixels (narrow)
+    const bool keep_runs = !WIDE && p.o_runs >= 0;
     double* out = p.out + row * (long long)p.F;
 
     // ---- phase 0: stage the patch, zero the counters
@@ -968,12 +970,31 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
 #pragma unroll
             for (int a = 0; a < RADB_MAX_ANGLES; a++)
                 if (a < nreq) push(req[a] != 0, ((UW)(unsigned)li << US) | (UW)(req[a] - 1u));
+            if (keep_runs && a_row >= 0) {  // append the row-run starts of this warp's pixels: one atomic per warp
+                const bool st = c && lev[ctr - 1] != c;
+                const unsigned ms = __ballot_sync(FULLMASK, st);
+                if (ms) {
+                    int rbase = 0;
+                    if (lane == 0) rbase = atomicAdd(&misc[6], __popc(ms));
+                    rbase = __shfl_sync(FULLMASK, rbase, 0);
+                    if (st) runs[rbase + __popc(ms & lt_mask)] = (unsigned short)li;
+                }
+            }
         }
         if (qn) drain(qn);
     }
     __syncthreads();
 
     // ---- phase 4: fold run lengths into their zone root; symmetrise the GLCM
+    const bool by_list = keep_runs && a_row >= 0;  // the run list exists: visit runs, not pixels
+    const int nruns = by_list ? misc[6] : 0;
+    const float inv_w = 1.0f / (float)W;
+    for (int k = tid; k < nruns; k += RADB_NTB) {
+        const unsigned li = runs[k];
+        const unsigned r = uf_find_ro<UW, UF<WIDE>::S>(lab, li);
+        if (r != li) atomicAdd(&lab[r], (UW)(lab[li] & ~ULO));  // only roots are ever added to
+    }
+    if (!by_list)
     for (int idx = tid; idx < nbox; idx += RADB_NTB) {
         const int yb = WIDE ? idx / bw : (int)(((float)idx + 0.5f) * inv_bw);
         const int y = by0 + yb, x = bx0 + (idx - yb * bw);
@@ -1004,6 +1025,23 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     __syncthreads();
 
     // ---- phase 5: zone roots -> GLSZM (dense + overflow)
+    auto emit_zone = [&](int c, int s) {
+        if (s <= p.s0) {
+            atomicAdd(&szm[(c - 1) * p.s0 + s - 1], 1);
+        } else {
+            int k = atomicAdd(&misc[5], 1);
+            if (k < p.ovf_cap) ovf[k] = ((unsigned)(c - 1) << 24) | (unsigned)s;  // level - 1 (<= 255) | size (< 2^24)
+        }
+        if (DBG && p.dbg_glszm) atomicAdd(&p.dbg_glszm[(patch * p.max_ng + (c - 1)) * (long long)HW + s - 1], 1);
+    };
+    for (int k = tid; k < nruns; k += RADB_NTB) {
+        const int li = runs[k];
+        const UW wl = lab[li];
+        if ((unsigned)(wl & ULO) != (unsigned)li) continue;
+        const int y = (int)(((float)li + 0.5f) * inv_w), x = li - y * W;  // exact for li < 65536
+        emit_zone((int)lev[(y + 1) * WP + x + XO], (int)(wl >> US));
+    }
+    if (!by_list)
     for (int idx = tid; idx < nbox; idx += RADB_NTB) {
         const int yb = WIDE ? idx / bw : (int)(((float)idx + 0.5f) * inv_bw);
         const int y = by0 + yb, x = bx0 + (idx - yb * bw);
@@ -1013,14 +1051,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int li = y * W + x;
         const UW wl = lab[li];
         if ((unsigned)(wl & ULO) != (unsigned)li) continue;
-        const int s = (int)(wl >> US);
-        if (s <= p.s0) {
-            atomicAdd(&szm[(c - 1) * p.s0 + s - 1], 1);
-        } else {
-            int k = atomicAdd(&misc[5], 1);
-            if (k < p.ovf_cap) ovf[k] = ((unsigned)(c - 1) << 24) | (unsigned)s;  // level - 1 (<= 255) | size (< 2^24)
-        }
-        if (DBG && p.dbg_glszm) atomicAdd(&p.dbg_glszm[(patch * p.max_ng + (c - 1)) * (long long)HW + s - 1], 1);
+        emit_zone(c, (int)(wl >> US));
     }
     __syncthreads();
 

@@ -61,6 +61,7 @@ struct RadbParams {
     // ---- build kernel: shared-memory byte offsets.  [o_rec, o_rec + rec_bytes) is the per-patch
     // RECORD (header + every integer matrix); the build kernel copies it to the global workspace
     // and the reduction kernels read it from there at the same relative offsets.
+    int o_runs;    // narrow mode: u16 list of the row-run start pixels (-1: not kept, the zone phases scan the bbox)
     int o_stage, o_mask, o_mbar, o_zero, o_lev, o_uq, o_lut, o_fo, o_rec, o_misc, o_hist, o_lhist, o_glcm, o_glrlm,
         o_gldm, o_ngc, o_ngn, o_szm, o_ovf, smem_total;
     int rec_bytes;       // record size in the global workspace
@@ -155,6 +156,19 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->rec_bytes = o - p->o_rec;
     p->smem_total = wide ? p->o_rec + p->rec_copy_bytes : o;
     if (!wide) p->rec_copy_bytes = p->rec_bytes;
+    // Run list: the along-row walk appends the start pixel of every run, and the zone phases (fold run lengths
+    // into roots, emit roots) visit the ~HW/5 runs instead of scanning the bounding box twice.  Kept only when
+    // its 2 * HW bytes do not cost a resident CTA (5 per SM at most: the register cap of the build kernel).
+    p->o_runs = -1;
+    if (!wide && p->HW <= 65535) {
+        const int sm = 227 * 1024, with = p->smem_total + radb_align(p->HW * 2, 16);
+        int before = sm / (p->smem_total + 1024), after = sm / (with + 1024);
+        if (before > 5) before = 5;
+        if (after >= before && after >= 1) {
+            p->o_runs = p->smem_total;
+            p->smem_total = with;
+        }
+    }
     p->g_lev = 0;
     p->g_lab = radb_align((H + 2) * p->WP * p->lev_bytes, 16);
     p->scr_bytes = wide ? (p->g_lab + (long long)p->HW * 8 + 15) / 16 * 16 : 0;  // 16-byte multiple: uint4 stores
