@@ -154,6 +154,7 @@ static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParam
     p.symmetric = pl.s.symmetrical_glcm ? 1 : 0;
     p.alpha = (int)floor(pl.s.gldm_alpha);
     p.bin_width = pl.s.bin_width;
+    p.bw_int = (pl.s.bin_width >= 1.0 && pl.s.bin_width <= 255.0 && pl.s.bin_width == floor(pl.s.bin_width)) ? (int)pl.s.bin_width : 0;
     p.shift = pl.s.voxel_array_shift;
     p.max_ng = pl.max_ng;
     p.F = pl.F;

@@ -705,18 +705,29 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         int ng = 0;
         if (!st) {
             const double bw = p.bin_width;
-            low = vmin - py_mod(vmin, bw);
-            if (U8) {  // value -> level LUT: level = #edges <= x, edges = low + k*binWidth
-                for (int v = tid; v < 256; v += RADB_NTB) {
-                    int L = 0;
-                    if ((double)v >= vmin && (double)v <= vmax) {
-                        L = radb_level((double)v, low, bw);
-                        if (L > 255) L = 255;  // reported through status 4 below
+            if (U8 && p.bw_int) {
+                // uint8 pixels and an integer binWidth (25, 10: the reference's settings): the fp64 edges low + k*bw
+                // are exact integers, so the level is an integer quotient (float reciprocal, exact below 2^16)
+                const int ibw = p.bw_int, ivmin = (int)vmin, ivmax = (int)vmax, ilow = ivmin - ivmin % ibw;
+                const float rbw = 1.0f / (float)ibw;
+                low = (double)ilow;
+                for (int v = tid; v < 256; v += RADB_NTB)
+                    lut[v] = (v >= ivmin && v <= ivmax) ? (unsigned char)((int)(((float)(v - ilow) + 0.5f) * rbw) + 1) : 0;
+                ng = (int)(((float)(ivmax - ilow) + 0.5f) * rbw) + 1;
+            } else {
+                low = vmin - py_mod(vmin, bw);
+                if (U8) {  // value -> level LUT: level = #edges <= x, edges = low + k*binWidth
+                    for (int v = tid; v < 256; v += RADB_NTB) {
+                        int L = 0;
+                        if ((double)v >= vmin && (double)v <= vmax) {
+                            L = radb_level((double)v, low, bw);
+                            if (L > 255) L = 255;  // reported through status 4 below
+                        }
+                        lut[v] = (unsigned char)L;
                     }
-                    lut[v] = (unsigned char)L;
                 }
+                ng = radb_level(vmax, low, bw);
             }
-            ng = radb_level(vmax, low, bw);
             if (ng > p.max_ng) st = 4;
         }
         if (st) {
@@ -989,10 +1000,18 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     const bool by_list = keep_runs && a_row >= 0;  // the run list exists: visit runs, not pixels
     const int nruns = by_list ? misc[6] : 0;
     const float inv_w = 1.0f / (float)W;
+    // Unions link the larger pixel index under the smaller one, so a tall zone is a long parent chain.  The
+    // list is (nearly) in pixel order: round k of this loop handles runs above those of round k + 1, and every
+    // run re-parents itself straight to its root, so later rounds find short paths (the clocks showed the
+    // read-only finds of this phase at 15 % of the CTA's lifetime).
     for (int k = tid; k < nruns; k += RADB_NTB) {
         const unsigned li = runs[k];
-        const unsigned r = uf_find_ro<UW, UF<WIDE>::S>(lab, li);
-        if (r != li) atomicAdd(&lab[r], (UW)(lab[li] & ~ULO));  // only roots are ever added to
+        const unsigned r = uf_find<UW, UF<WIDE>::S>(lab, li);
+        if (r != li) {
+            const UW wl = ((volatile UW*)lab)[li];
+            ((volatile UW*)lab)[li] = (wl & ~ULO) | (UW)r;  // li is not a root: its size field is its own, static
+            atomicAdd(&lab[r], (UW)(wl & ~ULO));             // only roots are ever added to
+        }
     }
     if (!by_list)
     for (int idx = tid; idx < nbox; idx += RADB_NTB) {
@@ -1006,19 +1025,20 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             if (r != (unsigned)li) atomicAdd(&lab[r], (UW)(lab[li] & ~ULO));  // only roots are ever added to
         }
     }
-    if (p.symmetric) {
-        for (int a = 0; a < NA; a++) {
-            int* P = glcm + a * ng * ng;
-            for (int t = tid; t < ng * ng; t += RADB_NTB) {
-                int i = t / ng, j = t - i * ng;
-                if (i > j) continue;
-                if (i == j) {
-                    P[t] *= 2;
-                } else {
-                    int s = P[i * ng + j] + P[j * ng + i];
-                    P[i * ng + j] = s;
-                    P[j * ng + i] = s;
-                }
+    if (p.symmetric) {  // all angles in one flat loop; (a, i, j) by float reciprocals (exact: indices < 2^18)
+        const int ng2 = ng * ng, tot = NA * ng2;
+        const float r2 = 1.0f / (float)ng2, r1 = 1.0f / (float)ng;
+        for (int t = tid; t < tot; t += RADB_NTB) {
+            const int a = (WIDE && p.big) ? t / ng2 : (int)(((float)t + 0.5f) * r2), cell = t - a * ng2;
+            const int i = (WIDE && p.big) ? cell / ng : (int)(((float)cell + 0.5f) * r1), j = cell - i * ng;
+            if (i > j) continue;
+            int* P = glcm + a * ng2;
+            if (i == j) {
+                P[cell] *= 2;
+            } else {
+                const int sum = P[cell] + P[j * ng + i];
+                P[cell] = sum;
+                P[j * ng + i] = sum;
             }
         }
     }

@@ -44,6 +44,7 @@ struct RadbParams {
     int symmetric;
     int alpha;
     double bin_width;
+    int bw_int;    // bin_width when it is an integer in 1..255 (uint8 fast path of the level LUT), else 0
     double shift;
     int max_ng;
     int nr;        // GLRLM columns = max(H, W)
