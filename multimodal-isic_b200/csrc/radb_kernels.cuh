@@ -824,8 +824,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 if (dy == 0) {
                     const int base = (by0 + l + 1) * WP + bx0 + XO, lbase = (by0 + l) * W + bx0;
                     int st = 0;
+                    int gn = lev[base];  // software-pipelined: the next level is in flight while this one is processed
                     for (int x = 0; x < bw; x++) {
-                        const int g = lev[base + x];
+                        const int g = gn;
+                        gn = lev[base + x + 1];  // one past the bbox is the zero border or another pixel: in bounds
                         if (g != cur) {
                             if (cur) {
                                 add_run<WIDE>(R, (cur - 1) * nr + len - 1);
@@ -848,19 +850,21 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                     const int sdx = dx * dy;  // x step per +1 in y (runs are direction-agnostic)
                     int x = l, brk = 0;
                     int pos = (by0 + 1) * WP + bx0 + XO;
+                    int gn = lev[pos + x];  // software-pipelined like the row walk
                     for (int y = 0; y < bh; y++) {
-                        const int g = lev[pos + x];
-                        if (g != cur || brk) {
-                            if (cur) { add_run<WIDE>(R, (cur - 1) * nr + len - 1); mylen = len > mylen ? len : mylen; }
-                            cur = g;
-                            len = 0;
-                        }
-                        len++;
+                        const int g = gn, brk_here = brk;
                         pos += WP;
                         x += sdx;
                         brk = 0;
                         if (x >= bw) { x = 0; brk = 1; }          // wrapped diagonal: the next pixel is not
                         else if (x < 0) { x = bw - 1; brk = 1; }  // a neighbour of this one
+                        gn = lev[pos + x];  // row below the bbox on the last step: the zero border, in bounds
+                        if (g != cur || brk_here) {
+                            if (cur) { add_run<WIDE>(R, (cur - 1) * nr + len - 1); mylen = len > mylen ? len : mylen; }
+                            cur = g;
+                            len = 0;
+                        }
+                        len++;
                     }
                     if (cur) { add_run<WIDE>(R, (cur - 1) * nr + len - 1); mylen = len > mylen ? len : mylen; }
                 }

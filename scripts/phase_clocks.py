@@ -1,0 +1,90 @@
+#!/usr/bin/env python
+"""Per-phase clock64() timing of the build kernel (experiment tool, not part of the product).
+
+Makes an instrumented copy of multimodal-isic_b200/csrc under build/clk/: thread 0 of every CTA stores clock64()
+after each phase barrier into a side buffer, and the patched launch() prints the average cycles per phase when
+RADB_CLK is set.  The instrumented library is slower than the product (extra barriers); the SHARES are what it is for.
+
+  python scripts/phase_clocks.py            # here: writes + compiles build/clk/libradb_clk.so
+  gpurun -- 'RADB_CLK=1 RADB_LIB=build/clk/libradb_clk.so python scripts/profile_kernel.py --patches 32768 --launches 2'
+"""
+import os
+import re
+import shutil
+import subprocess
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SRC = os.path.join(ROOT, "multimodal-isic_b200", "csrc")
+DST = os.path.join(ROOT, "build", "clk")
+os.makedirs(DST, exist_ok=True)
+for f in os.listdir(SRC):
+    if f.endswith((".h", ".cuh", ".cu", ".cpp")):
+        shutil.copy(os.path.join(SRC, f), os.path.join(DST, f))
+
+# ---- kernel: clock marks after the barrier that closes each phase
+lines = open(os.path.join(SRC, "radb_kernels.cuh")).read().split("\n")
+sync = [i for i, l in enumerate(lines) if l.strip() == "__syncthreads();"]
+ph = {}
+for i, l in enumerate(lines):
+    m = re.match(r"\s*// ---- (phase [0-9a-z]+)", l)
+    if m:
+        ph[m.group(1)] = i
+before = lambda i: max(j for j in sync if j < i)
+after = lambda i: min(j for j in sync if j > i)
+between = [j for j in sync if ph["phase 1"] < j < ph["phase 2"]]
+marks = [before(ph["phase 1"]), between[0], between[-1], before(ph["phase 3a"]), before(ph["phase 3b"]),
+         before(ph["phase 4"]), before(ph["phase 5"]), after(ph["phase 5"]), after(ph["phase 6"])]
+out = []
+for i, l in enumerate(lines):
+    out.append(l)
+    if i in marks:
+        out.append("    if (tid == 0 && p.clk) p.clk[patch * 16 + %d] = clock64();" % (marks.index(i) + 1))
+s = "\n".join(out)
+s = s.replace("    // ---- phase 0: stage the patch, zero the counters",
+              "    if (tid == 0 && p.clk) p.clk[patch * 16 + 0] = clock64();\n    // ---- phase 0: stage the patch, zero the counters", 1)
+tail = "        for (int i = tid; i < n16; i += RADB_NTB) dst[i] = src[i];\n    }\n}"
+assert tail in s
+s = s.replace(tail, tail[:-1] + "    __syncthreads();\n    if (tid == 0 && p.clk) p.clk[patch * 16 + 10] = clock64();\n}", 1)
+open(os.path.join(DST, "radb_kernels.cuh"), "w").write(s)
+
+# ---- params: the side buffer
+s = open(os.path.join(SRC, "radb_params.h")).read()
+anchor = "    unsigned char* ws;        // [B][rec_bytes]"
+assert anchor in s
+open(os.path.join(DST, "radb_params.h"), "w").write(s.replace(anchor, "    long long* clk;\n" + anchor))
+
+# ---- launch(): allocate, pass, dump
+s = open(os.path.join(SRC, "radb_api.cu")).read()
+a1 = "    cudaStream_t rs = piped ? h->red_stream : st;"
+a2 = "        q.B = n;\n"
+a3 = "    e = cudaGetLastError();\n    if (e != cudaSuccess) return cuda_fail(e, \"radb kernel launch\");"
+assert a1 in s and a2 in s and a3 in s
+s = s.replace(a1, a1 + "\n    static long long* g_clk = nullptr;\n    if (!g_clk) cudaMalloc(&g_clk, (size_t)200000 * 16 * 8);\n"
+                       "    cudaMemsetAsync(g_clk, 0, (size_t)200000 * 16 * 8, st);", 1)
+s = s.replace(a2, a2 + "        q.clk = (n <= 200000) ? g_clk : nullptr;\n", 1)
+dump = r'''    if (getenv("RADB_CLK")) {
+        cudaDeviceSynchronize();
+        const long long nb = p.B < chunk ? p.B : chunk;
+        std::vector<long long> hc((size_t)nb * 16);
+        cudaMemcpy(hc.data(), g_clk, hc.size() * 8, cudaMemcpyDeviceToHost);
+        double acc[11] = {0};
+        long long cnt = 0;
+        for (long long i = 0; i < nb; i++) {
+            const long long* c = &hc[i * 16];
+            if (!c[0] || !c[10]) continue;
+            cnt++;
+            for (int k = 1; k <= 10; k++) acc[k] += (double)(c[k] - c[k - 1]);
+        }
+        static const char* nm[11] = {"", "p0 stage+zero", "p1 hist/bbox", "validity+lut", "p2 discretise", "p3a walks",
+                                     "p3b neighbourhood", "p4 fold+symm", "p5 zones", "misc9", "p6 record copy"};
+        double tot = 0;
+        for (int k = 1; k <= 10; k++) tot += acc[k];
+        fprintf(stderr, "phase clocks (avg cycles per CTA over %lld patches, total %.0f):\n", cnt, tot / cnt);
+        for (int k = 1; k <= 10; k++) fprintf(stderr, "  %-20s %8.0f  %5.1f%%\n", nm[k], acc[k] / cnt, 100 * acc[k] / tot);
+    }
+'''
+s = s.replace(a3, dump + a3, 1)
+open(os.path.join(DST, "radb_api.cu"), "w").write(s)
+subprocess.check_call(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
+                       "-shared", "-o", "libradb_clk.so", "radb_api.cu", "radb_hostpack.cpp"], cwd=DST)
+print("built", os.path.join(DST, "libradb_clk.so"))
