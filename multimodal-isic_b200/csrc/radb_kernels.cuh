@@ -260,6 +260,21 @@ __device__ __forceinline__ int get_run(const unsigned* base, int cell, int wide)
     return wide ? (int)base[cell] : get_u16(base, cell);
 }
 
+// sum of the four bytes of a word (IDP.4A)
+__device__ __forceinline__ unsigned bytes_sum4(unsigned w, unsigned acc)
+{
+#ifdef RADB_EMU
+    return acc + (w & 0xffu) + ((w >> 8) & 0xffu) + ((w >> 16) & 0xffu) + (w >> 24);
+#else
+    return __dp4a(w, 0x01010101u, acc);
+#endif
+}
+// 0x80 in every byte position where the byte of w is non-zero
+__device__ __forceinline__ unsigned bytes_nz4(unsigned w)
+{
+    return (((w & 0x7f7f7f7fu) + 0x7f7f7f7fu) | w) & 0x80808080u;
+}
+
 // per-byte equality of two packed 4-byte words: 0x80 in every byte position where a == b (exact)
 __device__ __forceinline__ unsigned bytes_eq4(unsigned a, unsigned b)
 {
@@ -922,17 +937,34 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 const int sw = lev[ctr + WP - 1], s_ = lev[ctr + WP], se = lev[ctr + WP + 1];
                 int* g0 = glcm + (c - 1) * ng - 1;
                 const int ngng = ng * ng;
-                if (se) atomicAdd(&g0[se], 1);
-                if (e_) atomicAdd(&g0[ngng + e_], 1);
-                if (ne) atomicAdd(&g0[2 * ngng + ne], 1);
-                if (s_) atomicAdd(&g0[3 * ngng + s_], 1);
-                const int cnt = (nw != 0) + (n_ != 0) + (ne != 0) + (w_ != 0) + (e_ != 0) + (sw != 0) + (s_ != 0) + (se != 0);
-                const int sum = nw + n_ + ne + w_ + e_ + sw + s_ + se;  // levels outside the ROI are 0
+                // Unconditional increments: a neighbour outside the ROI (level 0) is redirected to a scratch word
+                // of the record header instead of branching around the atomic -- `if (x) atomicAdd(..)` costs
+                // BSSY / BRA / BSYNC per counter in the innermost loop, and the plain form keeps the compiler's
+                // ATOMS.POPC.INC (same-address lanes are combined by the hardware).
+                int* const trash = ((WIDE && p.big) ? (int*)(g_rec + (p.o_misc - p.o_rec)) : misc) + 30;
+                atomicAdd(se ? &g0[se] : trash, 1);
+                atomicAdd(e_ ? &g0[ngng + e_] : trash, 1);
+                atomicAdd(ne ? &g0[2 * ngng + ne] : trash, 1);
+                atomicAdd(s_ ? &g0[3 * ngng + s_] : trash, 1);
                 const int al = p.alpha;
+                int cnt, sum, dep;
+                if (!L16 && al == 0) {
+                    // eight u8 neighbours in two words: counts by byte-parallel tests + popc, the sum by IDP.4A
+                    // (GLDM with alpha = 0, the pyradiomics default: dependent <=> equal level)
+                    const unsigned q0 = (unsigned)nw | ((unsigned)n_ << 8) | ((unsigned)ne << 16) | ((unsigned)w_ << 24);
+                    const unsigned q1 = (unsigned)e_ | ((unsigned)sw << 8) | ((unsigned)s_ << 16) | ((unsigned)se << 24);
+                    const unsigned c4 = (unsigned)c * 0x01010101u;
+                    cnt = __popc(bytes_nz4(q0)) + __popc(bytes_nz4(q1));
+                    sum = (int)bytes_sum4(q0, bytes_sum4(q1, 0u));
+                    dep = __popc(bytes_eq4(q0, c4)) + __popc(bytes_eq4(q1, c4));
+                } else {
+                    cnt = (nw != 0) + (n_ != 0) + (ne != 0) + (w_ != 0) + (e_ != 0) + (sw != 0) + (s_ != 0) + (se != 0);
+                    sum = nw + n_ + ne + w_ + e_ + sw + s_ + se;  // levels outside the ROI are 0
 #define RADB_DEP(v) ((v) != 0 && ((v) - c <= al) && (c - (v) <= al))
-                const int dep = RADB_DEP(nw) + RADB_DEP(n_) + RADB_DEP(ne) + RADB_DEP(w_) + RADB_DEP(e_) + RADB_DEP(sw) +
-                                RADB_DEP(s_) + RADB_DEP(se);
+                    dep = RADB_DEP(nw) + RADB_DEP(n_) + RADB_DEP(ne) + RADB_DEP(w_) + RADB_DEP(e_) + RADB_DEP(sw) +
+                          RADB_DEP(s_) + RADB_DEP(se);
 #undef RADB_DEP
+                }
                 atomicAdd(&gldm[(c - 1) * nd + dep], 1);
                 if (cnt) {
                     int num = cnt * c - sum;
