@@ -62,7 +62,8 @@ enum {
  * RadiomicsFeatureExtractor.execute forwards to every feature class. */
 typedef struct radb_settings {
     double bin_width;          /* params.yml:96  binWidth (10); pyradiomics default 25 */
-    int32_t bin_count;         /* binCount; 0 = unused (fixed-width binning) */
+    int32_t bin_count;         /* binCount (params.yml:97): > 0 splits the ROI range into this many bins (numpy.histogram
+                                  edges, last edge + 1) and takes precedence over bin_width; 0 = fixed-width binning */
     int32_t label;             /* params.yml:93  label (255) */
     int32_t n_angles;          /* unidirectional offsets resolved on the host from force2D /
                                   force2Ddimension (params.yml:100): 1 (row-only, the literal

@@ -541,8 +541,8 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
     const double N = (double)sN, rN = radb_div(1.0, N);
     double r0[5] = {(double)sI, (double)sJ, (double)sIJ, (double)sD2, (double)sC2};  // exact integers < 2^53
     warp_sum_n(r0, tb.red, lane);
-    const double ux = r0[0] * rN;
-    const double uy = r0[1] * rN;
+    const double ux = radb_div(r0[0], N);  // true divisions: exactly 1 for a one-level matrix (sigma = 0, Correlation = 1)
+    const double uy = radb_div(r0[1], N);
     const double autoc = r0[2] * rN;
     const double contrast = r0[3] * rN;
     const double energy = r0[4] * rN * rN;

@@ -65,8 +65,8 @@ struct Plan {
 // Validates settings; returns 0 or a RADB_E_* code with a message.
 static inline int make_plan(const radb_settings& s, Plan& pl, std::string& err)
 {
-    if (!(s.bin_width > 0) || !isfinite(s.bin_width)) { err = "bin_width must be > 0"; return RADB_E_INVALID; }
-    if (s.bin_count != 0) { err = "binCount binning is not implemented (fixed binWidth only)"; return RADB_E_UNSUPPORTED; }
+    if (s.bin_count < 0) { err = "bin_count must be >= 0"; return RADB_E_INVALID; }
+    if (s.bin_count == 0 && (!(s.bin_width > 0) || !isfinite(s.bin_width))) { err = "bin_width must be > 0"; return RADB_E_INVALID; }
     if (s.n_angles < 1 || s.n_angles > RADB_MAX_ANGLES) { err = "n_angles must be 1..4 (distance-1 offsets in a plane)"; return RADB_E_INVALID; }
     for (int a = 0; a < s.n_angles; a++) {
         int dy = s.angles[a][0], dx = s.angles[a][1];
@@ -99,6 +99,7 @@ static inline int make_plan(const radb_settings& s, Plan& pl, std::string& err)
         }
     }
     int ng = s.max_ng;
+    if (s.bin_count > 0) ng = s.bin_count;  // binCount: the top bin always holds the ROI maximum, so Ng = binCount
     if (ng <= 0) ng = (int)floor(255.0 / s.bin_width) + 1;  // uint8 pixels: levels 1..floor(255/bw)+1
     if (ng > 256) { err = "more than 256 gray levels"; return RADB_E_UNSUPPORTED; }
     pl.max_ng = ng;
@@ -136,7 +137,7 @@ static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParam
         case RADB_DTYPE_F64: pix_bytes = 8; break;
         default: err = "unknown pixel dtype"; return RADB_E_INVALID;
     }
-    if (dtype != RADB_DTYPE_U8 && pl.s.max_ng <= 0) {
+    if (dtype != RADB_DTYPE_U8 && pl.s.max_ng <= 0 && pl.s.bin_count <= 0) {
         err = "max_ng must be given for non-uint8 pixels (the gray-level count cannot be bounded from the dtype)";
         return RADB_E_INVALID;
     }
@@ -153,8 +154,9 @@ static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParam
     for (int a = 0; a < pl.s.n_angles; a++) { p.ang_y[a] = pl.s.angles[a][0]; p.ang_x[a] = pl.s.angles[a][1]; }
     p.symmetric = pl.s.symmetrical_glcm ? 1 : 0;
     p.alpha = (int)floor(pl.s.gldm_alpha);
-    p.bin_width = pl.s.bin_width;
-    p.bw_int = (pl.s.bin_width >= 1.0 && pl.s.bin_width <= 255.0 && pl.s.bin_width == floor(pl.s.bin_width)) ? (int)pl.s.bin_width : 0;
+    p.bin_width = pl.s.bin_count > 0 ? 1.0 : pl.s.bin_width;
+    p.bin_count = pl.s.bin_count;
+    p.bw_int = (pl.s.bin_count <= 0 && pl.s.bin_width >= 1.0 && pl.s.bin_width <= 255.0 && pl.s.bin_width == floor(pl.s.bin_width)) ? (int)pl.s.bin_width : 0;
     p.shift = pl.s.voxel_array_shift;
     p.max_ng = pl.max_ng;
     p.F = pl.F;

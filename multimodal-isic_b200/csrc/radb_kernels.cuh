@@ -505,11 +505,14 @@ __device__ void fo_generic(const RadbParams& p, const PT* img, const unsigned ch
 }
 
 // A.3 binImage: gray level of x = number of fp64 edges (low + k*bw, as numpy.arange builds them) <= x
+// The edges are formed as NumPy forms them (numpy.arange / numpy.linspace: a rounded product, then a rounded
+// sum): no fused multiply-add, or a pixel that sits exactly on an edge could land one level off.
+__device__ __forceinline__ double radb_edge(double low, long long k, double bw) { return __dadd_rn(low, __dmul_rn((double)k, bw)); }
 __device__ __noinline__ int radb_level(double x, double low, double bw)
 {
     long long k = (long long)floor((x - low) / bw);
-    while (low + (double)k * bw > x) k--;
-    while (low + (double)(k + 1) * bw <= x) k++;
+    while (radb_edge(low, k, bw) > x) k--;
+    while (radb_edge(low, k + 1, bw) <= x) k++;
     return (int)(k + 1);
 }
 
@@ -690,6 +693,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     __syncthreads();
     // ROI validity (A.1 step 2, imageoperations.checkMask) and the bin edges (A.3 getBinEdges)
     double low = 0, roi_min = 0, roi_max = 0;
+    double bwv = p.bin_width;   // bin width in effect (binCount: derived from the ROI range)
+    int lcap = 0x7fffffff;      // binCount: the number of bins caps the level
     {
         const int np = misc[0];
         int st = 0;
@@ -720,7 +725,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         int ng = 0;
         if (!st) {
             const double bw = p.bin_width;
-            if (U8 && p.bw_int) {
+            if (U8 && p.bw_int && p.bin_count <= 0) {
                 // uint8 pixels and an integer binWidth (25, 10: the reference's settings): the fp64 edges low + k*bw
                 // are exact integers, so the level is an integer quotient (float reciprocal, exact below 2^16)
                 const int ibw = p.bw_int, ivmin = (int)vmin, ivmax = (int)vmax, ilow = ivmin - ivmin % ibw;
@@ -730,18 +735,30 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                     lut[v] = (v >= ivmin && v <= ivmax) ? (unsigned char)((int)(((float)(v - ilow) + 0.5f) * rbw) + 1) : 0;
                 ng = (int)(((float)(ivmax - ilow) + 0.5f) * rbw) + 1;
             } else {
-                low = vmin - py_mod(vmin, bw);
+                if (p.bin_count > 0) {
+                    // binCount (imageoperations.getBinEdges): numpy.histogram's edges = linspace(min, max, n + 1)
+                    // (a flat ROI gets the range min -+ 0.5), the last edge moved to max + 1, so level = #edges <= x
+                    // among the first n: the same counting with low = min, width = (max - min) / n, capped at n
+                    const bool flat = !(vmax > vmin);
+                    low = flat ? vmin - 0.5 : vmin;
+                    bwv = flat ? 1.0 / (double)p.bin_count : (vmax - vmin) / (double)p.bin_count;
+                    lcap = p.bin_count;
+                } else {
+                    low = vmin - py_mod(vmin, bw);
+                }
                 if (U8) {  // value -> level LUT: level = #edges <= x, edges = low + k*binWidth
                     for (int v = tid; v < 256; v += RADB_NTB) {
                         int L = 0;
                         if ((double)v >= vmin && (double)v <= vmax) {
-                            L = radb_level((double)v, low, bw);
+                            L = radb_level((double)v, low, bwv);
+                            L = L > lcap ? lcap : L;
                             if (L > 255) L = 255;  // reported through status 4 below
                         }
                         lut[v] = (unsigned char)L;
                     }
                 }
-                ng = radb_level(vmax, low, bw);
+                ng = radb_level(vmax, low, bwv);
+                ng = ng > lcap ? lcap : ng;
             }
             if (ng > p.max_ng) st = 4;
         }
@@ -786,7 +803,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 if (U8) {
                     L = lut[(int)s_img[i]];
                 } else {
-                    L = (LT)radb_level((double)s_img[i], low, p.bin_width);
+                    const int Lv = radb_level((double)s_img[i], low, bwv);
+                    L = (LT)(Lv > lcap ? lcap : Lv);
                     atomicAdd(&lhist[L - 1], 1);
                 }
             }

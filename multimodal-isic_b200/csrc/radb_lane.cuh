@@ -309,7 +309,7 @@ __device__ int glcm_lane(const RadbTabs& tb, const int* P, int n, LaneMem lm, do
     }
     if (sN == 0) return 0;
     const double N = (double)sN, rN = radb_div(1.0, N);
-    const double ux = (double)sI * rN;  // = uy
+    const double ux = radb_div((double)sI, N);  // = uy; a true division: exactly 1 for a one-level matrix (sigma = 0)
     const double autoc = (double)sIJ * rN, contrast = (double)sD2 * rN, energy = (double)sC2 * rN * rN;
     const double maxp = (double)maxc * rN;
     const double log2N = tab_log2(tb, (int)sN);

@@ -44,6 +44,7 @@ struct RadbParams {
     int symmetric;
     int alpha;
     double bin_width;
+    int bin_count; // > 0: binCount binning (the ROI range split into this many bins), bin_width is ignored
     int bw_int;    // bin_width when it is an integer in 1..255 (uint8 fast path of the level LUT), else 0
     double shift;
     int max_ng;

@@ -17,7 +17,7 @@ class RadbError(RuntimeError):
 
 class Engine:
     def __init__(self, bin_width, label, angles, symmetrical_glcm=True, gldm_alpha=0.0, voxel_array_shift=0.0,
-                 classes=_abi.CLASS_ORDER, max_ng=0, device=0):
+                 classes=_abi.CLASS_ORDER, max_ng=0, device=0, bin_count=0):
         if not torch.cuda.is_available():
             raise RadbError("radb: no CUDA device visible -- the radiomic engine has no CPU fallback")
         self.lib = _abi.load_library()
@@ -25,7 +25,7 @@ class Engine:
         self.label = int(label)
         self.n_angles = len(angles)
         self._settings = _abi.make_settings(bin_width, label, angles, symmetrical_glcm, gldm_alpha,
-                                            voxel_array_shift, classes, max_ng, device)
+                                            voxel_array_shift, classes, max_ng, device, bin_count)
         h = ctypes.c_void_p()
         rc = self.lib.radb_create(ctypes.byref(self._settings), ctypes.byref(h))
         if rc != 0:
@@ -76,8 +76,8 @@ class Engine:
     def _check(self, images, masks):
         if images.dtype not in self.DTYPES:
             raise NotImplementedError("pixel dtype %s is not implemented (uint8, uint16, float32, float64)" % images.dtype)
-        if images.dtype != torch.uint8 and self._settings.max_ng <= 0:
-            raise RadbError("non-uint8 pixels need an engine created with max_ng (gray-level bound)")
+        if images.dtype != torch.uint8 and self._settings.max_ng <= 0 and self._settings.bin_count <= 0:
+            raise RadbError("non-uint8 pixels need an engine created with max_ng (gray-level bound) or bin_count")
         if masks.dtype != torch.uint8:
             raise TypeError("masks must be uint8")
         if images.dim() != 3 or images.shape != masks.shape:

@@ -43,9 +43,10 @@ class RadiomicsExtractor:
         self.device = int(device)
         eng_classes, self._perm = self.params.engine_columns()
         s = self.params.settings
+        bc = self.params.bin_count
         self.engine = Engine(self.params.bin_width, self.params.label, self.params.angles(2),
                              bool(s["symmetricalGLCM"]), float(s["gldm_a"]), float(s["voxelArrayShift"]),
-                             eng_classes, max_ng, self.device)
+                             eng_classes, max_ng, self.device, bc)
         self._engine_args = (self.params.bin_width, self.params.label, self.params.angles(2),
                              bool(s["symmetricalGLCM"]), float(s["gldm_a"]), float(s["voxelArrayShift"]), eng_classes)
         self._engines_ng = {}  # engines for non-uint8 pixels, keyed by their gray-level bound
@@ -57,7 +58,7 @@ class RadiomicsExtractor:
             tex_classes = [c for c in eng_classes if c != "shape2D"]
             self._derived_engine = Engine(self.params.bin_width, self.params.label, self.params.angles(2),
                                           bool(s["symmetricalGLCM"]), float(s["gldm_a"]), float(s["voxelArrayShift"]),
-                                          tex_classes, min(255, int(255.0 // self.params.bin_width) + 3), self.device)
+                                          tex_classes, min(255, int(255.0 // self.params.bin_width) + 3), self.device, bc)
         self.feature_names = self.params.feature_names()
         self._perm_t = None
         self._identity = self._perm == list(range(self.engine.F))
@@ -169,7 +170,7 @@ class RadiomicsExtractor:
         on the data, so an engine sized for this batch's largest ROI range (rounded up to a multiple of
         8 levels) is created on demand and cached."""
         t = torch.as_tensor(images)
-        if t.dtype == torch.uint8:
+        if t.dtype == torch.uint8 or self.params.bin_count:  # binCount: Ng = binCount whatever the pixel type
             return self.engine, self.pipeline
         m = torch.as_tensor(masks) == self.params.label
         f = t.to(torch.float64) if t.dtype != torch.uint16 else t.to(torch.int32).to(torch.float64)
@@ -222,7 +223,7 @@ class RadiomicsExtractor:
 
         img_pool, mask_pool, img_off, mask_off, hw = pack_ragged(images, masks)
         engine = self.engine
-        if img_pool.dtype != np.uint8:
+        if img_pool.dtype != np.uint8 and not self.params.bin_count:
             engine, _ = self._engine_for_pool(images, masks)
         dev = torch.device("cuda", self.device)
         ip = torch.as_tensor(img_pool.view(np.int16) if img_pool.dtype == np.uint16 else img_pool).to(dev)

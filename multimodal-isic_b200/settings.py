@@ -52,7 +52,7 @@ SUPPORTED_IMAGE_TYPES = {"Original", "Square", "SquareRoot", "Logarithm", "Expon
 IMAGE_TYPE_CODES = {"Square": 1, "SquareRoot": 2, "Logarithm": 3, "Exponential": 4}  # radb_derive_image
 # settings whose non-default value would change results and that the engine does not implement
 _UNSUPPORTED_IF_SET = ("normalize", "removeOutliers", "resampledPixelSpacing", "resegmentRange", "weightingNorm",
-                       "binCount", "minimumROISize")
+                       "minimumROISize")
 
 
 def in_plane_angles(ndim=2, distances=(1,), force2D=False, force2Ddimension=0):
@@ -123,6 +123,8 @@ class Settings:
                 raise NotImplementedError("setting %r=%r is not implemented by the B200 engine" % (k, s[k]))
         if not float(s["binWidth"]) > 0:
             raise ValueError("binWidth must be > 0")
+        if s.get("binCount") is not None and not (1 <= int(s["binCount"]) <= 256):
+            raise NotImplementedError("binCount must be 1..256")
         skipped_types = [t for t in self.enabledImagetypes if t not in SUPPORTED_IMAGE_TYPES]
         if skipped_types:
             self._complain("image types %s are not implemented yet and are skipped" % skipped_types)
@@ -153,6 +155,11 @@ class Settings:
     @property
     def bin_width(self):
         return float(self.settings["binWidth"])
+
+    @property
+    def bin_count(self):
+        """pyradiomics: when binCount is set it takes precedence over binWidth (imageoperations.getBinEdges)."""
+        return int(self.settings["binCount"] or 0)
 
     def angles(self, ndim=2):
         s = self.settings

@@ -164,6 +164,10 @@ inline double __dmul_rn(double a, double b) {
     volatile double r = a * b;  // a separately rounded product even when the harness is built with FMA contraction
     return r;
 }
+inline double __dadd_rn(double a, double b) {
+    volatile double r = a + b;
+    return r;
+}
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline int __ffs(int v) { return __builtin_ffs(v); }

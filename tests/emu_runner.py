@@ -39,12 +39,12 @@ class EmuRunner:
         return self.lib.radb_emu_is_wide(ctypes.byref(s), H, W)
 
     def run(self, imgs, masks, bin_width=10, label=255, angles=((0, 1),), symmetrical=True, alpha=0,
-            classes=_abi.CLASS_ORDER, max_ng=0):
+            classes=_abi.CLASS_ORDER, max_ng=0, bin_count=0):
         imgs = np.ascontiguousarray(imgs)
         dtype = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3}[imgs.dtype]
         masks = np.ascontiguousarray(masks, dtype=np.uint8)
         B, H, W = imgs.shape
-        s = _abi.make_settings(bin_width, label, angles, symmetrical, alpha, classes=classes, max_ng=max_ng)
+        s = _abi.make_settings(bin_width, label, angles, symmetrical, alpha, classes=classes, max_ng=max_ng, bin_count=bin_count)
         F = self.lib.radb_emu_feature_count(ctypes.byref(s))
         ng = self.lib.radb_emu_max_ng(ctypes.byref(s))
         assert F > 0 and ng > 0, self.lib.radb_emu_last_error()

@@ -96,8 +96,11 @@ def test_settings_class_order_and_feature_subset():
     assert pkg.Settings({"binWidth": 25, "force2D": False}).angles() == orc.angles(2)[0]
     with pytest.raises(ValueError):
         pkg.Settings({"featureClass": {"glcm": ["Homogeneity1"]}})
+    assert pkg.Settings({"setting": {"binCount": 16}}).bin_count == 16 and pkg.Settings({"setting": {}}).bin_count == 0
     with pytest.raises(NotImplementedError):
-        pkg.Settings({"setting": {"binCount": 16}})
+        pkg.Settings({"setting": {"binCount": 1000}})
+    with pytest.raises(NotImplementedError):
+        pkg.Settings({"setting": {"weightingNorm": "euclidean"}})
 
 
 def test_feature_name_tables_agree():

@@ -123,6 +123,22 @@ def test_emu_many_gray_levels_big_mode(emu, ng_cap, bw):
     assert r["ng"].max() > (200 if bw == 8 else 100)
 
 
+@pytest.mark.parametrize("dt", [np.uint8, np.float64])
+def test_emu_bin_count(emu, dt):
+    """binCount binning (imageoperations.getBinEdges): the ROI range split into n bins by numpy.histogram's edges
+    (last edge + 1), including ROIs whose edges fall exactly on pixel values, a flat ROI and a two-valued ROI."""
+    g, masks = synth.make_patches(5, 24, 22, seed=13)
+    g[1] = (g[1] // 16) * 16                 # pixel values on a lattice: edges hit pixel values exactly
+    if dt == np.uint8:  # (flat *float* ROIs: Skewness / Kurtosis deviate on purpose, DESIGN.md section 7)
+        g[2][masks[2] == 255] = 77           # flat ROI: numpy.histogram uses the range min -+ 0.5
+    g[3] = np.where(g[3] > 120, 200, 50)     # two values
+    imgs = g if dt == np.uint8 else (np.sqrt(g.astype(np.float64)) * 3.0 - 7.0)
+    for n in (1, 6, 20, 64):
+        r = emu.run(imgs, masks, 25, 255, INPLANE, bin_count=n)
+        assert compare_with_oracle(r, imgs, masks, dict(label=255, binCount=n, force2D=False)) == 5
+        assert r["ng"].max() == n
+
+
 def test_emu_golden_fixture(emu):
     z = np.load(os.path.join(GOLD, "oracle_features_seed0.npz"))
     r = emu.run(z["images"][:2], z["masks"][:2], 10, 255, INPLANE)

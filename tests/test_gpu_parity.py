@@ -515,3 +515,22 @@ def test_packed_mask_transfer_path(gpu_pkg):
     pk = torch.as_tensor(np.packbits(masks.reshape(-1) == 255, bitorder="little")).cuda()
     eng.unpack_mask(pk, d)
     assert torch.equal(d.cpu() == 255, torch.as_tensor(masks == 255)) and set(d.unique().tolist()) <= {0, 255}
+
+
+@pytest.mark.parametrize("dt", [np.uint8, np.float32])
+def test_bin_count_binning(gpu_pkg, dt):
+    """binCount (pyradiomics imageoperations.getBinEdges): n bins over the ROI range, numpy.histogram edges."""
+    g, masks = gpu_pkg.synth.make_patches(6, 40, 36, seed=21)
+    g[1] = (g[1] // 16) * 16
+    if dt == np.uint8:
+        g[2][masks[2] == 255] = 90
+    imgs = g if dt == np.uint8 else (np.sqrt(g.astype(np.float64)) * 3.0 - 7.0).astype(np.float32)
+    for n in (1, 16, 100):
+        eng = gpu_pkg.Engine(25, 255, INPLANE, bin_count=n)
+        r = eng.debug_matrices(torch.as_tensor(imgs).cuda(), torch.as_tensor(masks).cuda())
+        assert compare_with_oracle(r, imgs, masks, dict(label=255, binCount=n, force2D=False)) == 6
+    ex = gpu_pkg.RadiomicsExtractor({"setting": {"label": 255, "binCount": 16}})
+    out, st = ex.extract_batch(torch.as_tensor(imgs).cuda(), torch.as_tensor(masks).cuda())
+    eng = gpu_pkg.Engine(25, 255, INPLANE, bin_count=16)
+    r = eng.debug_matrices(torch.as_tensor(imgs).cuda(), torch.as_tensor(masks).cuda())
+    np.testing.assert_allclose(out.cpu().numpy(), r["features"], rtol=1e-8, atol=1e-12)
