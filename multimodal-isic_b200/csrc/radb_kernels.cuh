@@ -640,14 +640,17 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                     const unsigned v4 = v4p[q];
                     ymin = y < ymin ? y : ymin;
                     ymax = y > ymax ? y : ymax;
+                    // branch-free: the pixel count and the x extent come from the bit positions of `eq` (0x80 per
+                    // selected byte); unselected pixels increment a scratch word of the record header, so the four
+                    // histogram updates are unconditional ATOMS.POPC.INC without BSSY / BRA / BSYNC around them
+                    np += __popc(eq);
+                    const int kmin = (__ffs((int)eq) - 1) >> 3, kmax = (31 - __clz((int)eq)) >> 3;
+                    xmin = x0 + kmin < xmin ? x0 + kmin : xmin;
+                    xmax = x0 + kmax > xmax ? x0 + kmax : xmax;
+                    int* const trash = misc + 30;
 #pragma unroll
                     for (int k = 0; k < 4; k++)
-                        if (eq & (0x80u << (8 * k))) {
-                            np++;
-                            xmin = x0 + k < xmin ? x0 + k : xmin;
-                            xmax = x0 + k > xmax ? x0 + k : xmax;
-                            atomicAdd(&hist[(v4 >> (8 * k)) & 0xffu], 1);
-                        }
+                        atomicAdd((eq & (0x80u << (8 * k))) ? &hist[(v4 >> (8 * k)) & 0xffu] : trash, 1);
                 }
         } else
         for (int y = warp; y < H; y += RADB_NTB / 32)
@@ -790,8 +793,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 const unsigned v4 = v4p[q];
                 unsigned w = 0;
 #pragma unroll
-                for (int k = 0; k < 4; k++)
-                    if (eq & (0x80u << (8 * k))) w |= (unsigned)lut[(v4 >> (8 * k)) & 0xffu] << (8 * k);
+                for (int k = 0; k < 4; k++) w |= (unsigned)lut[(v4 >> (8 * k)) & 0xffu] << (8 * k);  // four unconditional lookups
+                w &= (eq >> 7) * 0xffu;  // keep the ROI bytes (eq: 0x80 per selected byte -> 0xff per selected byte)
                 ((unsigned*)((unsigned char*)lev + (y + 1) * WP + XO))[xq] = w;  // u8 levels; XO = 4 and WP % 4 == 0: aligned
             }
     } else
@@ -881,6 +884,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                     }
                 } else {
                     const int sdx = dx * dy;  // x step per +1 in y (runs are direction-agnostic)
+                    const int xwrap = sdx > 0 ? bw : -1, xre = sdx > 0 ? 0 : bw - 1;  // leaving the bbox on this side / re-entry column
                     int x = l, brk = 0;
                     int pos = (by0 + 1) * WP + bx0 + XO;
                     int gn = lev[pos + x];  // software-pipelined like the row walk
@@ -888,9 +892,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                         const int g = gn, brk_here = brk;
                         pos += WP;
                         x += sdx;
-                        brk = 0;
-                        if (x >= bw) { x = 0; brk = 1; }          // wrapped diagonal: the next pixel is not
-                        else if (x < 0) { x = bw - 1; brk = 1; }  // a neighbour of this one
+                        brk = (x == xwrap);   // wrapped diagonal: the next pixel is not a neighbour of this one
+                        x = brk ? xre : x;    // (vertical lines: sdx = 0 never reaches xwrap = -1)
                         gn = lev[pos + x];  // row below the bbox on the last step: the zero border, in bounds
                         if (g != cur || brk_here) {
                             if (cur) { add_run<WIDE>(R, (cur - 1) * nr + len - 1); mylen = len > mylen ? len : mylen; }
