@@ -220,3 +220,24 @@ def test_record_decode_pool_keeps_order(tmp_path):
                 assert np.array_equal(sg, m)
     with pytest.raises(FileNotFoundError):
         RadiomicsExtractor._load_records(recs + [{"image_path": str(tmp_path / "nope.png"), "segmentation_path": recs[0]["segmentation_path"]}], 3)
+
+
+def test_settings_parse_the_reference_parameter_file():
+    """The reference's own params.yml (RadiomicExtractor.py:15), when the checkout is present (it is not on the GPU
+    box): label 255, binWidth 10, force2D -> one along-row angle, every image type listed; the implemented ones give
+    9 shape2D + 93 x (Original, Square, SquareRoot, Logarithm, Exponential) columns per channel."""
+    path = "/root/reference/params.yml"
+    if not os.path.exists(path):
+        pytest.skip("reference checkout not present")
+    with warnings.catch_warnings(record=True) as w:
+        warnings.simplefilter("always")
+        s = pkg.Settings(path)
+    assert s.label == 255 and s.bin_width == 10.0 and s.bin_count == 0 and s.angles() == [(0, 1)]
+    assert list(s.enabledImagetypes) == ["Original", "Wavelet", "LoG", "Square", "SquareRoot", "Logarithm", "Exponential", "Gradient"]
+    assert s.image_types == ["Original", "Square", "SquareRoot", "Logarithm", "Exponential"]
+    msg = " ".join(str(x.message) for x in w)
+    assert "Wavelet" in msg and "LoG" in msg and "Gradient" in msg
+    names = s.feature_names()
+    assert len(names) == 9 + 93 * 5 and names[0].startswith("original_shape2D_") and names[9] == "original_firstorder_10Percentile"
+    assert sum(n.startswith("exponential_") for n in names) == 93
+    assert not any(n.startswith("diagnostics_") for n in names)  # additionalInfo: False (params.yml:62)
