@@ -405,6 +405,12 @@ def test_fuzz_random_shapes_patterns_masks(gpu_pkg):
         pats = [_fuzz_patch(rng, H, W, int(rng.integers(0, 5))) for _ in range(5)]
         imgs = np.stack([p[0] for p in pats])
         masks = np.stack([p[1] for p in pats])
+        if trial % 7 == 6:  # binCount binning instead of a fixed width
+            n = int(rng.integers(1, 65))
+            eng = gpu_pkg.Engine(25, 255, ang, True, 0, 0.0, ALL_CLASSES, bin_count=n)
+            r = _dbg(eng, imgs, masks)
+            total += compare_with_oracle(r, imgs, masks, dict(label=255, binCount=n, force2D=literal), classes=ALL_CLASSES)
+            continue
         r = _dbg(_engine(gpu_pkg, bw, ang, classes=ALL_CLASSES), imgs, masks)
         total += compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=bw, force2D=literal), classes=ALL_CLASSES)
     assert total > 3 * trials
