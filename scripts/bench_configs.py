@@ -92,8 +92,30 @@ def config4_binwidth_sweep():
              invalid=int((st != 0).sum()))
 
 
+def reference_workload(n_images=128):
+    """What extract_radiomics.py actually feeds (RadiomicExtractor.py:29-48, params.yml): whole 600x450 BGR dermoscopy
+    images (HAM10000 size) with one lesion mask each -> gray / R / G / B planes on the device -> 4 executes per image,
+    binWidth 10, force2D (literal: one along-row angle), shape2D + 93 features; wide mode (one CTA per plane)."""
+    H, W = 450, 600
+    g, m = pkg.synth.make_patches(8, H, W, seed=70)
+    rng = np.random.default_rng(0)
+    bgr = np.stack([np.stack([np.clip(g[i % 8].astype(int) + rng.integers(-20, 20), 0, 255).astype(np.uint8) for _ in range(3)], -1)
+                    for i in range(n_images)])
+    msk = np.stack([m[i % 8] for i in range(n_images)])
+    ex = pkg.RadiomicsExtractor({"setting": {"label": 255, "binWidth": 10, "force2D": True},
+                                 "featureClass": {k: None for k in ("firstorder", "shape2D", "glcm", "gldm", "glrlm", "glszm", "ngtdm")}})
+    db, dm = torch.as_tensor(bgr).cuda(), torch.as_tensor(msk).cuda()
+    out, st = ex.engine.extract_bgr(db, dm)
+    ms = timed(lambda: ex.engine.extract_bgr(db, dm), reps=3, warm=1)
+    emit(config="reference workload: whole 600x450 BGR images, 4 executes per image (gray/R/G/B), binWidth 10, literal force2D, 102 features",
+         images=n_images, ms=ms, images_per_s=n_images / ms * 1e3, executes_per_s=4 * n_images / ms * 1e3,
+         mpixels_per_s=4 * n_images * H * W / ms / 1e3, invalid=int((st != 0).sum()))
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["2", "3", "4"]
+    which = sys.argv[1:] or ["ref", "2", "3", "4"]
+    if "ref" in which:
+        reference_workload()
     if "2" in which:
         config2_tiled_images()
     if "3" in which:
