@@ -399,11 +399,13 @@ __device__ double mcc_task_g8(const int* P, const int* px, const int* py, int n,
     }
     __syncwarp(gm);
     if (m < 2) return 0.0;
+    // d shares its array with v and e2 with w: step k writes d[k], e2[k] and uses v[r], w[r] for r > k only
+    // (tri(m) + 2m doubles per matrix instead of tri(m) + 4m: one more resident CTA per SM at Ng 26)
     double* M = ws;
     double* v = ws + m * (m + 1) / 2;
     double* w = v + m;
-    double* d = w + m;
-    double* e2 = d + m;
+    double* d = v;
+    double* e2 = w;
     for (int r = gl; r < m; r += 8) d[r] = radb_div(1.0, radb_sqrt((double)px[idx[r]]));
     __syncwarp(gm);
     for (int r = gl; r < m; r += 8) {

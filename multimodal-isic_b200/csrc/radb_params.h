@@ -211,7 +211,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     o = 0;
     p->g8_px = o; o += radb_align(ng * 4, 16);
     p->g8_idx = o; o += radb_align(ng, 16);
-    p->g8_mcc = o; o += radb_align(p->mcc_stride * 8, 16);
+    p->g8_mcc = o; o += radb_align((ng * (ng + 1) / 2 + 2 * ng) * 8, 16);  // M + (d | v) + (e2 | w), see mcc_task_g8
     p->g8_group_bytes = o;
     p->g8_smem_total = (RADB_NTM / 32) * 4 * p->g8_group_bytes;
     p->ml_doubles = 2 * ng + 16 > 32 ? 2 * ng + 16 : 32;  // >= RADB_LANE_MAX_OVF / 2 slots for the sorted overflow list
