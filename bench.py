@@ -266,10 +266,15 @@ def gpu_arm(args):
     h_out = torch.empty((B, F), dtype=torch.float64).pin_memory()
     h_st = torch.empty((B,), dtype=torch.int32).pin_memory()
 
+    e2e_dev = torch.empty((B, F), dtype=torch.float64, device=dev) if world > 1 else None
+    e2e_gathered = torch.empty((world * B, F), dtype=torch.float64, device=dev) if world > 1 else None
+
     def e2e_step():
-        ex.pipeline.run(h_img, h_msk, h_out, h_st)
+        # host buffers in, host rows out; N > 1: the rows THIS run produced are also kept on the device and
+        # all-gathered (the path's only collective), so every rank ends the step holding the e2e result
+        ex.pipeline.run(h_img, h_msk, h_out, h_st, device_out=e2e_dev)
         if world > 1:
-            dist.all_gather_into_tensor(gathered, out)  # same collective on the device-resident block
+            dist.all_gather_into_tensor(e2e_gathered, e2e_dev)
 
     for _ in range(2):
         e2e_step()
@@ -286,6 +291,35 @@ def gpu_arm(args):
         sampler.stop_flag.set()
         sampler.join(2)
     same = bool(torch.equal(h_out, out.cpu()))
+    # ---- N > 1: one step outside the timed region, checked end to end -- rank 0 receives every rank's input
+    # shard (broadcast), recomputes it on its own GPU and compares the gathered blocks bit for bit
+    # (/root/reference/RadiomicExtractor.py:63-65: the fan-out is order-preserving)
+    gather_ok = None
+    if world > 1:
+        step()
+        torch.cuda.synchronize()
+        ok = True
+        t_img, t_msk = torch.empty_like(imgs), torch.empty_like(masks)
+        t_out = torch.empty((B, F), dtype=torch.float64, device=dev)
+        for r in range(world):
+            if rank == r:
+                t_img.copy_(imgs)
+                t_msk.copy_(masks)
+            dist.broadcast(t_img, src=r)
+            dist.broadcast(t_msk, src=r)
+            if rank == 0:
+                ex.engine.extract_device(t_img, t_msk, t_out, status)
+                ok = ok and bool(torch.equal(gathered[r * B:(r + 1) * B].view(torch.int64), t_out.view(torch.int64)))
+                ok = ok and bool(torch.equal(e2e_gathered[r * B:(r + 1) * B].view(torch.int64), t_out.view(torch.int64)))
+        del t_img, t_msk, t_out
+        gather_ok = ok
+        ex.engine.extract_device(imgs, masks, out, status)  # restore this rank's status / rows
+        torch.cuda.synchronize()
+    # per-rank kernel time (the scaling tail: is it rank skew or the collective?)
+    rank_kms = torch.zeros(world, dtype=torch.float64, device=dev)
+    rank_kms[rank] = kms
+    if world > 1:
+        dist.all_reduce(rank_kms)
 
     alt = {}
     if not args.no_alt and world == 1:
@@ -353,6 +387,11 @@ def gpu_arm(args):
                     "masks": ("packed to 1 bit per pixel by %d host threads (radb_pack_mask_host), expanded on the device"
                               % ex.pipeline.pack_threads) if ex.pipeline.pack_masks else "uint8, as handed over"},
             "gpu_launches": int(launches),
+            "multi_gpu": None if world == 1 else {
+                "gathered_equals_single_gpu_rows": gather_ok,
+                "kernel_ms_per_rank": [round(float(x), 4) for x in rank_kms.cpu().tolist()],
+                "note": "gathered (device-resident step) and e2e_gathered (host-to-host step) compared bit for bit on rank 0 "
+                        "with a single-GPU recomputation of every rank's shard, outside the timed region"},
             "clocks": sampler.summary(),
             "invalid_rows": bad,
             "alt": alt,

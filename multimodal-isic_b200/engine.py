@@ -34,6 +34,7 @@ class Engine:
         self.F = self.lib.radb_feature_count(self._h)
         self.names = [self.lib.radb_feature_name(self._h, i).decode() for i in range(self.F)]
         self.max_ng = self.lib.radb_max_ng(self._h)
+        self.has_packed = hasattr(self.lib, "radb_extract_packed")
 
     def close(self):
         if getattr(self, "_h", None):
@@ -270,64 +271,82 @@ class HostPipeline:
     enables it when this process has at least 8 host cores to itself (``os.cpu_count() // LOCAL_WORLD_SIZE``):
     with eight ranks on one host the packing threads would only compete for the same memory bandwidth."""
 
-    def __init__(self, engine, chunk=8192, pack_masks=None, pack_threads=None, slots=6):
+    def __init__(self, engine, chunk=8192, pack_masks=None, pack_threads=None, slots=6, slot_bytes=128 << 20):
         import os
 
         self.engine = engine
         self.chunk = int(chunk)
+        self.slot_bytes = int(slot_bytes)  # pinned / device bytes of one image buffer of one slot, at most
         self.slots = max(2, int(slots))  # chunks in flight: the host packs / enqueues ahead of the device
         self._bufs = None
         self._key = None
         self._pool = None
+        self._n = 0  # patches per slot of the current buffers
         cores = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
-        self.pack_threads = int(pack_threads) if pack_threads else min(cores, 8)  # memory bound beyond ~8 threads
-        self.pack_masks = bool(pack_masks) if pack_masks is not None else cores >= 8
+        # packing is memory bound beyond ~8 threads; a rank that shares the host with others keeps 2-4 threads
+        self.pack_threads = int(pack_threads) if pack_threads else max(2, min(cores, 8))
+        self.pack_masks = bool(pack_masks) if pack_masks is not None else True
         self.h2d_bytes = 0  # bytes copied host -> device by the last run()
 
-    def _ensure(self, H, W, dtype=torch.uint8):
+    def slot_patches(self, B, H, W, itemsize):
+        """Patches per slot: the chunk size, capped by the batch and by ``slot_bytes`` per image buffer, so that a
+        ten-image call at the reference's 600x450 size pins ~10 images, not 8192 of them."""
+        n = min(self.chunk, max(1, int(B)), max(1, self.slot_bytes // (H * W * itemsize)))
+        return max(1, n)
+
+    def _ensure(self, n, H, W, dtype=torch.uint8):
         key = (H, W, dtype)
-        if self._key == key:
+        if self._key == key and self._n >= n:
             return
         dev = torch.device("cuda", self.engine.device)
-        n, F = self.chunk, self.engine.F
-        self._bufs = []
+        F = self.engine.F
+        self._bufs = None  # release the previous buffers first
+        bufs = []
         for _ in range(self.slots):
-            self._bufs.append(dict(
+            bufs.append(dict(
                 h_img=torch.empty((n, H, W), dtype=dtype).pin_memory(),
                 h_msk=torch.empty((n, H, W), dtype=torch.uint8).pin_memory(),
                 d_img=torch.empty((n, H, W), dtype=dtype, device=dev),
-                d_msk=torch.empty((n, H, W), dtype=torch.uint8, device=dev),
-                h_pk=torch.empty(((n * H * W + 7) // 8,), dtype=torch.uint8).pin_memory(),
-                d_pk=torch.empty(((n * H * W + 7) // 8,), dtype=torch.uint8, device=dev),
+                h_pk=torch.empty(((n * H * W + 7) // 8 + 16,), dtype=torch.uint8).pin_memory(),
+                d_pk=torch.empty(((n * H * W + 7) // 8 + 16,), dtype=torch.uint8, device=dev),
+                d_msk=None,
                 d_out=torch.empty((n, F), dtype=torch.float64, device=dev),
                 d_st=torch.empty((n,), dtype=torch.int32, device=dev),
                 stream=torch.cuda.Stream(dev), done=torch.cuda.Event()))
+        self._bufs = bufs
         self._key = key
+        self._n = n
 
-    def run(self, images, masks, out=None, status=None):
+    def run(self, images, masks, out=None, status=None, device_out=None):
         """``images``/``masks``: host arrays [B, H, W] (images uint8/uint16/float32/float64, masks uint8; NumPy or CPU tensors; pinned tensors
-        skip the staging copy).  Returns host ``(features [B, F] float64, status [B] int32)``."""
+        skip the staging copy).  Returns host ``(features [B, F] float64, status [B] int32)``.  ``device_out``
+        (optional ``[B, F]`` float64 CUDA tensor) also keeps the rows on the device -- the multi-GPU driver
+        all-gathers them from there."""
         images = torch.as_tensor(images)
         masks = torch.as_tensor(masks)
         if images.is_cuda:
             raise ValueError("HostPipeline takes host buffers; use Engine.extract_device for device tensors")
         B, H, W = images.shape
         F = self.engine.F
-        self._ensure(H, W, images.dtype)
+        chunk = self.slot_patches(B, H, W, images.element_size())
+        self._ensure(chunk, H, W, images.dtype)
         if out is None:
             out = torch.empty((B, F), dtype=torch.float64).pin_memory()
         if status is None:
             status = torch.empty((B,), dtype=torch.int32).pin_memory()
         pinned_in = images.is_pinned() and masks.is_pinned()
-        pack = self.pack_masks and masks.dtype == torch.uint8 and masks.is_contiguous()
+        # masks cross the link at 1 bit per pixel and are consumed packed by the kernels (radb_extract_packed);
+        # patches whose pixel count is not a multiple of 128 bits keep the byte masks (16-byte aligned bit rows)
+        pack = self.pack_masks and masks.dtype == torch.uint8 and masks.is_contiguous() and (H * W) % 128 == 0
         self.h2d_bytes = 0
-        starts = list(range(0, B, self.chunk))
+        starts = list(range(0, B, chunk))
+        dev = torch.device("cuda", self.engine.device)
 
         def prepare(k):
             """Host work of chunk k, one chunk ahead of the enqueue loop on a helper thread: wait until the
             slot has drained, then pack the masks (the C call releases the GIL and fans out to pack_threads)."""
             s0 = starts[k]
-            n0 = min(self.chunk, B - s0)
+            n0 = min(chunk, B - s0)
             bk = self._bufs[k % self.slots]
             bk["done"].synchronize()
             if pack:
@@ -339,12 +358,13 @@ class HostPipeline:
             self._pool = ThreadPoolExecutor(1)
         fut = self._pool.submit(prepare, 0) if starts else None
         for k, s in enumerate(starts):
-            n = min(self.chunk, B - s)
+            n = min(chunk, B - s)
             b = self._bufs[k % self.slots]
             fut.result()
             if k + 1 < len(starts):
                 fut = self._pool.submit(prepare, k + 1)
-            nb = (n * H * W + 7) // 8
+            nb = n * H * W // 8
+            d_out = device_out[s:s + n] if device_out is not None else b["d_out"][:n]
             with torch.cuda.stream(b["stream"]):
                 if pinned_in:
                     b["d_img"][:n].copy_(images[s:s + n], non_blocking=True)
@@ -353,16 +373,25 @@ class HostPipeline:
                     b["d_img"][:n].copy_(b["h_img"][:n], non_blocking=True)
                 if pack:
                     b["d_pk"][:nb].copy_(b["h_pk"][:nb], non_blocking=True)
-                    self.engine.unpack_mask(b["d_pk"], b["d_msk"][:n], stream=b["stream"])
-                elif pinned_in:
-                    b["d_msk"][:n].copy_(masks[s:s + n], non_blocking=True)
+                    self.h2d_bytes += n * H * W * images.element_size() + nb
+                    if self.engine.has_packed:
+                        self.engine.extract_packed(b["d_img"][:n], b["d_pk"], d_out, b["d_st"][:n], stream=b["stream"])
+                    else:  # library without radb_extract_packed: expand on the device first
+                        if b["d_msk"] is None or b["d_msk"].shape[0] < n:
+                            b["d_msk"] = torch.empty((self._n, H, W), dtype=torch.uint8, device=dev)
+                        self.engine.unpack_mask(b["d_pk"], b["d_msk"][:n], stream=b["stream"])
+                        self.engine.extract_device(b["d_img"][:n], b["d_msk"][:n], d_out, b["d_st"][:n], stream=b["stream"])
                 else:
-                    b["h_msk"][:n].copy_(masks[s:s + n])
-                    b["d_msk"][:n].copy_(b["h_msk"][:n], non_blocking=True)
-                self.h2d_bytes += n * H * W * images.element_size() + (nb if pack else n * H * W)
-                self.engine.extract_device(b["d_img"][:n], b["d_msk"][:n], b["d_out"][:n], b["d_st"][:n],
-                                           stream=b["stream"])
-                out[s:s + n].copy_(b["d_out"][:n], non_blocking=True)
+                    if b["d_msk"] is None or b["d_msk"].shape[0] < n:
+                        b["d_msk"] = torch.empty((self._n, H, W), dtype=torch.uint8, device=dev)
+                    if pinned_in:
+                        b["d_msk"][:n].copy_(masks[s:s + n], non_blocking=True)
+                    else:
+                        b["h_msk"][:n].copy_(masks[s:s + n])
+                        b["d_msk"][:n].copy_(b["h_msk"][:n], non_blocking=True)
+                    self.h2d_bytes += n * H * W * images.element_size() + n * H * W
+                    self.engine.extract_device(b["d_img"][:n], b["d_msk"][:n], d_out, b["d_st"][:n], stream=b["stream"])
+                out[s:s + n].copy_(d_out, non_blocking=True)
                 status[s:s + n].copy_(b["d_st"][:n], non_blocking=True)
                 b["done"].record(b["stream"])
         for b in self._bufs:

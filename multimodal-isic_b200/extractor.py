@@ -35,12 +35,20 @@ class RadiomicsExtractor:
 
     ``param_file`` is the pyradiomics YAML path the reference passes (``'params.yml'``) or the
     equivalent dict.  Extra keyword-only arguments are B200-side knobs: ``device`` (CUDA
-    ordinal), ``strict`` (raise instead of warn for enabled-but-unimplemented image types /
-    classes), ``chunk`` (patches per pipelined H2D chunk), ``max_ng``."""
+    ordinal), ``strict`` (default True: enabled-but-unimplemented image types / classes raise
+    ``NotImplementedError``; False: they are logged at ERROR level, skipped and listed in
+    ``skipped_image_types``), ``chunk`` (patches per pipelined H2D chunk), ``max_ng``."""
 
-    def __init__(self, param_file, *, device=0, strict=False, chunk=8192, max_ng=0, **setting_overrides):
+    def __init__(self, param_file, *, device=0, strict=True, chunk=8192, max_ng=0, **setting_overrides):
         self.params = Settings(param_file, strict=strict, **setting_overrides)
+        self.skipped_image_types = list(self.params.skipped_image_types)
         self.device = int(device)
+        # U1 (oracle/U1_ANGLES.md): say which angle reading is in effect -- the literal one for the reference's
+        # own file (2-D arrays + force2D: True -> one along-row offset) is the unverified one
+        ang = self.params.angles(2)
+        self.angle_reading = ("literal force2D on a 2-D array: %d offset(s) %s" % (len(ang), ang)
+                              if self.params.settings["force2D"] else "in-plane: %d offsets %s" % (len(ang), ang))
+        logger.warning("radb angle semantics: %s (see oracle/U1_ANGLES.md)", self.angle_reading)
         eng_classes, self._perm = self.params.engine_columns()
         s = self.params.settings
         bc = self.params.bin_count

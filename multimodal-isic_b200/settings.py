@@ -4,12 +4,15 @@
 CUDA engine needs."""
 from __future__ import annotations
 
+import logging
 import warnings
 from collections import OrderedDict
 
 import yaml
 
 from ._abi import CLASS_ORDER
+
+logger = logging.getLogger(__name__)
 
 # pyradiomics defaults (featureextractor._getDefaultSettings / per-class kwargs.get defaults)
 DEFAULTS = OrderedDict(
@@ -52,7 +55,7 @@ SUPPORTED_IMAGE_TYPES = {"Original", "Square", "SquareRoot", "Logarithm", "Expon
 IMAGE_TYPE_CODES = {"Square": 1, "SquareRoot": 2, "Logarithm": 3, "Exponential": 4}  # radb_derive_image
 # settings whose non-default value would change results and that the engine does not implement
 _UNSUPPORTED_IF_SET = ("normalize", "removeOutliers", "resampledPixelSpacing", "resegmentRange", "weightingNorm",
-                       "minimumROISize")
+                       "minimumROISize", "preCrop")
 
 
 def in_plane_angles(ndim=2, distances=(1,), force2D=False, force2Ddimension=0):
@@ -88,7 +91,11 @@ def in_plane_angles(ndim=2, distances=(1,), force2D=False, force2Ddimension=0):
 class Settings:
     """Resolved settings + enabled image types / feature classes (file order preserved)."""
 
-    def __init__(self, params=None, strict=False, **overrides):
+    def __init__(self, params=None, strict=True, **overrides):
+        """``strict`` (default): an enabled image type or feature class this engine does not implement raises
+        ``NotImplementedError`` naming it -- a drop-in must not silently emit a narrower column set (the
+        reference's driver silences warnings, extract_radiomics.py:13-19).  ``strict=False`` logs at ERROR level,
+        warns, skips them and lists them in ``skipped_image_types`` / ``skipped_classes``."""
         if params is None:
             params = {}
         if isinstance(params, (str, bytes)) or hasattr(params, "__fspath__"):
@@ -98,9 +105,11 @@ class Settings:
             raise TypeError("param_file must be a path or a dict")
         if not any(k in params for k in ("setting", "imageType", "featureClass")):
             params = {"setting": dict(params)}  # a bare settings dict
+        given = dict(params.get("setting") or {})
+        given.update(overrides)
         self.settings = OrderedDict(DEFAULTS)
-        self.settings.update(params.get("setting") or {})
-        self.settings.update(overrides)
+        self.settings.update(given)
+        self._given = given
         # pyradiomics: no imageType section -> Original only; no featureClass section -> all classes
         image_types = params.get("imageType")
         self.enabledImagetypes = OrderedDict((k, v or {}) for k, v in (image_types or {"Original": {}}).items())
@@ -109,11 +118,14 @@ class Settings:
             feature_class = OrderedDict((c, []) for c in ("firstorder", "glcm", "gldm", "glrlm", "glszm", "ngtdm"))
         self.enabledFeatures = OrderedDict((k, list(v) if v else []) for k, v in feature_class.items())
         self.strict = strict
+        self.skipped_image_types = []
+        self.skipped_classes = []
         self._validate()
 
     def _complain(self, msg):
         if self.strict:
-            raise NotImplementedError(msg)
+            raise NotImplementedError(msg + " (pass strict=False to skip them explicitly)")
+        logger.error(msg)
         warnings.warn(msg, RuntimeWarning, stacklevel=4)
 
     def _validate(self):
@@ -121,25 +133,30 @@ class Settings:
         for k in _UNSUPPORTED_IF_SET:
             if s.get(k) not in (None, False):
                 raise NotImplementedError("setting %r=%r is not implemented by the B200 engine" % (k, s[k]))
+        if int(s.get("minimumROIDimensions", 2)) != 2:
+            # the kernels hard-code pyradiomics' default (ROI must span both axes: status 3 otherwise)
+            raise NotImplementedError("minimumROIDimensions=%r is not implemented (only the default 2)" % s["minimumROIDimensions"])
+        if self._given.get("additionalInfo") is True:
+            # pyradiomics would add non-numeric diagnostics_* keys; the reference switches them off (params.yml:62)
+            raise NotImplementedError("additionalInfo: True (diagnostics_* keys) is not implemented; the reference sets it False")
         if not float(s["binWidth"]) > 0:
             raise ValueError("binWidth must be > 0")
         if s.get("binCount") is not None and not (1 <= int(s["binCount"]) <= 256):
             raise NotImplementedError("binCount must be 1..256")
         skipped_types = [t for t in self.enabledImagetypes if t not in SUPPORTED_IMAGE_TYPES]
         if skipped_types:
-            self._complain("image types %s are not implemented yet and are skipped" % skipped_types)
+            self._complain("image types %s are enabled but not implemented by the B200 engine" % skipped_types)
+        self.skipped_image_types = skipped_types
         self.image_types = [t for t in self.enabledImagetypes if t in SUPPORTED_IMAGE_TYPES]
         if not self.image_types:
             raise NotImplementedError("no implemented image type is enabled")
         skipped_cls = [c for c in self.enabledFeatures if c not in SUPPORTED_CLASSES]
         if skipped_cls:
-            self._complain("feature classes %s are not implemented yet and are skipped" % skipped_cls)
+            self._complain("feature classes %s are enabled but not implemented by the B200 engine" % skipped_cls)
+        self.skipped_classes = skipped_cls
         self.classes = [c for c in self.enabledFeatures if c in SUPPORTED_CLASSES]
-        if "shape2D" in self.classes and not s.get("force2D", False):
-            # pyradiomics featureextractor.computeShape: shape2D is only extracted with force2D
-            warnings.warn("parameter force2D must be set to True to enable shape2D extraction", RuntimeWarning,
-                          stacklevel=4)
-            self.classes.remove("shape2D")
+        # pyradiomics featureextractor.computeShape: the "force2D must be True" rule belongs to 3-D input; the
+        # reference passes 2-D images (RadiomicExtractor.py:31,36), for which shape2D is computed regardless
         if not self.classes:
             raise ValueError("no implemented feature class is enabled")
         for c in self.classes:

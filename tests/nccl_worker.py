@@ -1,0 +1,96 @@
+"""torchrun worker of tests/test_gpu_multi.py: the patch-sharded multi-GPU data plane on REAL engines over NCCL.
+
+The reference fans records over a process pool and gets the results back IN ORDER
+(/root/reference/RadiomicExtractor.py:60-65: ``pool.imap``).  Here every rank extracts its shard on its own
+GPU and the rows are all-gathered; this worker checks, on every rank, that the gathered matrix equals the
+rows one GPU computes for the whole list (bit for bit), for both drivers:
+
+* ``OverlappedGather`` (equal shards, sliced, the all-gather of slice k under the extraction of slice k+1:
+  what ``bench.py --gpus N`` runs), and
+* ``sharded_extract`` (cost-balanced contiguous shards of unequal length, padded all-gather).
+
+plus 16 rows spot-checked against the oracle on rank 0.  Prints ``NCCL_WORKER_OK`` per rank.
+Launch:  python -m torch.distributed.run --nproc-per-node 2 --master-addr 127.0.0.1 --master-port P tests/nccl_worker.py
+"""
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+import torch  # noqa: E402
+import torch.distributed as dist  # noqa: E402
+
+import multimodal_isic_b200 as pkg  # noqa: E402
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    dist.init_process_group("nccl", device_id=dev)
+    settings = {"label": 255, "binWidth": 25, "force2D": False}
+    ex = pkg.RadiomicsExtractor({"setting": settings}, device=local)
+    F = ex.engine.F
+
+    # ---- the whole list (every rank builds the same one from the same seed, on the host)
+    rows = 1536  # per rank
+    n = world * rows
+    imgs, masks = pkg.synth.make_patches(256, 64, seed=11)
+    reps = (n + 255) // 256
+    rng = np.random.default_rng(5)
+    order = rng.permutation(256 * reps)[:n]
+    imgs = np.tile(imgs, (reps, 1, 1))[order]
+    masks = np.tile(masks, (reps, 1, 1))[order]
+    # unequal costs: shrink the ROI of the second half of the list (cheaper patches at the end)
+    masks[n // 2:, :24] = 0
+    d_img, d_msk = torch.as_tensor(imgs).to(dev), torch.as_tensor(masks).to(dev)
+    want, want_st = ex.engine.extract_device(d_img, d_msk)  # one GPU, the whole list
+    torch.cuda.synchronize()
+
+    # ---- 1. OverlappedGather: equal shards, sliced, overlapped all-gather
+    for pieces in (1, 2, 4):
+        lo = rank * rows
+        out = torch.zeros((rows, F), dtype=torch.float64, device=dev)
+        status = torch.zeros((rows,), dtype=torch.int32, device=dev)
+        gathered = torch.zeros((n, F), dtype=torch.float64, device=dev)
+        og = pkg.OverlappedGather(rows, F, world, dev, pieces=pieces)
+
+        def extract_slice(a, b, o, s):
+            ex.engine.extract_device(d_img[lo + a:lo + b], d_msk[lo + a:lo + b], o, s)
+
+        for _ in range(2):  # twice: buffer re-use across steps
+            og.run(extract_slice, out, status, gathered)
+        torch.cuda.synchronize()
+        assert torch.equal(gathered.view(torch.int64), want.view(torch.int64)), "OverlappedGather(pieces=%d) rows differ" % pieces
+
+    # ---- 2. sharded_extract: cost-balanced shards of unequal length
+    costs = (masks == 255).reshape(n, -1).sum(1).astype(np.float64)
+
+    def extract_fn(a, b):
+        return ex.engine.extract_device(d_img[a:b], d_msk[a:b])
+
+    full, st, bounds = pkg.sharded_extract(extract_fn, n, costs)
+    torch.cuda.synchronize()
+    lens = [bounds[r + 1] - bounds[r] for r in range(world)]
+    assert len(set(lens)) > 1, "the cost model should give unequal shards: %s" % lens
+    assert torch.equal(full.view(torch.int64), want.view(torch.int64)), "sharded_extract rows differ"
+    assert torch.equal(st, want_st)
+
+    # ---- 3. oracle spot checks (rank 0): 16 rows of the gathered matrix
+    if rank == 0:
+        from oracle import cmatrices, radiomics_oracle as orc
+
+        cmatrices.build()
+        got = full.cpu().numpy()
+        for b in np.linspace(0, n - 1, 16).astype(int):
+            ref = np.array(list(orc.execute(imgs[b], masks[b], settings, matrix_backend=cmatrices).values()))
+            np.testing.assert_allclose(got[b], ref, rtol=1e-6, atol=1e-9)
+    dist.barrier()
+    print("NCCL_WORKER_OK rank %d/%d shards %s" % (rank, world, lens), flush=True)
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -74,7 +74,7 @@ def test_settings_reference_like_file(tmp_path):
     f.write_text(REFERENCE_LIKE_PARAMS)
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
-        s = pkg.Settings(str(f))
+        s = pkg.Settings(str(f), strict=False)
     assert any("Wavelet" in str(x.message) for x in w)
     assert s.label == 255 and s.bin_width == 10.0
     assert s.angles() == orc.angles(2, force2D=True)[0] == [(0, 1)]          # literal force2D on 2-D input
@@ -83,7 +83,7 @@ def test_settings_reference_like_file(tmp_path):
     # 102 = 9 shape2D + 93 (dataset.py:42), shape keys first
     assert s.feature_names() == orc.feature_names(("shape2D",) + orc.CLASS_ORDER) and len(s.feature_names()) == 102
     with pytest.raises(NotImplementedError):
-        pkg.Settings(str(f), strict=True)
+        pkg.Settings(str(f))  # strict is the default: a drop-in must not silently narrow the column set
 
 
 def test_settings_class_order_and_feature_subset():
@@ -108,12 +108,29 @@ def test_feature_name_tables_agree():
     assert pkg.FEATURE_NAMES["shape2D"] == orc.SHAPE2D_NAMES
 
 
-def test_shape2d_needs_force2d():
-    with pytest.warns(RuntimeWarning, match="force2D must be set"):
-        s = pkg.Settings({"setting": {"force2D": False}, "featureClass": {"shape2D": [], "glcm": []}})
-    assert s.classes == ["glcm"]
+def test_shape2d_on_2d_input_does_not_need_force2d():
+    # pyradiomics featureextractor.computeShape: the force2D rule belongs to 3-D input; 2-D input (what the
+    # reference passes, RadiomicExtractor.py:31,36) computes shape2D regardless
+    s = pkg.Settings({"setting": {"force2D": False}, "featureClass": {"shape2D": [], "glcm": []}})
+    assert s.classes == ["shape2D", "glcm"]
     s = pkg.Settings({"setting": {"force2D": True}, "featureClass": {"glcm": [], "shape2D": ["Perimeter"]}})
     assert s.feature_names()[0] == "original_shape2D_Perimeter" and s.engine_columns()[0] == ["shape2D", "glcm"]
+
+
+def test_result_affecting_settings_are_rejected_not_ignored():
+    for bad in ({"minimumROIDimensions": 1}, {"preCrop": True}, {"additionalInfo": True}, {"normalize": True}):
+        with pytest.raises(NotImplementedError):
+            pkg.Settings({"setting": bad})
+    pkg.Settings({"setting": {"minimumROIDimensions": 2, "preCrop": False, "additionalInfo": False}})
+
+
+def test_unimplemented_image_types_raise_by_default():
+    cfg = {"imageType": {"Original": {}, "LBP2D": {}}, "setting": {"label": 255}}
+    with pytest.raises(NotImplementedError, match="LBP2D"):
+        pkg.Settings(cfg)
+    with pytest.warns(RuntimeWarning, match="LBP2D"):
+        s = pkg.Settings(cfg, strict=False)
+    assert s.skipped_image_types == ["LBP2D"] and s.image_types == ["Original"]
 
 
 def test_shard_bounds():
@@ -143,7 +160,7 @@ def test_settings_derived_image_types():
     p = yaml.safe_load(REFERENCE_LIKE_PARAMS)
     p["imageType"].update({"Square": {}, "SquareRoot": {}, "Logarithm": {}, "Exponential": {}, "Gradient": {}})
     with pytest.warns(RuntimeWarning, match="Wavelet"):
-        s = pkg.Settings(p)
+        s = pkg.Settings(p, strict=False)
     assert s.image_types == ["Original", "Square", "SquareRoot", "Logarithm", "Exponential"]
     names = s.feature_names()
     assert len(names) == 102 + 4 * 93                      # shape once, one 93-block per image type
@@ -231,7 +248,7 @@ def test_settings_parse_the_reference_parameter_file():
         pytest.skip("reference checkout not present")
     with warnings.catch_warnings(record=True) as w:
         warnings.simplefilter("always")
-        s = pkg.Settings(path)
+        s = pkg.Settings(path, strict=False)
     assert s.label == 255 and s.bin_width == 10.0 and s.bin_count == 0 and s.angles() == [(0, 1)]
     assert list(s.enabledImagetypes) == ["Original", "Wavelet", "LoG", "Square", "SquareRoot", "Logarithm", "Exponential", "Gradient"]
     assert s.image_types == ["Original", "Square", "SquareRoot", "Logarithm", "Exponential"]
