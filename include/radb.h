@@ -135,6 +135,16 @@ int radb_extract_bgr(radb_handle* h, const uint8_t* bgr, const uint8_t* mask, in
  * instead of n_bytes, and expand it on the device with radb_unpack_mask (DEVICE pointers, stream-ordered;
  * `mask` gets `label` where the bit is set and a different value elsewhere) before radb_extract. */
 int radb_pack_mask_host(const uint8_t* mask, int64_t n_bytes, int label, uint8_t* packed, int threads);
+
+/* radb_extract with bit-packed masks consumed directly by the kernels (no expansion pass, 1/8 of the mask bytes in
+ * HBM and over the link): per patch ceil(H*W/8) bytes, bit i (LSB first) <=> pixel i is in the ROI, i.e. what
+ * `mask == label` gives at RadiomicExtractor.py:38; `mask_stride_b` = bytes between the bit streams of consecutive
+ * patches (>= ceil(H*W/8); 16-byte multiples keep the TMA staging path).  radb_pack_mask_host over a contiguous
+ * [B][H][W] mask buffer produces exactly this layout when H*W is a multiple of 8 (stride H*W/8). */
+int radb_pack_masks_host(const uint8_t* mask, int64_t n_patches, int64_t hw, int label, uint8_t* packed,
+                         int64_t stride_b, int threads); /* per-patch streams at `stride_b` bytes: any H*W (HOST pointers) */
+int radb_extract_packed(radb_handle* h, const void* img, int dtype, const uint8_t* mask_bits, int64_t B, int H, int W,
+                        int64_t img_stride_b, int64_t mask_stride_b, double* out, int32_t* status, void* cuda_stream);
 int radb_unpack_mask(radb_handle* h, const uint8_t* packed, int64_t n_bytes, uint8_t* mask, void* cuda_stream);
 
 /* imageType filters of the parameter file (params.yml:141-144; pyradiomics imageoperations.getSquareImage,
@@ -143,6 +153,18 @@ int radb_unpack_mask(radb_handle* h, const uint8_t* packed, int64_t n_bytes, uin
  * (feed it to radb_extract with RADB_DTYPE_F64); mx = int32 [n] device scratch. */
 int radb_derive_image(radb_handle* h, const uint8_t* img, int64_t n_images, int64_t HW, int type, double* out,
                       int32_t* mx, void* cuda_stream);
+
+/* Filtered image types of the parameter file (params.yml:138-140,145; pyradiomics imageoperations.getGradientImage ->
+ * sitk.GradientMagnitude, getLoGImage -> sitk.LaplacianRecursiveGaussian with NormalizeAcrossScale, getWaveletImage
+ * -> level-1 stationary coif1 transform) for uint8 images [n][H][W]; DEVICE pointers, stream-ordered:
+ *   type 5 Gradient          -> out float32 [n][H][W]                                  (scratch may be null)
+ *   type 6 LoG, param=sigma  -> out float32 [n][H][W]; scratch >= n*H*W*12 bytes       (H, W >= 4)
+ *   type 7 Wavelet: flags bit 0 set = transform along x only (pyradiomics' axis removal for force2D on a 2-D
+ *                   array) -> out float64 [n][2][H][W] = wavelet-H, wavelet-L; flags 0 -> out float64 [n][4][H][W]
+ *                   = wavelet-LH, -HL, -HH, -LL (first letter <-> x); scratch >= n*2*(H+1)*(W+1)*8 bytes
+ * Feed the result to radb_extract with RADB_DTYPE_F32 / RADB_DTYPE_F64. */
+int radb_filter_image(radb_handle* h, const uint8_t* img, int64_t n_images, int H, int W, int type, double param,
+                      int flags, void* out, void* scratch, void* cuda_stream);
 
 /* Same launch as radb_extract, additionally dumping the discretised image and the integer
  * texture matrices the features were reduced from (what pyradiomics' cMatrices.calculate_*

@@ -44,6 +44,22 @@ struct radb_handle {
     std::vector<cudaEvent_t> events;  // 4 per chunk: start, after build, after angle, after misc
 };
 
+// Every entry point that launches work selects the handle's device and restores the caller's on return
+// (a multi-GPU process must not find its current device changed by a library call).
+struct DeviceGuard {
+    int prev;
+    bool switched;
+    explicit DeviceGuard(int dev) : prev(-1), switched(false)
+    {
+        cudaGetDevice(&prev);
+        if (prev != dev) switched = cudaSetDevice(dev) == cudaSuccess;
+    }
+    ~DeviceGuard()
+    {
+        if (switched && prev >= 0) cudaSetDevice(prev);
+    }
+};
+
 static int fail(int code, const std::string& msg)
 {
     g_err = msg;
@@ -120,7 +136,9 @@ extern "C" void radb_destroy(radb_handle* h)
 static int64_t chunk_for(const radb_handle* h, const RadbParams& p, int64_t B)
 {
     const size_t per = (size_t)p.rec_bytes + (size_t)p.scr_bytes;
-    int64_t n = (int64_t)(((size_t)1 << 30) / per);  // <= 1 GiB
+    // <= 1 GiB of records per slot; 4 GiB when a record is large (many gray levels: 1 MB per patch at 256 levels),
+    // so that a chunk still fills the 148 SMs several times over
+    int64_t n = (int64_t)(((size_t)(per > (256u << 10) ? 4 : 1) << 30) / per);
     const int64_t want = h->chunk > 0 ? h->chunk : RADB_CHUNK;
     if (n > want) n = want;
     n -= n % 4;  // keeps the 4 planes of an image (shared mask) in one chunk
@@ -165,13 +183,9 @@ extern "C" int radb_reserve(radb_handle* h, int H, int W, int dtype, int64_t max
     std::string err;
     int rc = radb::fill_params(h->plan, H, W, dtype, p, err);
     if (rc) return fail(rc, err);
-    int cur = -1;
-    cudaGetDevice(&cur);
-    if (cur != h->device) cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     unsigned char* unused = nullptr;
-    rc = ensure_ws(h, p, max_batch, cuda_stream, &unused);
-    if (cur >= 0 && cur != h->device) cudaSetDevice(cur);
-    return rc;
+    return ensure_ws(h, p, max_batch, cuda_stream, &unused);
 }
 extern "C" int radb_feature_count(const radb_handle* h) { return h ? h->plan.F : RADB_E_INVALID; }
 extern "C" const char* radb_feature_name(const radb_handle* h, int i)
@@ -209,12 +223,7 @@ static int set_smem(radb_handle* h, K kernel, int which, int bytes)
 static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
 {
     cudaError_t e;
-    int cur = -1;
-    cudaGetDevice(&cur);
-    if (cur != h->device) {
-        e = cudaSetDevice(h->device);
-        if (e != cudaSuccess) return cuda_fail(e, "cudaSetDevice");
-    }
+    DeviceGuard guard(h->device);
     const bool dbg = p.dbg_levels || p.dbg_glcm || p.dbg_glrlm || p.dbg_glszm || p.dbg_gldm || p.dbg_ng;
     typedef void (*build_fn)(const RadbParams);
     build_fn build = nullptr;
@@ -236,6 +245,8 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     if (no_lane) p.use_lane = 0;
     if (!rc) rc = p.use_lane ? set_smem(h, radb_angle_lane_kernel, 3, p.l_smem_total) : set_smem(h, radb_angle_kernel, 1, p.a_smem_total);
     if (!rc && p.use_lane == 2) rc = set_smem(h, radb_mcc_g8_kernel, 5, p.g8_smem_total);
+    if (p.use_lane) p.use_lanczos = 0;  // (RADB_NO_LANE forces the warp-per-angle kernel; its layout was made for Lanczos or dense)
+    if (!rc && p.use_lanczos) rc = set_smem(h, radb_mcc_lanczos_kernel, 6, p.z_smem_total);
     if (!rc && p.off_shape >= 0) rc = set_smem(h, radb_shape_kernel, 8, p.s_smem_total);
     if (!rc) rc = set_smem(h, radb_misc_kernel, 2, p.m_smem_total);
     p.only_big_ovf = (!no_lane && p.ml_smem_total <= 96 * 1024) ? 1 : 0;
@@ -320,6 +331,10 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
             radb_mcc_g8_kernel<<<(unsigned)((n + RADB_NTM / 32 - 1) / (RADB_NTM / 32)), RADB_NTM, p.g8_smem_total, rs>>>(q);
             h->launches += 1;
         }
+        if (p.use_lanczos && p.off_glcm >= 0) {
+            radb_mcc_lanczos_kernel<<<(unsigned)(n * p.n_angles), RADB_NTZ, p.z_smem_total, rs>>>(q);
+            h->launches += 1;
+        }
         if (p.use_lane)
             radb_angle_lane_kernel<<<(unsigned)((n * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, p.l_smem_total, rs>>>(q);
         else
@@ -346,15 +361,17 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
 }
 
 static int setup(radb_handle* h, const void* img, int dtype, const uint8_t* mask, int64_t B, int H, int W,
-                 int64_t img_stride_b, int64_t mask_stride_b, double* out, int32_t* status, RadbParams& p)
+                 int64_t img_stride_b, int64_t mask_stride_b, double* out, int32_t* status, RadbParams& p, int mask_bits = 0)
 {
     if (!h || !img || !mask || !out || !status) return fail(RADB_E_INVALID, "null argument");
     if (B < 0) return fail(RADB_E_INVALID, "negative batch size");
     std::string err;
     int rc = radb::fill_params(h->plan, H, W, dtype, p, err);
     if (rc) return fail(rc, err);
-    if (img_stride_b < (int64_t)H * W * p.pix_bytes || mask_stride_b < (int64_t)H * W)
+    const int64_t mask_bytes = mask_bits ? ((int64_t)H * W + 7) / 8 : (int64_t)H * W;
+    if (img_stride_b < (int64_t)H * W * p.pix_bytes || mask_stride_b < mask_bytes)
         return fail(RADB_E_INVALID, "patch stride smaller than the patch");
+    p.mask_bits = mask_bits ? 1 : 0;
     p.img = img;
     p.mask = mask;
     p.img_stride = img_stride_b;
@@ -364,7 +381,7 @@ static int setup(radb_handle* h, const void* img, int dtype, const uint8_t* mask
     p.B = B;
     // TMA bulk copies need 16-byte aligned sources and sizes
     p.use_tma = !p.wide && ((uintptr_t)img % 16 == 0) && ((uintptr_t)mask % 16 == 0) && (img_stride_b % 16 == 0) &&
-                (mask_stride_b % 16 == 0) && (p.HW % 16 == 0) && (img_stride_b % p.pix_bytes == 0);
+                (mask_stride_b % 16 == 0) && (p.HW % 16 == 0) && (mask_bytes % 16 == 0) && (img_stride_b % p.pix_bytes == 0);
     return RADB_OK;
 }
 
@@ -374,6 +391,21 @@ extern "C" int radb_extract(radb_handle* h, const void* img, int dtype, const ui
 {
     RadbParams p;
     int rc = setup(h, img, dtype, mask, B, H, W, img_stride_b, mask_stride_b, out, status, p);
+    if (rc) return rc;
+    if (B == 0) return RADB_OK;
+    return launch(h, p, dtype, cuda_stream);
+}
+
+// Same as radb_extract with bit-packed masks: `mask_bits` holds, per patch, ceil(H*W/8) bytes whose bit i (LSB
+// first) says whether pixel i belongs to the ROI (what `mask == label` would give, RadiomicExtractor.py:38);
+// `mask_stride_b` = bytes between the streams of consecutive patches.  The kernels read the bits directly: a mask
+// crosses the host link and HBM at 1/8 of the bytes (radb_pack_masks_host produces this layout).
+extern "C" int radb_extract_packed(radb_handle* h, const void* img, int dtype, const uint8_t* mask_bits, int64_t B, int H,
+                                   int W, int64_t img_stride_b, int64_t mask_stride_b, double* out, int32_t* status,
+                                   void* cuda_stream)
+{
+    RadbParams p;
+    int rc = setup(h, img, dtype, mask_bits, B, H, W, img_stride_b, mask_stride_b, out, status, p, 1);
     if (rc) return rc;
     if (B == 0) return RADB_OK;
     return launch(h, p, dtype, cuda_stream);
@@ -393,9 +425,7 @@ extern "C" int radb_extract_ragged(radb_handle* h, const void* img_pool, int dty
     std::string err;
     int rc = radb::group_ragged(n, hw, groups, err);
     if (rc) return fail(rc, err);
-    int cur = -1;
-    cudaGetDevice(&cur);
-    if (cur != h->device) cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     // device copy of the index lists: [img_off | mask_off | rows] per group, group after group
     radb_handle::Ws* w = nullptr;
     for (auto& e : h->ws)
@@ -523,9 +553,7 @@ extern "C" int radb_extract_bgr(radb_handle* h, const uint8_t* bgr, const uint8_
     int rc = setup(h, planes, RADB_DTYPE_U8, mask, n_images * 4, H, W, HW, HW, out, status, p);
     if (rc) return rc;
     p.mask_group = 4;
-    int cur = -1;
-    cudaGetDevice(&cur);
-    if (cur != h->device) cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const long long threads = n_images * ((HW + 3) / 4);
     radb_bgr_planes_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(bgr, planes, n_images, HW);
     h->launches += 1;
@@ -537,9 +565,7 @@ extern "C" int radb_unpack_mask(radb_handle* h, const uint8_t* packed, int64_t n
 {
     if (!h || !packed || !mask || n_bytes < 0) return fail(RADB_E_INVALID, "bad argument");
     if (n_bytes == 0) return RADB_OK;
-    int cur = -1;
-    cudaGetDevice(&cur);
-    if (cur != h->device) cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     const long long threads = (n_bytes + 15) / 16;
     radb_unpack_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(packed, n_bytes, h->plan.s.label, mask);
     h->launches += 1;
@@ -558,9 +584,7 @@ extern "C" int radb_derive_image(radb_handle* h, const uint8_t* img, int64_t n_i
     if (type < 1 || type > 4) return fail(RADB_E_UNSUPPORTED, "image type not implemented (1 Square, 2 SquareRoot, 3 Logarithm, 4 Exponential)");
     if (n_images <= 0 || HW <= 0) return RADB_OK;
     cudaStream_t st = (cudaStream_t)cuda_stream;
-    int cur = -1;
-    cudaGetDevice(&cur);
-    if (cur != h->device) cudaSetDevice(h->device);
+    DeviceGuard guard(h->device);
     cudaError_t e = cudaMemsetAsync(mx, 0, (size_t)n_images * 4, st);
     if (e != cudaSuccess) return cuda_fail(e, "cudaMemsetAsync");
     const long long t1 = n_images * ((HW + 3) / 4), t2 = n_images * HW;
@@ -569,5 +593,63 @@ extern "C" int radb_derive_image(radb_handle* h, const uint8_t* img, int64_t n_i
     h->launches += 2;
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "radb_derive_image launch");
+    return RADB_OK;
+}
+
+// Filtered image types of the parameter file (params.yml:138-140,145; pyradiomics imageoperations.getGradientImage,
+// getLoGImage, getWaveletImage) for uint8 images [n][H][W] (DEVICE pointers, stream-ordered):
+//   type 5 Gradient          -> out float32 [n][H][W]                              (scratch unused)
+//   type 6 LoG, param=sigma  -> out float32 [n][H][W]; scratch >= n*H*W*12 bytes   (needs H, W >= 4)
+//   type 7 Wavelet (coif1, level 1): flags bit 0 set = transform along x only (force2D on a 2-D array)
+//                              -> out float64 [n][2][H][W] = wavelet-H, wavelet-L;
+//                            flags 0 -> out float64 [n][4][H][W] = wavelet-LH, -HL, -HH, -LL;
+//                              scratch >= n*2*(H+1)*(W+1)*8 bytes
+extern "C" int radb_filter_image(radb_handle* h, const uint8_t* img, int64_t n_images, int H, int W, int type, double param,
+                                 int flags, void* out, void* scratch, void* cuda_stream)
+{
+    if (!h || !img || !out) return fail(RADB_E_INVALID, "null argument");
+    if (n_images < 0 || H < 1 || W < 1) return fail(RADB_E_INVALID, "bad image size");
+    if (n_images == 0) return RADB_OK;
+    cudaStream_t st = (cudaStream_t)cuda_stream;
+    DeviceGuard guard(h->device);
+    const long long HW = (long long)H * W, npx = n_images * HW;
+    const int T = 256;
+    if (type == RADB_IT_GRADIENT) {
+        radb_gradient_kernel<<<(unsigned)((npx + T - 1) / T), T, 0, st>>>(img, n_images, H, W, (float*)out);
+        h->launches += 1;
+    } else if (type == RADB_IT_WAVELET) {
+        if (flags & 1) {
+            radb_wavelet_x_kernel<<<(unsigned)((npx + T - 1) / T), T, 0, st>>>(img, n_images, H, W, (double*)out);
+            h->launches += 1;
+        } else {
+            if (!scratch) return fail(RADB_E_INVALID, "wavelet: scratch buffer required");
+            const long long npp = n_images * (long long)(H + (H & 1)) * (W + (W & 1));
+            radb_wavelet_rows_kernel<<<(unsigned)((npp + T - 1) / T), T, 0, st>>>(img, n_images, H, W, (double*)scratch);
+            radb_wavelet_cols_kernel<<<(unsigned)((npx + T - 1) / T), T, 0, st>>>((const double*)scratch, n_images, H, W, (double*)out);
+            h->launches += 2;
+        }
+    } else if (type == RADB_IT_LOG) {
+        if (!scratch) return fail(RADB_E_INVALID, "LoG: scratch buffer required");
+        if (H < 4 || W < 4) return fail(RADB_E_INVALID, "LoG: ITK's recursive Gaussian needs at least 4 pixels per axis");
+        if (!(param > 0)) return fail(RADB_E_INVALID, "LoG: sigma must be > 0");
+        RadbIir c0, c2;
+        radb::deriche_coefficients(param, 0, c0.N, c0.D, c0.M, c0.BN, c0.BM);
+        radb::deriche_coefficients(param, 2, c2.N, c2.D, c2.M, c2.BN, c2.BM);
+        double* scr = (double*)scratch;            // anti-causal pass of the line being filtered
+        float* tmp = (float*)(scr + npx);          // second-derivative image between the two passes of a dimension
+        const long long rows = n_images * H, cols = n_images * W;
+        const int TL = 64;
+        // ITK dimension 0 (x): d2/dx2 along rows, smoothing along columns -> out
+        radb_iir_u8_kernel<<<(unsigned)((rows + TL - 1) / TL), TL, 0, st>>>(img, tmp, scr, n_images, H, W, 0, c2, 0);
+        radb_iir_f32_kernel<<<(unsigned)((cols + TL - 1) / TL), TL, 0, st>>>(tmp, (float*)out, scr, n_images, H, W, 1, c0, 0);
+        // ITK dimension 1 (y): d2/dy2 along columns, smoothing along rows, accumulated in float32
+        radb_iir_u8_kernel<<<(unsigned)((cols + TL - 1) / TL), TL, 0, st>>>(img, tmp, scr, n_images, H, W, 1, c2, 0);
+        radb_iir_f32_kernel<<<(unsigned)((rows + TL - 1) / TL), TL, 0, st>>>(tmp, (float*)out, scr, n_images, H, W, 0, c0, 1);
+        h->launches += 4;
+    } else {
+        return fail(RADB_E_UNSUPPORTED, "radb_filter_image: type must be 5 (Gradient), 6 (LoG) or 7 (Wavelet)");
+    }
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "radb_filter_image launch");
     return RADB_OK;
 }

@@ -499,8 +499,9 @@ __device__ double mcc_task_g8(const int* P, const int* px, const int* py, int n,
 // ------------------------------------------------------------------ GLCM features (one warp, one angle)
 // A.6.  P holds the final integer counts of this angle (symmetrised when symmetricalGLCM).
 // Returns 0 when the angle is empty (upstream deletes it from the nanmean).
+// `mcc_pre`: the MCC of this angle when radb_mcc_lanczos_kernel has already computed it (null: computed here).
 __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, int n, int* px, int* py, int* padd,
-                         int* psub, double* ws, unsigned char* idx, double* o, int lane)
+                         int* psub, double* ws, unsigned char* idx, double* o, int lane, const double* mcc_pre = (const double*)0)
 {
     const bool sym = p.symmetric != 0;
     if (sym) py = px;  // symmetric matrix: identical marginals
@@ -648,7 +649,7 @@ __device__ int glcm_task(const RadbParams& p, const RadbTabs& tb, const int* P, 
         if (psub[k]) dvar += (double)psub[k] * rN * ((double)k - da) * ((double)k - da);
     dvar = warp_sum(dvar);
     __syncwarp();
-    const double mcc = mcc_task(P, px, py, n, p.symmetric, ws, idx, lane);
+    const double mcc = mcc_pre ? *mcc_pre : mcc_task(P, px, py, n, p.symmetric, ws, idx, lane);
     if (lane == 0) {
         const double sigx = radb_sqrt(ssq), sigy = radb_sqrt(ssqy);
         const double div = fmax(hx, hy);

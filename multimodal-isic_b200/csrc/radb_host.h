@@ -174,7 +174,7 @@ static inline int fill_params(const Plan& pl, int H, int W, int dtype, RadbParam
     p.wide = 0;
     p.big = 0;
     radb_layout(&p, pix_bytes);
-    if ((long long)H * W > 65535 || p.smem_total > 110 * 1024 || pl.max_ng > 255) {
+    if ((long long)H * (W + 1) > 65535 || p.smem_total > 110 * 1024 || pl.max_ng > 255) {
         p.wide = 1;
         radb_layout(&p, pix_bytes);
         if (p.smem_total > 200 * 1024 || p.a_smem_total > 200 * 1024 || pl.max_ng > 255) {
@@ -212,6 +212,63 @@ static inline int group_ragged(long long n, const int32_t* hw, std::vector<Ragge
         g->idx.push_back(i);
     }
     return 0;
+}
+
+// ITK RecursiveGaussianImageFilter::SetUp (Deriche's 4th-order recursive Gaussian; spacing 1, NormalizeAcrossScale
+// on): the coefficient sets of the zero-order (order = 0) and second-order (order = 2) filters.  Same formulas, in
+// the same order, as oracle/image_filters.py:_deriche_coefficients.  out: N[4], D[4], M[4], BN[4], BM[4].
+static inline void deriche_coefficients(double sigma, int order, double* N, double* D, double* M, double* BN, double* BM)
+{
+    const double sd = sigma;
+    const double W1 = 0.6681, L1 = -1.3932, W2 = 2.0787, L2 = -1.3732;
+    const double A1[3] = {1.3530, -0.6724, -1.3563}, B1[3] = {1.8151, -3.4327, 5.2318};
+    const double A2[3] = {-0.3531, 0.6724, 0.3446}, B2[3] = {0.0902, 0.6100, -2.2355};
+    const double c1 = cos(W1 / sd), c2 = cos(W2 / sd), s1 = sin(W1 / sd), s2 = sin(W2 / sd);
+    const double e1 = exp(L1 / sd), e2 = exp(L2 / sd);
+    auto ncoef = [&](double a1, double b1, double a2, double b2, double* n, double& SN, double& DN, double& EN) {
+        n[0] = a1 + a2;
+        n[1] = e2 * (b2 * s2 - (a2 + 2 * a1) * c2);
+        n[1] += e1 * (b1 * s1 - (a1 + 2 * a2) * c1);
+        n[2] = (a1 + a2) * c2 * c1;
+        n[2] -= b1 * c2 * s1 + b2 * c1 * s2;
+        n[2] *= 2 * e1 * e2;
+        n[2] += a2 * e1 * e1 + a1 * e2 * e2;
+        n[3] = e2 * e1 * e1 * (b2 * s2 - a2 * c2);
+        n[3] += e1 * e2 * e2 * (b1 * s1 - a1 * c1);
+        SN = n[0] + n[1] + n[2] + n[3];
+        DN = n[1] + 2 * n[2] + 3 * n[3];
+        EN = n[1] + 4 * n[2] + 9 * n[3];
+    };
+    D[3] = e1 * e1 * e2 * e2;
+    D[2] = -2 * c1 * e1 * e2 * e2;
+    D[2] += -2 * c2 * e2 * e1 * e1;
+    D[1] = 4 * c2 * c1 * e1 * e2;
+    D[1] += e1 * e1 + e2 * e2;
+    D[0] = -2 * (e2 * c2 + e1 * c1);
+    const double SD = 1.0 + D[0] + D[1] + D[2] + D[3];
+    const double DD = D[0] + 2 * D[1] + 3 * D[2] + 4 * D[3];
+    const double ED = D[0] + 4 * D[1] + 9 * D[2] + 16 * D[3];
+    if (order == 0) {
+        double n[4], SN, DN, EN;
+        ncoef(A1[0], B1[0], A2[0], B2[0], n, SN, DN, EN);
+        const double alpha0 = 2 * SN / SD - n[0];
+        for (int k = 0; k < 4; k++) N[k] = n[k] / alpha0;
+    } else {
+        const double scale = sigma * sigma;
+        double a[4], b[4], SN0, DN0, EN0, SN2, DN2, EN2;
+        ncoef(A1[0], B1[0], A2[0], B2[0], a, SN0, DN0, EN0);
+        ncoef(A1[2], B1[2], A2[2], B2[2], b, SN2, DN2, EN2);
+        const double beta = -(2 * SN2 - SD * b[0]) / (2 * SN0 - SD * a[0]);
+        const double SN = SN2 + beta * SN0, DN = DN2 + beta * DN0, EN = EN2 + beta * EN0;
+        const double alpha2 = (EN * SD * SD - ED * SN * SD - 2 * DN * DD * SD + 2 * DD * DD * SN) / (SD * SD * SD);
+        for (int k = 0; k < 4; k++) N[k] = (b[k] + beta * a[k]) * (scale / alpha2);
+    }
+    M[0] = N[1] - D[0] * N[0];
+    M[1] = N[2] - D[1] * N[0];
+    M[2] = N[3] - D[2] * N[0];
+    M[3] = -D[3] * N[0];
+    const double SNs = N[0] + N[1] + N[2] + N[3], SMs = M[0] + M[1] + M[2] + M[3], SDs = 1.0 + D[0] + D[1] + D[2] + D[3];
+    for (int k = 0; k < 4; k++) { BN[k] = D[k] * SNs / SDs; BM[k] = D[k] * SMs / SDs; }
 }
 
 // 1/k^2 and log2(k) tables read by the reduction kernels (device copies are made at radb_create)

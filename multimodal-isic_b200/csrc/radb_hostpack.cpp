@@ -67,3 +67,42 @@ extern "C" int radb_pack_mask_host(const uint8_t* mask, int64_t n_bytes, int lab
     for (auto& th : pool) th.join();
     return 0;
 }
+
+// Per-patch variant for radb_extract_packed: n_patches masks of `hw` bytes each, back to back; patch b's bit stream
+// starts at packed + b * stride_b (stride_b >= ceil(hw / 8); padding bits/bytes are zeroed), bit i <=> mask byte i
+// equals `label`.  With hw a multiple of 32 and stride_b == hw / 8 this is the same stream radb_pack_mask_host
+// writes, and the whole buffer is packed in large blocks; otherwise patches are dealt to the threads one by one.
+extern "C" int radb_pack_masks_host(const uint8_t* mask, int64_t n_patches, int64_t hw, int label, uint8_t* packed,
+                                    int64_t stride_b, int threads)
+{
+    if (!mask || !packed || n_patches < 0 || hw < 1 || stride_b < (hw + 7) / 8) return -1;
+    if (hw % 32 == 0 && stride_b == hw / 8) return radb_pack_mask_host(mask, n_patches * hw, label, packed, threads);
+    if (label < 0 || label > 255) {
+        memset(packed, 0, (size_t)(n_patches * stride_b));
+        return 0;
+    }
+    void (*fn)(const uint8_t*, int64_t, uint8_t, uint8_t*) = pack_scalar;
+#ifdef RADB_X86
+    if (__builtin_cpu_supports("avx2")) fn = pack_avx2;
+#endif
+    if (threads < 1) threads = 1;
+    if (threads > 64) threads = 64;
+    const int64_t used = (hw + 7) / 8;
+    auto work = [=](int t, int nt) {
+        const int64_t per = (n_patches + nt - 1) / nt;
+        const int64_t lo = t * per, hi = lo + per < n_patches ? lo + per : n_patches;
+        for (int64_t b = lo; b < hi; b++) {
+            uint8_t* o = packed + b * stride_b;
+            fn(mask + b * hw, hw, (uint8_t)label, o);
+            if (stride_b > used) memset(o + used, 0, (size_t)(stride_b - used));
+        }
+    };
+    if (threads == 1 || n_patches * hw <= (1 << 20)) {
+        work(0, 1);
+        return 0;
+    }
+    std::vector<std::thread> pool;
+    for (int t = 0; t < threads; t++) pool.emplace_back(work, t, threads);
+    for (auto& th : pool) th.join();
+    return 0;
+}

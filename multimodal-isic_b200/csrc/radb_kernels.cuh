@@ -281,6 +281,14 @@ __device__ __forceinline__ unsigned bytes_eq4(unsigned a, unsigned b)
     const unsigned t = a ^ b;
     return ~(((t & 0x7f7f7f7fu) + 0x7f7f7f7fu) | t) & 0x80808080u;
 }
+__device__ __forceinline__ unsigned radb_roi4(const unsigned char* m, int q, unsigned label4, int packed)
+{
+    if (packed) {  // nibble q of the bit stream -> one bit per byte (multiply spreads bit k to bit 8k), as 0x80 flags
+        const unsigned nib = ((unsigned)m[q >> 1] >> ((q & 1) * 4)) & 0xfu;
+        return ((nib * 0x00204081u) & 0x01010101u) << 7;
+    }
+    return bytes_eq4(((const unsigned*)m)[q], label4);
+}
 
 // Python-style modulo (sign of the divisor), as numpy's % in imageoperations.getBinEdges
 __device__ __forceinline__ double py_mod(double a, double b)
@@ -289,6 +297,15 @@ __device__ __forceinline__ double py_mod(double a, double b)
     if (r != 0.0 && ((r < 0.0) != (b < 0.0))) r += b;
     return r;
 }
+
+// ROI membership of pixel i: byte masks compare with the label (imageoperations.getMask: mask == label); bit-packed
+// masks (radb_extract_packed: bit i of the patch's stream, set = ROI) test the bit.  `packed` is kernel-uniform.
+__device__ __forceinline__ bool radb_roi(const unsigned char* m, int i, int label, int packed)
+{
+    return packed ? (((unsigned)m[i >> 3] >> (i & 7)) & 1u) != 0u : ((int)m[i] == label);
+}
+// four consecutive pixels q*4 .. q*4+3 at once: 0x80 in byte k <=> pixel k is in the ROI
+__device__ __forceinline__ unsigned radb_roi4(const unsigned char* m, int q, unsigned label4, int packed);
 
 // dense batches: patch k is row k; ragged batches: the group-local patch k maps to output row rows[k]
 __device__ __forceinline__ long long radb_row(const RadbParams& p, long long patch) { return p.rows ? p.rows[patch] : patch; }
@@ -299,6 +316,8 @@ __device__ __forceinline__ const unsigned char* radb_mask_ptr(const RadbParams& 
 
 #include "radb_features.cuh"
 #include "radb_lane.cuh"
+#include "radb_lanczos.cuh"
+#include "radb_filters.cuh"
 
 // ------------------------------------------------------------------ first-order for non-uint8 pixels
 // uint8 patches get all 18 first-order features from the 256-bin raw histogram (fo_task_u8, misc
@@ -389,13 +408,13 @@ __device__ void fo_generic(const RadbParams& p, const PT* img, const unsigned ch
     // ---- pass 1: mean; pass 2: central moments, MAD, energy
     double a1[2] = {0, 0};
     for (int i = tid; i < HW; i += RADB_NTB)
-        if ((int)msk[i] == p.label) { const double x = (double)img[i]; a1[0] += x; a1[1] += (x + shift) * (x + shift); }
+        if (radb_roi(msk, i, p.label, p.mask_bits)) { const double x = (double)img[i]; a1[0] += x; a1[1] += (x + shift) * (x + shift); }
     cta_sum(a1, slots, tid);
     // a flat ROI has mean == its value exactly (a rounded sum/N would leave spurious 1e-30 moments)
     const double mean = (vmn == vmx) ? vmn : a1[0] * rN, en = a1[1];
     double a2[4] = {0, 0, 0, 0};
     for (int i = tid; i < HW; i += RADB_NTB)
-        if ((int)msk[i] == p.label) {
+        if (radb_roi(msk, i, p.label, p.mask_bits)) {
             const double x = (double)img[i], d = x - mean, d2 = d * d;
             a2[0] += d2; a2[1] += d2 * d; a2[2] += d2 * d2; a2[3] += fabs(d);
         }
@@ -420,7 +439,7 @@ __device__ void fo_generic(const RadbParams& p, const PT* img, const unsigned ch
         const int ngr = ngroups[0];
         const bool first = (sh == KY::BITS - 8);
         for (int i = tid; i < HW; i += RADB_NTB)
-            if ((int)msk[i] == p.label) {
+            if (radb_roi(msk, i, p.label, p.mask_bits)) {
                 const unsigned long long k = KY::key(img[i]);
                 const unsigned long long kh = first ? 0ULL : (k >> (sh + 8));
                 const int b = (int)((k >> sh) & 255ULL);
@@ -463,7 +482,7 @@ __device__ void fo_generic(const RadbParams& p, const PT* img, const unsigned ch
     // ---- robust MAD: values inside [p10, p90]
     double a3[2] = {0, 0};
     for (int i = tid; i < HW; i += RADB_NTB)
-        if ((int)msk[i] == p.label) {
+        if (radb_roi(msk, i, p.label, p.mask_bits)) {
             const double x = (double)img[i];
             if (x >= p10 && x <= p90) { a3[0] += x; a3[1] += 1.0; }
         }
@@ -471,7 +490,7 @@ __device__ void fo_generic(const RadbParams& p, const PT* img, const unsigned ch
     const double rin = 1.0 / a3[1], in_mean = a3[0] * rin;
     double a4[3] = {0, 0, 0};
     for (int i = tid; i < HW; i += RADB_NTB)
-        if ((int)msk[i] == p.label) {
+        if (radb_roi(msk, i, p.label, p.mask_bits)) {
             const double x = (double)img[i];
             if (x >= p10 && x <= p90) a4[0] += fabs(x - in_mean);
         }
@@ -543,6 +562,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     const UW ULO = (((UW)1) << US) - 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, HW = p.HW, WP = p.WP, XO = p.xo, NA = p.n_angles, NB = 2 * p.n_angles;
+    const int LP = p.lp;  // pitch of the union-find array (pixel (y, x) <-> word y * LP + x)
     const PT* g_img = (const PT*)((const unsigned char*)p.img + (p.img_off ? p.img_off[patch] : patch * p.img_stride));
     const unsigned char* g_msk = radb_mask_ptr(p, patch);
     const long long row = radb_row(p, patch);
@@ -576,7 +596,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         if (tid == 0) mbar_init(bar, 1);
         __syncthreads();
         if (tid == 0) {
-            const unsigned ib = (unsigned)(HW * sizeof(PT)), mb = (unsigned)HW;
+            const unsigned ib = (unsigned)(HW * sizeof(PT)), mb = (unsigned)(p.mask_bits ? (HW + 7) >> 3 : HW);
             mbar_expect_tx(bar, ib + mb);
             tma_load_1d(smem + p.o_stage, g_img, ib, bar);
             tma_load_1d(smem + p.o_mask, g_msk, mb, bar);
@@ -611,9 +631,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         {
             PT* d_img = (PT*)(smem + p.o_stage);
             unsigned char* d_msk = smem + p.o_mask;
+            const int mbytes = p.mask_bits ? (HW + 7) >> 3 : HW;
             for (int i = tid; i < HW; i += RADB_NTB) {
                 d_img[i] = g_img[i];
-                d_msk[i] = g_msk[i];
+                if (i < mbytes) d_msk[i] = g_msk[i];
             }
         }
     }
@@ -630,11 +651,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             const int WQ = W >> 2, NQ = HW >> 2;
             const float inv_wq = 1.0f / (float)WQ;
             const unsigned l4 = (unsigned)(p.label & 0xff) * 0x01010101u;
-            const unsigned* m4p = (const unsigned*)s_msk;
             const unsigned* v4p = (const unsigned*)s_img;
-            if (p.label >= 0 && p.label <= 255)
+            if (p.mask_bits || (p.label >= 0 && p.label <= 255))
                 for (int q = tid; q < NQ; q += RADB_NTB) {
-                    const unsigned eq = bytes_eq4(m4p[q], l4);
+                    const unsigned eq = radb_roi4(s_msk, q, l4, p.mask_bits);
                     if (!eq) continue;
                     const int y = (int)(((float)q + 0.5f) * inv_wq), x0 = (q - y * WQ) << 2;
                     const unsigned v4 = v4p[q];
@@ -656,7 +676,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         for (int y = warp; y < H; y += RADB_NTB / 32)
             for (int x = lane; x < W; x += 32) {
                 int i = y * W + x;
-                if ((int)s_msk[i] == p.label) {
+                if (radb_roi(s_msk, i, p.label, p.mask_bits)) {
                     np++;
                     ymin = y < ymin ? y : ymin;
                     ymax = y > ymax ? y : ymax;
@@ -783,11 +803,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int WQ = W >> 2, NQ = HW >> 2;
         const float inv_wq = 1.0f / (float)WQ;
         const unsigned l4 = (unsigned)(p.label & 0xff) * 0x01010101u;
-        const unsigned* m4p = (const unsigned*)s_msk;
         const unsigned* v4p = (const unsigned*)s_img;
-        if (p.label >= 0 && p.label <= 255)
+        if (p.mask_bits || (p.label >= 0 && p.label <= 255))
             for (int q = tid; q < NQ; q += RADB_NTB) {
-                const unsigned eq = bytes_eq4(m4p[q], l4);
+                const unsigned eq = radb_roi4(s_msk, q, l4, p.mask_bits);
                 if (!eq) continue;  // the level image is pre-zeroed
                 const int y = (int)(((float)q + 0.5f) * inv_wq), xq = q - y * WQ;
                 const unsigned v4 = v4p[q];
@@ -802,7 +821,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         for (int x = lane; x < W; x += 32) {
             int i = y * W + x;
             LT L = 0;
-            if ((int)s_msk[i] == p.label) {
+            if (radb_roi(s_msk, i, p.label, p.mask_bits)) {
                 if (U8) {
                     L = lut[(int)s_img[i]];
                 } else {
@@ -832,7 +851,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     for (int a = 0; a < NA; a++)
         if (p.ang_y[a] == 0) a_row = a;
     if (a_row < 0) {  // no along-row connectivity: every ROI pixel starts as its own run of length 1
-        for (int i = tid; i < HW; i += RADB_NTB) lab[i] = (((UW)1) << US) | (UW)i;
+        for (int i = tid; i < H * LP; i += RADB_NTB) lab[i] = (((UW)1) << US) | (UW)i;
     }
 
     // ---- phase 3a: line walks over the ROI bounding box.  One thread walks one line along one
@@ -858,7 +877,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             for (int l = first; l < nlines; l += RADB_NTB) {
                 int cur = 0, len = 0;
                 if (dy == 0) {
-                    const int base = (by0 + l + 1) * WP + bx0 + XO, lbase = (by0 + l) * W + bx0;
+                    const int base = (by0 + l + 1) * WP + bx0 + XO, lbase = (by0 + l) * LP + bx0;
                     int st = 0;
                     int gn = lev[base];  // software-pipelined: the next level is in flight while this one is processed
                     for (int x = 0; x < bw; x++) {
@@ -916,7 +935,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         int doff[RADB_MAX_ANGLES], loff[RADB_MAX_ANGLES];
         for (int a = 0; a < RADB_MAX_ANGLES; a++) {
             doff[a] = a < NA ? p.ang_y[a] * WP + p.ang_x[a] : 0;
-            loff[a] = a < NA ? p.ang_y[a] * W + p.ang_x[a] : 0;
+            loff[a] = a < NA ? p.ang_y[a] * LP + p.ang_x[a] : 0;
         }
         const int nd = NB + 1;
         const bool inplane = (NA == 4);  // all 8 neighbours: run-adjacency union rules apply
@@ -946,7 +965,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             const int y = by0 + yb, x = bx0 + (idx - yb * bw);
             const int ctr = (y + 1) * WP + x + XO;
             const int c = idx < nbox ? (int)lev[ctr] : 0;
-            const int li = y * W + x;
+            const int li = y * LP + x;
             unsigned req[RADB_MAX_ANGLES];  // union partner + 1 (0 = none)
 #pragma unroll
             for (int a = 0; a < RADB_MAX_ANGLES; a++) req[a] = 0;
@@ -996,10 +1015,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 // 8-connectivity between row runs: one union per pair of touching runs.
                 const bool is_start = w_ != c, is_end = e_ != c;
                 if (n_ == c) {
-                    if (is_start || nw != c) req[0] = (unsigned)(li - W) + 1u;
+                    if (is_start || nw != c) req[0] = (unsigned)(li - LP) + 1u;
                 } else {
-                    if (nw == c && is_start) req[0] = (unsigned)(li - W - 1) + 1u;
-                    if (ne == c && is_end) req[1] = (unsigned)(li - W + 1) + 1u;
+                    if (nw == c && is_start) req[0] = (unsigned)(li - LP - 1) + 1u;
+                    if (ne == c && is_end) req[1] = (unsigned)(li - LP + 1) + 1u;
                 }
             } else if (c) {
                 int dep = 0, cnt = 0, sum = 0;
@@ -1056,7 +1075,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     // ---- phase 4: fold run lengths into their zone root; symmetrise the GLCM
     const bool by_list = keep_runs && a_row >= 0;  // the run list exists: visit runs, not pixels
     const int nruns = by_list ? misc[6] : 0;
-    const float inv_w = 1.0f / (float)W;
+    const float inv_lp = 1.0f / (float)LP;
     // Unions link the larger pixel index under the smaller one, so a tall zone is a long parent chain.  The
     // list is (nearly) in pixel order: round k of this loop handles runs above those of round k + 1, and every
     // run re-parents itself straight to its root, so later rounds find short paths (the clocks showed the
@@ -1077,7 +1096,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int ctr = (y + 1) * WP + x + XO;
         const int c = lev[ctr];
         if (c && (a_row < 0 || lev[ctr - 1] != c)) {  // run start
-            const int li = y * W + x;
+            const int li = y * LP + x;
             const unsigned r = uf_find_ro<UW, UF<WIDE>::S>(lab, (unsigned)li);
             if (r != (unsigned)li) atomicAdd(&lab[r], (UW)(lab[li] & ~ULO));  // only roots are ever added to
         }
@@ -1115,7 +1134,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int li = runs[k];
         const UW wl = lab[li];
         if ((unsigned)(wl & ULO) != (unsigned)li) continue;
-        const int y = (int)(((float)li + 0.5f) * inv_w), x = li - y * W;  // exact for li < 65536
+        const int y = (int)(((float)li + 0.5f) * inv_lp), x = li - y * LP;  // exact for li < 65536
         emit_zone((int)lev[(y + 1) * WP + x + XO], (int)(wl >> US));
     }
     if (!by_list)
@@ -1125,7 +1144,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int ctr = (y + 1) * WP + x + XO;
         const int c = lev[ctr];
         if (!c || (a_row >= 0 && lev[ctr - 1] == c)) continue;
-        const int li = y * W + x;
+        const int li = y * LP + x;
         const UW wl = lab[li];
         if ((unsigned)(wl & ULO) != (unsigned)li) continue;
         emit_zone(c, (int)(wl >> US));
@@ -1197,7 +1216,8 @@ __device__ void radb_angle_cta(const RadbParams& p, long long patch, unsigned ch
         double* mccws = p.big ? (double*)(p.ws_scr + patch * p.scr_bytes + p.g_mcc) + (long long)a * p.mcc_stride
                               : (double*)(ws + p.a_mcc);
         ok = glcm_task(p, tb, P, ng, (int*)(ws + p.a_px), (int*)(ws + p.a_py), (int*)(ws + p.a_padd),
-                       (int*)(ws + p.a_psub), mccws, ws + p.a_idx, fsc + a * RADB_FSC_STRIDE, lane);
+                       (int*)(ws + p.a_psub), mccws, ws + p.a_idx, fsc + a * RADB_FSC_STRIDE, lane,
+                       p.use_lanczos ? (const double*)(misc + RADB_REC_MCC_INT) + a : (const double*)0);
         if (lane == 0) valid[a] = ok;
     }
     __syncthreads();
@@ -1347,10 +1367,10 @@ __device__ void radb_shape_cta(const RadbParams& p, long long patch, unsigned ch
     for (int t = tid; t < ncell; t += RADB_NT) {
         const int iy = t / cw - 1, ix = t - (iy + 1) * cw - 1;
         const bool in0 = iy >= 0, in1 = iy + 1 < H, jn0 = ix >= 0, jn1 = ix + 1 < W;
-        const int c0 = (in0 && jn0) ? ((int)m[iy * W + ix] == label) : 0;
-        const int c1 = (in0 && jn1) ? ((int)m[iy * W + ix + 1] == label) : 0;
-        const int c2 = (in1 && jn1) ? ((int)m[(iy + 1) * W + ix + 1] == label) : 0;
-        const int c3 = (in1 && jn0) ? ((int)m[(iy + 1) * W + ix] == label) : 0;
+        const int c0 = (in0 && jn0) ? (int)radb_roi(m, iy * W + ix, label, p.mask_bits) : 0;
+        const int c1 = (in0 && jn1) ? (int)radb_roi(m, iy * W + ix + 1, label, p.mask_bits) : 0;
+        const int c2 = (in1 && jn1) ? (int)radb_roi(m, (iy + 1) * W + ix + 1, label, p.mask_bits) : 0;
+        const int c3 = (in1 && jn0) ? (int)radb_roi(m, (iy + 1) * W + ix, label, p.mask_bits) : 0;
         const int k = c0 + c1 + c2 + c3;
         if (c2) {  // pixel (iy+1, ix+1) is visited exactly once as corner 2
             const long long y = iy + 1, x = ix + 1;
@@ -1417,10 +1437,12 @@ __device__ void radb_shape_cta(const RadbParams& p, long long patch, unsigned ch
         const long long* T = (const long long*)cta;  // n, sy, sx, syy, sxx, sxy, eighths, #straight, #diagonal
         const double N = (double)T[0];
         const double rN2 = 1.0 / (N * N);
-        // covariance of the coordinates / sqrt(N): population second moments
-        const double a = (double)(T[0] * T[3] - T[1] * T[1]) * rN2;  // var(y)
-        const double c = (double)(T[0] * T[4] - T[2] * T[2]) * rN2;  // var(x)
-        const double b = (double)(T[0] * T[5] - T[1] * T[2]) * rN2;  // cov(x, y)
+        // covariance of the coordinates / sqrt(N): population second moments.  N * sum(y^2) reaches 2^72 for a full
+        // 4096 x 4096 mask (int64 overflows beyond ~1700 x 1700): the exact numerators are formed in 128 bits
+        typedef __int128 i128;
+        const double a = (double)((i128)T[0] * T[3] - (i128)T[1] * T[1]) * rN2;  // var(y)
+        const double c = (double)((i128)T[0] * T[4] - (i128)T[2] * T[2]) * rN2;  // var(x)
+        const double b = (double)((i128)T[0] * T[5] - (i128)T[1] * T[2]) * rN2;  // cov(x, y)
         const double hd = 0.5 * (a - c), rad = sqrt(hd * hd + b * b), mid = 0.5 * (a + c);
         double e1 = mid + rad, e0 = mid - rad;
         if (e0 < 0 && e0 > -1e-10) e0 = 0;
@@ -1463,6 +1485,11 @@ __global__ void __launch_bounds__(RADB_NTM) radb_mcc_g8_kernel(const RadbParams 
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
     radb_mcc_g8_cta(p, (long long)blockIdx.x, radb_smem);
+}
+__global__ void __launch_bounds__(RADB_NTZ) radb_mcc_lanczos_kernel(const RadbParams p)
+{
+    extern __shared__ __align__(16) unsigned char radb_smem[];
+    radb_mcc_lanczos_cta(p, (long long)blockIdx.x, radb_smem);
 }
 __global__ void __launch_bounds__(RADB_NT) radb_misc_lane_kernel(const RadbParams p)
 {

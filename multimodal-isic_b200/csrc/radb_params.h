@@ -2,6 +2,7 @@
 // the kernels (radb_kernels.cuh) and the CPU emulation harness under tests/emu.
 #pragma once
 #include <stdint.h>
+#include <stdlib.h>
 
 #define RADB_NT 128          // threads per CTA of the reduction kernels (4 warps); one CTA per patch
 #ifndef RADB_NTB
@@ -36,6 +37,8 @@ struct RadbParams {
     int* status;            // [B]
     long long B;
     int H, W, WP, HW;
+    int lp;        // pitch (words) of the union-find array: odd in narrow mode so that a warp whose lanes walk 32 rows hits 32 banks
+    int mask_bits; // 1: `mask` is bit-packed (bit i of a patch's stream <-> pixel i, set = ROI), mask_stride in bytes of that stream
     int xo;        // column of pixel x = 0 inside a padded level-image row (left border width)
     int vec4;      // uint8 narrow patches with W % 4 == 0: 4 pixels per shared-memory load in the discretise phases
     int label;
@@ -83,6 +86,8 @@ struct RadbParams {
     // use_lane: 0 warp-per-angle kernel | 1 thread-per-angle kernel incl. MCC (Ng <= 14) | 2 thread-per-angle kernel
     // without the matrix storage + radb_mcc_g8_kernel for the eigenproblems (Ng <= 40)
     int g8_px, g8_idx, g8_mcc, g8_group_bytes, g8_smem_total;  // MCC kernel: per-group shared-memory layout
+    // ---- Lanczos MCC kernel (radb_lanczos.cuh): more than 40 gray levels, symmetric GLCM, one CTA per (patch, angle)
+    int use_lanczos, z_rowptr, z_ent, z_vec, z_tri, z_cap, z_smem_total;
     // ---- misc lane kernel: one thread per (patch, class); the warp-level misc kernel then only serves GLSZM
     // patches with a long overflow list (only_big_ovf = 1)
     int ml_doubles, ml_smem_total, only_big_ovf;
@@ -103,6 +108,8 @@ struct RadbParams {
 };
 
 static inline int radb_align(int v, int a) { return (v + a - 1) / a * a; }
+// A/B switch (tests, profiling): RADB_NO_LANCZOS=1 keeps the dense Householder MCC of the warp-per-angle kernel
+static inline int radb_no_lanczos(void) { return getenv("RADB_NO_LANCZOS") != 0; }
 
 // Fills WP/HW/nr/s0/ovf_cap and every shared-memory / record offset from H, W, max_ng, n_angles
 // and p->wide.  Record layout (both modes): header, hist, lhist, glcm, gldm, ngc, ngn, szm | glrlm, ovf.
@@ -112,6 +119,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->lev_bytes = ng > 255 ? 2 : 1;
     p->pix_bytes = pix_bytes;
     p->HW = H * W;
+    p->lp = (!wide && W % 2 == 0) ? W + 1 : W;
     p->vec4 = (!wide && pix_bytes == 1 && W % 4 == 0) ? 1 : 0;
     p->xo = p->vec4 ? 4 : 1;
     p->WP = radb_align(W + p->xo + 1, 4);
@@ -121,7 +129,38 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->ovf_cap = p->HW / (p->s0 + 1) + 1;
     p->ninv = ng > p->nr ? ng : p->nr;
     if (p->ninv < p->s0) p->ninv = p->s0;
-    p->mcc_stride = ng * (ng + 1) / 2 + 4 * ng;
+    // ---- lane kernel: replaces the angle kernel for symmetric GLCMs whose per-thread workspace fits
+    p->l_nap = na <= 1 ? 1 : (na <= 2 ? 2 : 4);
+    p->l_doubles = ng * (ng + 1) / 2 + 2 * ng;
+    if (p->l_doubles < (p->nr + 1) / 2 + 1) p->l_doubles = (p->nr + 1) / 2 + 1;
+    p->l_smem_total = p->l_doubles * 8 * RADB_LSTRIDE;
+    // (>= 3 resident CTAs per SM: with fewer the serial per-thread chains are latency-bound and the
+    // warp-per-angle kernel wins -- measured at Ng 26: 1.55 ms vs 1.16 ms per 8192 patches)
+    p->use_lane = (p->symmetric && p->l_smem_total <= 72 * 1024) ? 1 : 0;
+    if (!p->use_lane && p->symmetric && !big && ng <= 40) {
+        // mid-size matrices: the per-thread scratch only holds the marginals (2 * ng slots); the eigenproblems go
+        // to the MCC kernel, one warp per patch
+        p->use_lane = 2;
+        p->l_doubles = 2 * ng;
+        if (p->l_doubles < (p->nr + 1) / 2 + 1) p->l_doubles = (p->nr + 1) / 2 + 1;
+        p->l_smem_total = p->l_doubles * 8 * RADB_LSTRIDE;
+        if (p->l_smem_total > 72 * 1024) p->use_lane = 0;
+    }
+    // Lanczos MCC kernel: CSR copy of one angle's non-zeros (<= min(ng^2, 2 * #voxel pairs) entries, counts < 2^16)
+    {
+        long long cap = (long long)ng * ng, pairs = 2LL * p->HW;
+        if (cap > pairs) cap = pairs;
+        int o = 0;
+        p->z_rowptr = o; o += radb_align((ng + 2) * 4, 16);
+        p->z_ent = o; o += radb_align((int)(cap < (1 << 20) ? cap : (1 << 20)) * 4, 16);
+        p->z_vec = o; o += 5 * ng * 8;
+        p->z_tri = o; o += (2 * 448 + 16) * 8 + 64;  // al, be2 [RADB_LZ_KMAX], slots, shared scalars (kernel: al + RADB_LZ_KMAX)
+        p->z_cap = (int)(cap < (1 << 20) ? cap : (1 << 20));
+        p->z_smem_total = o;
+        p->use_lanczos = (!p->use_lane && p->symmetric && ng <= 256 && p->HW <= 32767 && o <= 200 * 1024 && !radb_no_lanczos()) ? 1 : 0;
+    }
+    p->mcc_stride = ng * (ng + 1) / 2 + 4 * ng;  // dense MCC workspace of the warp-per-angle kernel (doubles per angle)
+    if (p->use_lanczos) p->mcc_stride = 0;       // the Lanczos kernel solves the eigenproblems: only the marginal tables remain
     if (p->mcc_stride < 2 * ng + 8) p->mcc_stride = 2 * ng + 8;
     int o = 0;
     // ---- build kernel
@@ -131,7 +170,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
         int stage_bytes = radb_align(p->HW * pix_bytes, 16);
         p->o_mask = o + stage_bytes;      // raw mask (TMA destination)
         int both = stage_bytes + radb_align(p->HW, 16);
-        int lab_bytes = radb_align(p->HW * 4, 16);   // union-find words (parent | size << 16)
+        int lab_bytes = radb_align(H * p->lp * 4, 16);   // union-find words (parent | size << 16), pitch lp
         o += both > lab_bytes ? both : lab_bytes;
     }
     p->o_mbar = o; o += 16;
@@ -176,6 +215,12 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->scr_bytes = wide ? (p->g_lab + (long long)p->HW * 8 + 15) / 16 * 16 : 0;  // 16-byte multiple: uint4 stores
     p->g_mcc = 0;  // big: the MCC workspaces re-use the scratch once the build kernel is done with it
     if (big && p->scr_bytes < (long long)na * p->mcc_stride * 8) p->scr_bytes = (long long)na * p->mcc_stride * 8;
+    o = 0;
+    p->g8_px = o; o += radb_align(ng * 4, 16);
+    p->g8_idx = o; o += radb_align(ng, 16);
+    p->g8_mcc = o; o += radb_align((ng * (ng + 1) / 2 + 2 * ng) * 8, 16);  // M + (d | v) + (e2 | w), see mcc_task_g8
+    p->g8_group_bytes = o;
+    p->g8_smem_total = (RADB_NTM / 32) * 4 * p->g8_group_bytes;
     // ---- angle kernel
     o = 0;
     p->a_px = o; o += radb_align(ng * 4, 16);
@@ -191,29 +236,6 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->a_fsc = o; o += RADB_MAX_ANGLES * RADB_FSC_STRIDE * 8;
     p->a_valid = o; o += 16 * 4;
     p->a_smem_total = o;
-    // ---- lane kernel: replaces the angle kernel for symmetric GLCMs whose per-thread workspace fits
-    p->l_nap = na <= 1 ? 1 : (na <= 2 ? 2 : 4);
-    p->l_doubles = ng * (ng + 1) / 2 + 2 * ng;
-    if (p->l_doubles < (p->nr + 1) / 2 + 1) p->l_doubles = (p->nr + 1) / 2 + 1;
-    p->l_smem_total = p->l_doubles * 8 * RADB_LSTRIDE;
-    // (>= 3 resident CTAs per SM: with fewer the serial per-thread chains are latency-bound and the
-    // warp-per-angle kernel wins -- measured at Ng 26: 1.55 ms vs 1.16 ms per 8192 patches)
-    p->use_lane = (p->symmetric && p->l_smem_total <= 72 * 1024) ? 1 : 0;
-    if (!p->use_lane && p->symmetric && !big && ng <= 40) {
-        // mid-size matrices: the per-thread scratch only holds the marginals (2 * ng slots); the eigenproblems go
-        // to the MCC kernel, one warp per patch
-        p->use_lane = 2;
-        p->l_doubles = 2 * ng;
-        if (p->l_doubles < (p->nr + 1) / 2 + 1) p->l_doubles = (p->nr + 1) / 2 + 1;
-        p->l_smem_total = p->l_doubles * 8 * RADB_LSTRIDE;
-        if (p->l_smem_total > 72 * 1024) p->use_lane = 0;
-    }
-    o = 0;
-    p->g8_px = o; o += radb_align(ng * 4, 16);
-    p->g8_idx = o; o += radb_align(ng, 16);
-    p->g8_mcc = o; o += radb_align((ng * (ng + 1) / 2 + 2 * ng) * 8, 16);  // M + (d | v) + (e2 | w), see mcc_task_g8
-    p->g8_group_bytes = o;
-    p->g8_smem_total = (RADB_NTM / 32) * 4 * p->g8_group_bytes;
     p->ml_doubles = 2 * ng + 16 > 32 ? 2 * ng + 16 : 32;  // >= RADB_LANE_MAX_OVF / 2 slots for the sorted overflow list
     p->ml_smem_total = 4 * p->ml_doubles * 32 * 8;
     // ---- misc kernel

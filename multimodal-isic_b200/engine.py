@@ -105,6 +105,31 @@ class Engine:
             raise RadbError("radb_extract failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
         return out, status
 
+    def extract_packed(self, images, mask_bits, out=None, status=None, stream=None, stride_b=0):
+        """``images`` [B, H, W] device tensor, ``mask_bits`` device uint8 tensor holding the bit-packed masks
+        (radb_extract_packed: bit i of patch b at byte ``b * stride_b + i // 8``, LSB first, set = ROI;
+        ``stride_b`` defaults to ``packed_stride(H, W)``, the layout ``pack_masks_host`` writes)."""
+        if images.dtype not in self.DTYPES or mask_bits.dtype != torch.uint8:
+            raise TypeError("images must be uint8/uint16/float32/float64 and mask_bits uint8")
+        if images.dim() != 3 or not (images.is_cuda and mask_bits.is_cuda and images.is_contiguous() and mask_bits.is_contiguous()):
+            raise ValueError("images [B, H, W] and mask_bits must be contiguous CUDA tensors")
+        B, H, W = images.shape
+        stride = int(stride_b) if stride_b else self.packed_stride(H, W)
+        if stride < (H * W + 7) // 8 or mask_bits.numel() < B * stride:
+            raise ValueError("mask_bits holds fewer than B * stride bytes (stride >= ceil(H*W/8))")
+        dev = images.device
+        if out is None:
+            out = torch.empty((B, self.F), dtype=torch.float64, device=dev)
+        if status is None:
+            status = torch.empty((B,), dtype=torch.int32, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = self.lib.radb_extract_packed(self._h, images.data_ptr(), self.DTYPES[images.dtype], mask_bits.data_ptr(), B, H, W,
+                                          H * W * images.element_size(), stride, out.data_ptr(), status.data_ptr(),
+                                          st.cuda_stream)
+        if rc != 0:
+            raise RadbError("radb_extract_packed failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+        return out, status
+
     def extract_ragged(self, img_pool, mask_pool, img_off, mask_off, hw, out=None, status=None, stream=None):
         """Variable-size batch (radb_extract_ragged): ``img_pool`` / ``mask_pool`` are 1-D device tensors
         holding the patches back to back, ``img_off`` / ``mask_off`` (int64, BYTES) and ``hw`` ([n, 2] int32)
@@ -175,6 +200,24 @@ class Engine:
         if rc != 0:
             raise RadbError("radb_pack_mask_host failed (%d)" % rc)
 
+    @staticmethod
+    def packed_stride(H, W):
+        """Bytes between the bit streams of consecutive patches: ceil(H*W/8) rounded up to 16 (TMA staging)."""
+        return ((H * W + 7) // 8 + 15) // 16 * 16
+
+    def pack_masks_host(self, masks, packed, threads):
+        """Per-patch packing for ``extract_packed`` (radb_pack_masks_host): ``masks`` [n, H, W] uint8 host tensor ->
+        ``packed`` host bytes, patch b at ``b * packed_stride(H, W)``."""
+        if masks.is_cuda or packed.is_cuda or masks.dtype != torch.uint8 or packed.dtype != torch.uint8:
+            raise TypeError("pack_masks_host takes uint8 host tensors")
+        n, H, W = masks.shape
+        stride = self.packed_stride(H, W)
+        if not (masks.is_contiguous() and packed.is_contiguous()) or packed.numel() < n * stride:
+            raise ValueError("masks / packed must be contiguous and packed large enough")
+        rc = self.lib.radb_pack_masks_host(masks.data_ptr(), n, H * W, self.label, packed.data_ptr(), stride, int(threads))
+        if rc != 0:
+            raise RadbError("radb_pack_masks_host failed (%d)" % rc)
+
     def unpack_mask(self, packed, masks, stream=None):
         """Device half (radb_unpack_mask): ``packed`` device bytes -> ``masks`` uint8 device tensor (label where set)."""
         if not (packed.is_cuda and masks.is_cuda) or masks.dtype != torch.uint8 or not masks.is_contiguous():
@@ -197,6 +240,37 @@ class Engine:
                                         mx.data_ptr(), st.cuda_stream)
         if rc != 0:
             raise RadbError("radb_derive_image failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+        return out
+
+    def filter_image(self, images, kind, sigma=0.0, x_only=False, stream=None):
+        """Filtered image types (radb_filter_image) of uint8 device images [B, H, W]:
+        ``kind`` "Gradient" -> float32 [B, H, W]; "LoG" (``sigma``) -> float32 [B, H, W]; "Wavelet" -> float64
+        [B, K, H, W] with K = 2 (wavelet-H, wavelet-L; ``x_only``: pyradiomics' force2D axis removal) or 4
+        (wavelet-LH, -HL, -HH, -LL)."""
+        if images.dtype != torch.uint8 or not images.is_cuda or not images.is_contiguous() or images.dim() != 3:
+            raise ValueError("filter_image takes contiguous uint8 CUDA images [B, H, W]")
+        B, H, W = images.shape
+        dev = images.device
+        code = {"Gradient": 5, "LoG": 6, "Wavelet": 7}[kind]
+        scratch = None
+        if kind == "Gradient":
+            out = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+        elif kind == "LoG":
+            if H < 4 or W < 4:
+                raise ValueError("LoG needs at least 4 pixels per axis (ITK recursive Gaussian)")
+            out = torch.empty((B, H, W), dtype=torch.float32, device=dev)
+            scratch = torch.empty((B * H * W * 12 + 16,), dtype=torch.uint8, device=dev)
+        else:
+            out = torch.empty((B, 2 if x_only else 4, H, W), dtype=torch.float64, device=dev)
+            if not x_only:
+                scratch = torch.empty((B * 2 * (H + 1) * (W + 1),), dtype=torch.float64, device=dev)
+        st = stream if stream is not None else torch.cuda.current_stream(dev)
+        rc = self.lib.radb_filter_image(self._h, images.data_ptr(), B, H, W, code, float(sigma), 1 if x_only else 0,
+                                        out.data_ptr(), scratch.data_ptr() if scratch is not None else None, st.cuda_stream)
+        if rc != 0:
+            raise RadbError("radb_filter_image failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+        if scratch is not None:
+            scratch.record_stream(st)
         return out
 
     def debug_matrices(self, images, masks):
@@ -305,10 +379,10 @@ class HostPipeline:
         for _ in range(self.slots):
             bufs.append(dict(
                 h_img=torch.empty((n, H, W), dtype=dtype).pin_memory(),
-                h_msk=torch.empty((n, H, W), dtype=torch.uint8).pin_memory(),
+                h_msk=None,
                 d_img=torch.empty((n, H, W), dtype=dtype, device=dev),
-                h_pk=torch.empty(((n * H * W + 7) // 8 + 16,), dtype=torch.uint8).pin_memory(),
-                d_pk=torch.empty(((n * H * W + 7) // 8 + 16,), dtype=torch.uint8, device=dev),
+                h_pk=torch.empty((n * Engine.packed_stride(H, W),), dtype=torch.uint8).pin_memory(),
+                d_pk=torch.empty((n * Engine.packed_stride(H, W),), dtype=torch.uint8, device=dev),
                 d_msk=None,
                 d_out=torch.empty((n, F), dtype=torch.float64, device=dev),
                 d_st=torch.empty((n,), dtype=torch.int32, device=dev),
@@ -337,7 +411,8 @@ class HostPipeline:
         pinned_in = images.is_pinned() and masks.is_pinned()
         # masks cross the link at 1 bit per pixel and are consumed packed by the kernels (radb_extract_packed);
         # patches whose pixel count is not a multiple of 128 bits keep the byte masks (16-byte aligned bit rows)
-        pack = self.pack_masks and masks.dtype == torch.uint8 and masks.is_contiguous() and (H * W) % 128 == 0
+        pack = self.pack_masks and masks.dtype == torch.uint8 and masks.is_contiguous() and self.engine.has_packed
+        pstride = self.engine.packed_stride(H, W)
         self.h2d_bytes = 0
         starts = list(range(0, B, chunk))
         dev = torch.device("cuda", self.engine.device)
@@ -350,7 +425,7 @@ class HostPipeline:
             bk = self._bufs[k % self.slots]
             bk["done"].synchronize()
             if pack:
-                self.engine.pack_mask_host(masks[s0:s0 + n0], bk["h_pk"], self.pack_threads)
+                self.engine.pack_masks_host(masks[s0:s0 + n0], bk["h_pk"], self.pack_threads)
 
         if self._pool is None:
             from concurrent.futures import ThreadPoolExecutor
@@ -363,7 +438,7 @@ class HostPipeline:
             fut.result()
             if k + 1 < len(starts):
                 fut = self._pool.submit(prepare, k + 1)
-            nb = n * H * W // 8
+            nb = n * pstride
             d_out = device_out[s:s + n] if device_out is not None else b["d_out"][:n]
             with torch.cuda.stream(b["stream"]):
                 if pinned_in:
@@ -374,19 +449,15 @@ class HostPipeline:
                 if pack:
                     b["d_pk"][:nb].copy_(b["h_pk"][:nb], non_blocking=True)
                     self.h2d_bytes += n * H * W * images.element_size() + nb
-                    if self.engine.has_packed:
-                        self.engine.extract_packed(b["d_img"][:n], b["d_pk"], d_out, b["d_st"][:n], stream=b["stream"])
-                    else:  # library without radb_extract_packed: expand on the device first
-                        if b["d_msk"] is None or b["d_msk"].shape[0] < n:
-                            b["d_msk"] = torch.empty((self._n, H, W), dtype=torch.uint8, device=dev)
-                        self.engine.unpack_mask(b["d_pk"], b["d_msk"][:n], stream=b["stream"])
-                        self.engine.extract_device(b["d_img"][:n], b["d_msk"][:n], d_out, b["d_st"][:n], stream=b["stream"])
+                    self.engine.extract_packed(b["d_img"][:n], b["d_pk"], d_out, b["d_st"][:n], stream=b["stream"])
                 else:
                     if b["d_msk"] is None or b["d_msk"].shape[0] < n:
                         b["d_msk"] = torch.empty((self._n, H, W), dtype=torch.uint8, device=dev)
                     if pinned_in:
                         b["d_msk"][:n].copy_(masks[s:s + n], non_blocking=True)
                     else:
+                        if b["h_msk"] is None or b["h_msk"].shape[0] < n:
+                            b["h_msk"] = torch.empty((self._n, H, W), dtype=torch.uint8).pin_memory()
                         b["h_msk"][:n].copy_(masks[s:s + n])
                         b["d_msk"][:n].copy_(b["h_msk"][:n], non_blocking=True)
                     self.h2d_bytes += n * H * W * images.element_size() + n * H * W

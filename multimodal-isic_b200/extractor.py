@@ -62,7 +62,7 @@ class RadiomicsExtractor:
         self.derived_types = [t for t in self.params.image_types if t != "Original"]
         self._has_original = "Original" in self.params.image_types
         self._derived_engine = None
-        if self.derived_types:
+        if any(t in IMAGE_TYPE_CODES for t in self.derived_types):
             tex_classes = [c for c in eng_classes if c != "shape2D"]
             self._derived_engine = Engine(self.params.bin_width, self.params.label, self.params.angles(2),
                                           bool(s["symmetricalGLCM"]), float(s["gldm_a"]), float(s["voxelArrayShift"]),
@@ -173,25 +173,32 @@ class RadiomicsExtractor:
             self._perm_t = torch.as_tensor(self._perm, device=out.device)
         return out.index_select(1, self._perm_t)
 
-    def _engine_for(self, images, masks):
+    def _engine_for(self, images, masks, texture_only=False):
         """uint8 pixels: the engine sized from binWidth.  Other pixel types: the gray-level count depends
         on the data, so an engine sized for this batch's largest ROI range (rounded up to a multiple of
-        8 levels) is created on demand and cached."""
+        8 levels) is created on demand and cached.  ``texture_only``: without shape2D (filtered image types)."""
         t = torch.as_tensor(images)
-        if t.dtype == torch.uint8 or self.params.bin_count:  # binCount: Ng = binCount whatever the pixel type
+        if (t.dtype == torch.uint8 or self.params.bin_count) and not texture_only:  # binCount: Ng = binCount whatever the pixel type
             return self.engine, self.pipeline
-        m = torch.as_tensor(masks) == self.params.label
-        f = t.to(torch.float64) if t.dtype != torch.uint16 else t.to(torch.int32).to(torch.float64)
-        big = torch.finfo(torch.float64).max
-        lo = torch.where(m, f, torch.full_like(f, big)).flatten(1).amin(1)
-        hi = torch.where(m, f, torch.full_like(f, -big)).flatten(1).amax(1)
-        ok = hi >= lo
-        span = float(((hi - lo)[ok] / self.params.bin_width).max().item()) if bool(ok.any()) else 0.0
-        ng = min(256, (int(span) + 3 + 7) // 8 * 8)
-        if ng not in self._engines_ng:
-            eng = Engine(*self._engine_args, max_ng=ng, device=self.device)
-            self._engines_ng[ng] = (eng, HostPipeline(eng, self.pipeline.chunk))
-        return self._engines_ng[ng]
+        if self.params.bin_count:
+            ng = int(self.params.bin_count)
+        else:
+            m = torch.as_tensor(masks) == self.params.label
+            f = t.to(torch.float64) if t.dtype != torch.uint16 else t.to(torch.int32).to(torch.float64)
+            big = torch.finfo(torch.float64).max
+            lo = torch.where(m, f, torch.full_like(f, big)).flatten(1).amin(1)
+            hi = torch.where(m, f, torch.full_like(f, -big)).flatten(1).amax(1)
+            ok = hi >= lo
+            span = float(((hi - lo)[ok] / self.params.bin_width).max().item()) if bool(ok.any()) else 0.0
+            ng = min(256, (int(span) + 3 + 7) // 8 * 8)
+        key = (ng, texture_only)
+        if key not in self._engines_ng:
+            args = list(self._engine_args)
+            if texture_only:
+                args[6] = [c for c in args[6] if c != "shape2D"]
+            eng = Engine(*args, max_ng=ng, device=self.device, bin_count=self.params.bin_count)
+            self._engines_ng[key] = (eng, HostPipeline(eng, self.pipeline.chunk))
+        return self._engines_ng[key]
 
     def extract_batch(self, images, masks, strict=False):
         """``images`` ``[B, H, W]`` uint8 (the reference's cv2 planes), uint16, float32 or float64; ``masks``
@@ -252,23 +259,40 @@ class RadiomicsExtractor:
             if roi.size:
                 span = max(span, float(roi.max()) - float(roi.min()))
         ng = min(256, (int(span / self.params.bin_width) + 3 + 7) // 8 * 8)
-        if ng not in self._engines_ng:
+        key = (ng, False)
+        if key not in self._engines_ng:
             eng = Engine(*self._engine_args, max_ng=ng, device=self.device)
-            self._engines_ng[ng] = (eng, HostPipeline(eng, self.pipeline.chunk))
-        return self._engines_ng[ng]
+            self._engines_ng[key] = (eng, HostPipeline(eng, self.pipeline.chunk))
+        return self._engines_ng[key]
 
     # ---- several image types ------------------------------------------------------------------
     def _device_blocks(self, images, masks, first=None):
-        """[shape | block per image type] for uint8 device images; ``first`` = precomputed (out, status) of
-        the Original/shape engine."""
+        """[shape | one block per filtered image, in pyradiomics' order] for uint8 device images; ``first`` =
+        precomputed (out, status) of the Original/shape engine."""
         if images.dtype != torch.uint8:
             raise NotImplementedError("derived image types are implemented for uint8 input images")
         out0, status = first if first is not None else self.engine.extract_device(images, masks)
         nshape = 9 if "shape2D" in self.params.classes else 0
-        blocks = [out0 if self._has_original else out0[:, :nshape]]
-        for t in self.derived_types:
-            der = self.engine.derive_image(images, IMAGE_TYPE_CODES[t])
-            o, st = self._derived_engine.extract_device(der, masks)
+        blocks = [out0[:, :nshape]] if nshape else []  # shape descriptors come first, whatever the image-type order
+        wave = None
+        for name, t, arg in self.params.blocks:
+            if t == "Original":
+                blocks.append(out0[:, nshape:])
+                continue
+            if t in IMAGE_TYPE_CODES:  # point-wise types: float64 images in the original intensity range
+                o, st = self._derived_engine.extract_device(self.engine.derive_image(images, IMAGE_TYPE_CODES[t]), masks)
+            else:
+                if t == "Wavelet":
+                    if wave is None:  # one transform yields every band
+                        wave = self.engine.filter_image(images, "Wavelet", x_only=bool(self.params.settings["force2D"]))
+                    img = wave[:, arg].contiguous()
+                elif t == "LoG":
+                    img = self.engine.filter_image(images, "LoG", sigma=arg)
+                else:
+                    img = self.engine.filter_image(images, "Gradient")
+                # the gray-level range of a filtered image depends on the data: an engine sized for this batch
+                eng, _ = self._engine_for(img, masks, texture_only=True)
+                o, st = eng.extract_device(img, masks)
             blocks.append(o)
             status = torch.maximum(status, st)
         return torch.cat(blocks, dim=1), status

@@ -51,7 +51,7 @@ FEATURE_NAMES = {
                 "PerimeterSurfaceRatio", "PixelSurface", "Sphericity"],
 }
 SUPPORTED_CLASSES = set(CLASS_ORDER) | {"shape2D"}
-SUPPORTED_IMAGE_TYPES = {"Original", "Square", "SquareRoot", "Logarithm", "Exponential"}
+SUPPORTED_IMAGE_TYPES = {"Original", "Square", "SquareRoot", "Logarithm", "Exponential", "Gradient", "LoG", "Wavelet"}
 IMAGE_TYPE_CODES = {"Square": 1, "SquareRoot": 2, "Logarithm": 3, "Exponential": 4}  # radb_derive_image
 # settings whose non-default value would change results and that the engine does not implement
 _UNSUPPORTED_IF_SET = ("normalize", "removeOutliers", "resampledPixelSpacing", "resegmentRange", "weightingNorm",
@@ -150,6 +150,7 @@ class Settings:
         self.image_types = [t for t in self.enabledImagetypes if t in SUPPORTED_IMAGE_TYPES]
         if not self.image_types:
             raise NotImplementedError("no implemented image type is enabled")
+        self.blocks = self._image_blocks()
         skipped_cls = [c for c in self.enabledFeatures if c not in SUPPORTED_CLASSES]
         if skipped_cls:
             self._complain("feature classes %s are enabled but not implemented by the B200 engine" % skipped_cls)
@@ -163,6 +164,40 @@ class Settings:
             unknown = [f for f in self.enabledFeatures[c] if f not in FEATURE_NAMES[c]]
             if unknown:
                 raise ValueError("unknown / deprecated features for class %s: %s" % (c, unknown))
+
+    def _image_blocks(self):
+        """One entry per filtered image pyradiomics would yield, in its order (imageType file order; the images of one
+        type in the order of imageoperations.get*Image): ``(feature-name prefix, image type, argument)``."""
+        s = self.settings
+        blocks = []
+        for t in self.image_types:
+            opt = self.enabledImagetypes.get(t) or {}
+            if t == "Wavelet":
+                if opt.get("wavelet", "coif1") != "coif1" or int(opt.get("level", 1)) != 1 or int(opt.get("start_level", 0)) != 0:
+                    raise NotImplementedError("Wavelet: only the pyradiomics defaults (coif1, level 1, start_level 0) are implemented")
+                if s.get("force2D", False):
+                    # getWaveletImage: axes = [1, 0] minus force2Ddimension (the same axis removal as the texture
+                    # angles, oracle/U1_ANGLES.md) -> a 1-D transform
+                    if int(s.get("force2Ddimension", 0)) != 0:
+                        raise NotImplementedError("Wavelet with force2Ddimension != 0 is not implemented")
+                    blocks += [("wavelet-H", t, 0), ("wavelet-L", t, 1)]
+                else:
+                    blocks += [("wavelet-%s" % b, t, k) for k, b in enumerate(("LH", "HL", "HH", "LL"))]
+            elif t == "LoG":
+                sig = opt.get("sigma")
+                if not sig:
+                    raise ValueError("LoG: no sigma values given (pyradiomics yields no image without them)")
+                for v in sig:
+                    if not float(v) > 0:
+                        raise ValueError("LoG: sigma must be > 0")
+                    blocks.append(("log-sigma-%s-mm-3D" % str(v).replace(".", "-"), t, float(v)))
+            elif t == "Gradient":
+                if opt.get("gradientUseSpacing", s.get("gradientUseSpacing", True)) is not True:
+                    pass  # spacing is (1, 1) for GetImageFromArray images: same result either way
+                blocks.append(("gradient", t, None))
+            else:
+                blocks.append((t.lower(), t, None))
+        return blocks
 
     # ---- resolved views
     @property
@@ -192,10 +227,10 @@ class Settings:
         names = []
         if "shape2D" in self.classes:
             names += ["original_shape2D_%s" % f for f in self._class_features("shape2D")]
-        for t in self.image_types:
+        for name, _, _ in self.blocks:
             for c in self.classes:
                 if c != "shape2D":
-                    names += ["%s_%s_%s" % (t.lower(), c, f) for f in self._class_features(c)]
+                    names += ["%s_%s_%s" % (name, c, f) for f in self._class_features(c)]
         return names
 
     def engine_columns(self):
@@ -204,7 +239,7 @@ class Settings:
         ``perm`` maps that super-row to ``feature_names()``."""
         eng_classes = [c for c in ("shape2D",) + tuple(CLASS_ORDER) if c in self.classes]
         eng_names = ["original_shape2D_%s" % f for f in FEATURE_NAMES["shape2D"]] if "shape2D" in eng_classes else []
-        for t in self.image_types:
-            eng_names += ["%s_%s_%s" % (t.lower(), c, f) for c in eng_classes if c != "shape2D" for f in FEATURE_NAMES[c]]
+        for name, _, _ in self.blocks:
+            eng_names += ["%s_%s_%s" % (name, c, f) for c in eng_classes if c != "shape2D" for f in FEATURE_NAMES[c]]
         pos = {n: i for i, n in enumerate(eng_names)}
         return eng_classes, [pos[n] for n in self.feature_names()]

@@ -694,14 +694,25 @@ def matrices(image, mask, settings=None, matrix_backend=None):
 
 def execute_image_types(image, mask, settings=None, classes=CLASS_ORDER, image_types=("Original",), matrix_backend=None):
     """``execute`` over several enabled image types in file order: shape first (once), then one block of
-    texture / first-order features per image type, keys prefixed with the image-type name."""
+    texture / first-order features per filtered image, keys prefixed with pyradiomics' image name.
+    ``image_types``: names, or a mapping name -> options (``{"LoG": {"sigma": [1.0, 2.0]}}``) as in the
+    ``imageType`` section of the parameter file (/root/reference/params.yml:137-145)."""
+    from . import image_filters as flt
+
+    s = resolve_settings(settings)
     out = OrderedDict()
     if "shape2D" in classes:
         out.update(execute(image, mask, settings, classes=("shape2D",)))
     rest = tuple(c for c in classes if c != "shape2D")
-    for t in image_types:
-        arr, name = derived_image(image, t)
-        out.update(execute(arr, mask, settings, classes=rest, image_type=name, matrix_backend=matrix_backend))
+    items = image_types.items() if hasattr(image_types, "items") else [(t, {}) for t in image_types]
+    for t, opt in items:
+        if t in ("Gradient", "LoG", "Wavelet"):
+            imgs = flt.filtered_images(image, t, opt or {}, s["force2D"], s["force2Ddimension"])
+        else:
+            arr, name = derived_image(image, t)
+            imgs = {name: arr}
+        for name, arr in imgs.items():
+            out.update(execute(arr, mask, settings, classes=rest, image_type=name, matrix_backend=matrix_backend))
     return out
 
 

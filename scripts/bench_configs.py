@@ -73,23 +73,29 @@ def config3_mixed_sizes(n_each=1500):
         emit(config="configs[3] size class %dx%d alone" % (H, H), patches=len(idx), ms=ms, patches_per_s=len(idx) / ms * 1e3)
 
 
-def config4_binwidth_sweep():
-    """64x64 uint16 intensities in [0, 2048): binWidth 8..64 <-> 256..32 gray levels"""
+def config4_binwidth_sweep(n_patches=1000000):
+    """BASELINE.json configs[4]: 64x64 uint16 intensities in [0, 2048): binWidth 8..64 <-> 256..32 gray levels,
+    `n_patches` patches per binWidth (1 M by default; the 256 distinct synthetic patches are tiled on the device)."""
     g, m = pkg.synth.make_patches(256, 64, seed=60, dtype=np.uint16, vmax=2047)
-    for bw, n in ((64, 16384), (32, 16384), (16, 2048), (8, 512)):
-        reps = (n + 255) // 256
-        gi = torch.as_tensor(np.tile(g, (reps, 1, 1))[:n].view(np.int16)).cuda().view(torch.uint16)
-        mi = torch.as_tensor(np.tile(m, (reps, 1, 1))[:n]).cuda()
+    g0 = torch.as_tensor(g.view(np.int16)).cuda()
+    m0 = torch.as_tensor(m).cuda()
+    reps = (n_patches + 255) // 256
+    gi = g0.repeat(reps, 1, 1)[:n_patches].contiguous().view(torch.uint16)
+    mi = m0.repeat(reps, 1, 1)[:n_patches].contiguous()
+    for bw in (64, 32, 16, 8):
+        n = n_patches
         eng = pkg.Engine(bw, 255, pkg.in_plane_angles(), max_ng=2048 // bw)
+        probe = min(n, 4096)
+        eng.extract_device(gi[:probe], mi[:probe])
         eng.set_profiling(True)
-        out, st = eng.extract_device(gi, mi)
+        out, st = eng.extract_device(gi[:probe], mi[:probe])
         torch.cuda.synchronize()
-        eng.kernel_ms()
-        ms = timed(lambda: eng.extract_device(gi, mi), reps=3, warm=1)
-        parts = {k: v / 4 for k, v in eng.kernel_ms().items()}
+        parts = eng.kernel_ms()
+        eng.set_profiling(False)
+        ms = timed(lambda: eng.extract_device(gi, mi), reps=2, warm=1)
         emit(config="configs[4]: binWidth sweep on 64x64 uint16 patches", binWidth=bw, max_ng=2048 // bw, patches=n, ms=ms,
-             patches_per_s=n / ms * 1e3, kernel_ms_parts=parts, smem_build_bytes=eng.smem_bytes(64, 64, pkg._abi.DTYPE_U16),
-             invalid=int((st != 0).sum()))
+             patches_per_s=n / ms * 1e3, probe_patches=probe, kernel_ms_parts_probe=parts,
+             smem_build_bytes=eng.smem_bytes(64, 64, pkg._abi.DTYPE_U16), invalid_in_probe=int((st != 0).sum()))
 
 
 def reference_workload(n_images=128):
@@ -121,4 +127,5 @@ if __name__ == "__main__":
     if "3" in which:
         config3_mixed_sizes()
     if "4" in which:
-        config4_binwidth_sweep()
+        n = [int(a.split("=")[1]) for a in which if a.startswith("n=")]
+        config4_binwidth_sweep(n[0] if n else 1000000)

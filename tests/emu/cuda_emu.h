@@ -164,6 +164,10 @@ inline double __dmul_rn(double a, double b) {
     volatile double r = a * b;  // a separately rounded product even when the harness is built with FMA contraction
     return r;
 }
+inline float __fadd_rn(float a, float b) {
+    volatile float r = a + b;
+    return r;
+}
 inline double __dadd_rn(double a, double b) {
     volatile double r = a + b;
     return r;

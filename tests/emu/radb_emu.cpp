@@ -51,6 +51,8 @@ static int emu_launch(RadbParams& p, int dtype, int64_t B)
     if (getenv("RADB_NO_LANE")) p.use_lane = 0;
     if (p.use_lane && p.l_smem_total > mx) mx = p.l_smem_total;
     if (p.use_lane == 2 && p.g8_smem_total > mx) mx = p.g8_smem_total;
+    if (p.use_lane) p.use_lanczos = 0;
+    if (p.use_lanczos && p.z_smem_total > mx) mx = p.z_smem_total;
     p.only_big_ovf = (!getenv("RADB_NO_LANE") && p.ml_smem_total <= 96 * 1024) ? 1 : 0;
     if (p.only_big_ovf && p.ml_smem_total > mx) mx = p.ml_smem_total;
     std::vector<unsigned char> smem((size_t)mx + 64);
@@ -70,6 +72,8 @@ static int emu_launch(RadbParams& p, int dtype, int64_t B)
         case RADB_DTYPE_F64: EMU_BUILD(double) break;
         default: g_err = "unknown dtype"; return -1;
     }
+    if (p.use_lanczos && p.off_glcm >= 0)
+        emu::launch((unsigned)(B * p.n_angles), RADB_NTZ, [&]() { radb_mcc_lanczos_cta(p, (long long)blockIdx.x, sm); });
     if (p.use_lane == 2 && p.off_glcm >= 0)
         emu::launch((unsigned)((B + RADB_NTM / 32 - 1) / (RADB_NTM / 32)), RADB_NTM, [&]() { radb_mcc_g8_cta(p, (long long)blockIdx.x, sm); });
     if (p.use_lane)
@@ -82,6 +86,10 @@ static int emu_launch(RadbParams& p, int dtype, int64_t B)
     if (p.off_shape >= 0) emu::launch((unsigned)B, RADB_NT, [&]() { radb_shape_cta(p, (long long)blockIdx.x, sm); });
     return 0;
 }
+
+static int g_mask_bits = 0;
+// the next radb_emu_extract call reads `mask` as bit-packed streams (radb_extract_packed)
+extern "C" void radb_emu_set_mask_bits(int on) { g_mask_bits = on ? 1 : 0; }
 
 // Host-pointer twin of radb_debug_matrices.
 extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dtype, const uint8_t* mask, int64_t B,
@@ -99,6 +107,7 @@ extern "C" int radb_emu_extract(const radb_settings* s, const void* img, int dty
     p.mask = mask;
     p.img_stride = img_stride_b;
     p.mask_stride = mask_stride_b;
+    p.mask_bits = g_mask_bits;
     p.out = out;
     p.status = status;
     p.B = B;
@@ -157,6 +166,38 @@ extern "C" int radb_emu_extract_ragged(const radb_settings* s, const void* img_p
         p.B = (long long)g.idx.size();
         rc = emu_launch(p, dtype, p.B);
         if (rc) return rc;
+    }
+    return 0;
+}
+
+// Host twin of radb_filter_image (Gradient / LoG / Wavelet kernels of radb_filters.cuh), one "thread" per loop index.
+extern "C" int radb_emu_filter(const uint8_t* img, int64_t n, int H, int W, int type, double param, int flags, void* out,
+                               void* scratch)
+{
+    const long long HW = (long long)H * W, npx = n * HW;
+    if (type == RADB_IT_GRADIENT) {
+        for (long long t = 0; t < npx; t++) radb_gradient_px(img, n, H, W, (float*)out, t);
+    } else if (type == RADB_IT_WAVELET) {
+        if (flags & 1) {
+            for (long long t = 0; t < npx; t++) radb_wavelet_x_px(img, n, H, W, (double*)out, t);
+        } else {
+            const long long npp = n * (long long)(H + (H & 1)) * (W + (W & 1));
+            for (long long t = 0; t < npp; t++) radb_wavelet_rows_px(img, n, H, W, (double*)scratch, t);
+            for (long long t = 0; t < npx; t++) radb_wavelet_cols_px((const double*)scratch, n, H, W, (double*)out, t);
+        }
+    } else if (type == RADB_IT_LOG) {
+        if (H < 4 || W < 4) return -1;
+        RadbIir c0, c2;
+        radb::deriche_coefficients(param, 0, c0.N, c0.D, c0.M, c0.BN, c0.BM);
+        radb::deriche_coefficients(param, 2, c2.N, c2.D, c2.M, c2.BN, c2.BM);
+        double* scr = (double*)scratch;
+        float* tmp = (float*)(scr + npx);
+        for (long long t = 0; t < n * H; t++) radb_iir_thread<true>(img, tmp, scr, n, H, W, 0, c2, 0, t);
+        for (long long t = 0; t < n * W; t++) radb_iir_thread<false>(tmp, (float*)out, scr, n, H, W, 1, c0, 0, t);
+        for (long long t = 0; t < n * W; t++) radb_iir_thread<true>(img, tmp, scr, n, H, W, 1, c2, 0, t);
+        for (long long t = 0; t < n * H; t++) radb_iir_thread<false>(tmp, (float*)out, scr, n, H, W, 0, c0, 1, t);
+    } else {
+        return -3;
     }
     return 0;
 }

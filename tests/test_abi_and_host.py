@@ -72,18 +72,17 @@ def test_no_cpu_fallback_without_gpu():
 def test_settings_reference_like_file(tmp_path):
     f = tmp_path / "params.yml"
     f.write_text(REFERENCE_LIKE_PARAMS)
-    with warnings.catch_warnings(record=True) as w:
-        warnings.simplefilter("always")
-        s = pkg.Settings(str(f), strict=False)
-    assert any("Wavelet" in str(x.message) for x in w)
-    assert s.label == 255 and s.bin_width == 10.0
+    s = pkg.Settings(str(f))  # strict (default): every enabled image type is implemented
+    assert s.label == 255 and s.bin_width == 10.0 and not s.skipped_image_types
     assert s.angles() == orc.angles(2, force2D=True)[0] == [(0, 1)]          # literal force2D on 2-D input
     assert list(s.enabledImagetypes) == ["Original", "Wavelet", "LoG"]
     assert list(s.enabledFeatures) == ["firstorder", "shape2D", "glcm", "gldm", "glrlm", "glszm", "ngtdm"]
-    # 102 = 9 shape2D + 93 (dataset.py:42), shape keys first
-    assert s.feature_names() == orc.feature_names(("shape2D",) + orc.CLASS_ORDER) and len(s.feature_names()) == 102
-    with pytest.raises(NotImplementedError):
-        pkg.Settings(str(f))  # strict is the default: a drop-in must not silently narrow the column set
+    # 102 = 9 shape2D + 93 (dataset.py:42), shape keys first; then one 93-block per filtered image
+    n = s.feature_names()
+    assert n[:102] == orc.feature_names(("shape2D",) + orc.CLASS_ORDER)
+    prefixes = [b[0] for b in s.blocks]
+    assert prefixes[:3] == ["original", "wavelet-H", "wavelet-L"] and all(p.startswith("log-sigma-") for p in prefixes[3:])
+    assert len(n) == 9 + 93 * len(prefixes)
 
 
 def test_settings_class_order_and_feature_subset():
@@ -158,15 +157,25 @@ def test_dataframe_contract():
 
 def test_settings_derived_image_types():
     p = yaml.safe_load(REFERENCE_LIKE_PARAMS)
-    p["imageType"].update({"Square": {}, "SquareRoot": {}, "Logarithm": {}, "Exponential": {}, "Gradient": {}})
-    with pytest.warns(RuntimeWarning, match="Wavelet"):
-        s = pkg.Settings(p, strict=False)
-    assert s.image_types == ["Original", "Square", "SquareRoot", "Logarithm", "Exponential"]
+    p["imageType"] = {"Original": {}, "Square": {}, "SquareRoot": {}, "Logarithm": {}, "Exponential": {}, "Gradient": {}}
+    s = pkg.Settings(p)
+    assert s.image_types == ["Original", "Square", "SquareRoot", "Logarithm", "Exponential", "Gradient"]
     names = s.feature_names()
-    assert len(names) == 102 + 4 * 93                      # shape once, one 93-block per image type
+    assert len(names) == 102 + 5 * 93                      # shape once, one 93-block per image type
     assert names[:9] == ["original_shape2D_%s" % f for f in orc.SHAPE2D_NAMES]
-    assert names[102] == "square_firstorder_10Percentile" and names[-1] == "exponential_ngtdm_Strength"
+    assert names[102] == "square_firstorder_10Percentile" and names[-1] == "gradient_ngtdm_Strength"
     assert s.engine_columns()[1] == list(range(len(names)))
+    # wavelet band names follow pyradiomics' axis removal: force2D -> 1-D transform along x
+    p["imageType"] = {"Wavelet": {}}
+    assert [b[0] for b in pkg.Settings(p).blocks] == ["wavelet-H", "wavelet-L"]
+    p["setting"]["force2D"] = False
+    assert [b[0] for b in pkg.Settings(p).blocks] == ["wavelet-LH", "wavelet-HL", "wavelet-HH", "wavelet-LL"]
+    p["imageType"] = {"Wavelet": {"wavelet": "db2"}}
+    with pytest.raises(NotImplementedError):
+        pkg.Settings(p)
+    p["imageType"] = {"LoG": {}}
+    with pytest.raises(ValueError):
+        pkg.Settings(p)
 
 
 def test_pack_ragged_layout():
@@ -241,20 +250,19 @@ def test_record_decode_pool_keeps_order(tmp_path):
 
 def test_settings_parse_the_reference_parameter_file():
     """The reference's own params.yml (RadiomicExtractor.py:15), when the checkout is present (it is not on the GPU
-    box): label 255, binWidth 10, force2D -> one along-row angle, every image type listed; the implemented ones give
-    9 shape2D + 93 x (Original, Square, SquareRoot, Logarithm, Exponential) columns per channel."""
+    box): label 255, binWidth 10, force2D -> one along-row angle; every enabled image type is implemented (strict
+    parsing succeeds): 9 shape2D + 93 x 11 filtered images (Original, wavelet-H/L, LoG sigma 1/2/3, Square, SquareRoot,
+    Logarithm, Exponential, Gradient) per channel."""
     path = "/root/reference/params.yml"
     if not os.path.exists(path):
         pytest.skip("reference checkout not present")
-    with warnings.catch_warnings(record=True) as w:
-        warnings.simplefilter("always")
-        s = pkg.Settings(path, strict=False)
+    s = pkg.Settings(path)
     assert s.label == 255 and s.bin_width == 10.0 and s.bin_count == 0 and s.angles() == [(0, 1)]
     assert list(s.enabledImagetypes) == ["Original", "Wavelet", "LoG", "Square", "SquareRoot", "Logarithm", "Exponential", "Gradient"]
-    assert s.image_types == ["Original", "Square", "SquareRoot", "Logarithm", "Exponential"]
-    msg = " ".join(str(x.message) for x in w)
-    assert "Wavelet" in msg and "LoG" in msg and "Gradient" in msg
+    assert not s.skipped_image_types and s.image_types == list(s.enabledImagetypes)
+    assert [b[0] for b in s.blocks] == ["original", "wavelet-H", "wavelet-L", "log-sigma-1-0-mm-3D", "log-sigma-2-0-mm-3D",
+                                        "log-sigma-3-0-mm-3D", "square", "squareroot", "logarithm", "exponential", "gradient"]
     names = s.feature_names()
-    assert len(names) == 9 + 93 * 5 and names[0].startswith("original_shape2D_") and names[9] == "original_firstorder_10Percentile"
+    assert len(names) == 9 + 93 * 11 and names[0].startswith("original_shape2D_") and names[9] == "original_firstorder_10Percentile"
     assert sum(n.startswith("exponential_") for n in names) == 93
     assert not any(n.startswith("diagnostics_") for n in names)  # additionalInfo: False (params.yml:62)

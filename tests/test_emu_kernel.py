@@ -289,3 +289,92 @@ def test_emu_address_sanitizer(tmp_path):
                        capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "AddressSanitizer" not in r.stderr and "runtime error" not in r.stderr, r.stderr[-2000:]
     assert "u16 [0 0]" in r.stdout
+
+
+@pytest.mark.parametrize("hw,dt,angles,force2d", [((64, 64), np.uint8, INPLANE, False), ((16, 12), np.uint8, INPLANE, False),
+                                                  ((13, 7), np.uint8, LITERAL, True), ((24, 24), np.float32, INPLANE, False)])
+def test_emu_packed_masks_give_identical_rows(emu, hw, dt, angles, force2d):
+    """radb_extract_packed: the kernels read 1-bit masks directly; rows and every matrix must be bit-identical to the
+    byte-mask call (TMA-size aligned and ragged sizes, vectorised and generic paths, non-uint8 first-order)."""
+    H, W = hw
+    if hw == (16, 12):
+        imgs, masks = edge_case_batch()
+    else:
+        imgs, masks = synth.make_patches(3, H, W, seed=21)
+    kw = dict(max_ng=64) if dt != np.uint8 else {}
+    imgs = imgs.astype(dt)
+    a = emu.run(imgs, masks, 10, 255, angles, classes=("shape2D",) + tuple(orc.CLASS_ORDER), **kw)
+    b = emu.run(imgs, masks, 10, 255, angles, classes=("shape2D",) + tuple(orc.CLASS_ORDER), packed=True, **kw)
+    for k in a:
+        np.testing.assert_array_equal(a[k], b[k], err_msg=k)
+    assert (a["status"] == 0).any()
+
+
+@pytest.mark.parametrize("bw,ng_cap,size", [(32, 64, 64), (8, 256, 48), (16, 128, 32)])
+def test_emu_lanczos_mcc_matches_oracle_and_dense_path(emu, monkeypatch, bw, ng_cap, size):
+    """More than 40 gray levels: radb_mcc_lanczos_kernel (deflated Lanczos over the CSR non-zeros, one CTA per
+    (patch, angle)) replaces the dense Householder tridiagonalisation of the warp-per-angle kernel.  Both must match
+    the oracle's eigvals-based MCC; RADB_NO_LANCZOS forces the dense path (different arithmetic, same value)."""
+    g, masks = synth.make_patches(3, size, seed=41, dtype=np.uint16, vmax=2047)
+    g[2] = (np.indices((size, size)).sum(0) * 37 % 2048).astype(np.uint16)  # diagonal stripes: few distinct pairs
+    r = emu.run(g, masks, bw, 255, INPLANE, max_ng=ng_cap)
+    s = dict(label=255, binWidth=bw, force2D=False)
+    assert compare_with_oracle(r, g, masks, s) == 3
+    monkeypatch.setenv("RADB_NO_LANCZOS", "1")
+    r2 = emu.run(g, masks, bw, 255, INPLANE, max_ng=ng_cap)
+    assert compare_with_oracle(r2, g, masks, s, check_matrices=False) == 3
+    k = orc.feature_names().index("original_glcm_MCC")
+    np.testing.assert_allclose(r["features"][:, k], r2["features"][:, k], rtol=1e-9, atol=1e-11)
+    assert not np.array_equal(r["features"][:, k], r2["features"][:, k])  # really two code paths
+
+
+def test_emu_lanczos_mcc_edge_spectra(emu):
+    """Edge spectra through the Lanczos path (max_ng 64 selects it): a checkerboard (lambda = -1: the spectral radius
+    of the deflated operator is |lambda_min|), a flat ROI (one level: MCC = 1 by definition), two level groups that
+    never touch (lambda = 1 twice: MCC = 1), a 2x2 ROI, sparse ROIs with empty angles."""
+    imgs, masks = edge_case_batch(H=20, W=20)
+    imgs = imgs.astype(np.uint16) * 4
+    yy, xx = np.mgrid[:20, :20]
+    imgs[6] = np.where(xx < 10, 100 + 40 * ((yy + xx) % 2), 900 + 40 * (yy % 2))  # two blocks of levels ...
+    masks[6] = 255
+    masks[6, :, 9:11] = 0                                                           # ... separated by a gap
+    r = emu.run(imgs, masks, 16, 255, INPLANE, max_ng=64)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=16, force2D=False)) == 6
+    k = orc.feature_names().index("original_glcm_MCC")
+    assert r["features"][6, k] == pytest.approx(1.0, abs=1e-9) and r["features"][5, k] == pytest.approx(1.0, abs=1e-9)
+
+
+@pytest.mark.parametrize("hw", [(16, 20), (9, 13), (64, 64)])
+def test_emu_filtered_image_types_bit_exact(emu, hw):
+    """Gradient / LoG / Wavelet kernels (radb_filters.cuh) against oracle/image_filters.py: same operation order, no
+    fused multiply-adds -> bit-identical pixels (even and odd sizes: the wavelet pads odd sizes by a wrapped sample)."""
+    import ctypes
+
+    from oracle import image_filters as flt
+
+    H, W = hw
+    rng = np.random.default_rng(7)
+    n = 3
+    imgs = rng.integers(0, 256, (n, H, W)).astype(np.uint8)
+    imgs[1] = synth.make_patches(1, H, W, seed=3)[0][0]
+    p = lambda a: a.ctypes.data_as(ctypes.c_void_p)
+    emu.lib.radb_emu_filter.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                        ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    scratch = np.zeros(n * 2 * (H + 1) * (W + 1) + n * H * W * 2, np.float64)
+    out = np.zeros((n, H, W), np.float32)
+    assert emu.lib.radb_emu_filter(p(imgs), n, H, W, 5, 0.0, 0, p(out), p(scratch)) == 0
+    for b in range(n):
+        np.testing.assert_array_equal(out[b].astype(np.float64), flt.gradient_image(imgs[b]))
+    for sigma in (1.0, 2.0, 3.0):
+        assert emu.lib.radb_emu_filter(p(imgs), n, H, W, 6, sigma, 0, p(out), p(scratch)) == 0
+        for b in range(n):
+            np.testing.assert_array_equal(out[b].astype(np.float64), flt.log_image(imgs[b], sigma))
+    w4 = np.zeros((n, 4, H, W))
+    assert emu.lib.radb_emu_filter(p(imgs), n, H, W, 7, 0.0, 0, p(w4), p(scratch)) == 0
+    w2 = np.zeros((n, 2, H, W))
+    assert emu.lib.radb_emu_filter(p(imgs), n, H, W, 7, 0.0, 1, p(w2), p(scratch)) == 0
+    for b in range(n):
+        for k, (name, arr) in enumerate(flt.wavelet_images(imgs[b]).items()):
+            np.testing.assert_array_equal(w4[b, k], arr, err_msg=name)
+        for k, (name, arr) in enumerate(flt.wavelet_images(imgs[b], force2D=True).items()):
+            np.testing.assert_array_equal(w2[b, k], arr, err_msg=name)

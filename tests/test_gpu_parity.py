@@ -363,6 +363,48 @@ def test_derived_image_types_batch_and_record_path(gpu_pkg, tmp_path):
         np.testing.assert_allclose(list(res[ch].values()), list(ref.values()), rtol=RTOL, atol=ATOL)
 
 
+REFERENCE_IMAGE_TYPES = {"Original": {}, "Wavelet": {}, "LoG": {"sigma": [1.0, 2.0, 3.0]}, "Square": {}, "SquareRoot": {},
+                         "Logarithm": {}, "Exponential": {}, "Gradient": {}}  # /root/reference/params.yml:137-145
+
+
+@pytest.mark.parametrize("force2d", [True, False])
+def test_reference_image_type_list_incl_wavelet_log_gradient(gpu_pkg, tmp_path, force2d):
+    """Every image type the reference's params.yml enables (Original, Wavelet, LoG sigma 1/2/3, Square, SquareRoot,
+    Logarithm, Exponential, Gradient): 9 + 11 x 93 columns per channel under the literal force2D reading (wavelet-H,
+    wavelet-L), 9 + 13 x 93 with the in-plane reading (wavelet-LH/HL/HH/LL); batched tensors and the record path
+    against the oracle (oracle/image_filters.py restates ITK / PyWavelets; parity unpinned)."""
+    import cv2
+
+    params = {"setting": {"label": 255, "binWidth": 10, "force2D": force2d, "symmetricalGLCM": True, "additionalInfo": False},
+              "imageType": REFERENCE_IMAGE_TYPES,
+              "featureClass": {c: [] for c in ("firstorder", "shape2D", "glcm", "gldm", "glrlm", "glszm", "ngtdm")}}
+    ex = gpu_pkg.RadiomicsExtractor(params)
+    assert len(ex.feature_names) == 9 + (11 if force2d else 13) * 93 and not ex.skipped_image_types
+    imgs, masks = gpu_pkg.synth.make_patches(2, 40, 52, seed=25)
+    out, st = ex.extract_batch(torch.as_tensor(imgs).cuda(), torch.as_tensor(masks).cuda())
+    out = out.cpu().numpy()
+    assert not st.cpu().numpy().any()
+    for b in range(2):
+        ref = orc.execute_image_types(imgs[b], masks[b], params["setting"], classes=ALL_CLASSES,
+                                      image_types=REFERENCE_IMAGE_TYPES, matrix_backend=cmatrices)
+        assert list(ref.keys()) == ex.feature_names
+        bad = [(k, r, g) for k, r, g in zip(ref, ref.values(), out[b]) if not np.isclose(g, r, rtol=RTOL, atol=ATOL, equal_nan=True)]
+        assert not bad, bad[:5]
+    if force2d:  # the reference's own call pattern: a record on disk, 4 channels
+        rng = np.random.default_rng(2)
+        bgr = np.stack([np.clip(imgs[0].astype(int) + rng.integers(-20, 20, imgs[0].shape), 0, 255) for _ in range(3)], -1).astype(np.uint8)
+        ip, sp = str(tmp_path / "i.png"), str(tmp_path / "s.png")
+        cv2.imwrite(ip, bgr)
+        cv2.imwrite(sp, masks[0])
+        res = ex.parallell_extraction([{"image_path": ip, "segmentation_path": sp}])[0]
+        ref = orc.execute_image_types(bgr[:, :, 2], masks[0], params["setting"], classes=ALL_CLASSES,
+                                      image_types=REFERENCE_IMAGE_TYPES, matrix_backend=cmatrices)
+        assert list(res["red"].keys()) == list(ref.keys())
+        np.testing.assert_allclose(list(res["red"].values()), list(ref.values()), rtol=RTOL, atol=ATOL)
+        df = gpu_pkg.features_to_dataframe([res])
+        assert df.shape == (1, 4 * (9 + 11 * 93)) and df.columns[9 + 93] == "wavelet-H_firstorder_10Percentile_gs"
+
+
 def _fuzz_patch(rng, H, W, kind):
     yy, xx = np.mgrid[:H, :W]
     if kind == 0:      # white noise
