@@ -206,18 +206,29 @@ extern "C" int radb_smem_bytes(const radb_handle* h, int H, int W, int dtype)
     return p.smem_total;
 }
 
+// cudaFuncAttributeMaxDynamicSharedMemorySize belongs to the kernel (per device), not to a handle: two handles with
+// different gray-level bounds share the same kernel instances, so the configured maximum is tracked per (device,
+// kernel) for the whole process and only ever raised.
+static int g_smem_set[64][40];
 template <typename K>
 static int set_smem(radb_handle* h, K kernel, int which, int bytes)
 {
     if (bytes > h->smem_optin) return fail(RADB_E_SMEM, "shared memory request exceeds the device opt-in limit");
-    if (bytes > h->smem_set[which]) {
+    int* cur = &g_smem_set[h->device & 63][which];
+    if (bytes > *cur) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         if (e != cudaSuccess) return cuda_fail(e, "cudaFuncSetAttribute(MaxDynamicSharedMemorySize)");
         cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared);
-        h->smem_set[which] = bytes;
+        *cur = bytes;
     }
     return RADB_OK;
 }
+
+#define RADB_CHECK_LAUNCH(name)                                                                        \
+    do {                                                                                               \
+        cudaError_t le_ = cudaPeekAtLastError();                                                       \
+        if (le_ != cudaSuccess) { cudaGetLastError(); return cuda_fail(le_, name " launch"); }        \
+    } while (0)
 
 // One pass = three kernels over a chunk of patches, stream-ordered, sharing the record workspace.
 static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
@@ -322,6 +333,7 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         if (piped && c >= 2) cudaStreamWaitEvent(st, h->sync_events[2 * (c - 2) + 1], 0);  // slot free again
         mark();
         build<<<(unsigned)n, RADB_NTB, p.smem_total, st>>>(q);
+        RADB_CHECK_LAUNCH("radb_build_kernel");
         mark();
         if (piped) {
             cudaEventRecord(h->sync_events[2 * c], st);
@@ -329,22 +341,27 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         }
         if (p.use_lane == 2 && p.off_glcm >= 0) {
             radb_mcc_g8_kernel<<<(unsigned)((n + RADB_NTM / 32 - 1) / (RADB_NTM / 32)), RADB_NTM, p.g8_smem_total, rs>>>(q);
+            RADB_CHECK_LAUNCH("radb_mcc_g8_kernel");
             h->launches += 1;
         }
         if (p.use_lanczos && p.off_glcm >= 0) {
             radb_mcc_lanczos_kernel<<<(unsigned)(n * p.n_angles), RADB_NTZ, p.z_smem_total, rs>>>(q);
+            RADB_CHECK_LAUNCH("radb_mcc_lanczos_kernel");
             h->launches += 1;
         }
         if (p.use_lane)
             radb_angle_lane_kernel<<<(unsigned)((n * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, p.l_smem_total, rs>>>(q);
         else
             radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, rs>>>(q);
+        RADB_CHECK_LAUNCH(p.use_lane ? "radb_angle_lane_kernel" : "radb_angle_kernel");
         mark();
         if (p.only_big_ovf) {
             radb_misc_lane_kernel<<<(unsigned)((n + RADB_NT - 1) / RADB_NT), RADB_NT, p.ml_smem_total, rs>>>(q);
+            RADB_CHECK_LAUNCH("radb_misc_lane_kernel");
             h->launches += 1;
         }
         radb_misc_kernel<<<(unsigned)n, RADB_NT, p.m_smem_total, rs>>>(q);
+        RADB_CHECK_LAUNCH("radb_misc_kernel");
         if (p.off_shape >= 0) {
             radb_shape_kernel<<<(unsigned)n, RADB_NT, p.s_smem_total, rs>>>(q);
             h->launches += 1;
