@@ -43,6 +43,11 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=15.0, help="target wall time of the CPU baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-alt", action="store_true", help="skip the secondary (binWidth 10 / literal) measurements")
+    ap.add_argument("--no-e2e", action="store_true", help="device-resident measurement only (parameter sweeps)")
+    ap.add_argument("--e2e-pack", default="auto", choices=["auto", "on", "off"], help="host-side mask packing of the e2e path")
+    ap.add_argument("--pack-threads", type=int, default=0)
+    ap.add_argument("--slices", default="0.6,0.4",
+                    help="N > 1: fractions of the shard extracted per slice (the all-gather of a slice overlaps the next slice)")
     return ap.parse_args()
 
 
@@ -149,7 +154,7 @@ def workload_config(args, patches_per_step, F):
         "binWidth": args.bin_width,
         "angles": "literal force2D on 2-D input (1 angle, 2 neighbours)" if args.literal_force2d
         else "in-plane (4 angles, 8 neighbours)",
-        "label": 255, "parallelism": "patch-sharded, one process per GPU, all-gather of the feature block (sliced, overlapped with the extraction)",
+        "label": 255, "parallelism": "patch-sharded (block-cyclic), one process per GPU, all-gather of the feature block in two slices (60 / 40 %) overlapped with the extraction, written in place",
         "l2_policy": "inputs (%.0f MB per step) larger than the 126 MB L2" % (patches_per_step * args.size * args.size * 2 / 1e6),
     }
 
@@ -199,10 +204,16 @@ def gpu_arm(args):
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
+    # N > 1: keep this rank's pinned staging buffers on the NUMA node of its GPU (before anything is allocated)
+    numa = pkg.numa.bind_to_gpu_node(local) if world > 1 else None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     st = settings_dict(args)
     ex = pkg.RadiomicsExtractor({"setting": st}, device=local)
+    if args.e2e_pack != "auto":
+        ex.pipeline.pack_masks = args.e2e_pack == "on"
+    if args.pack_threads:
+        ex.pipeline.pack_threads = args.pack_threads
     F = ex.engine.F
     B, H = args.patches, args.size
     # every rank owns a different shard of the (virtual) global patch list
@@ -210,9 +221,11 @@ def gpu_arm(args):
     out = torch.empty((B, F), dtype=torch.float64, device=dev)
     status = torch.empty((B,), dtype=torch.int32, device=dev)
     gathered = torch.empty((world * B, F), dtype=torch.float64, device=dev) if world > 1 else None
-    # N > 1: the shard is extracted in two slices and the all-gather of the first (NCCL on a side stream)
-    # overlaps the extraction of the second; the step ends when the full [world * B, F] matrix is on every rank
-    og = pkg.OverlappedGather(B, F, world, dev, pieces=2) if world > 1 else None
+    # N > 1: the shard is extracted in `pieces` slices and the all-gather of slice k (NCCL on a side stream) overlaps
+    # the extraction of slice k+1; the global patch list is dealt to the ranks in blocks (block-cyclic), so every
+    # slice's all-gather lands in its final rows; the step ends when the full [world * B, F] matrix is on every rank
+    pieces = tuple(float(x) for x in args.slices.split(","))
+    og = pkg.OverlappedGather(B, F, world, dev, pieces=pieces) if world > 1 else None  # block-cyclic: zero-copy gather
 
     def extract_slice(lo, hi, o, s):
         ex.engine.extract_device(imgs[lo:hi], masks[lo:hi], o, s)
@@ -276,11 +289,11 @@ def gpu_arm(args):
         if world > 1:
             dist.all_gather_into_tensor(e2e_gathered, e2e_dev)
 
-    for _ in range(2):
+    for _ in range(0 if args.no_e2e else 2):
         e2e_step()
     barrier()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
+    for _ in range(1 if args.no_e2e else args.steps):
         e2e_step()
     barrier()
     e2e_s = torch.tensor([time.perf_counter() - t0], device=dev)
@@ -291,6 +304,8 @@ def gpu_arm(args):
         sampler.stop_flag.set()
         sampler.join(2)
     same = bool(torch.equal(h_out, out.cpu()))
+    e2e_stats = dict(h2d=ex.pipeline.h2d_bytes, packed=ex.pipeline.packed_chunks, chunks=ex.pipeline.total_chunks,
+                     pack_on=ex.pipeline.pack_masks, threads=ex.pipeline.pack_threads)
     # ---- N > 1: one step outside the timed region, checked end to end -- rank 0 receives every rank's input
     # shard (broadcast), recomputes it on its own GPU and compares the gathered blocks bit for bit
     # (/root/reference/RadiomicExtractor.py:63-65: the fan-out is order-preserving)
@@ -309,7 +324,8 @@ def gpu_arm(args):
             dist.broadcast(t_msk, src=r)
             if rank == 0:
                 ex.engine.extract_device(t_img, t_msk, t_out, status)
-                ok = ok and bool(torch.equal(gathered[r * B:(r + 1) * B].view(torch.int64), t_out.view(torch.int64)))
+                gidx = torch.as_tensor(og.global_index(r, np.arange(B)), device=dev)  # rows of rank r's patches in `gathered`
+                ok = ok and bool(torch.equal(gathered.index_select(0, gidx).view(torch.int64), t_out.view(torch.int64)))
                 ok = ok and bool(torch.equal(e2e_gathered[r * B:(r + 1) * B].view(torch.int64), t_out.view(torch.int64)))
         del t_img, t_msk, t_out
         gather_ok = ok
@@ -321,7 +337,44 @@ def gpu_arm(args):
     if world > 1:
         dist.all_reduce(rank_kms)
 
+    # ---- the discretise / histogram / first-order stage on its own (class mask: firstorder): the one stage of the path
+    # that is HBM-shaped (north_star: "achieved HBM GB/s ... for the discretise/first-order stage")
+    stage1 = None
+    if world == 1:
+        ex1 = pkg.RadiomicsExtractor({"setting": st, "featureClass": {"firstorder": []}}, device=local)
+        o1 = torch.empty((B, ex1.engine.F), dtype=torch.float64, device=dev)
+        for _ in range(3):
+            ex1.engine.extract_device(imgs, masks, o1, status)
+        m1 = timed(lambda: ex1.engine.extract_device(imgs, masks, o1, status), args.steps) / args.steps
+        b1 = bytes_per_patch(H, H, ex1.engine.F)
+        same_cols = bool(torch.equal(o1, out[:, :ex1.engine.F])) if ex.engine.names[:18] == ex1.engine.names else None
+        stage1 = {"classes": "firstorder only (18 features): TMA staging, ROI histogram, bin edges, level histogram, fp64 reductions",
+                  "ms_per_step": m1, "patches_per_s": B / (m1 / 1e3), "bytes_per_patch": b1,
+                  "achieved_gbs": B * b1 / (m1 / 1e3) / 1e9, "equals_full_pass_columns": same_cols}
+        ex.engine.extract_device(imgs, masks, out, status)  # restore status of the full pass
+        torch.cuda.synchronize()
+        del ex1, o1
+
     alt = {}
+    if not args.no_alt:
+        # callers that already hold bit-packed masks (radb_pack_masks_host's layout) skip the host packing entirely
+        h_pk = torch.empty((B, ex.engine.packed_stride(H, H)), dtype=torch.uint8).pin_memory()
+        ex.engine.pack_masks_host(h_msk, h_pk.view(-1), 8)
+        h_out2 = torch.empty((B, F), dtype=torch.float64).pin_memory()
+        for _ in range(2):
+            ex.pipeline.run(h_img, h_pk, h_out2, h_st, masks_packed=True)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            ex.pipeline.run(h_img, h_pk, h_out2, h_st, masks_packed=True)
+        barrier()
+        tp = torch.tensor([time.perf_counter() - t0], device=dev)
+        if world > 1:
+            dist.all_reduce(tp, op=dist.ReduceOp.MAX)
+        alt["e2e_masks_already_packed"] = {"value": world * B * args.steps / float(tp.item()), "unit": UNIT,
+                                           "h2d_bytes_per_step": int(world * ex.pipeline.h2d_bytes),
+                                           "rows_equal": bool(torch.equal(h_out2, h_out))}
+        del h_pk, h_out2
     if not args.no_alt and world == 1:
         for name, s2 in (("binWidth10_inplane", {"label": 255, "binWidth": 10.0, "force2D": False}),
                          ("binWidth10_literal_force2D", {"label": 255, "binWidth": 10.0, "force2D": True})):
@@ -377,15 +430,19 @@ def gpu_arm(args):
                          "dominant_share": kparts[dom] / kms,
                          "dominant_achieved": B * bpp / (kparts[dom] / 1e3) / 1e9,
                          "bytes_per_patch": bpp, "peak_source": peak_src,
+                         "stage1_firstorder_only": None if stage1 is None else dict(stage1, frac=stage1["achieved_gbs"] / peak),
                          "note": "algorithmic bytes = H*W px + H*W mask + 8*F per patch over the summed duration of "
                                  "the kernels of a pass (build / angle reductions / misc reductions); dominant_achieved uses the dominant kernel's duration "
                                  "alone. The pass is issue/latency bound (shared-memory atomics, fp64), not HBM "
                                  "bound (DESIGN.md, profiles/)"},
             "cpu_baseline": cpu,
-            "e2e": {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(world * ex.pipeline.h2d_bytes),
+            "e2e": {"value": total / e2e_s, "unit": UNIT, "h2d_bytes_per_step": int(world * e2e_stats["h2d"]),
                     "d2h_bytes_per_step": int(world * B * (F * 8 + 4)), "matches_device_path": same,
-                    "masks": ("packed to 1 bit per pixel by %d host threads (radb_pack_mask_host), expanded on the device"
-                              % ex.pipeline.pack_threads) if ex.pipeline.pack_masks else "uint8, as handed over"},
+                    "h2d_gbs_per_rank": e2e_stats["h2d"] * args.steps / e2e_s / 1e9,
+                    "masks": "uint8 masks handed over (as the reference does); %d of %d chunks per step packed to 1 bit per "
+                             "pixel by %d host threads and read packed by the kernels (radb_extract_packed)"
+                             % (e2e_stats["packed"], e2e_stats["chunks"], e2e_stats["threads"]),
+                    "numa": numa},
             "gpu_launches": int(launches),
             "multi_gpu": None if world == 1 else {
                 "gathered_equals_single_gpu_rows": gather_ok,

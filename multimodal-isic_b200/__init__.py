@@ -6,4 +6,4 @@ from .settings import FEATURE_NAMES, Settings, in_plane_angles  # noqa: F401
 from .engine import Engine, HostPipeline, RadbError, pack_ragged  # noqa: F401
 from .extractor import RadiomicsExtractor, features_to_dataframe  # noqa: F401
 from .sharded import OverlappedGather, all_gather_rows, shard_bounds, sharded_extract  # noqa: F401
-from . import synth  # noqa: F401
+from . import numa, synth  # noqa: F401

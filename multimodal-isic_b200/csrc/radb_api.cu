@@ -38,7 +38,8 @@ struct radb_handle {
     double* d_inv2;
     double* d_tlog;
     int64_t chunk;               // patches per chunk (0: RADB_CHUNK env / default); radb_set_chunk
-    cudaStream_t red_stream;     // high-priority stream of the reduction kernels (multi-chunk batches only)
+    cudaStream_t red_stream;     // high-priority side stream of the GLCM / GLRLM reduction kernels
+    cudaStream_t red_stream2;    // second side stream: first-order / GLDM / NGTDM / GLSZM / shape reductions (concurrent with the first)
     std::vector<cudaEvent_t> sync_events;  // build-done / reduce-done events of the two-stream pipeline (re-used)
     bool profiling;              // record CUDA events around every kernel (radb_set_profiling)
     std::vector<cudaEvent_t> events;  // 4 per chunk: start, after build, after angle, after misc
@@ -89,6 +90,7 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
     h->d_inv2 = h->d_tlog = nullptr;
     h->profiling = false;
     h->red_stream = nullptr;
+    h->red_stream2 = nullptr;
     h->chunk = 0;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -128,6 +130,7 @@ extern "C" void radb_destroy(radb_handle* h)
     for (auto ev : h->sync_events) cudaEventDestroy(ev);
     for (auto ev : h->events) cudaEventDestroy(ev);
     if (h->red_stream) cudaStreamDestroy(h->red_stream);
+    if (h->red_stream2) cudaStreamDestroy(h->red_stream2);
     delete h;
 }
 
@@ -279,22 +282,26 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     // (radb_set_profiling) needs the kernels back to back: profiling runs serialise on the caller's stream.
     static const bool no_overlap = getenv("RADB_NO_OVERLAP") != nullptr;
     const long long nchunks = (p.B + chunk - 1) / chunk;
-    const bool piped = nchunks > 1 && !h->profiling && !no_overlap;
+    // (single-chunk calls of at least 4096 patches fork too: the two reduction families are latency-bound kernels with
+    // few resident warps and run side by side)
+    const bool piped = (nchunks > 1 || p.B >= 4096) && !h->profiling && !no_overlap;
     if (piped) {
         if (!h->red_stream) {
             int lo = 0, hi = 0;
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
             e = cudaStreamCreateWithPriority(&h->red_stream, cudaStreamNonBlocking, hi);
+            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->red_stream2, cudaStreamNonBlocking, hi);
             if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreateWithPriority");
         }
-        while ((long long)h->sync_events.size() < 2 * nchunks) {
+        while ((long long)h->sync_events.size() < 3 * nchunks) {
             cudaEvent_t ev;
             e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
             if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
             h->sync_events.push_back(ev);
         }
     }
-    cudaStream_t rs = piped ? h->red_stream : st;
+    cudaStream_t rs = piped ? h->red_stream : st;    // GLCM / GLRLM (+ MCC) reductions
+    cudaStream_t ms = piped ? h->red_stream2 : st;   // first-order / GLDM / NGTDM / GLSZM / shape reductions
     long long done = 0;
     for (long long c = 0; done < p.B; c++) {
         const long long n = p.B - done < chunk ? p.B - done : chunk;
@@ -330,15 +337,20 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
             cudaEventRecord(ev, st);
             h->events.push_back(ev);
         };
-        if (piped && c >= 2) cudaStreamWaitEvent(st, h->sync_events[2 * (c - 2) + 1], 0);  // slot free again
+        if (piped && c >= 2) {  // slot free again: both reduction families of chunk c - 2 are done
+            cudaStreamWaitEvent(st, h->sync_events[3 * (c - 2) + 1], 0);
+            cudaStreamWaitEvent(st, h->sync_events[3 * (c - 2) + 2], 0);
+        }
         mark();
         build<<<(unsigned)n, RADB_NTB, p.smem_total, st>>>(q);
         RADB_CHECK_LAUNCH("radb_build_kernel");
         mark();
         if (piped) {
-            cudaEventRecord(h->sync_events[2 * c], st);
-            cudaStreamWaitEvent(rs, h->sync_events[2 * c], 0);
+            cudaEventRecord(h->sync_events[3 * c], st);
+            cudaStreamWaitEvent(rs, h->sync_events[3 * c], 0);
+            cudaStreamWaitEvent(ms, h->sync_events[3 * c], 0);
         }
+        const bool angle_classes = p.off_glcm >= 0 || p.off_glrlm >= 0;  // nothing to reduce per angle otherwise
         if (p.use_lane == 2 && p.off_glcm >= 0) {
             radb_mcc_g8_kernel<<<(unsigned)((n + RADB_NTM / 32 - 1) / (RADB_NTM / 32)), RADB_NTM, p.g8_smem_total, rs>>>(q);
             RADB_CHECK_LAUNCH("radb_mcc_g8_kernel");
@@ -349,29 +361,37 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
             RADB_CHECK_LAUNCH("radb_mcc_lanczos_kernel");
             h->launches += 1;
         }
-        if (p.use_lane)
+        if (!angle_classes)
+            h->launches -= 1;
+        else if (p.use_lane)
             radb_angle_lane_kernel<<<(unsigned)((n * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, p.l_smem_total, rs>>>(q);
         else
             radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, rs>>>(q);
         RADB_CHECK_LAUNCH(p.use_lane ? "radb_angle_lane_kernel" : "radb_angle_kernel");
         mark();
         if (p.only_big_ovf) {
-            radb_misc_lane_kernel<<<(unsigned)((n + RADB_NT - 1) / RADB_NT), RADB_NT, p.ml_smem_total, rs>>>(q);
+            radb_misc_lane_kernel<<<(unsigned)((n + RADB_NT - 1) / RADB_NT), RADB_NT, p.ml_smem_total, ms>>>(q);
             RADB_CHECK_LAUNCH("radb_misc_lane_kernel");
             h->launches += 1;
         }
-        radb_misc_kernel<<<(unsigned)n, RADB_NT, p.m_smem_total, rs>>>(q);
+        radb_misc_kernel<<<(unsigned)n, RADB_NT, p.m_smem_total, ms>>>(q);
         RADB_CHECK_LAUNCH("radb_misc_kernel");
         if (p.off_shape >= 0) {
-            radb_shape_kernel<<<(unsigned)n, RADB_NT, p.s_smem_total, rs>>>(q);
+            radb_shape_kernel<<<(unsigned)n, RADB_NT, p.s_smem_total, ms>>>(q);
             h->launches += 1;
         }
         mark();
-        if (piped) cudaEventRecord(h->sync_events[2 * c + 1], rs);
+        if (piped) {
+            cudaEventRecord(h->sync_events[3 * c + 1], rs);
+            cudaEventRecord(h->sync_events[3 * c + 2], ms);
+        }
         h->launches += 3;
         done += n;
     }
-    if (piped) cudaStreamWaitEvent(st, h->sync_events[2 * (nchunks - 1) + 1], 0);  // the side stream is in order
+    if (piped) {  // the side streams are in order: joining their last events joins everything
+        cudaStreamWaitEvent(st, h->sync_events[3 * (nchunks - 1) + 1], 0);
+        cudaStreamWaitEvent(st, h->sync_events[3 * (nchunks - 1) + 2], 0);
+    }
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "radb kernel launch");
     return RADB_OK;

@@ -798,6 +798,22 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     __syncthreads();
     const int ng = misc[8];
 
+    // Only first-order features enabled (the discretise / histogram stage on its own: the HBM-bound part of the
+    // path): uint8 pixels need neither the level image nor any texture matrix -- level histogram from the raw
+    // histogram through the LUT, publish the head of the record, done.
+    const bool dbg_on = DBG && (p.dbg_levels || p.dbg_glcm || p.dbg_glrlm || p.dbg_glszm || p.dbg_gldm || p.dbg_ngn);
+    const bool tex = dbg_on || p.off_glcm >= 0 || p.off_gldm >= 0 || p.off_glrlm >= 0 || p.off_glszm >= 0 || p.off_ngtdm >= 0;
+    if (!tex && U8) {
+        for (int v = tid; v < 256; v += RADB_NTB)
+            if (hist[v]) atomicAdd(&lhist[lut[v] - 1], hist[v]);
+        __syncthreads();
+        const uint4* src = (const uint4*)(smem + p.o_rec);
+        uint4* dst = (uint4*)g_rec;
+        const int n16 = ((p.big ? p.o_gldm : p.o_glcm) - p.o_rec) / 16;  // header + raw histogram + level histogram
+        for (int i = tid; i < n16; i += RADB_NTB) dst[i] = src[i];
+        return;
+    }
+
     // ---- phase 2: discretised level image (padded, 0 outside the ROI) + level histogram
     if (U8 && p.vec4) {
         const int WQ = W >> 2, NQ = HW >> 2;

@@ -345,7 +345,7 @@ class HostPipeline:
     enables it when this process has at least 8 host cores to itself (``os.cpu_count() // LOCAL_WORLD_SIZE``):
     with eight ranks on one host the packing threads would only compete for the same memory bandwidth."""
 
-    def __init__(self, engine, chunk=8192, pack_masks=None, pack_threads=None, slots=6, slot_bytes=128 << 20):
+    def __init__(self, engine, chunk=8192, pack_masks=None, pack_threads=None, slots=6, slot_bytes=128 << 20, adaptive=False):
         import os
 
         self.engine = engine
@@ -356,11 +356,18 @@ class HostPipeline:
         self._key = None
         self._pool = None
         self._n = 0  # patches per slot of the current buffers
-        cores = max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))))
-        # packing is memory bound beyond ~8 threads; a rank that shares the host with others keeps 2-4 threads
-        self.pack_threads = int(pack_threads) if pack_threads else max(2, min(cores, 8))
-        self.pack_masks = bool(pack_masks) if pack_masks is not None else True
+        ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+        cores = max(1, (os.cpu_count() or 1) // ranks)
+        self.pack_threads = int(pack_threads) if pack_threads else max(2, min(cores, 8))  # memory bound beyond ~8 threads
+        # Default policy (measured, scripts/e2e_modes.py -> profiles/r2_e2e_modes.jsonl): one rank per host with >= 8
+        # cores packs (9.2 vs 6.7 M patches/s: the link is the bound and packing takes 7/16 of its bytes away); several
+        # ranks per host do not -- their aggregate host-to-device rate is bound by the HOST (76 GB/s at 2 ranks, 165 GB/s
+        # at 8, well below ranks x 55 GB/s), and the packing threads read the same mask bytes the DMA engines would.
+        self.pack_masks = bool(pack_masks) if pack_masks is not None else (ranks == 1 and cores >= 8)
         self.h2d_bytes = 0  # bytes copied host -> device by the last run()
+        self.adaptive = bool(adaptive)  # pack a chunk's masks only while the host keeps ahead of the link (see run())
+        self._host_ahead = True
+        self.packed_chunks = self.total_chunks = 0
 
     def slot_patches(self, B, H, W, itemsize):
         """Patches per slot: the chunk size, capped by the batch and by ``slot_bytes`` per image buffer, so that a
@@ -391,11 +398,12 @@ class HostPipeline:
         self._key = key
         self._n = n
 
-    def run(self, images, masks, out=None, status=None, device_out=None):
+    def run(self, images, masks, out=None, status=None, device_out=None, masks_packed=False):
         """``images``/``masks``: host arrays [B, H, W] (images uint8/uint16/float32/float64, masks uint8; NumPy or CPU tensors; pinned tensors
         skip the staging copy).  Returns host ``(features [B, F] float64, status [B] int32)``.  ``device_out``
         (optional ``[B, F]`` float64 CUDA tensor) also keeps the rows on the device -- the multi-GPU driver
-        all-gathers them from there."""
+        all-gathers them from there.  ``masks_packed``: ``masks`` already holds the bit-packed streams
+        (``[B, packed_stride(H, W)]`` uint8, the layout of ``pack_masks_host``): no host packing at all."""
         images = torch.as_tensor(images)
         masks = torch.as_tensor(masks)
         if images.is_cuda:
@@ -411,21 +419,41 @@ class HostPipeline:
         pinned_in = images.is_pinned() and masks.is_pinned()
         # masks cross the link at 1 bit per pixel and are consumed packed by the kernels (radb_extract_packed);
         # patches whose pixel count is not a multiple of 128 bits keep the byte masks (16-byte aligned bit rows)
-        pack = self.pack_masks and masks.dtype == torch.uint8 and masks.is_contiguous() and self.engine.has_packed
         pstride = self.engine.packed_stride(H, W)
+        if masks_packed:
+            if masks.dtype != torch.uint8 or masks.dim() != 2 or masks.shape[0] != B or masks.shape[1] != pstride or not masks.is_contiguous():
+                raise ValueError("masks_packed: masks must be a contiguous uint8 [B, %d] tensor" % pstride)
+        pack = (not masks_packed) and self.pack_masks and masks.dtype == torch.uint8 and masks.is_contiguous() and self.engine.has_packed
         self.h2d_bytes = 0
+        self.packed_chunks = 0
         starts = list(range(0, B, chunk))
+        self.total_chunks = len(starts)
         dev = torch.device("cuda", self.engine.device)
+
+        import time
 
         def prepare(k):
             """Host work of chunk k, one chunk ahead of the enqueue loop on a helper thread: wait until the
-            slot has drained, then pack the masks (the C call releases the GIL and fans out to pack_threads)."""
+            slot has drained, then pack the masks (the C call releases the GIL and fans out to pack_threads).
+            Adaptive: packing trades host work for link bytes, so it only pays while the host is AHEAD of the link.
+            If the slot had to be waited for, the link / device is the bottleneck -> pack; if it was already free the
+            host is the bottleneck (few cores per rank) -> hand this chunk's masks over as bytes.  Returns whether
+            the chunk was packed."""
             s0 = starts[k]
             n0 = min(chunk, B - s0)
             bk = self._bufs[k % self.slots]
+            t0 = time.perf_counter()
             bk["done"].synchronize()
-            if pack:
+            waited = time.perf_counter() - t0 > 30e-6
+            if not pack:
+                return False
+            do = (not self.adaptive) or waited or (k < self.slots and self._host_ahead)
+            if k >= self.slots:
+                self._host_ahead = waited
+            if do:
                 self.engine.pack_masks_host(masks[s0:s0 + n0], bk["h_pk"], self.pack_threads)
+                self.packed_chunks += 1
+            return do
 
         if self._pool is None:
             from concurrent.futures import ThreadPoolExecutor
@@ -435,7 +463,7 @@ class HostPipeline:
         for k, s in enumerate(starts):
             n = min(chunk, B - s)
             b = self._bufs[k % self.slots]
-            fut.result()
+            packed = fut.result()
             if k + 1 < len(starts):
                 fut = self._pool.submit(prepare, k + 1)
             nb = n * pstride
@@ -446,7 +474,15 @@ class HostPipeline:
                 else:
                     b["h_img"][:n].copy_(images[s:s + n])
                     b["d_img"][:n].copy_(b["h_img"][:n], non_blocking=True)
-                if pack:
+                if masks_packed:
+                    src = masks[s:s + n].reshape(-1)
+                    if not pinned_in:
+                        b["h_pk"][:nb].copy_(src)
+                        src = b["h_pk"][:nb]
+                    b["d_pk"][:nb].copy_(src, non_blocking=True)
+                    self.h2d_bytes += n * H * W * images.element_size() + nb
+                    self.engine.extract_packed(b["d_img"][:n], b["d_pk"], d_out, b["d_st"][:n], stream=b["stream"])
+                elif packed:
                     b["d_pk"][:nb].copy_(b["h_pk"][:nb], non_blocking=True)
                     self.h2d_bytes += n * H * W * images.element_size() + nb
                     self.engine.extract_packed(b["d_img"][:n], b["d_pk"], d_out, b["d_st"][:n], stream=b["stream"])

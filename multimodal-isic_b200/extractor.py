@@ -142,13 +142,33 @@ class RadiomicsExtractor:
         with ThreadPoolExecutor(int(n_workers)) as pool:
             return list(pool.map(RadiomicsExtractor._load_record, list_of_dicts))  # map() keeps the input order
 
-    def parallell_extraction(self, list_of_dicts, n_processes=None):  # RadiomicExtractor.py:58-71
+    def parallell_extraction(self, list_of_dicts, n_processes=None, window=None):  # RadiomicExtractor.py:58-71
         """Order-preserving extraction of all records.  ``n_processes`` (default ``cpu_count() - 1``, as in the
-        reference) is the width of the host decode pool; the feature fan-out is over GPU CTAs.  Records of
-        equal image size are batched into one launch sequence."""
+        reference) is the width of the host decode pool; the feature fan-out is over GPU CTAs.  Records are streamed
+        in windows of ``window`` records (default 8 per decode thread, at least 32): window k+1 is decoded on the
+        pool while window k is on the GPU, so host memory holds two windows, not the whole data set (the reference
+        streams records through ``pool.imap``).  Records of equal image size inside a window share a launch."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
+
         logger.info("Extraction mode: parallel")
         t0 = time.time()
-        results = self._extract_records(self._load_records(list_of_dicts, n_processes))
+        n_workers = int(n_processes) if n_processes else max(1, (os.cpu_count() or 2) - 1)
+        window = int(window) if window else max(32, 8 * n_workers)
+        records = list(list_of_dicts)
+        results = []
+        if len(records) <= window or n_workers <= 1:
+            results = self._extract_records(self._load_records(records, n_workers))
+        else:
+            with ThreadPoolExecutor(n_workers) as pool:
+                def submit(lo):
+                    return [pool.submit(self._load_record, r) for r in records[lo:lo + window]]
+
+                pending = submit(0)
+                for lo in range(0, len(records), window):
+                    loaded = [f.result() for f in pending]  # input order; a decode error propagates as in the reference
+                    pending = submit(lo + window) if lo + window < len(records) else []
+                    results.extend(self._extract_records(loaded))
         h, m, s = self._convert_time(t0, time.time())
         logger.info(f" Time taken: {h}h:{m}m:{s}s")
         return results

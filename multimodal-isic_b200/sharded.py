@@ -70,49 +70,105 @@ def sharded_extract(extract_fn, n_patches, costs=None, group=None, F=None):
 
 
 class OverlappedGather:
-    """Equal shards (weak scaling: every rank owns ``rows`` patches): the local shard is extracted in
-    ``pieces`` slices, and the all-gather of slice k (NCCL over NVLink, on a side stream) overlaps the
-    extraction of slice k+1, so only the last slice's collective is exposed.  ``gathered`` is the full
-    ``[world * rows, F]`` matrix in rank-major (= original) order on every rank.
+    """Equal shards (weak scaling: every rank owns ``rows`` patches): the local shard is extracted in slices, and
+    the all-gather of slice k (NCCL over NVLink, on a side stream) overlaps the extraction of slice k+1, so only the
+    last slice's collective is exposed.  ``pieces`` = number of equal slices, or a sequence of fractions
+    (e.g. ``(0.5, 0.3, 0.15, 0.05)``: a small last slice keeps the exposed collective small, large early slices keep
+    the thread-level reduction kernels at several waves).  Slices alternate between two extraction streams, so the
+    latency-bound reduction kernels of slice k run under the build kernel of slice k+1.
+
+    Global order (``layout="block_cyclic"``, the default): the global patch list is dealt to the ranks slice by slice --
+    slice k of rank r holds global rows ``world * bounds[k] + r * n_k + i`` (``n_k`` = slice length).
+    ``all_gather_into_tensor`` of slice k then writes the contiguous global rows
+    ``[world * bounds[k], world * bounds[k + 1])`` in place: no staging buffer and no re-ordering copy.
+    ``layout="contiguous"`` keeps rank r's shard at global rows ``[r * rows, (r + 1) * rows)`` (gathered through a
+    staging buffer and copied).  ``global_index(r, local)`` maps either way.
 
     ``extract_fn(lo, hi, out, status)`` writes the rows of local patches ``[lo, hi)`` into the given
     slices, asynchronously on the current stream (``Engine.extract_device`` does).  On CPU tensors
     (gloo tests) the same slicing runs without streams."""
 
-    def __init__(self, rows, F, world, device, pieces=2, group=None):
+    def __init__(self, rows, F, world, device, pieces=2, group=None, layout=None):
         self.rows, self.F, self.world, self.group = int(rows), int(F), int(world), group
-        self.pieces = max(1, min(int(pieces), self.rows or 1))
-        self.bounds = [self.rows * k // self.pieces for k in range(self.pieces + 1)]
+        if isinstance(pieces, (list, tuple)):
+            cum, b = 0.0, [0]
+            for f in pieces[:-1]:
+                cum += float(f)
+                b.append(min(self.rows, max(b[-1], int(round(self.rows * cum)))))
+            b.append(self.rows)
+            self.bounds = [b[0]] + [x for i, x in enumerate(b[1:]) if x > b[i]]  # drop empty slices
+        else:
+            k = max(1, min(int(pieces), self.rows or 1))
+            self.bounds = [self.rows * i // k for i in range(k + 1)]
+        self.pieces = len(self.bounds) - 1
+        self.layout = layout or "block_cyclic"
+        if self.layout not in ("block_cyclic", "contiguous"):
+            raise ValueError("layout must be block_cyclic or contiguous")
         self.cuda = torch.device(device).type == "cuda"
         mx = max((self.bounds[k + 1] - self.bounds[k] for k in range(self.pieces)), default=0)
-        # one staging buffer per slice: slice k's collective may still be running when slice k+1 is extracted
-        self.tmp = [torch.empty((self.world, mx, self.F), dtype=torch.float64, device=device) for _ in range(self.pieces)]
+        # contiguous layout: one staging buffer per slice (slice k's collective may still run when slice k+1 is extracted)
+        self.tmp = ([torch.empty((self.world, mx, self.F), dtype=torch.float64, device=device) for _ in range(self.pieces)]
+                    if self.layout == "contiguous" else None)
         self.comm = torch.cuda.Stream(device=device) if self.cuda and self.world > 1 else None
+        self.work = [torch.cuda.Stream(device=device) for _ in range(2)] if self.cuda and self.pieces > 1 else None
+
+    def global_index(self, rank, local):
+        """Global row of local patch ``local`` of rank ``rank`` (NumPy arrays or ints)."""
+        if self.layout == "contiguous":
+            return rank * self.rows + local
+        b = np.asarray(self.bounds)
+        k = np.searchsorted(b, local, side="right") - 1
+        return self.world * b[k] + rank * (b[k + 1] - b[k]) + (local - b[k])
+
+    def _slice_view(self, gathered, k):
+        lo, hi = self.bounds[k], self.bounds[k + 1]
+        return gathered[self.world * lo: self.world * hi]
 
     def run(self, extract_fn, out, status, gathered):
-        g = gathered.view(self.world, self.rows, self.F)
-        cur = torch.cuda.current_stream(out.device) if self.comm is not None else None
+        cur = torch.cuda.current_stream(out.device) if self.cuda else None
         if self.comm is not None:
             self.comm.wait_stream(cur)  # the previous step's consumers of `gathered` / tmp are done
+        if self.work is not None:
+            for w in self.work:
+                w.wait_stream(cur)
+        g = gathered.view(self.world, self.rows, self.F) if self.layout == "contiguous" else None
         for k in range(self.pieces):
             lo, hi = self.bounds[k], self.bounds[k + 1]
-            extract_fn(lo, hi, out[lo:hi], status[lo:hi])
+            ws = self.work[k % 2] if self.work is not None else cur
+            if self.work is not None:
+                with torch.cuda.stream(ws):
+                    extract_fn(lo, hi, out[lo:hi], status[lo:hi])
+            else:
+                extract_fn(lo, hi, out[lo:hi], status[lo:hi])
             if self.world == 1:
-                g[0, lo:hi].copy_(out[lo:hi])
+                dst = g[0, lo:hi] if g is not None else self._slice_view(gathered, k)
+                if self.work is not None:
+                    with torch.cuda.stream(ws):
+                        dst.copy_(out[lo:hi])
+                else:
+                    dst.copy_(out[lo:hi])
                 continue
             if self.comm is not None:
                 ev = torch.cuda.Event()
-                ev.record(cur)
+                ev.record(ws)
                 self.comm.wait_event(ev)
                 with torch.cuda.stream(self.comm):
-                    flat = self.tmp[k].view(-1, self.F)[: self.world * (hi - lo)].view(self.world, hi - lo, self.F)
-                    dist.all_gather_into_tensor(flat, out[lo:hi], group=self.group)
-                    g[:, lo:hi].copy_(flat)
+                    if g is None:
+                        dist.all_gather_into_tensor(self._slice_view(gathered, k), out[lo:hi], group=self.group)  # in place
+                    else:
+                        flat = self.tmp[k].view(-1, self.F)[: self.world * (hi - lo)].view(self.world, hi - lo, self.F)
+                        dist.all_gather_into_tensor(flat, out[lo:hi], group=self.group)
+                        g[:, lo:hi].copy_(flat)
             else:
                 parts = [torch.empty((hi - lo, self.F), dtype=out.dtype) for _ in range(self.world)]
                 dist.all_gather(parts, out[lo:hi].contiguous(), group=self.group)
+                n = hi - lo
                 for r in range(self.world):
-                    g[r, lo:hi].copy_(parts[r])
-        if self.comm is not None:
-            cur.wait_stream(self.comm)
+                    (g[r, lo:hi] if g is not None else self._slice_view(gathered, k)[r * n:(r + 1) * n]).copy_(parts[r])
+        if self.cuda:
+            if self.work is not None:
+                for w in self.work:
+                    cur.wait_stream(w)
+            if self.comm is not None:
+                cur.wait_stream(self.comm)
         return gathered

@@ -92,7 +92,7 @@ def config2(rank, world, dev, images_per_gpu=48):
          hbm_gbs_aggregate=n * (128 * 128 * 2 + 744) / ms / 1e6)
 
 
-def config3(rank, world, dev, n_each_per_gpu=1500):
+def config3(rank, world, dev, n_each_per_gpu=1500, sorted_list=False):
     n_each = n_each_per_gpu * world
     images, masks = [], []
     for k, H in enumerate((32, 64, 224)):
@@ -100,9 +100,10 @@ def config3(rank, world, dev, n_each_per_gpu=1500):
         for i in range(n_each):
             images.append(g[i % 64])
             masks.append(m[i % 64])
-    order = np.random.default_rng(0).permutation(len(images))
-    images = [images[i] for i in order]
-    masks = [masks[i] for i in order]
+    if not sorted_list:
+        order = np.random.default_rng(0).permutation(len(images))
+        images = [images[i] for i in order]
+        masks = [masks[i] for i in order]
     n = len(images)
     ip, mp, io, mo, hw = pkg.pack_ragged(images, masks)
     dip, dmp = torch.as_tensor(ip).to(dev), torch.as_tensor(mp).to(dev)
@@ -116,6 +117,7 @@ def config3(rank, world, dev, n_each_per_gpu=1500):
 
         ms, ranks, bounds, full, st = timed_sharded(extract, n, costs, world, dev, reps=3, warm=1)
         emit(rank, config="configs[3]: mixed patch sizes 32/64/224 (1:1:1), mask coverage 2-100 %, cost-balanced shards",
+             list_order="sorted by size (all 32s, then 64s, then 224s): the load-imbalance stress" if sorted_list else "shuffled",
              n_gpus=world, nccl_ranks=dist.get_world_size(), patches=n, cost_model=name,
              shard_patches=[bounds[r + 1] - bounds[r] for r in range(world)], ms_step=ms, patches_per_s=n / ms * 1e3,
              mpixels_per_s=float(area.sum()) / ms / 1e3, ms_per_gpu=ranks,
@@ -132,6 +134,7 @@ def main():
         config2(rank, world, dev)
     if "3" in which:
         config3(rank, world, dev)
+        config3(rank, world, dev, sorted_list=True)
     dist.destroy_process_group()
 
 

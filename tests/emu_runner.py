@@ -39,7 +39,7 @@ class EmuRunner:
         return self.lib.radb_emu_is_wide(ctypes.byref(s), H, W)
 
     def run(self, imgs, masks, bin_width=10, label=255, angles=((0, 1),), symmetrical=True, alpha=0,
-            classes=_abi.CLASS_ORDER, max_ng=0, bin_count=0, packed=False):
+            classes=_abi.CLASS_ORDER, max_ng=0, bin_count=0, packed=False, matrices=True):
         """``packed``: hand the masks over bit-packed (radb_extract_packed's layout) instead of as bytes."""
         imgs = np.ascontiguousarray(imgs)
         dtype = {np.dtype(np.uint8): 0, np.dtype(np.uint16): 1, np.dtype(np.float32): 2, np.dtype(np.float64): 3}[imgs.dtype]
@@ -61,8 +61,9 @@ class EmuRunner:
             mstride = masks.shape[1]
         self.lib.radb_emu_set_mask_bits(int(packed))
         rc = self.lib.radb_emu_extract(ctypes.byref(s), p(imgs), dtype, p(masks), B, H, W, H * W * imgs.itemsize, mstride,
-                                       *[p(r[k]) for k in ("features", "status", "levels", "glcm", "glrlm", "glszm",
-                                                           "gldm", "ngtdm_n", "ngtdm_s", "ng")])
+                                       *[p(r[k]) if (matrices or k in ("features", "status")) else None
+                                         for k in ("features", "status", "levels", "glcm", "glrlm", "glszm",
+                                                   "gldm", "ngtdm_n", "ngtdm_s", "ng")])
         self.lib.radb_emu_set_mask_bits(0)
         assert rc == 0, self.lib.radb_emu_last_error()
         return r

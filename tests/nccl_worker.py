@@ -50,20 +50,20 @@ def main():
     torch.cuda.synchronize()
 
     # ---- 1. OverlappedGather: equal shards, sliced, overlapped all-gather
-    for pieces in (1, 2, 4):
-        lo = rank * rows
+    for pieces, layout in ((1, "contiguous"), (2, "contiguous"), (4, "block_cyclic"), ((0.5, 0.3, 0.15, 0.05), "block_cyclic")):
         out = torch.zeros((rows, F), dtype=torch.float64, device=dev)
         status = torch.zeros((rows,), dtype=torch.int32, device=dev)
         gathered = torch.zeros((n, F), dtype=torch.float64, device=dev)
-        og = pkg.OverlappedGather(rows, F, world, dev, pieces=pieces)
+        og = pkg.OverlappedGather(rows, F, world, dev, pieces=pieces, layout=layout)
 
-        def extract_slice(a, b, o, s):
-            ex.engine.extract_device(d_img[lo + a:lo + b], d_msk[lo + a:lo + b], o, s)
+        def extract_slice(a, b, o, s, og=og):
+            g0 = int(og.global_index(rank, a))  # a slice is a contiguous run of global rows in both layouts
+            ex.engine.extract_device(d_img[g0:g0 + (b - a)], d_msk[g0:g0 + (b - a)], o, s)
 
         for _ in range(2):  # twice: buffer re-use across steps
             og.run(extract_slice, out, status, gathered)
         torch.cuda.synchronize()
-        assert torch.equal(gathered.view(torch.int64), want.view(torch.int64)), "OverlappedGather(pieces=%d) rows differ" % pieces
+        assert torch.equal(gathered.view(torch.int64), want.view(torch.int64)), "OverlappedGather(%d, %s) rows differ" % (pieces, layout)
 
     # ---- 2. sharded_extract: cost-balanced shards of unequal length
     costs = (masks == 255).reshape(n, -1).sum(1).astype(np.float64)

@@ -378,3 +378,24 @@ def test_emu_filtered_image_types_bit_exact(emu, hw):
             np.testing.assert_array_equal(w4[b, k], arr, err_msg=name)
         for k, (name, arr) in enumerate(flt.wavelet_images(imgs[b], force2D=True).items()):
             np.testing.assert_array_equal(w2[b, k], arr, err_msg=name)
+
+
+def test_emu_first_order_only_stage(emu):
+    """Only ``firstorder`` enabled: the build kernel stops after the histogram stage (no level image, no texture
+    matrices); the 18 features must still match the oracle, edge cases included."""
+    imgs, masks = synth.make_patches(3, 64, seed=8)
+    e, em_ = edge_case_batch(H=64, W=64)
+    imgs, masks = np.concatenate([imgs, e]), np.concatenate([masks, em_])
+    r = emu.run(imgs, masks, 25, 255, INPLANE, classes=("firstorder",), matrices=False)  # no debug dumps: the short path
+    s = dict(label=255, binWidth=25, force2D=False)
+    assert r["features"].shape[1] == 18 and not r["levels"].any()
+    n = 0
+    for b in range(len(imgs)):
+        try:
+            ref = orc.execute(imgs[b], masks[b], s, classes=("firstorder",))
+        except ValueError:
+            assert np.isnan(r["features"][b]).all() and r["status"][b] != 0
+            continue
+        n += 1
+        np.testing.assert_allclose(r["features"][b], list(ref.values()), rtol=1e-6, atol=1e-9)
+    assert n >= 8

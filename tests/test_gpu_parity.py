@@ -206,6 +206,9 @@ def test_record_path_matches_reference_call_pattern(gpu_pkg, tmp_path):
             assert res[k][ch] == ser[k][ch]
     df = gpu_pkg.features_to_dataframe(res)
     assert df.shape == (3, 4 * 102)
+    # streamed in windows (decode of window k+1 under the GPU work of window k): same rows, same order
+    win = ex.parallell_extraction(recs * 3, n_processes=2, window=2)
+    assert len(win) == 9 and all(win[i] == res[i % 3] for i in range(9))
 
 
 def test_full_size_properties(gpu_pkg):

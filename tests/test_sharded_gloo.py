@@ -56,19 +56,22 @@ def _worker_overlapped(rank, world, port, rows, F, q):
     os.environ["MASTER_PORT"] = str(port)
     dist.init_process_group("gloo", rank=rank, world_size=world)
 
-    def fake_extract(lo, hi, out, status):  # stands in for Engine.extract_device on this rank's slice
-        idx = torch.arange(rank * rows + lo, rank * rows + hi, dtype=torch.float64)
-        out.copy_(idx[:, None] * 10 + torch.arange(F, dtype=torch.float64)[None, :])
-        status.copy_((idx % 3 == 0).to(torch.int32))
-
     ok = True
-    for pieces in (1, 2, 3, rows + 5):
-        og = pkg.OverlappedGather(rows, F, world, "cpu", pieces=pieces)
+    for pieces, layout in ((1, None), (2, "contiguous"), (3, None), (rows + 5, None), (1, "block_cyclic"), (11, "block_cyclic"),
+                           ((0.5, 0.3, 0.15, 0.05), None), ((0.6, 0.4), "contiguous")):
+        og = pkg.OverlappedGather(rows, F, world, "cpu", pieces=pieces, layout=layout)
+
+        def fake_extract(lo, hi, out, status, og=og):  # stands in for Engine.extract_device on this rank's slice
+            idx = torch.as_tensor(og.global_index(rank, np.arange(lo, hi)), dtype=torch.float64)
+            out.copy_(idx[:, None] * 10 + torch.arange(F, dtype=torch.float64)[None, :])
+            status.copy_((idx % 3 == 0).to(torch.int32))
+
         out, status = torch.zeros((rows, F), dtype=torch.float64), torch.zeros(rows, dtype=torch.int32)
         gathered = torch.zeros((world * rows, F), dtype=torch.float64)
         og.run(fake_extract, out, status, gathered)
         want = torch.arange(world * rows, dtype=torch.float64)[:, None] * 10 + torch.arange(F, dtype=torch.float64)
         ok = ok and torch.equal(gathered, want) and og.bounds[0] == 0 and og.bounds[-1] == rows
+        ok = ok and sorted(int(og.global_index(r, l)) for r in range(world) for l in range(rows)) == list(range(world * rows))
     q.put((rank, bool(ok)))
     dist.destroy_process_group()
 
