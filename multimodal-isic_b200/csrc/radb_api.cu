@@ -39,6 +39,7 @@ struct radb_handle {
     double* d_tlog;
     int64_t chunk;               // patches per chunk (0: RADB_CHUNK env / default); radb_set_chunk
     cudaStream_t red_stream;     // high-priority side stream of the GLCM / GLRLM reduction kernels
+    cudaStream_t red_stream3;    // third side stream: the warp-per-angle kernel next to the Lanczos MCC kernel (many gray levels)
     cudaStream_t red_stream2;    // second side stream: first-order / GLDM / NGTDM / GLSZM / shape reductions (concurrent with the first)
     std::vector<cudaEvent_t> sync_events;  // build-done / reduce-done events of the two-stream pipeline (re-used)
     bool profiling;              // record CUDA events around every kernel (radb_set_profiling)
@@ -91,6 +92,7 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
     h->profiling = false;
     h->red_stream = nullptr;
     h->red_stream2 = nullptr;
+    h->red_stream3 = nullptr;
     h->chunk = 0;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -131,6 +133,7 @@ extern "C" void radb_destroy(radb_handle* h)
     for (auto ev : h->events) cudaEventDestroy(ev);
     if (h->red_stream) cudaStreamDestroy(h->red_stream);
     if (h->red_stream2) cudaStreamDestroy(h->red_stream2);
+    if (h->red_stream3) cudaStreamDestroy(h->red_stream3);
     delete h;
 }
 
@@ -291,9 +294,10 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
             cudaDeviceGetStreamPriorityRange(&lo, &hi);
             e = cudaStreamCreateWithPriority(&h->red_stream, cudaStreamNonBlocking, hi);
             if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->red_stream2, cudaStreamNonBlocking, hi);
+            if (e == cudaSuccess) e = cudaStreamCreateWithPriority(&h->red_stream3, cudaStreamNonBlocking, hi);
             if (e != cudaSuccess) return cuda_fail(e, "cudaStreamCreateWithPriority");
         }
-        while ((long long)h->sync_events.size() < 3 * nchunks) {
+        while ((long long)h->sync_events.size() < 4 * nchunks) {
             cudaEvent_t ev;
             e = cudaEventCreateWithFlags(&ev, cudaEventDisableTiming);
             if (e != cudaSuccess) return cuda_fail(e, "cudaEventCreate");
@@ -302,6 +306,7 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     }
     cudaStream_t rs = piped ? h->red_stream : st;    // GLCM / GLRLM (+ MCC) reductions
     cudaStream_t ms = piped ? h->red_stream2 : st;   // first-order / GLDM / NGTDM / GLSZM / shape reductions
+    cudaStream_t as = (piped && p.use_lanczos) ? h->red_stream3 : rs;  // warp-per-angle kernel beside the Lanczos kernel
     long long done = 0;
     for (long long c = 0; done < p.B; c++) {
         const long long n = p.B - done < chunk ? p.B - done : chunk;
@@ -338,17 +343,17 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
             h->events.push_back(ev);
         };
         if (piped && c >= 2) {  // slot free again: both reduction families of chunk c - 2 are done
-            cudaStreamWaitEvent(st, h->sync_events[3 * (c - 2) + 1], 0);
-            cudaStreamWaitEvent(st, h->sync_events[3 * (c - 2) + 2], 0);
+            cudaStreamWaitEvent(st, h->sync_events[4 * (c - 2) + 1], 0);
+            cudaStreamWaitEvent(st, h->sync_events[4 * (c - 2) + 2], 0);
         }
         mark();
         build<<<(unsigned)n, RADB_NTB, p.smem_total, st>>>(q);
         RADB_CHECK_LAUNCH("radb_build_kernel");
         mark();
         if (piped) {
-            cudaEventRecord(h->sync_events[3 * c], st);
-            cudaStreamWaitEvent(rs, h->sync_events[3 * c], 0);
-            cudaStreamWaitEvent(ms, h->sync_events[3 * c], 0);
+            cudaEventRecord(h->sync_events[4 * c], st);
+            cudaStreamWaitEvent(rs, h->sync_events[4 * c], 0);
+            cudaStreamWaitEvent(ms, h->sync_events[4 * c], 0);
         }
         const bool angle_classes = p.off_glcm >= 0 || p.off_glrlm >= 0;  // nothing to reduce per angle otherwise
         if (p.use_lane == 2 && p.off_glcm >= 0) {
@@ -361,13 +366,23 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
             RADB_CHECK_LAUNCH("radb_mcc_lanczos_kernel");
             h->launches += 1;
         }
+        if (as != rs) cudaStreamWaitEvent(as, h->sync_events[4 * c], 0);
         if (!angle_classes)
             h->launches -= 1;
         else if (p.use_lane)
             radb_angle_lane_kernel<<<(unsigned)((n * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, p.l_smem_total, rs>>>(q);
         else
-            radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, rs>>>(q);
+            radb_angle_kernel<<<(unsigned)n, RADB_NT, p.a_smem_total, as>>>(q);
         RADB_CHECK_LAUNCH(p.use_lane ? "radb_angle_lane_kernel" : "radb_angle_kernel");
+        if (as != rs) {  // rs joins the third stream: everything after this point on rs follows the angle kernel too
+            cudaEventRecord(h->sync_events[4 * c + 3], as);
+            cudaStreamWaitEvent(rs, h->sync_events[4 * c + 3], 0);
+        }
+        if (p.use_lanczos && p.off_glcm >= 0) {  // MCC column: after the Lanczos kernel (rs) and the angle kernel (as)
+            radb_mcc_combine_kernel<<<(unsigned)((n + 127) / 128), 128, 0, rs>>>(q);
+            RADB_CHECK_LAUNCH("radb_mcc_combine_kernel");
+            h->launches += 1;
+        }
         mark();
         if (p.only_big_ovf) {
             radb_misc_lane_kernel<<<(unsigned)((n + RADB_NT - 1) / RADB_NT), RADB_NT, p.ml_smem_total, ms>>>(q);
@@ -382,15 +397,15 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         }
         mark();
         if (piped) {
-            cudaEventRecord(h->sync_events[3 * c + 1], rs);
-            cudaEventRecord(h->sync_events[3 * c + 2], ms);
+            cudaEventRecord(h->sync_events[4 * c + 1], rs);
+            cudaEventRecord(h->sync_events[4 * c + 2], ms);
         }
         h->launches += 3;
         done += n;
     }
     if (piped) {  // the side streams are in order: joining their last events joins everything
-        cudaStreamWaitEvent(st, h->sync_events[3 * (nchunks - 1) + 1], 0);
-        cudaStreamWaitEvent(st, h->sync_events[3 * (nchunks - 1) + 2], 0);
+        cudaStreamWaitEvent(st, h->sync_events[4 * (nchunks - 1) + 1], 0);
+        cudaStreamWaitEvent(st, h->sync_events[4 * (nchunks - 1) + 2], 0);
     }
     e = cudaGetLastError();
     if (e != cudaSuccess) return cuda_fail(e, "radb kernel launch");

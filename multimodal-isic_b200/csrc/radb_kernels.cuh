@@ -1231,9 +1231,12 @@ __device__ void radb_angle_cta(const RadbParams& p, long long patch, unsigned ch
         const int* P = (const int*)(rec + (p.o_glcm - p.o_rec)) + a * ng * ng;
         double* mccws = p.big ? (double*)(p.ws_scr + patch * p.scr_bytes + p.g_mcc) + (long long)a * p.mcc_stride
                               : (double*)(ws + p.a_mcc);
+        // use_lanczos: the MCC column is written by radb_mcc_combine_kernel (the Lanczos kernel runs concurrently
+        // with this one); a placeholder stands in here
+        const double mcc_placeholder = 0.0;
         ok = glcm_task(p, tb, P, ng, (int*)(ws + p.a_px), (int*)(ws + p.a_py), (int*)(ws + p.a_padd),
                        (int*)(ws + p.a_psub), mccws, ws + p.a_idx, fsc + a * RADB_FSC_STRIDE, lane,
-                       p.use_lanczos ? (const double*)(misc + RADB_REC_MCC_INT) + a : (const double*)0);
+                       p.use_lanczos ? &mcc_placeholder : (const double*)0);
         if (lane == 0) valid[a] = ok;
     }
     __syncthreads();
@@ -1506,6 +1509,10 @@ __global__ void __launch_bounds__(RADB_NTZ) radb_mcc_lanczos_kernel(const RadbPa
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
     radb_mcc_lanczos_cta(p, (long long)blockIdx.x, radb_smem);
+}
+__global__ void radb_mcc_combine_kernel(const RadbParams p)
+{
+    radb_mcc_combine_thread(p, (long long)blockIdx.x * blockDim.x + threadIdx.x);
 }
 __global__ void __launch_bounds__(RADB_NT) radb_misc_lane_kernel(const RadbParams p)
 {

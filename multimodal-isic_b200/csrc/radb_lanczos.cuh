@@ -133,8 +133,10 @@ __device__ void radb_mcc_lanczos_cta(const RadbParams& p, long long cta, unsigne
     __syncthreads();
     const int m = ishare[0];
     const double Ntot = dshare[0];
-    if (m < 2 || rowptr[n] > p.z_cap) {  // < 2 levels in this angle: no second eigenvalue (capacity: cannot happen, see host)
-        if (tid == 0) *out_mcc = 0.0;
+    if (m < 2 || rowptr[n] > p.z_cap) {
+        // no voxel pair in this angle: NaN (the angle is left out of the mean, A.6); one level only: no second
+        // eigenvalue, 0 (capacity: cannot happen, see radb_layout)
+        if (tid == 0) *out_mcc = Ntot > 0.0 ? 0.0 : nan_f64();
         return;
     }
     // ---- pass 2: fill the entries in (row, column) order; scaling vectors
@@ -252,7 +254,7 @@ __device__ void radb_mcc_lanczos_cta(const RadbParams& p, long long cta, unsigne
         beta_prev = beta;
         __syncthreads();
         // check points: every 16 steps from 32 on, the last step, breakdown
-        const bool check = breakdown || K == kcap || (K >= 32 && (K & 15) == 0);
+        const bool check = breakdown || K == kcap || (K >= 32 && (K & 7) == 0);
         if (check) {
             // The extreme Ritz values move outwards monotonically with K (interlacing), so "nothing of T_K lies beyond the
             // previous extremes + 1e-12" proves convergence with two Sturm counts; only otherwise are they recomputed
@@ -265,11 +267,34 @@ __device__ void radb_mcc_lanczos_cta(const RadbParams& p, long long cta, unsigne
                 same = ishare[0] && ishare[1];
                 __syncthreads();
             }
-            if (!same) lz_extremes(al, be2, K, ishare, tid, emax, emin);  // Ritz values of T_K lie inside [-1, 1] like B's spectrum
+            // recomputed at K = 32, 48, 64, ... (and at the end); the check points in between only run the two-count test
+            const bool full = !same && (!have_prev || breakdown || K == kcap || (K & 15) == 0);
+            if (full) lz_extremes(al, be2, K, ishare, tid, emax, emin);  // Ritz values of T_K lie inside [-1, 1] like B's spectrum
+            if (!same && !full) continue;
             have_prev = true;
             rho = fmax(fabs(emax), fabs(emin));
             if (breakdown || K == kcap || same) done = true;
         }
     }
     if (tid == 0) *out_mcc = rho;
+}
+
+// MCC column of the output row = mean of the per-angle values the Lanczos kernel left in the record header over the
+// non-empty angles (NaN = empty angle), 1 for a one-level ROI (glcm.py's flat-region rule); one thread per patch.
+// Runs after both radb_mcc_lanczos_kernel and radb_angle_kernel (which writes a placeholder into the column).
+__device__ void radb_mcc_combine_thread(const RadbParams& p, long long patch)
+{
+    if (patch >= p.B || p.off_glcm < 0) return;
+    const long long row = radb_row(p, patch);
+    if (p.status[row] != 0) return;
+    const unsigned char* rec = p.ws + patch * (long long)p.rec_bytes;
+    const int* misc = (const int*)(rec + (p.o_misc - p.o_rec));
+    const double* v = (const double*)(misc + RADB_REC_MCC_INT);
+    double s = 0.0;
+    int k = 0;
+    for (int a = 0; a < p.n_angles; a++)
+        if (v[a] == v[a]) { s += v[a]; k++; }
+    double r = k ? s / (double)k : nan_f64();
+    if (misc[9] < 2) r = 1.0;
+    p.out[row * (long long)p.F + p.off_glcm + 19] = r;
 }

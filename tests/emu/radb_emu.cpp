@@ -80,6 +80,8 @@ static int emu_launch(RadbParams& p, int dtype, int64_t B)
         emu::launch((unsigned)((B * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, [&]() { radb_angle_lane_cta(p, (long long)blockIdx.x, sm); });
     else
         emu::launch((unsigned)B, RADB_NT, [&]() { radb_angle_cta(p, (long long)blockIdx.x, sm); });
+    if (p.use_lanczos && p.off_glcm >= 0)
+        for (long long b = 0; b < B; b++) radb_mcc_combine_thread(p, b);
     if (p.only_big_ovf)
         emu::launch((unsigned)((B + RADB_NT - 1) / RADB_NT), RADB_NT, [&]() { radb_misc_lane_cta(p, (long long)blockIdx.x, sm); });
     emu::launch((unsigned)B, RADB_NT, [&]() { radb_misc_cta(p, (long long)blockIdx.x, sm); });
