@@ -365,6 +365,7 @@ class HostPipeline:
         # at 8, well below ranks x 55 GB/s), and the packing threads read the same mask bytes the DMA engines would.
         self.pack_masks = bool(pack_masks) if pack_masks is not None else (ranks == 1 and cores >= 8)
         self.h2d_bytes = 0  # bytes copied host -> device by the last run()
+        self.timeline = None  # set to [] to record per-chunk CUDA-event marks of the next run() (scripts/e2e_timeline.py)
         self.adaptive = bool(adaptive)  # pack a chunk's masks only while the host keeps ahead of the link (see run())
         self._host_ahead = True
         self.packed_chunks = self.total_chunks = 0
@@ -468,6 +469,14 @@ class HostPipeline:
                 fut = self._pool.submit(prepare, k + 1)
             nb = n * pstride
             d_out = device_out[s:s + n] if device_out is not None else b["d_out"][:n]
+            tl = None
+            if self.timeline is not None:
+                tl = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+                if not self.timeline:
+                    self._tl0 = torch.cuda.Event(enable_timing=True)
+                    self._tl0.record(b["stream"])
+                self.timeline.append((k, n, tl))
+                tl[0].record(b["stream"])
             with torch.cuda.stream(b["stream"]):
                 if pinned_in:
                     b["d_img"][:n].copy_(images[s:s + n], non_blocking=True)
@@ -481,10 +490,14 @@ class HostPipeline:
                         src = b["h_pk"][:nb]
                     b["d_pk"][:nb].copy_(src, non_blocking=True)
                     self.h2d_bytes += n * H * W * images.element_size() + nb
+                    if tl is not None:
+                        tl[1].record(b["stream"])
                     self.engine.extract_packed(b["d_img"][:n], b["d_pk"], d_out, b["d_st"][:n], stream=b["stream"])
                 elif packed:
                     b["d_pk"][:nb].copy_(b["h_pk"][:nb], non_blocking=True)
                     self.h2d_bytes += n * H * W * images.element_size() + nb
+                    if tl is not None:
+                        tl[1].record(b["stream"])
                     self.engine.extract_packed(b["d_img"][:n], b["d_pk"], d_out, b["d_st"][:n], stream=b["stream"])
                 else:
                     if b["d_msk"] is None or b["d_msk"].shape[0] < n:
@@ -497,10 +510,24 @@ class HostPipeline:
                         b["h_msk"][:n].copy_(masks[s:s + n])
                         b["d_msk"][:n].copy_(b["h_msk"][:n], non_blocking=True)
                     self.h2d_bytes += n * H * W * images.element_size() + n * H * W
+                    if tl is not None:
+                        tl[1].record(b["stream"])
                     self.engine.extract_device(b["d_img"][:n], b["d_msk"][:n], d_out, b["d_st"][:n], stream=b["stream"])
+                if tl is not None:
+                    tl[2].record(b["stream"])
                 out[s:s + n].copy_(d_out, non_blocking=True)
                 status[s:s + n].copy_(b["d_st"][:n], non_blocking=True)
+                if tl is not None:
+                    tl[3].record(b["stream"])
                 b["done"].record(b["stream"])
         for b in self._bufs:
             b["done"].synchronize()
         return out, status
+
+    def timeline_ms(self):
+        """Per-chunk marks of the run recorded with ``timeline = []``: (chunk, patches, H2D start, H2D end = kernels start,
+        kernels end, D2H end), milliseconds since the first chunk's H2D start."""
+        torch.cuda.synchronize()
+        rows = [(k, n) + tuple(self._tl0.elapsed_time(e) for e in ev) for k, n, ev in self.timeline]
+        self.timeline = None
+        return rows
