@@ -11,7 +11,9 @@
 #ifndef RADB_NTB_MINB
 #define RADB_NTB_MINB 5      // min resident build CTAs per SM (register cap: 48)
 #endif
+#ifndef RADB_NTL
 #define RADB_NTL 64          // threads per CTA of the lane kernel: one THREAD per (patch, angle)
+#endif
 #define RADB_LSTRIDE RADB_NTL   // fp64 slot stride of its per-thread scratch (slot-major)
 #define RADB_NTM 64          // threads per CTA of the MCC kernel: one WARP per patch, 8 lanes per angle
 #define RADB_MAX_ANGLES 4    // unidirectional offsets at distance 1 in a plane
