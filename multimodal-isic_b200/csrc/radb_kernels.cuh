@@ -240,6 +240,21 @@ __device__ __forceinline__ void uf_union(W* L, unsigned a, unsigned b)
     }
 }
 
+// 32-bit shared-memory addresses (line walks of the build kernel): address arithmetic in one register, the
+// update as a plain `red.shared` (the CPU emulation uses ordinary pointers)
+#ifdef RADB_EMU
+typedef uintptr_t radb_saddr;
+__device__ __forceinline__ radb_saddr radb_to_saddr(const void* p) { return (radb_saddr)p; }
+__device__ __forceinline__ void radb_red_add(radb_saddr a, unsigned v) { atomicAdd((unsigned*)a, v); }
+#else
+typedef unsigned radb_saddr;
+__device__ __forceinline__ radb_saddr radb_to_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void radb_red_add(radb_saddr a, unsigned v)
+{
+    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+}
+#endif
+
 // GLRLM counters: packed u16 pairs updated with one 32-bit atomic (narrow) or plain u32 (wide)
 __device__ __forceinline__ void add_u16(unsigned* base, int cell)
 {
@@ -872,76 +887,95 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
 
     // ---- phase 3a: line walks over the ROI bounding box.  One thread walks one line along one
     // angle, so every lane runs the same trip count: GLRLM runs for all angles; the along-row
-    // walk also writes label = run start and the run length (seed of the zone sizes).  Diagonal
-    // lines are wrapped inside the bbox (a wrap forces a run break), so every angle is bw (or bh)
-    // lines of equal length.
+    // walk also writes, for every ROI pixel, label = run start | (position inside the run) << US, so the
+    // END pixel of a run carries the run length (seed of the zone sizes).  Diagonal lines are wrapped
+    // inside the bbox (a wrap forces a run break), so every angle is bw (or bh) lines of equal length.
+    // The steps are branch-free: a run ends where the NEXT level differs (outside the bbox every level is
+    // 0), and the counter update of a step that ends no run goes to a per-thread scratch word instead of
+    // branching around the atomic (a divergent run-end block ran at 13 of 32 lanes and was 30 % of the
+    // kernel's instructions).  Narrow mode tracks the byte address of the u16 counter of (level 0, current
+    // position) and the increment (1 or 1 << 16: the GLRLM pitch is even, so the half alternates with the
+    // position), which leaves one multiply-add, one mask and one select per step for the address.
+    // Task layout: the rows (padded to whole warps), then the lines of all other angles back to back -- they
+    // run the same code with per-thread data (x step, counter base), so warps are filled across angles.
     {
-        const int nr = p.nr;
-        int t0 = 0;
-        // when all the lines of all angles fit one round of the CTA, every angle starts on a warp boundary:
-        // a warp then walks one kind of line (row / column / diagonal) instead of diverging over two kinds
-        const int lines_max = bh > bw ? bh : bw;
-        const bool warp_aligned = NA * ((lines_max + 31) & ~31) <= RADB_NTB;
-        for (int a = 0; a < NA; a++) {
-            const int dy = p.ang_y[a], dx = p.ang_x[a];
-            const int nlines = (dy == 0) ? bh : bw;
-            // tasks [t0, t0 + nlines) belong to angle a; thread tid takes tasks tid, tid+NT, ...
-            int first = tid - (t0 % RADB_NTB);
-            if (first < 0) first += RADB_NTB;
+        const int nrp = p.nrp;
+        const int row_tasks = a_row >= 0 ? bh : 0, row_slots = (row_tasks + 31) & ~31;
+        int oth[RADB_MAX_ANGLES] = {0, 0, 0, 0}, noth = 0;
+        for (int a = 0; a < NA; a++)
+            if (a != a_row) oth[noth++] = a;
+        const int ntasks = row_slots + noth * bw;
+        const radb_saddr trash = radb_to_saddr((unsigned*)(smem + p.o_uq) + tid);  // the union queues are idle until phase 3b
+        const unsigned gpitch = 2u * (unsigned)nrp;  // bytes per level of the u16 counters
+        for (int t = tid; t < ntasks; t += RADB_NTB) {
+            const bool is_row = t < row_slots;
+            if (is_row && t >= row_tasks) continue;
+            int a = a_row, l = t;
+            if (!is_row) {
+                const int u = t - row_slots, k = (int)(((float)u + 0.5f) * inv_bw);
+                a = oth[0];
+                if (k == 1) a = oth[1];
+                if (k == 2) a = oth[2];
+                if (k == 3) a = oth[3];
+                l = u - k * bw;
+            }
             unsigned* R = (unsigned*)(glrlm_base + a * p.glrlm_stride);
-            int mylen = 0;  // longest run this thread saw: one atomicMax per thread, not per run
-            for (int l = first; l < nlines; l += RADB_NTB) {
-                int cur = 0, len = 0;
-                if (dy == 0) {
-                    const int base = (by0 + l + 1) * WP + bx0 + XO, lbase = (by0 + l) * LP + bx0;
-                    int st = 0;
-                    int gn = lev[base];  // software-pipelined: the next level is in flight while this one is processed
-                    for (int x = 0; x < bw; x++) {
-                        const int g = gn;
-                        gn = lev[base + x + 1];  // one past the bbox is the zero border or another pixel: in bounds
-                        if (g != cur) {
-                            if (cur) {
-                                add_run<WIDE>(R, (cur - 1) * nr + len - 1);
-                                lab[lbase + st] = ((UW)len << US) | (UW)(lbase + st);
-                                mylen = len > mylen ? len : mylen;
-                            }
-                            cur = g;
-                            len = 0;
-                            st = x;
-                        }
-                        len++;
-                        if (g) lab[lbase + x] = (UW)(lbase + st);
+            // narrow: kc = byte address of the u16 counter (level 0, current position) -- one level row below R
+            const radb_saddr kc0 = radb_to_saddr(R) - gpitch;
+            radb_saddr kc = kc0, kmax = kc0 - 2;
+            unsigned val = 1u;
+            int rl = 0, mylen = 0;  // wide: position inside the current run, longest run
+            bool endp = true;       // "the previous pixel ended a run"
+            if (is_row) {
+                const int base = (by0 + l + 1) * WP + bx0 + XO, lbase = (by0 + l) * LP + bx0;
+                int gn = lev[base];  // software-pipelined: the next level is in flight while this one is processed
+                int rp = 0;          // position inside the run (the label needs it in both modes)
+                for (int x = 0; x < bw; x++) {
+                    const int g = gn;
+                    gn = lev[base + x + 1];  // one past the bbox is the zero border or a pixel outside the ROI: level 0
+                    rp = endp ? 1 : rp + 1;
+                    if (g) lab[lbase + x] = ((UW)rp << US) | (UW)(lbase + x - rp + 1);
+                    if (WIDE) {
+                        endp = (gn != g);
+                        if (endp && g) { atomicAdd(&R[(g - 1) * nrp + rp - 1], 1u); mylen = rp > mylen ? rp : mylen; }
+                    } else {
+                        kc = endp ? kc0 : kc + 2;
+                        val = endp ? 1u : val ^ 0x10001u;
+                        endp = (gn != g);
+                        const radb_saddr w = (kc + (unsigned)g * gpitch) & ~(radb_saddr)3;
+                        radb_red_add((endp && g) ? w : trash, val);
+                        if (g) kmax = kc > kmax ? kc : kmax;
                     }
-                    if (cur) {
-                        add_run<WIDE>(R, (cur - 1) * nr + len - 1);
-                        lab[lbase + st] = ((UW)len << US) | (UW)(lbase + st);
-                        mylen = len > mylen ? len : mylen;
+                }
+            } else {
+                const int sdx = p.ang_x[a] * p.ang_y[a];  // x step per +1 in y (runs are direction-agnostic)
+                const int xwrap = sdx > 0 ? bw : -1, xre = sdx > 0 ? 0 : bw - 1;  // leaving the bbox on this side / re-entry column
+                int x = l;
+                int pos = (by0 + 1) * WP + bx0 + XO;
+                int gn = lev[pos + x];  // software-pipelined like the row walk
+                for (int y = 0; y < bh; y++) {
+                    const int g = gn;
+                    pos += WP;
+                    x += sdx;
+                    const bool brk = (x == xwrap);  // wrapped diagonal: the next pixel is not a neighbour of this one
+                    x = brk ? xre : x;              // (vertical lines: sdx = 0 never reaches xwrap = -1)
+                    gn = lev[pos + x];  // row below the bbox on the last step: the zero border, in bounds
+                    if (WIDE) {
+                        rl = endp ? 1 : rl + 1;
+                        endp = (gn != g) || brk;
+                        if (endp && g) { atomicAdd(&R[(g - 1) * nrp + rl - 1], 1u); mylen = rl > mylen ? rl : mylen; }
+                    } else {
+                        kc = endp ? kc0 : kc + 2;
+                        val = endp ? 1u : val ^ 0x10001u;
+                        endp = (gn != g) || brk;
+                        const radb_saddr w = (kc + (unsigned)g * gpitch) & ~(radb_saddr)3;
+                        radb_red_add((endp && g) ? w : trash, val);
+                        if (g) kmax = kc > kmax ? kc : kmax;
                     }
-                } else {
-                    const int sdx = dx * dy;  // x step per +1 in y (runs are direction-agnostic)
-                    const int xwrap = sdx > 0 ? bw : -1, xre = sdx > 0 ? 0 : bw - 1;  // leaving the bbox on this side / re-entry column
-                    int x = l, brk = 0;
-                    int pos = (by0 + 1) * WP + bx0 + XO;
-                    int gn = lev[pos + x];  // software-pipelined like the row walk
-                    for (int y = 0; y < bh; y++) {
-                        const int g = gn, brk_here = brk;
-                        pos += WP;
-                        x += sdx;
-                        brk = (x == xwrap);   // wrapped diagonal: the next pixel is not a neighbour of this one
-                        x = brk ? xre : x;    // (vertical lines: sdx = 0 never reaches xwrap = -1)
-                        gn = lev[pos + x];  // row below the bbox on the last step: the zero border, in bounds
-                        if (g != cur || brk_here) {
-                            if (cur) { add_run<WIDE>(R, (cur - 1) * nr + len - 1); mylen = len > mylen ? len : mylen; }
-                            cur = g;
-                            len = 0;
-                        }
-                        len++;
-                    }
-                    if (cur) { add_run<WIDE>(R, (cur - 1) * nr + len - 1); mylen = len > mylen ? len : mylen; }
                 }
             }
+            if (!WIDE) mylen = (int)(kmax + 2 - kc0) >> 1;
             if (mylen) atomicMax(&misc[10 + a], mylen);  // record header: longest run of angle a
-            t0 += warp_aligned ? ((nlines + 31) & ~31) : nlines;
         }
     }
     __syncthreads();
@@ -1073,8 +1107,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
 #pragma unroll
             for (int a = 0; a < RADB_MAX_ANGLES; a++)
                 if (a < nreq) push(req[a] != 0, ((UW)(unsigned)li << US) | (UW)(req[a] - 1u));
-            if (keep_runs && a_row >= 0) {  // append the row-run starts of this warp's pixels: one atomic per warp
-                const bool st = c && lev[ctr - 1] != c;
+            if (keep_runs && a_row >= 0) {  // append the row-run ends of this warp's pixels: one atomic per warp
+                const bool st = c && lev[ctr + 1] != c;
                 const unsigned ms = __ballot_sync(FULLMASK, st);
                 if (ms) {
                     int rbase = 0;
@@ -1089,6 +1123,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     __syncthreads();
 
     // ---- phase 4: fold run lengths into their zone root; symmetrise the GLCM
+    // A run is visited through its END pixel e, whose size field holds the run length (the line walk wrote
+    // position-in-run into every pixel; without an along-row angle every pixel is a run of one).  The start
+    // pixel of a run -- the only pixel of a run that can be a root -- holds 1, so a root collects
+    // len - 1 from its own run and len from every other run of its zone: size field of a root = zone size.
     const bool by_list = keep_runs && a_row >= 0;  // the run list exists: visit runs, not pixels
     const int nruns = by_list ? misc[6] : 0;
     const float inv_lp = 1.0f / (float)LP;
@@ -1096,26 +1134,22 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     // list is (nearly) in pixel order: round k of this loop handles runs above those of round k + 1, and every
     // run re-parents itself straight to its root, so later rounds find short paths (the clocks showed the
     // read-only finds of this phase at 15 % of the CTA's lifetime).
-    for (int k = tid; k < nruns; k += RADB_NTB) {
-        const unsigned li = runs[k];
-        const unsigned r = uf_find<UW, UF<WIDE>::S>(lab, li);
-        if (r != li) {
-            const UW wl = ((volatile UW*)lab)[li];
-            ((volatile UW*)lab)[li] = (wl & ~ULO) | (UW)r;  // li is not a root: its size field is its own, static
-            atomicAdd(&lab[r], (UW)(wl & ~ULO));             // only roots are ever added to
-        }
-    }
+    auto fold_run = [&](unsigned e) {
+        const unsigned r = uf_find<UW, UF<WIDE>::S>(lab, e);
+        if (r == e) return;  // a one-pixel run that is its zone's root: its size field already counts it
+        const UW we = ((volatile UW*)lab)[e];  // e is not a root: its size field is static
+        const unsigned len = (unsigned)(we >> US);
+        ((volatile UW*)lab)[e] = (we & ~ULO) | (UW)r;
+        atomicAdd(&lab[r], (UW)(len - (e - len + 1u == r ? 1u : 0u)) << US);  // only roots are ever added to
+    };
+    for (int k = tid; k < nruns; k += RADB_NTB) fold_run(runs[k]);
     if (!by_list)
     for (int idx = tid; idx < nbox; idx += RADB_NTB) {
         const int yb = WIDE ? idx / bw : (int)(((float)idx + 0.5f) * inv_bw);
         const int y = by0 + yb, x = bx0 + (idx - yb * bw);
         const int ctr = (y + 1) * WP + x + XO;
         const int c = lev[ctr];
-        if (c && (a_row < 0 || lev[ctr - 1] != c)) {  // run start
-            const int li = y * LP + x;
-            const unsigned r = uf_find_ro<UW, UF<WIDE>::S>(lab, (unsigned)li);
-            if (r != (unsigned)li) atomicAdd(&lab[r], (UW)(lab[li] & ~ULO));  // only roots are ever added to
-        }
+        if (c && (a_row < 0 || lev[ctr + 1] != c)) fold_run((unsigned)(y * LP + x));  // run end
     }
     if (p.symmetric) {  // all angles in one flat loop; (a, i, j) by float reciprocals (exact: indices < 2^18)
         const int ng2 = ng * ng, tot = NA * ng2;
@@ -1146,12 +1180,19 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         }
         if (DBG && p.dbg_glszm) atomicAdd(&p.dbg_glszm[(patch * p.max_ng + (c - 1)) * (long long)HW + s - 1], 1);
     };
+    // a run end e whose run starts at a root emits that zone (a root that is its run's end is a one-pixel run)
+    auto emit_run = [&](unsigned e, int c) {
+        const UW we = lab[e];
+        if ((unsigned)(we & ULO) == e) { emit_zone(c, (int)(we >> US)); return; }
+        const unsigned s = e - (unsigned)(we >> US) + 1u;
+        if (s == e) return;
+        const UW ws = lab[s];
+        if ((unsigned)(ws & ULO) == s) emit_zone(c, (int)(ws >> US));
+    };
     for (int k = tid; k < nruns; k += RADB_NTB) {
-        const int li = runs[k];
-        const UW wl = lab[li];
-        if ((unsigned)(wl & ULO) != (unsigned)li) continue;
-        const int y = (int)(((float)li + 0.5f) * inv_lp), x = li - y * LP;  // exact for li < 65536
-        emit_zone((int)lev[(y + 1) * WP + x + XO], (int)(wl >> US));
+        const int e = runs[k];
+        const int y = (int)(((float)e + 0.5f) * inv_lp), x = e - y * LP;  // exact for e < 65536
+        emit_run((unsigned)e, (int)lev[(y + 1) * WP + x + XO]);
     }
     if (!by_list)
     for (int idx = tid; idx < nbox; idx += RADB_NTB) {
@@ -1159,11 +1200,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int y = by0 + yb, x = bx0 + (idx - yb * bw);
         const int ctr = (y + 1) * WP + x + XO;
         const int c = lev[ctr];
-        if (!c || (a_row >= 0 && lev[ctr - 1] == c)) continue;
-        const int li = y * LP + x;
-        const UW wl = lab[li];
-        if ((unsigned)(wl & ULO) != (unsigned)li) continue;
-        emit_zone(c, (int)(wl >> US));
+        if (!c || (a_row >= 0 && lev[ctr + 1] == c)) continue;
+        emit_run((unsigned)(y * LP + x), c);
     }
     __syncthreads();
 
@@ -1180,7 +1218,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         for (int a = 0; a < NA; a++)
             for (int t = tid; t < ng * p.nr; t += RADB_NTB)
                 p.dbg_glrlm[((patch * NA + a) * p.max_ng + t / p.nr) * p.nr + t % p.nr] =
-                    get_run((const unsigned*)(glrlm_base + a * p.glrlm_stride), t, WIDE);
+                    get_run((const unsigned*)(glrlm_base + a * p.glrlm_stride), (t / p.nr) * p.nrp + t % p.nr, WIDE);
     if (DBG && p.dbg_gldm)
         for (int t = tid; t < ng * (NB + 1); t += RADB_NTB)
             p.dbg_gldm[patch * p.max_ng * (NB + 1) + t] = gldm[t];
@@ -1226,7 +1264,7 @@ __device__ void radb_angle_cta(const RadbParams& p, long long patch, unsigned ch
         for (int i = lane; i < (p.a_idx - p.a_px) / 4; i += 32) ((int*)(ws + p.a_px))[i] = 0;
         __syncwarp();
         const unsigned* R = (const unsigned*)(rec + (p.o_glrlm - p.o_rec) + a * p.glrlm_stride);
-        int ok = glrlm_task(tb, R, p.wide, ng, p.nr, misc[10 + a], (int*)(ws + p.a_pr), fsc + a * RADB_FSC_STRIDE + RADB_GLCM_NF, lane);
+        int ok = glrlm_task(tb, R, p.wide, ng, p.nrp, misc[10 + a], (int*)(ws + p.a_pr), fsc + a * RADB_FSC_STRIDE + RADB_GLCM_NF, lane);
         if (lane == 0) valid[4 + a] = ok;
         const int* P = (const int*)(rec + (p.o_glcm - p.o_rec)) + a * ng * ng;
         double* mccws = p.big ? (double*)(p.ws_scr + patch * p.scr_bytes + p.g_mcc) + (long long)a * p.mcc_stride

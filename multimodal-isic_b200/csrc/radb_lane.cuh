@@ -486,7 +486,7 @@ __device__ void radb_angle_lane_cta(const RadbParams& p, long long cta, unsigned
         for (int i = 0; i < RADB_GLRLM_NF; i++) f[i] = 0.0;
         int ok = 0;
         if (live)
-            ok = glrlm_lane(tb, (const unsigned*)(rec + (p.o_glrlm - p.o_rec) + a * p.glrlm_stride), p.wide, ng, p.nr,
+            ok = glrlm_lane(tb, (const unsigned*)(rec + (p.o_glrlm - p.o_rec) + a * p.glrlm_stride), p.wide, ng, p.nrp,
                             misc[10 + a], lm, f);
         lane_mean<RADB_GLRLM_NF>(f, ok, NAP);
         if (patch_ok) lane_store<RADB_GLRLM_NF>(f, NAP, a, out + p.off_glrlm);

@@ -54,6 +54,7 @@ struct RadbParams {
     double shift;
     int max_ng;
     int nr;        // GLRLM columns = max(H, W)
+    int nrp;       // pitch of a GLRLM row (nr rounded up to even: a row of packed u16 counters starts on a word)
     int s0;        // dense GLSZM columns (zone sizes 1..s0); larger zones go to the overflow list
     int ovf_cap;
     int F;
@@ -127,6 +128,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->WP = radb_align(W + p->xo + 1, 4);
     if (p->vec4 && (p->WP / 4) % 2 == 0) p->WP += 4;  // odd word stride: row walks stay bank-conflict free
     p->nr = H > W ? H : W;
+    p->nrp = (p->nr + 1) & ~1;
     p->s0 = wide ? 64 : 16;
     p->ovf_cap = p->HW / (p->s0 + 1) + 1;
     p->ninv = ng > p->nr ? ng : p->nr;
@@ -192,7 +194,7 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->o_ngn = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] sum |cnt*i - sum(neigh)|
     p->o_szm = o; o += radb_align(ng * p->s0 * 4, 16);
     p->rec_copy_bytes = o - p->o_rec;
-    p->glrlm_stride = radb_align(ng * p->nr * (wide ? 4 : 2), 16);
+    p->glrlm_stride = radb_align(ng * p->nrp * (wide ? 4 : 2), 16);
     p->o_glrlm = o; o += na * p->glrlm_stride;             // wide: lives in the global record only
     p->o_ovf = o; o += radb_align(p->ovf_cap * 4, 16);     // wide: lives in the global record only
     if (big) { p->o_glcm = o; o += radb_align(na * ng * ng * 4, 16); }  // big: GLCM in the global record only
