@@ -284,6 +284,16 @@ __device__ __forceinline__ unsigned bytes_sum4(unsigned w, unsigned acc)
     return __dp4a(w, 0x01010101u, acc);
 #endif
 }
+// dot product of the four bytes of w with the four bytes of m, plus acc (IDP.4A)
+__device__ __forceinline__ unsigned bytes_dot4(unsigned w, unsigned m, unsigned acc)
+{
+#ifdef RADB_EMU
+    for (int k = 0; k < 4; k++) acc += ((w >> (8 * k)) & 0xffu) * ((m >> (8 * k)) & 0xffu);
+    return acc;
+#else
+    return __dp4a(w, m, acc);
+#endif
+}
 // 0x80 in every byte position where the byte of w is non-zero
 __device__ __forceinline__ unsigned bytes_nz4(unsigned w)
 {
@@ -981,6 +991,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     __syncthreads();
 
     // ---- phase 3b: neighbourhood pass over the bbox -> GLCM, GLDM, NGTDM, zone unions
+    // GLCM counters while they are built: row pitch gp, angle stride gas.  Padded (gp = ng + 1): level 0 -- a
+    // neighbour or a centre outside the ROI -- has its own row and column, so the increments need no test.
+    const int gp = p.glcm_pad ? ng + 1 : ng, gas = gp * gp;
+    int* const glcm0 = p.glcm_pad ? glcm : glcm - (ng + 1);  // cell (level i, level j) of angle a: glcm0[a * gas + i * gp + j]
     {
         int doff[RADB_MAX_ANGLES], loff[RADB_MAX_ANGLES];
         for (int a = 0; a < RADB_MAX_ANGLES; a++) {
@@ -991,7 +1005,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const bool inplane = (NA == 4);  // all 8 neighbours: run-adjacency union rules apply
         // Union requests are queued per warp and executed 32 at a time, so that the
         // data-dependent find loops run with (nearly) all lanes busy.
-        UW* uq = (UW*)(smem + p.o_uq) + warp * 64;
+        const int QCAP = p.uq_cap;
+        UW* uq = (UW*)(smem + p.o_uq) + warp * QCAP;
         int qn = 0;
         const unsigned lt_mask = (1u << lane) - 1u;
         auto drain = [&](int count) {
@@ -1009,6 +1024,108 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             __syncwarp();
             if (qn >= 32) drain(32);
         };
+        if (!WIDE && !L16 && p.lev4 && p.glcm_pad && inplane && p.alpha == 0 && keep_runs && a_row == 1) {
+            // Four pixels per thread: the level image is read as aligned 32-bit words (3 rows x 3 words), the eight
+            // neighbours of the four pixels of the centre word are byte permutes of those, and the neighbour
+            // counts (NGTDM), equal-level counts (GLDM, alpha = 0) and the run-adjacency / run-end tests are
+            // byte-parallel over the four pixels.  The four in-plane angles in their canonical order
+            // (radb_host.h: make_plan): 0 (1,1) f=SE | 1 (0,1) f=E | 2 (-1,1) f=NE | 3 (1,0) f=S.
+            const unsigned* lev32 = (const unsigned*)lev;
+            const int WPW = WP >> 2;
+            const int qx0 = bx0 >> 2, nqx = ((bx0 + bw - 1) >> 2) - qx0 + 1, nq = bh * nqx;
+            const float inv_nqx = 1.0f / (float)nqx;
+            int* const gldm_p = gldm - nd;          // row of level c at gldm_p + c * nd (level 0: the pad in front)
+            int* const ngc_p = ngc - NB - 1;        // cell (level c, count n >= 1) at ngc_p + c * NB + n
+            int* const ngn_p = ngn - NB - 1;
+            int* const trash = misc + 30;
+            for (int base = 0; base < nq; base += RADB_NTB) {  // uniform trip count (warp collectives below)
+                const int idx = base + tid;
+                const int yb = (int)(((float)idx + 0.5f) * inv_nqx);
+                const int y = by0 + yb, qx = qx0 + (idx - yb * nqx);
+                const unsigned* wp = lev32 + (y + 1) * WPW + 1 + qx;
+                const unsigned C = idx < nq ? wp[0] : 0u;
+                const int li0 = y * LP + 4 * qx;   // union-find index of the word's first pixel
+                unsigned F = 0;  // per pixel k (byte k): bit 0 union with N, bit 1 with NW, bit 2 with NE, bit 3 row-run end
+                if (C) {
+                    const unsigned U0 = wp[-WPW - 1], U1 = wp[-WPW], U2 = wp[-WPW + 1];
+                    const unsigned M0 = wp[-1], M2 = wp[1];
+                    const unsigned D0 = wp[WPW - 1], D1 = wp[WPW], D2 = wp[WPW + 1];
+                    const unsigned NWw = __byte_perm(U0, U1, 0x6543), NEw = __byte_perm(U1, U2, 0x4321);
+                    const unsigned Ww = __byte_perm(M0, C, 0x6543), Ew = __byte_perm(C, M2, 0x4321);
+                    const unsigned SWw = __byte_perm(D0, D1, 0x6543), SEw = __byte_perm(D1, D2, 0x4321);
+                    // 0x80 flags per byte: neighbour level == centre level
+                    const unsigned eNW = bytes_eq4(NWw, C), eN = bytes_eq4(U1, C), eNE = bytes_eq4(NEw, C);
+                    const unsigned eW = bytes_eq4(Ww, C), eE = bytes_eq4(Ew, C);
+                    const unsigned eSW = bytes_eq4(SWw, C), eS = bytes_eq4(D1, C), eSE = bytes_eq4(SEw, C);
+                    const unsigned zC = bytes_nz4(C);
+                    // per-pixel counts in the four bytes (<= 8 each)
+                    const unsigned DEP = (eNW >> 7) + (eN >> 7) + (eNE >> 7) + (eW >> 7) + (eE >> 7) + (eSW >> 7) + (eS >> 7) + (eSE >> 7);
+                    const unsigned CNT = (bytes_nz4(NWw) >> 7) + (bytes_nz4(U1) >> 7) + (bytes_nz4(NEw) >> 7) + (bytes_nz4(Ww) >> 7) +
+                                         (bytes_nz4(Ew) >> 7) + (bytes_nz4(SWw) >> 7) + (bytes_nz4(D1) >> 7) + (bytes_nz4(SEw) >> 7);
+                    // 8-connectivity between row runs, one union per pair of touching runs: with the level above equal,
+                    // link to it if this pixel starts its run or the run above starts here; else link a run start to NW
+                    // and a run end to NE
+                    const unsigned rN = eN & ~(eW & eNW), rNW = ~eN & eNW & ~eW, rNE = ~eN & eNE & ~eE, rE = ~eE & 0x80808080u;
+                    F = (((rN >> 7) | (rNW >> 6) | (rNE >> 5) | (rE >> 4)) & (zC >> 7) * 0xfu);
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {
+                        const int c = (int)((C >> (8 * k)) & 0xffu);
+                        // the 8 neighbours' sum: three bytes of the row above, two of this row, three of the row below
+                        unsigned sum;
+                        if (k == 0) sum = bytes_dot4(NWw, 0x00010101u, bytes_dot4(Ww, 0x00010001u, bytes_dot4(SWw, 0x00010101u, 0u)));
+                        else if (k == 1) sum = bytes_dot4(U1, 0x00010101u, bytes_dot4(C, 0x00010001u, bytes_dot4(D1, 0x00010101u, 0u)));
+                        else if (k == 2) sum = bytes_dot4(U1, 0x01010100u, bytes_dot4(C, 0x01000100u, bytes_dot4(D1, 0x01010100u, 0u)));
+                        else sum = bytes_dot4(NEw, 0x01010100u, bytes_dot4(Ew, 0x01000100u, bytes_dot4(SEw, 0x01010100u, 0u)));
+                        int* const g = glcm0 + c * gp;  // a pixel outside the ROI (c = 0) counts into the garbage row
+                        atomicAdd(&g[(SEw >> (8 * k)) & 0xffu], 1);
+                        atomicAdd(&g[gas + ((Ew >> (8 * k)) & 0xffu)], 1);
+                        atomicAdd(&g[2 * gas + ((NEw >> (8 * k)) & 0xffu)], 1);
+                        atomicAdd(&g[3 * gas + ((D1 >> (8 * k)) & 0xffu)], 1);
+                        atomicAdd(&gldm_p[c * nd + (int)((DEP >> (8 * k)) & 0xffu)], 1);
+                        const int cnt = (int)((CNT >> (8 * k)) & 0xffu);
+                        int num = cnt * c - (int)sum;
+                        num = num < 0 ? -num : num;
+                        const bool has = cnt != 0;  // (c = 0 lands in the pads in front of the two arrays)
+                        atomicAdd(has ? &ngc_p[c * NB + cnt] : trash, 1);
+                        atomicAdd(has ? &ngn_p[c * NB + cnt] : trash, num);
+                    }
+                }
+                // queue the union requests and append the run ends: one warp scan over (requests | ends << 16)
+                const unsigned Fr = F & 0x07070707u, Fe = F & 0x08080808u;
+                const int mine = __popc(Fr) | (__popc(Fe) << 16);
+                const int excl = warp_excl_scan_i(mine, lane);
+                const int tot = __shfl_sync(FULLMASK, excl + mine, 31);
+                const int nreq = tot & 0xffff, nend = tot >> 16;
+                if (nend) {
+                    int rbase = 0;
+                    if (lane == 0) rbase = atomicAdd(&misc[6], nend);
+                    rbase = __shfl_sync(FULLMASK, rbase, 0) + (excl >> 16);
+                    for (unsigned f = Fe; f; f &= f - 1u) runs[rbase++] = (unsigned short)(li0 + ((__ffs((int)f) - 1) >> 3));
+                }
+                if (nreq) {
+                    if (qn + nreq <= QCAP) {
+                        int pos = qn + (excl & 0xffff);
+                        for (unsigned f = Fr; f; f &= f - 1u) {
+                            const int b = __ffs((int)f) - 1, t = b & 7;
+                            const unsigned li = (unsigned)(li0 + (b >> 3));
+                            uq[pos++] = ((UW)li << US) | (UW)(li - (unsigned)LP + (unsigned)(t == 0 ? 0 : (t == 1 ? -1 : 1)));
+                        }
+                        qn += nreq;
+                        __syncwarp();
+                        while (qn >= 32) drain(32);
+                    } else {  // (rare) more requests than the queue holds: pixel by pixel, at most 2 x 32 at a time
+#pragma unroll 1
+                        for (int k = 0; k < 4; k++) {
+                            const unsigned fk = (F >> (8 * k)) & 7u;
+                            const unsigned li = (unsigned)(li0 + k);
+                            push((fk & 3u) != 0u, ((UW)li << US) | (UW)(li - (unsigned)LP - ((fk & 2u) ? 1u : 0u)));
+                            push((fk & 4u) != 0u, ((UW)li << US) | (UW)(li - (unsigned)LP + 1u));
+                        }
+                    }
+                }
+            }
+            if (qn) { __syncwarp(); drain(qn); }
+        } else {
         for (int base = 0; base < nbox; base += RADB_NTB) {  // uniform trip count (warp collectives below)
             const int idx = base + tid;
             const int yb = WIDE ? idx / bw : (int)(((float)idx + 0.5f) * inv_bw);
@@ -1025,17 +1142,16 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 const int nw = lev[ctr - WP - 1], n_ = lev[ctr - WP], ne = lev[ctr - WP + 1];
                 const int w_ = lev[ctr - 1], e_ = lev[ctr + 1];
                 const int sw = lev[ctr + WP - 1], s_ = lev[ctr + WP], se = lev[ctr + WP + 1];
-                int* g0 = glcm + (c - 1) * ng - 1;
-                const int ngng = ng * ng;
+                int* g0 = glcm0 + c * gp;
                 // Unconditional increments: a neighbour outside the ROI (level 0) is redirected to a scratch word
                 // of the record header instead of branching around the atomic -- `if (x) atomicAdd(..)` costs
                 // BSSY / BRA / BSYNC per counter in the innermost loop, and the plain form keeps the compiler's
                 // ATOMS.POPC.INC (same-address lanes are combined by the hardware).
                 int* const trash = ((WIDE && p.big) ? (int*)(g_rec + (p.o_misc - p.o_rec)) : misc) + 30;
                 atomicAdd(se ? &g0[se] : trash, 1);
-                atomicAdd(e_ ? &g0[ngng + e_] : trash, 1);
-                atomicAdd(ne ? &g0[2 * ngng + ne] : trash, 1);
-                atomicAdd(s_ ? &g0[3 * ngng + s_] : trash, 1);
+                atomicAdd(e_ ? &g0[gas + e_] : trash, 1);
+                atomicAdd(ne ? &g0[2 * gas + ne] : trash, 1);
+                atomicAdd(s_ ? &g0[3 * gas + s_] : trash, 1);
                 const int al = p.alpha;
                 int cnt, sum, dep;
                 if (!L16 && al == 0) {
@@ -1078,7 +1194,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                         const int f = lev[ctr + doff[a]];
                         const int b = lev[ctr - doff[a]];
                         if (f) {
-                            atomicAdd(&glcm[(a * ng + c - 1) * ng + f - 1], 1);
+                            atomicAdd(&glcm0[a * gas + c * gp + f], 1);
                             cnt++;
                             sum += f;
                             int df = f - c;
@@ -1119,6 +1235,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             }
         }
         if (qn) drain(qn);
+        }
     }
     __syncthreads();
 
@@ -1151,12 +1268,25 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int c = lev[ctr];
         if (c && (a_row < 0 || lev[ctr + 1] != c)) fold_run((unsigned)(y * LP + x));  // run end
     }
-    if (p.symmetric) {  // all angles in one flat loop; (a, i, j) by float reciprocals (exact: indices < 2^18)
+    if (p.glcm_pad) {
+        // the padded counters become the record's compact [NA][ng][ng] matrix (symmetrised: P + P^T) in global
+        // memory; (a, i, j) by float reciprocals (exact: indices < 2^18)
         const int ng2 = ng * ng, tot = NA * ng2;
         const float r2 = 1.0f / (float)ng2, r1 = 1.0f / (float)ng;
+        int* const G = (int*)(g_rec + (p.o_glcm - p.o_rec));
         for (int t = tid; t < tot; t += RADB_NTB) {
-            const int a = (WIDE && p.big) ? t / ng2 : (int)(((float)t + 0.5f) * r2), cell = t - a * ng2;
-            const int i = (WIDE && p.big) ? cell / ng : (int)(((float)cell + 0.5f) * r1), j = cell - i * ng;
+            const int a = (int)(((float)t + 0.5f) * r2), cell = t - a * ng2;
+            const int i = (int)(((float)cell + 0.5f) * r1), j = cell - i * ng;
+            const int* P = glcm0 + a * gas;
+            int v = P[(i + 1) * gp + j + 1];
+            if (p.symmetric) v += P[(j + 1) * gp + i + 1];
+            G[t] = v;
+        }
+    } else if (p.symmetric) {  // big mode: in place in the global record, all angles in one flat loop
+        const int ng2 = ng * ng, tot = NA * ng2;
+        for (int t = tid; t < tot; t += RADB_NTB) {
+            const int a = t / ng2, cell = t - a * ng2;
+            const int i = cell / ng, j = cell - i * ng;
             if (i > j) continue;
             int* P = glcm + a * ng2;
             if (i == j) {
@@ -1210,10 +1340,12 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     if (DBG && p.dbg_levels)
         for (int i = tid; i < HW; i += RADB_NTB)
             p.dbg_levels[patch * HW + i] = lev[(i / W + 1) * WP + (i % W) + XO];
-    if (DBG && p.dbg_glcm)
+    if (DBG && p.dbg_glcm) {
+        const int* G = (const int*)(g_rec + (p.o_glcm - p.o_rec));  // compact, written in phase 4 (visible after the barrier)
         for (int a = 0; a < NA; a++)
             for (int t = tid; t < ng * ng; t += RADB_NTB)
-                p.dbg_glcm[((patch * NA + a) * p.max_ng + t / ng) * p.max_ng + t % ng] = glcm[a * ng * ng + t];
+                p.dbg_glcm[((patch * NA + a) * p.max_ng + t / ng) * p.max_ng + t % ng] = G[a * ng * ng + t];
+    }
     if (DBG && p.dbg_glrlm)
         for (int a = 0; a < NA; a++)
             for (int t = tid; t < ng * p.nr; t += RADB_NTB)
@@ -1234,7 +1366,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const uint4* src = (const uint4*)(smem + p.o_rec);
         uint4* dst = (uint4*)g_rec;
         const int n16 = p.rec_copy_bytes / 16;  // wide: GLRLM and the overflow list are already in place
-        for (int i = tid; i < n16; i += RADB_NTB) dst[i] = src[i];
+        // the GLCM region was written (compact) in phase 4; big mode keeps it out of the copied part altogether
+        const int g0 = p.glcm_pad ? (p.o_glcm - p.o_rec) / 16 : n16, g1 = p.glcm_pad ? (p.o_gldm - p.o_rec) / 16 : n16;
+        for (int i = tid; i < n16; i += RADB_NTB)
+            if (i < g0 || i >= g1) dst[i] = src[i];
     }
 }
 

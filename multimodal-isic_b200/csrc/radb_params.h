@@ -43,6 +43,11 @@ struct RadbParams {
     int mask_bits; // 1: `mask` is bit-packed (bit i of a patch's stream <-> pixel i, set = ROI), mask_stride in bytes of that stream
     int xo;        // column of pixel x = 0 inside a padded level-image row (left border width)
     int vec4;      // uint8 narrow patches with W % 4 == 0: 4 pixels per shared-memory load in the discretise phases
+    int lev4;      // narrow u8 level image with W % 4 == 0: pixel x at byte 4 + x of a row whose word pitch is odd
+                   // (the neighbourhood pass then works on aligned 4-pixel words, radb_build_cta)
+    int glcm_pad;  // 1: the build kernel counts into a (Ng + 1)^2 GLCM whose row / column 0 collect the pairs with a
+                   // pixel outside the ROI (no test per increment); it is written compact (Ng^2) to the global record
+    int uq_cap;    // entries per warp of the union request queues
     int label;
     int n_angles;
     int ang_y[RADB_MAX_ANGLES], ang_x[RADB_MAX_ANGLES];
@@ -123,10 +128,13 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->pix_bytes = pix_bytes;
     p->HW = H * W;
     p->lp = (!wide && W % 2 == 0) ? W + 1 : W;
-    p->vec4 = (!wide && pix_bytes == 1 && W % 4 == 0) ? 1 : 0;
-    p->xo = p->vec4 ? 4 : 1;
+    p->lev4 = (!wide && p->lev_bytes == 1 && W % 4 == 0) ? 1 : 0;
+    p->vec4 = (p->lev4 && pix_bytes == 1) ? 1 : 0;
+    p->glcm_pad = big ? 0 : 1;
+    p->uq_cap = 96;
+    p->xo = p->lev4 ? 4 : 1;
     p->WP = radb_align(W + p->xo + 1, 4);
-    if (p->vec4 && (p->WP / 4) % 2 == 0) p->WP += 4;  // odd word stride: row walks stay bank-conflict free
+    if (p->lev4 && (p->WP / 4) % 2 == 0) p->WP += 4;  // odd word stride: row walks stay bank-conflict free
     p->nr = H > W ? H : W;
     p->nrp = (p->nr + 1) & ~1;
     p->s0 = wide ? 64 : 16;
@@ -181,16 +189,21 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->o_zero = o;                        // everything from here on is zeroed at CTA start
     p->o_lev = o;
     if (!wide) o += radb_align((H + 2) * p->WP * p->lev_bytes, 16);
-    p->o_uq = o; o += (RADB_NTB / 32) * 64 * (wide ? 8 : 4);   // per-warp union request queues
+    p->o_uq = o; o += (RADB_NTB / 32) * p->uq_cap * (wide ? 8 : 4);   // per-warp union request queues
     p->o_lut = o; o += 256;
     p->o_fo = o; o += pix_bytes == 1 ? 16 : radb_align(64 * 8 + 16 * 8 + 10 * 8 + 10 * 8 + 10 * 4 + 10 * 4 + 8 + 10 * 256 * 4 + 64, 16);  // RADB_FO_SCRATCH
     p->o_rec = o;
     p->o_misc = o; o += 32 * 4;           // record header: [0] Np, [5] #overflow zones, [8] Ng, [9] #levels present, [10+a] longest run of angle a
     p->o_hist = o; o += 256 * 4;
     p->o_lhist = o; o += radb_align(ng * 4, 16);
-    p->o_glcm = o; if (!big) o += radb_align(na * ng * ng * 4, 16);
+    p->o_glcm = o; if (!big) o += radb_align(na * (ng + 1) * (ng + 1) * 4, 16);  // padded while it is built
+    // GLDM / NGTDM: a few garbage words in front of each, hit by the (branch-free) updates of the non-ROI pixels
+    // of a 4-pixel word (level 0 -> row -1)
+    o += radb_align((2 * na + 1) * 4, 16);
     p->o_gldm = o; o += radb_align(ng * (2 * na + 1) * 4, 16);
+    o += radb_align((2 * na + 1) * 4, 16);
     p->o_ngc = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] voxel counts per neighbour count
+    o += radb_align((2 * na + 1) * 4, 16);
     p->o_ngn = o; o += radb_align(ng * 2 * na * 4, 16);   // [ng][2na] sum |cnt*i - sum(neigh)|
     p->o_szm = o; o += radb_align(ng * p->s0 * 4, 16);
     p->rec_copy_bytes = o - p->o_rec;

@@ -172,6 +172,12 @@ inline double __dadd_rn(double a, double b) {
     volatile double r = a + b;
     return r;
 }
+inline unsigned __byte_perm(unsigned x, unsigned y, unsigned sel) {
+    const uint64_t v = ((uint64_t)y << 32) | x;
+    unsigned r = 0;
+    for (int i = 0; i < 4; i++) r |= (unsigned)((v >> (8 * ((sel >> (4 * i)) & 7u))) & 0xffu) << (8 * i);
+    return r;
+}
 inline int __popc(unsigned v) { return __builtin_popcount(v); }
 inline int __clz(int v) { return v ? __builtin_clz((unsigned)v) : 32; }
 inline int __ffs(int v) { return __builtin_ffs(v); }
