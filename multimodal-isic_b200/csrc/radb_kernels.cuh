@@ -1024,7 +1024,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             __syncwarp();
             if (qn >= 32) drain(32);
         };
-        if (!WIDE && !L16 && p.lev4 && p.glcm_pad && inplane && p.alpha == 0 && keep_runs && a_row == 1) {
+        if (!WIDE && !L16 && p.lev4 && p.glcm_pad && inplane && p.alpha == 0 && a_row == 1) {
             // Four pixels per thread: the level image is read as aligned 32-bit words (3 rows x 3 words), the eight
             // neighbours of the four pixels of the centre word are byte permutes of those, and the neighbour
             // counts (NGTDM), equal-level counts (GLDM, alpha = 0) and the run-adjacency / run-end tests are
@@ -1096,7 +1096,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 const int excl = warp_excl_scan_i(mine, lane);
                 const int tot = __shfl_sync(FULLMASK, excl + mine, 31);
                 const int nreq = tot & 0xffff, nend = tot >> 16;
-                if (nend) {
+                if (keep_runs && nend) {  // (without the list the zone phases find the run ends by scanning the bbox)
                     int rbase = 0;
                     if (lane == 0) rbase = atomicAdd(&misc[6], nend);
                     rbase = __shfl_sync(FULLMASK, rbase, 0) + (excl >> 16);
@@ -1251,15 +1251,19 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     // list is (nearly) in pixel order: round k of this loop handles runs above those of round k + 1, and every
     // run re-parents itself straight to its root, so later rounds find short paths (the clocks showed the
     // read-only finds of this phase at 15 % of the CTA's lifetime).
-    auto fold_run = [&](unsigned e) {
+    // returns the start pixel of the run if the run is its zone's root run, else 0xffff (no pixel index: H * LP <= 65535)
+    auto fold_run = [&](unsigned e) -> unsigned {
         const unsigned r = uf_find<UW, UF<WIDE>::S>(lab, e);
-        if (r == e) return;  // a one-pixel run that is its zone's root: its size field already counts it
+        if (r == e) return e;  // a one-pixel run that is its zone's root: its size field already counts it
         const UW we = ((volatile UW*)lab)[e];  // e is not a root: its size field is static
         const unsigned len = (unsigned)(we >> US);
+        const unsigned own = (e - len + 1u == r) ? 1u : 0u;
         ((volatile UW*)lab)[e] = (we & ~ULO) | (UW)r;
-        atomicAdd(&lab[r], (UW)(len - (e - len + 1u == r ? 1u : 0u)) << US);  // only roots are ever added to
+        atomicAdd(&lab[r], (UW)(len - own) << US);  // only roots are ever added to
+        return own ? r : 0xffffu;
     };
-    for (int k = tid; k < nruns; k += RADB_NTB) fold_run(runs[k]);
+    // the list entry of a root run becomes its start pixel, every other entry 0xffff: phase 5 then only touches roots
+    for (int k = tid; k < nruns; k += RADB_NTB) runs[k] = (unsigned short)fold_run(runs[k]);
     if (!by_list)
     for (int idx = tid; idx < nbox; idx += RADB_NTB) {
         const int yb = WIDE ? idx / bw : (int)(((float)idx + 0.5f) * inv_bw);
@@ -1301,6 +1305,12 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     __syncthreads();
 
     // ---- phase 5: zone roots -> GLSZM (dense + overflow)
+    if (warp == RADB_NTB / 32 - 1) {  // record header: number of gray levels present in the ROI (MCC: < 2 -> 1)
+        int nroi = 0;
+        for (int i = lane; i < ng; i += 32) nroi += lhist[i] > 0;
+        nroi = warp_sum_i(nroi);
+        if (lane == 0) misc[9] = nroi;
+    }
     auto emit_zone = [&](int c, int s) {
         if (s <= p.s0) {
             atomicAdd(&szm[(c - 1) * p.s0 + s - 1], 1);
@@ -1320,9 +1330,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         if ((unsigned)(ws & ULO) == s) emit_zone(c, (int)(ws >> US));
     };
     for (int k = tid; k < nruns; k += RADB_NTB) {
-        const int e = runs[k];
-        const int y = (int)(((float)e + 0.5f) * inv_lp), x = e - y * LP;  // exact for e < 65536
-        emit_run((unsigned)e, (int)lev[(y + 1) * WP + x + XO]);
+        const int r = runs[k];
+        if (r == 0xffff) continue;
+        const int y = (int)(((float)r + 0.5f) * inv_lp), x = r - y * LP;  // exact for r < 65536
+        emit_zone((int)lev[(y + 1) * WP + x + XO], (int)(lab[r] >> US));
     }
     if (!by_list)
     for (int idx = tid; idx < nbox; idx += RADB_NTB) {
@@ -1356,12 +1367,6 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             p.dbg_gldm[patch * p.max_ng * (NB + 1) + t] = gldm[t];
 
     // ---- phase 6: publish the record (header + every integer matrix) for the reduction kernels
-    if (tid == 0) {
-        int nroi = 0;  // number of gray levels present in the ROI (MCC: < 2 -> 1)
-        for (int i = 0; i < ng; i++) nroi += lhist[i] > 0;
-        misc[9] = nroi;
-    }
-    __syncthreads();
     {
         const uint4* src = (const uint4*)(smem + p.o_rec);
         uint4* dst = (uint4*)g_rec;

@@ -23,7 +23,7 @@ for f in os.listdir(SRC):
 
 # ---- kernel: clock marks after the barrier that closes each phase
 lines = open(os.path.join(SRC, "radb_kernels.cuh")).read().split("\n")
-sync = [i for i, l in enumerate(lines) if l.strip() == "__syncthreads();"]
+sync = [i for i, l in enumerate(lines) if l == "    __syncthreads();"]  # function-level barriers only
 ph = {}
 for i, l in enumerate(lines):
     m = re.match(r"\s*// ---- (phase [0-9a-z]+)", l)
@@ -33,7 +33,7 @@ before = lambda i: max(j for j in sync if j < i)
 after = lambda i: min(j for j in sync if j > i)
 between = [j for j in sync if ph["phase 1"] < j < ph["phase 2"]]
 marks = [before(ph["phase 1"]), between[0], between[-1], before(ph["phase 3a"]), before(ph["phase 3b"]),
-         before(ph["phase 4"]), before(ph["phase 5"]), after(ph["phase 5"]), after(ph["phase 6"])]
+         before(ph["phase 4"]), before(ph["phase 5"]), after(ph["phase 5"])]
 out = []
 for i, l in enumerate(lines):
     out.append(l)
@@ -42,9 +42,9 @@ for i, l in enumerate(lines):
 s = "\n".join(out)
 s = s.replace("    // ---- phase 0: stage the patch, zero the counters",
               "    if (tid == 0 && p.clk) p.clk[patch * 16 + 0] = clock64();\n    // ---- phase 0: stage the patch, zero the counters", 1)
-tail = "        for (int i = tid; i < n16; i += RADB_NTB) dst[i] = src[i];\n    }\n}"
+tail = "            if (i < g0 || i >= g1) dst[i] = src[i];\n    }\n}"
 assert tail in s
-s = s.replace(tail, tail[:-1] + "    __syncthreads();\n    if (tid == 0 && p.clk) p.clk[patch * 16 + 10] = clock64();\n}", 1)
+s = s.replace(tail, tail[:-1] + "    __syncthreads();\n    if (tid == 0 && p.clk) p.clk[patch * 16 + 9] = clock64();\n}", 1)
 open(os.path.join(DST, "radb_kernels.cuh"), "w").write(s)
 
 # ---- params: the side buffer
@@ -67,20 +67,20 @@ dump = r'''    if (getenv("RADB_CLK")) {
         const long long nb = p.B < chunk ? p.B : chunk;
         std::vector<long long> hc((size_t)nb * 16);
         cudaMemcpy(hc.data(), g_clk, hc.size() * 8, cudaMemcpyDeviceToHost);
-        double acc[11] = {0};
+        double acc[10] = {0};
         long long cnt = 0;
         for (long long i = 0; i < nb; i++) {
             const long long* c = &hc[i * 16];
-            if (!c[0] || !c[10]) continue;
+            if (!c[0] || !c[9]) continue;
             cnt++;
-            for (int k = 1; k <= 10; k++) acc[k] += (double)(c[k] - c[k - 1]);
+            for (int k = 1; k <= 9; k++) acc[k] += (double)(c[k] - c[k - 1]);
         }
-        static const char* nm[11] = {"", "p0 stage+zero", "p1 hist/bbox", "validity+lut", "p2 discretise", "p3a walks",
-                                     "p3b neighbourhood", "p4 fold+symm", "p5 zones", "misc9", "p6 record copy"};
+        static const char* nm[10] = {"", "p0 stage+zero", "p1 hist/bbox", "validity+lut", "p2 discretise", "p3a walks",
+                                     "p3b neighbourhood", "p4 fold+glcm out", "p5 zones", "p6 record copy"};
         double tot = 0;
-        for (int k = 1; k <= 10; k++) tot += acc[k];
+        for (int k = 1; k <= 9; k++) tot += acc[k];
         fprintf(stderr, "phase clocks (avg cycles per CTA over %lld patches, total %.0f):\n", cnt, tot / cnt);
-        for (int k = 1; k <= 10; k++) fprintf(stderr, "  %-20s %8.0f  %5.1f%%\n", nm[k], acc[k] / cnt, 100 * acc[k] / tot);
+        for (int k = 1; k <= 9; k++) fprintf(stderr, "  %-20s %8.0f  %5.1f%%\n", nm[k], acc[k] / cnt, 100 * acc[k] / tot);
     }
 '''
 s = s.replace(a3, dump + a3, 1)

@@ -132,3 +132,34 @@ def edge_case_batch(H=16, W=12, seed=3):
     masks[8, 0:2, 0:2] = 255                       # 2x2 ROI in a corner
     masks[7, 0, 0] = 128                           # other labels are not ROI
     return imgs, masks
+
+
+def word_pass_stress_batch(H=64, W=64):
+    """Patterns that stress the 4-pixel-word neighbourhood pass of the build kernel: checkerboards (two union requests per
+    pixel: the request queue's overflow path), diagonal stripes, one-pixel runs, bounding boxes that start at every
+    column offset inside a word, ragged masks, isolated pixels.  uint8, two to eleven levels at binWidth 25."""
+    rng = np.random.default_rng(11)
+    yy, xx = np.mgrid[:H, :W]
+    imgs, masks = [], []
+
+    def add(img, mask):
+        imgs.append(np.asarray(img, np.uint8))
+        masks.append(np.where(mask, 255, 0).astype(np.uint8))
+
+    full = np.ones((H, W), bool)
+    add(40 + 100 * ((xx + yy) & 1), full)                       # checkerboard: NW / NE unions everywhere
+    add(40 + 60 * ((xx + yy) % 3), full)                        # diagonal stripes
+    add(40 + 60 * ((xx - yy) % 3), full)                        # anti-diagonal stripes
+    add(40 + 100 * (xx & 1), full)                              # vertical one-pixel stripes
+    add(40 + 100 * (yy & 1), full)                              # horizontal stripes
+    add(rng.integers(0, 256, (H, W)), rng.random((H, W)) < 0.5)  # noise image, noise mask: isolated pixels
+    for off in range(4):                                        # bbox starting at x = 5 + off, width not a multiple of 4
+        m = np.zeros((H, W), bool)
+        m[3:H - 5, 5 + off:W - 6 - 2 * off] = True
+        add(40 + 100 * ((xx + yy) & 1), m)
+        add(rng.integers(0, 256, (H, W)), m & (rng.random((H, W)) < 0.9))
+    m = np.zeros((H, W), bool)
+    m[10:12, 7:9] = True                                        # 2 x 2 ROI inside one word pair
+    add(rng.integers(0, 256, (H, W)), m)
+    add(np.full((H, W), 77), full)                              # flat: one zone of H * W pixels
+    return np.stack(imgs), np.stack(masks)

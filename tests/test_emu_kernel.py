@@ -9,7 +9,7 @@ import pytest
 
 from multimodal_isic_b200 import synth
 from oracle import radiomics_oracle as orc
-from tests.emu_runner import compare_with_oracle, edge_case_batch
+from tests.emu_runner import compare_with_oracle, edge_case_batch, word_pass_stress_batch
 
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
 INPLANE = orc.angles(2)[0]
@@ -399,3 +399,11 @@ def test_emu_first_order_only_stage(emu):
         n += 1
         np.testing.assert_allclose(r["features"][b], list(ref.values()), rtol=1e-6, atol=1e-9)
     assert n >= 8
+
+
+@pytest.mark.parametrize("bw", [25, 10])
+def test_emu_word_pass_stress_patterns(emu, bw):
+    """The 4-pixels-per-thread neighbourhood pass (and its request-queue overflow path) on adversarial patterns."""
+    imgs, masks = word_pass_stress_batch(32, 32)
+    r = emu.run(imgs, masks, bw, 255, INPLANE)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=bw, force2D=False)) == len(imgs)

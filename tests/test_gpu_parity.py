@@ -8,7 +8,7 @@ import pytest
 import torch
 
 from oracle import cmatrices, radiomics_oracle as orc
-from tests.emu_runner import ATOL, RTOL, compare_with_oracle, edge_case_batch
+from tests.emu_runner import ATOL, RTOL, compare_with_oracle, edge_case_batch, word_pass_stress_batch
 
 pytestmark = pytest.mark.gpu
 GOLD = os.path.join(os.path.dirname(__file__), "golden")
@@ -119,6 +119,15 @@ def test_random_noise_many_levels(gpu_pkg):
     masks = np.where(rng.random((6, 40, 40)) < 0.8, 255, 0).astype(np.uint8)
     r = _dbg(_engine(gpu_pkg, 4), imgs, masks)  # 64 gray levels
     assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=4, force2D=False)) == 6
+
+
+@pytest.mark.parametrize("bw,hw", [(25, 64), (10, 64), (25, 32)])
+def test_word_pass_stress_patterns(gpu_pkg, bw, hw):
+    """The 4-pixels-per-thread neighbourhood pass (and its request-queue overflow path) on adversarial patterns:
+    checkerboards, stripes, noise masks, bounding boxes at every column offset inside a word."""
+    imgs, masks = word_pass_stress_batch(hw, hw)
+    r = _dbg(_engine(gpu_pkg, bw), imgs, masks)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=bw, force2D=False)) == len(imgs)
 
 
 def test_smooth_image_large_zones(gpu_pkg):
