@@ -245,13 +245,14 @@ __device__ __forceinline__ void uf_union(W* L, unsigned a, unsigned b)
 #ifdef RADB_EMU
 typedef uintptr_t radb_saddr;
 __device__ __forceinline__ radb_saddr radb_to_saddr(const void* p) { return (radb_saddr)p; }
-__device__ __forceinline__ void radb_red_add(radb_saddr a, unsigned v) { atomicAdd((unsigned*)a, v); }
+__device__ __forceinline__ void radb_red_add_if(bool on, radb_saddr a, unsigned v) { if (on) atomicAdd((unsigned*)a, v); }
 #else
 typedef unsigned radb_saddr;
 __device__ __forceinline__ radb_saddr radb_to_saddr(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void radb_red_add(radb_saddr a, unsigned v)
+// predicated (not branched-around, not redirected to a scratch word: lanes that are off do not touch shared memory)
+__device__ __forceinline__ void radb_red_add_if(bool on, radb_saddr a, unsigned v)
 {
-    asm volatile("red.shared.add.u32 [%0], %1;" ::"r"(a), "r"(v) : "memory");
+    asm volatile("{ .reg .pred p; setp.ne.u32 p, %2, 0; @p red.shared.add.u32 [%0], %1; }" ::"r"(a), "r"(v), "r"((unsigned)on) : "memory");
 }
 #endif
 
@@ -630,7 +631,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
 #endif
     {
         uint4* z = (uint4*)(smem + p.o_zero);
-        const int nz = (p.smem_total - p.o_zero) / 16;
+        const int nz = ((p.o_runs >= 0 ? p.o_runs : p.smem_total) - p.o_zero) / 16;  // (the run list is written before it is read)
         const uint4 zero = {0u, 0u, 0u, 0u};
         for (int i = tid; i < nz; i += RADB_NTB) z[i] = zero;
         if (WIDE) {  // level image + GLRLM counters in global memory
@@ -757,7 +758,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         if (U8) {
             int imin = 256, imax = -1;
             for (int k = 0; k < 8; k++) {
-                int v = lane * 8 + k;
+                const int v = k * 32 + lane;  // lane <-> bank
                 if (hist[v]) { imin = v < imin ? v : imin; imax = v > imax ? v : imax; }
             }
             vmin = (double)warp_min_i(imin);
@@ -901,11 +902,12 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     // END pixel of a run carries the run length (seed of the zone sizes).  Diagonal lines are wrapped
     // inside the bbox (a wrap forces a run break), so every angle is bw (or bh) lines of equal length.
     // The steps are branch-free: a run ends where the NEXT level differs (outside the bbox every level is
-    // 0), and the counter update of a step that ends no run goes to a per-thread scratch word instead of
-    // branching around the atomic (a divergent run-end block ran at 13 of 32 lanes and was 30 % of the
-    // kernel's instructions).  Narrow mode tracks the byte address of the u16 counter of (level 0, current
+    // 0), and the counter update is one PREDICATED `red.shared` per step instead of a divergent run-end block
+    // (which ran at 13 of 32 lanes and was 30 % of the kernel's instructions); lanes that end no run do not touch
+    // shared memory (redirecting them to scratch words cost bank conflicts: the shared-memory pipe is the second
+    // bottleneck of this kernel).  Narrow mode tracks the byte address of the u16 counter of (level 0, current
     // position) and the increment (1 or 1 << 16: the GLRLM pitch is even, so the half alternates with the
-    // position), which leaves one multiply-add, one mask and one select per step for the address.
+    // position), which leaves one multiply-add and one mask per step for the address.
     // Task layout: the rows (padded to whole warps), then the lines of all other angles back to back -- they
     // run the same code with per-thread data (x step, counter base), so warps are filled across angles.
     {
@@ -915,7 +917,6 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         for (int a = 0; a < NA; a++)
             if (a != a_row) oth[noth++] = a;
         const int ntasks = row_slots + noth * bw;
-        const radb_saddr trash = radb_to_saddr((unsigned*)(smem + p.o_uq) + tid);  // the union queues are idle until phase 3b
         const unsigned gpitch = 2u * (unsigned)nrp;  // bytes per level of the u16 counters
         for (int t = tid; t < ntasks; t += RADB_NTB) {
             const bool is_row = t < row_slots;
@@ -953,7 +954,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                         val = endp ? 1u : val ^ 0x10001u;
                         endp = (gn != g);
                         const radb_saddr w = (kc + (unsigned)g * gpitch) & ~(radb_saddr)3;
-                        radb_red_add((endp && g) ? w : trash, val);
+                        radb_red_add_if(endp && g, w, val);
                         if (g) kmax = kc > kmax ? kc : kmax;
                     }
                 }
@@ -979,7 +980,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                         val = endp ? 1u : val ^ 0x10001u;
                         endp = (gn != g) || brk;
                         const radb_saddr w = (kc + (unsigned)g * gpitch) & ~(radb_saddr)3;
-                        radb_red_add((endp && g) ? w : trash, val);
+                        radb_red_add_if(endp && g, w, val);
                         if (g) kmax = kc > kmax ? kc : kmax;
                     }
                 }
@@ -1247,19 +1248,30 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     const bool by_list = keep_runs && a_row >= 0;  // the run list exists: visit runs, not pixels
     const int nruns = by_list ? misc[6] : 0;
     const float inv_lp = 1.0f / (float)LP;
-    // Unions link the larger pixel index under the smaller one, so a tall zone is a long parent chain.  The
-    // list is (nearly) in pixel order: round k of this loop handles runs above those of round k + 1, and every
-    // run re-parents itself straight to its root, so later rounds find short paths (the clocks showed the
-    // read-only finds of this phase at 15 % of the CTA's lifetime).
+    // Unions link the larger pixel index under the smaller one, so a tall zone is a long parent chain (the clocks
+    // showed chain walks of ~40 hops: 15 % of a CTA's lifetime).  Every run start is owned by exactly one thread
+    // here and every chain node is a run start, so the chains are shortened by POINTER JUMPING: a thread keeps
+    // replacing its start pixel's parent by the grandparent until that is a root -- all chains halve together,
+    // ~log2(depth) steps instead of depth.  (Stores only touch non-roots, whose size field is static; only roots
+    // are ever added to.)
     // returns the start pixel of the run if the run is its zone's root run, else 0xffff (no pixel index: H * LP <= 65535)
     auto fold_run = [&](unsigned e) -> unsigned {
-        const unsigned r = uf_find<UW, UF<WIDE>::S>(lab, e);
-        if (r == e) return e;  // a one-pixel run that is its zone's root: its size field already counts it
-        const UW we = ((volatile UW*)lab)[e];  // e is not a root: its size field is static
-        const unsigned len = (unsigned)(we >> US);
-        const unsigned own = (e - len + 1u == r) ? 1u : 0u;
-        ((volatile UW*)lab)[e] = (we & ~ULO) | (UW)r;
-        atomicAdd(&lab[r], (UW)(len - own) << US);  // only roots are ever added to
+        volatile UW* L = (volatile UW*)lab;
+        const UW we = L[e];
+        if ((unsigned)(we & ULO) == e) return e;  // a one-pixel run that is its zone's root: its size field already counts it
+        const unsigned len = (unsigned)(we >> US), st = e - len + 1u;  // e is not a root: its size field (the run length) is static
+        UW ws = st == e ? we : L[st];
+        unsigned r;
+        while (true) {
+            const unsigned pa = (unsigned)(ws & ULO);
+            if (pa == st) { r = st; break; }
+            const unsigned g = (unsigned)(L[pa] & ULO);
+            if (g == pa) { r = pa; break; }
+            ws = (ws & ~ULO) | (UW)g;
+            L[st] = ws;
+        }
+        const unsigned own = (r == st) ? 1u : 0u;
+        atomicAdd(&lab[r], (UW)(len - own) << US);
         return own ? r : 0xffffu;
     };
     // the list entry of a root run becomes its start pixel, every other entry 0xffff: phase 5 then only touches roots

@@ -40,18 +40,27 @@ for i, l in enumerate(lines):
     if i in marks:
         out.append("    if (tid == 0 && p.clk) p.clk[patch * 16 + %d] = clock64();" % (marks.index(i) + 1))
 s = "\n".join(out)
+split = "    if (p.glcm_pad) {\n        // the padded counters become the record's compact"
+assert split in s
+s = s.replace(split, "    __syncthreads();\n    if (tid == 0 && p.clk) p.clk[patch * 16 + 12] = clock64();\n" + split, 1)
 s = s.replace("    // ---- phase 0: stage the patch, zero the counters",
               "    if (tid == 0 && p.clk) p.clk[patch * 16 + 0] = clock64();\n    // ---- phase 0: stage the patch, zero the counters", 1)
 tail = "            if (i < g0 || i >= g1) dst[i] = src[i];\n    }\n}"
 assert tail in s
 s = s.replace(tail, tail[:-1] + "    __syncthreads();\n    if (tid == 0 && p.clk) p.clk[patch * 16 + 9] = clock64();\n}", 1)
+# experiment switches (RADB_SKIP bits): 1 = no size atomics in the fold, 2 = no pointer jumping in the fold
+x1 = "        atomicAdd(&lab[r], (UW)(len - own) << US);"
+x2 = "        unsigned r;\n        while (true) {\n            const unsigned pa = (unsigned)(ws & ULO);"
+assert x1 in s and x2 in s
+s = s.replace(x1, "        if (!(p.dbg_skip & 1)) atomicAdd(&lab[r], (UW)(len - own) << US);", 1)
+s = s.replace(x2, "        unsigned r = st;\n        while (!(p.dbg_skip & 2)) {\n            const unsigned pa = (unsigned)(ws & ULO);", 1)
 open(os.path.join(DST, "radb_kernels.cuh"), "w").write(s)
 
 # ---- params: the side buffer
 s = open(os.path.join(SRC, "radb_params.h")).read()
 anchor = "    unsigned char* ws;        // [B][rec_bytes]"
 assert anchor in s
-open(os.path.join(DST, "radb_params.h"), "w").write(s.replace(anchor, "    long long* clk;\n" + anchor))
+open(os.path.join(DST, "radb_params.h"), "w").write(s.replace(anchor, "    long long* clk;\n    int dbg_skip;\n" + anchor))
 
 # ---- launch(): allocate, pass, dump
 s = open(os.path.join(SRC, "radb_api.cu")).read()
@@ -61,7 +70,7 @@ a3 = "    e = cudaGetLastError();\n    if (e != cudaSuccess) return cuda_fail(e,
 assert a1 in s and a2 in s and a3 in s
 s = s.replace(a1, a1 + "\n    static long long* g_clk = nullptr;\n    if (!g_clk) cudaMalloc(&g_clk, (size_t)200000 * 16 * 8);\n"
                        "    cudaMemsetAsync(g_clk, 0, (size_t)200000 * 16 * 8, st);", 1)
-s = s.replace(a2, a2 + "        q.clk = (n <= 200000) ? g_clk : nullptr;\n", 1)
+s = s.replace(a2, a2 + "        q.clk = (n <= 200000) ? g_clk : nullptr;\n        q.dbg_skip = getenv(\"RADB_SKIP\") ? atoi(getenv(\"RADB_SKIP\")) : 0;\n", 1)
 dump = r'''    if (getenv("RADB_CLK")) {
         cudaDeviceSynchronize();
         const long long nb = p.B < chunk ? p.B : chunk;
@@ -77,6 +86,17 @@ dump = r'''    if (getenv("RADB_CLK")) {
         }
         static const char* nm[10] = {"", "p0 stage+zero", "p1 hist/bbox", "validity+lut", "p2 discretise", "p3a walks",
                                      "p3b neighbourhood", "p4 fold+glcm out", "p5 zones", "p6 record copy"};
+        {
+            double f = 0;
+            long long c2 = 0;
+            for (long long i = 0; i < nb; i++) {
+                const long long* c = &hc[i * 16];
+                if (!c[0] || !c[9] || !c[12]) continue;
+                f += (double)(c[12] - c[6]);
+                c2++;
+            }
+            if (c2) fprintf(stderr, "  (p4 split: fold %.0f cycles, GLCM write-out = rest)\n", f / c2);
+        }
         double tot = 0;
         for (int k = 1; k <= 9; k++) tot += acc[k];
         fprintf(stderr, "phase clocks (avg cycles per CTA over %lld patches, total %.0f):\n", cnt, tot / cnt);
