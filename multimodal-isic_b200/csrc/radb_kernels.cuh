@@ -941,6 +941,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 const int base = (by0 + l + 1) * WP + bx0 + XO, lbase = (by0 + l) * LP + bx0;
                 int gn = lev[base];  // software-pipelined: the next level is in flight while this one is processed
                 int rp = 0;          // position inside the run (the label needs it in both modes)
+                RADB_UNROLL(RADB_WALK_UNROLL)
                 for (int x = 0; x < bw; x++) {
                     const int g = gn;
                     gn = lev[base + x + 1];  // one past the bbox is the zero border or a pixel outside the ROI: level 0
@@ -964,6 +965,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 int x = l;
                 int pos = (by0 + 1) * WP + bx0 + XO;
                 int gn = lev[pos + x];  // software-pipelined like the row walk
+                RADB_UNROLL(RADB_WALK_UNROLL)
                 for (int y = 0; y < bh; y++) {
                     const int g = gn;
                     pos += WP;

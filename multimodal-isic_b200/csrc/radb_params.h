@@ -11,6 +11,11 @@
 #ifndef RADB_NTB_MINB
 #define RADB_NTB_MINB 5      // min resident build CTAs per SM (register cap: 48)
 #endif
+#ifndef RADB_WALK_UNROLL
+#define RADB_WALK_UNROLL 4   // unroll factor of the line-walk loops of the build kernel
+#endif
+#define RADB_PRAGMA_(x) _Pragma(#x)
+#define RADB_UNROLL(n) RADB_PRAGMA_(unroll n)
 #ifndef RADB_NTL
 #define RADB_NTL 64          // threads per CTA of the lane kernel: one THREAD per (patch, angle)
 #endif
@@ -148,7 +153,11 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->l_smem_total = p->l_doubles * 8 * RADB_LSTRIDE;
     // (>= 3 resident CTAs per SM: with fewer the serial per-thread chains are latency-bound and the
     // warp-per-angle kernel wins -- measured at Ng 26: 1.55 ms vs 1.16 ms per 8192 patches)
+#ifdef RADB_FORCE_G8   // A/B build: the 8-lanes-per-angle MCC kernel also below 15 gray levels
+    p->use_lane = 0;
+#else
     p->use_lane = (p->symmetric && p->l_smem_total <= 72 * 1024) ? 1 : 0;
+#endif
     if (!p->use_lane && p->symmetric && !big && ng <= 40) {
         // mid-size matrices: the per-thread scratch only holds the marginals (2 * ng slots); the eigenproblems go
         // to the MCC kernel, one warp per patch

@@ -52,6 +52,14 @@ s = s.replace(tail, tail[:-1] + "    __syncthreads();\n    if (tid == 0 && p.clk
 x1 = "        atomicAdd(&lab[r], (UW)(len - own) << US);"
 x2 = "        unsigned r;\n        while (true) {\n            const unsigned pa = (unsigned)(ws & ULO);"
 assert x1 in s and x2 in s
+x3 = "radb_red_add_if(endp && g, w, val);"
+x4 = "atomicAdd(has ? &ngn_p[c * NB + cnt] : trash, num);"
+assert s.count(x3) == 2 and x4 in s
+s = s.replace(x3, "radb_red_add_if(endp && g && !(p.dbg_skip & 4), w, val);")   # 4 = no GLRLM updates in the line walks
+s = s.replace(x4, "if (!(p.dbg_skip & 8)) atomicAdd(has ? &ngn_p[c * NB + cnt] : trash, num);")  # 8 = no NGTDM numerator updates
+x5 = "    for (int k = tid; k < nruns; k += RADB_NTB) runs[k] = (unsigned short)fold_run(runs[k]);"
+assert x5 in s
+s = s.replace(x5, "    if (!(p.dbg_skip & 16))\n" + x5)   # 16 = no fold at all (timing floor of the phase)
 s = s.replace(x1, "        if (!(p.dbg_skip & 1)) atomicAdd(&lab[r], (UW)(len - own) << US);", 1)
 s = s.replace(x2, "        unsigned r = st;\n        while (!(p.dbg_skip & 2)) {\n            const unsigned pa = (unsigned)(ws & ULO);", 1)
 open(os.path.join(DST, "radb_kernels.cuh"), "w").write(s)
