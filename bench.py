@@ -46,7 +46,11 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true", help="device-resident measurement only (parameter sweeps)")
     ap.add_argument("--e2e-pack", default="auto", choices=["auto", "on", "off"], help="host-side mask packing of the e2e path")
     ap.add_argument("--pack-threads", type=int, default=0)
-    ap.add_argument("--slices", default="0.6,0.4",
+    ap.add_argument("--gather", default="slices", choices=["chunks", "slices"],
+                    help="N > 1: all-gather per engine chunk of ONE extraction call (completion events), or per separately "
+                         "extracted slice (--slices)")
+    ap.add_argument("--gather-chunks", type=int, default=4, help="chunks per shard in --gather chunks mode")
+    ap.add_argument("--slices", default="0.45,0.3,0.15,0.1",
                     help="N > 1: fractions of the shard extracted per slice (the all-gather of a slice overlaps the next slice)")
     return ap.parse_args()
 
@@ -154,7 +158,11 @@ def workload_config(args, patches_per_step, F):
         "binWidth": args.bin_width,
         "angles": "literal force2D on 2-D input (1 angle, 2 neighbours)" if args.literal_force2d
         else "in-plane (4 angles, 8 neighbours)",
-        "label": 255, "parallelism": "patch-sharded (block-cyclic), one process per GPU, all-gather of the feature block in two slices (60 / 40 %) overlapped with the extraction, written in place",
+        "label": 255, "parallelism": ("patch-sharded (block-cyclic), one process per GPU; one extraction call per step, the all-gather of each of "
+                                        "its %d chunks starts on the chunk's completion event and lands in place" % args.gather_chunks)
+        if args.gather == "chunks" else
+        ("patch-sharded (block-cyclic), one process per GPU, all-gather of the feature block in separately extracted slices "
+         "(%s) overlapped with the extraction, written in place" % args.slices),
         "l2_policy": "inputs (%.0f MB per step) larger than the 126 MB L2" % (patches_per_step * args.size * args.size * 2 / 1e6),
     }
 
@@ -225,13 +233,21 @@ def gpu_arm(args):
     # the extraction of slice k+1; the global patch list is dealt to the ranks in blocks (block-cyclic), so every
     # slice's all-gather lands in its final rows; the step ends when the full [world * B, F] matrix is on every rank
     pieces = tuple(float(x) for x in args.slices.split(","))
-    og = pkg.OverlappedGather(B, F, world, dev, pieces=pieces) if world > 1 else None  # block-cyclic: zero-copy gather
+    og = None
+    if world > 1 and args.gather == "chunks":
+        # one extraction call per step; the all-gather of chunk k waits for the engine's completion event of chunk k
+        ex.engine.set_chunk(-(-B // args.gather_chunks))
+        og = pkg.OverlappedGather(B, F, world, dev, bounds=pkg.OverlappedGather.chunk_bounds(ex.engine, B, H, H))
+    elif world > 1:
+        og = pkg.OverlappedGather(B, F, world, dev, pieces=pieces)  # block-cyclic: zero-copy gather
 
     def extract_slice(lo, hi, o, s):
         ex.engine.extract_device(imgs[lo:hi], masks[lo:hi], o, s)
 
     def step():
-        if world > 1:
+        if world > 1 and args.gather == "chunks":
+            og.run_chunked(ex.engine, imgs, masks, out, status, gathered)
+        elif world > 1:
             og.run(extract_slice, out, status, gathered)
         else:
             ex.engine.extract_device(imgs, masks, out, status)
@@ -331,6 +347,21 @@ def gpu_arm(args):
         gather_ok = ok
         ex.engine.extract_device(imgs, masks, out, status)  # restore this rank's status / rows
         torch.cuda.synchronize()
+    # ---- N > 1: where the step's time beyond one GPU's goes (outside the headline region, same timing rules):
+    # one un-sliced call, the sliced schedule without the collective, and the full step measured above
+    attribution = None
+    if world > 1:
+        def single_call():
+            ex.engine.extract_device(imgs, masks, out, status)
+        t_single = timed(single_call, args.steps) / args.steps
+        og.skip_collective = True
+        t_sliced = timed(step, args.steps) / args.steps
+        og.skip_collective = False
+        attribution = {"single_call_ms": t_single, "sliced_without_collective_ms": t_sliced,
+                       "sliced_with_collective_ms": ms / args.steps,
+                       "note": "max over ranks each: rank skew shows in single_call_ms vs the 1-GPU run, the slicing of the "
+                               "shard in the second figure, the exposed part of the all-gather (and its SM / memory "
+                               "interference) in the third"}
     # per-rank kernel time (the scaling tail: is it rank skew or the collective?)
     rank_kms = torch.zeros(world, dtype=torch.float64, device=dev)
     rank_kms[rank] = kms
@@ -447,6 +478,7 @@ def gpu_arm(args):
             "multi_gpu": None if world == 1 else {
                 "gathered_equals_single_gpu_rows": gather_ok,
                 "kernel_ms_per_rank": [round(float(x), 4) for x in rank_kms.cpu().tolist()],
+                "attribution": attribution,
                 "note": "gathered (device-resident step) and e2e_gathered (host-to-host step) compared bit for bit on rank 0 "
                         "with a single-GPU recomputation of every rank's shard, outside the timed region"},
             "clocks": sampler.summary(),

@@ -100,6 +100,16 @@ int radb_reserve(radb_handle* h, int H, int W, int dtype, int64_t max_batch, voi
  * kernel of chunk i+1 overlaps the reduction kernels of chunk i.  The workspace holds two chunks of records. */
 int radb_set_chunk(radb_handle* h, int64_t patches);
 
+/* Rows per chunk a dense call with B patches of HxW `dtype` will use (the chunks are equal but for the last one). */
+int64_t radb_chunk_rows(const radb_handle* h, int H, int W, int dtype, int64_t B);
+
+/* Completion events (cudaEvent_t[n]) for the chunks of the NEXT dense extraction call on this handle (one-shot):
+ * cuda_events[c] is recorded once the output rows of chunk c -- rows [c * radb_chunk_rows, ...) -- are final, so that
+ * a consumer on another stream (the multi-GPU driver's all-gather of a slice of rows) can start while later chunks are
+ * still being extracted.  The reference has no such hook: its fan-out returns whole lists
+ * (/root/reference/RadiomicExtractor.py:63-65). */
+int radb_set_chunk_events(radb_handle* h, void* const* cuda_events, int n);
+
 /* Dynamic shared memory (bytes) one CTA of the build kernel needs for HxW patches of `dtype`; < 0 if it cannot fit. */
 int radb_smem_bytes(const radb_handle* h, int H, int W, int dtype);
 

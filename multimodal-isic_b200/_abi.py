@@ -112,6 +112,10 @@ def load_library(path=None):
     lib.radb_launch_count.restype = i64
     lib.radb_set_chunk.argtypes = [vp, i64]
     lib.radb_set_chunk.restype = i32
+    lib.radb_chunk_rows.argtypes = [vp, i32, i32, i32, i64]
+    lib.radb_chunk_rows.restype = i64
+    lib.radb_set_chunk_events.argtypes = [vp, vp, i32]
+    lib.radb_set_chunk_events.restype = i32
     lib.radb_set_profiling.argtypes = [vp, i32]
     lib.radb_set_profiling.restype = i32
     lib.radb_kernel_ms.argtypes = [vp, ctypes.POINTER(ctypes.c_double * 3)]
@@ -127,7 +131,7 @@ def load_library(path=None):
 
 EXPORTED_SYMBOLS = (
     "radb_create", "radb_destroy", "radb_feature_count", "radb_feature_name", "radb_reserve", "radb_smem_bytes",
-    "radb_extract", "radb_extract_packed", "radb_extract_ragged", "radb_extract_bgr", "radb_pack_mask_host", "radb_pack_masks_host", "radb_unpack_mask", "radb_derive_image", "radb_filter_image", "radb_debug_matrices", "radb_max_ng", "radb_launch_count", "radb_set_chunk", "radb_set_profiling",
+    "radb_extract", "radb_extract_packed", "radb_extract_ragged", "radb_extract_bgr", "radb_pack_mask_host", "radb_pack_masks_host", "radb_unpack_mask", "radb_derive_image", "radb_filter_image", "radb_debug_matrices", "radb_max_ng", "radb_launch_count", "radb_set_chunk", "radb_chunk_rows", "radb_set_chunk_events", "radb_set_profiling",
     "radb_kernel_ms", "radb_last_error",
     "radb_version",
 )

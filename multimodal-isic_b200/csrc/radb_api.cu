@@ -42,6 +42,7 @@ struct radb_handle {
     cudaStream_t red_stream3;    // third side stream: the warp-per-angle kernel next to the Lanczos MCC kernel (many gray levels)
     cudaStream_t red_stream2;    // second side stream: first-order / GLDM / NGTDM / GLSZM / shape reductions (concurrent with the first)
     std::vector<cudaEvent_t> sync_events;  // build-done / reduce-done events of the two-stream pipeline (re-used)
+    std::vector<cudaEvent_t> chunk_events;  // caller's completion events for the chunks of the next call (radb_set_chunk_events)
     bool profiling;              // record CUDA events around every kernel (radb_set_profiling)
     std::vector<cudaEvent_t> events;  // 4 per chunk: start, after build, after angle, after misc
 };
@@ -202,6 +203,23 @@ extern "C" const char* radb_feature_name(const radb_handle* h, int i)
 extern "C" int radb_max_ng(const radb_handle* h) { return h ? h->plan.max_ng : RADB_E_INVALID; }
 extern "C" int64_t radb_launch_count(const radb_handle* h) { return h ? h->launches : 0; }
 
+extern "C" int64_t radb_chunk_rows(const radb_handle* h, int H, int W, int dtype, int64_t B)
+{
+    if (!h || B < 0) return RADB_E_INVALID;
+    RadbParams p;
+    std::string err;
+    int rc = radb::fill_params(h->plan, H, W, dtype, p, err);
+    if (rc) return fail(rc, err);
+    return chunk_for(h, p, B);
+}
+
+extern "C" int radb_set_chunk_events(radb_handle* h, void* const* cuda_events, int n)
+{
+    if (!h || n < 0 || (n > 0 && !cuda_events)) return fail(RADB_E_INVALID, "radb_set_chunk_events: bad arguments");
+    h->chunk_events.assign((const cudaEvent_t*)cuda_events, (const cudaEvent_t*)cuda_events + n);
+    return RADB_OK;
+}
+
 extern "C" int radb_smem_bytes(const radb_handle* h, int H, int W, int dtype)
 {
     if (!h) return RADB_E_INVALID;
@@ -239,6 +257,8 @@ static int set_smem(radb_handle* h, K kernel, int which, int bytes)
 // One pass = three kernels over a chunk of patches, stream-ordered, sharing the record workspace.
 static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
 {
+    std::vector<cudaEvent_t> user_events;
+    user_events.swap(h->chunk_events);  // one-shot: they belong to this launch, whatever its outcome
     cudaError_t e;
     DeviceGuard guard(h->device);
     const bool dbg = p.dbg_levels || p.dbg_glcm || p.dbg_glrlm || p.dbg_glszm || p.dbg_gldm || p.dbg_ng;
@@ -399,6 +419,12 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         if (piped) {
             cudaEventRecord(h->sync_events[4 * c + 1], rs);
             cudaEventRecord(h->sync_events[4 * c + 2], ms);
+        }
+        if (c < (long long)user_events.size() && user_events[c]) {
+            // rows [done, done + n) are final once both reduction families of this chunk are: the second family's
+            // stream joins the first one's event, then carries the caller's event
+            if (piped) cudaStreamWaitEvent(ms, h->sync_events[4 * c + 1], 0);
+            cudaEventRecord(user_events[c], ms);
         }
         h->launches += 3;
         done += n;

@@ -57,6 +57,23 @@ class Engine:
         if rc != 0:
             raise RadbError("radb_set_chunk failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
 
+    def chunk_rows(self, B, H, W, dtype=torch.uint8):
+        """Rows per chunk a dense call with ``B`` patches will use (radb_chunk_rows)."""
+        n = int(self.lib.radb_chunk_rows(self._h, int(H), int(W), self.DTYPES[dtype], int(B)))
+        if n < 0:
+            raise RadbError("radb_chunk_rows failed (%d): %s" % (n, self.lib.radb_last_error().decode()))
+        return n
+
+    def set_chunk_events(self, events):
+        """``events``: torch.cuda.Event list; event c is recorded when the rows of chunk c of the NEXT dense extraction
+        call are final (radb_set_chunk_events).  The events must exist on the device already (record them once)."""
+        import ctypes
+
+        arr = (ctypes.c_void_p * len(events))(*[int(e.cuda_event) for e in events])
+        rc = self.lib.radb_set_chunk_events(self._h, arr, len(events))
+        if rc != 0:
+            raise RadbError("radb_set_chunk_events failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+
     def set_profiling(self, on):
         self.lib.radb_set_profiling(self._h, int(bool(on)))
 

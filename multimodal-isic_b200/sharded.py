@@ -88,9 +88,12 @@ class OverlappedGather:
     slices, asynchronously on the current stream (``Engine.extract_device`` does).  On CPU tensors
     (gloo tests) the same slicing runs without streams."""
 
-    def __init__(self, rows, F, world, device, pieces=2, group=None, layout=None):
+    def __init__(self, rows, F, world, device, pieces=2, group=None, layout=None, bounds=None):
         self.rows, self.F, self.world, self.group = int(rows), int(F), int(world), group
-        if isinstance(pieces, (list, tuple)):
+        if bounds is not None:  # explicit slice boundaries (run_chunked: the engine's own chunk boundaries)
+            self.bounds = [int(b) for b in bounds]
+            assert self.bounds[0] == 0 and self.bounds[-1] == self.rows and all(a < b for a, b in zip(self.bounds, self.bounds[1:]))
+        elif isinstance(pieces, (list, tuple)):
             cum, b = 0.0, [0]
             for f in pieces[:-1]:
                 cum += float(f)
@@ -109,7 +112,9 @@ class OverlappedGather:
         # contiguous layout: one staging buffer per slice (slice k's collective may still run when slice k+1 is extracted)
         self.tmp = ([torch.empty((self.world, mx, self.F), dtype=torch.float64, device=device) for _ in range(self.pieces)]
                     if self.layout == "contiguous" else None)
-        self.comm = torch.cuda.Stream(device=device) if self.cuda and self.world > 1 else None
+        self.skip_collective = False  # measurement aid (bench.py attribution): run the slices, leave the collective out
+        # high priority: the collective's few CTAs must get SM slots while the extraction's grids keep every SM full
+        self.comm = torch.cuda.Stream(device=device, priority=-1) if self.cuda and self.world > 1 else None
         self.work = [torch.cuda.Stream(device=device) for _ in range(2)] if self.cuda and self.pieces > 1 else None
 
     def global_index(self, rank, local):
@@ -123,6 +128,42 @@ class OverlappedGather:
     def _slice_view(self, gathered, k):
         lo, hi = self.bounds[k], self.bounds[k + 1]
         return gathered[self.world * lo: self.world * hi]
+
+    def run_chunked(self, engine, images, masks, out, status, gathered):
+        """ONE extraction call for the whole shard: the engine pipelines its chunks (build kernel of chunk k + 1 under
+        the reduction kernels of chunk k, exactly as on one GPU) and records a completion event per chunk
+        (radb_set_chunk_events); the all-gather of chunk k's rows waits for event k on the communication stream.
+        ``bounds`` must be the engine's chunk boundaries (``chunk_bounds``); block-cyclic layout only."""
+        assert self.layout == "block_cyclic" and self.cuda
+        cur = torch.cuda.current_stream(out.device)
+        if getattr(self, "_events", None) is None:
+            self._events = [torch.cuda.Event() for _ in range(self.pieces)]
+            for e in self._events:
+                e.record(cur)  # materialise the CUDA events
+        if self.comm is not None:
+            self.comm.wait_stream(cur)  # the previous step's consumers of `gathered` are done
+        engine.set_chunk_events(self._events)
+        engine.extract_device(images, masks, out, status)
+        for k in range(self.pieces):
+            lo, hi = self.bounds[k], self.bounds[k + 1]
+            if self.world == 1:
+                cur.wait_event(self._events[k])
+                self._slice_view(gathered, k).copy_(out[lo:hi])
+                continue
+            if self.skip_collective:
+                continue
+            self.comm.wait_event(self._events[k])
+            with torch.cuda.stream(self.comm):
+                dist.all_gather_into_tensor(self._slice_view(gathered, k), out[lo:hi], group=self.group)  # in place
+        if self.comm is not None:
+            cur.wait_stream(self.comm)
+        return gathered
+
+    @staticmethod
+    def chunk_bounds(engine, rows, H, W, dtype=torch.uint8):
+        """Boundaries of the chunks a dense call with ``rows`` patches will use (for ``bounds=``)."""
+        n = engine.chunk_rows(rows, H, W, dtype)
+        return list(range(0, rows, n)) + [rows]
 
     def run(self, extract_fn, out, status, gathered):
         cur = torch.cuda.current_stream(out.device) if self.cuda else None
@@ -147,6 +188,8 @@ class OverlappedGather:
                         dst.copy_(out[lo:hi])
                 else:
                     dst.copy_(out[lo:hi])
+                continue
+            if self.skip_collective:
                 continue
             if self.comm is not None:
                 ev = torch.cuda.Event()

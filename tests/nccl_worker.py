@@ -7,6 +7,7 @@ rows one GPU computes for the whole list (bit for bit), for both drivers:
 
 * ``OverlappedGather`` (equal shards, sliced, the all-gather of slice k under the extraction of slice k+1:
   what ``bench.py --gpus N`` runs), and
+* ``OverlappedGather.run_chunked`` (one extraction call, per-chunk completion events: radb_set_chunk_events), and
 * ``sharded_extract`` (cost-balanced contiguous shards of unequal length, padded all-gather).
 
 plus 16 rows spot-checked against the oracle on rank 0.  Prints ``NCCL_WORKER_OK`` per rank.
@@ -64,6 +65,24 @@ def main():
             og.run(extract_slice, out, status, gathered)
         torch.cuda.synchronize()
         assert torch.equal(gathered.view(torch.int64), want.view(torch.int64)), "OverlappedGather(%d, %s) rows differ" % (pieces, layout)
+
+    # ---- 1b. one extraction call per step, the all-gather of chunk k on the engine's completion event of chunk k
+    # (what bench.py --gpus N runs by default): 4 chunks per shard
+    ex.engine.set_chunk(rows // 4)
+    bounds = pkg.OverlappedGather.chunk_bounds(ex.engine, rows, 64, 64)
+    assert len(bounds) == 5, bounds
+    og = pkg.OverlappedGather(rows, F, world, dev, bounds=bounds)
+    out = torch.zeros((rows, F), dtype=torch.float64, device=dev)
+    status = torch.zeros((rows,), dtype=torch.int32, device=dev)
+    gathered = torch.zeros((n, F), dtype=torch.float64, device=dev)
+    gidx = torch.as_tensor(og.global_index(rank, np.arange(rows)), device=dev)  # my local patches' global rows
+    my_img, my_msk = d_img.index_select(0, gidx), d_msk.index_select(0, gidx)
+    for _ in range(3):
+        gathered.zero_()
+        og.run_chunked(ex.engine, my_img, my_msk, out, status, gathered)
+    torch.cuda.synchronize()
+    assert torch.equal(gathered.view(torch.int64), want.view(torch.int64)), "run_chunked rows differ"
+    ex.engine.set_chunk(0)
 
     # ---- 2. sharded_extract: cost-balanced shards of unequal length
     costs = (masks == 255).reshape(n, -1).sum(1).astype(np.float64)
