@@ -157,11 +157,54 @@ static int64_t chunk_for(const radb_handle* h, const RadbParams& p, int64_t B)
     return eq < n ? eq : n;
 }
 
+// Chunk sizes of a dense call.  Default: equal chunks (chunk_for).  A decreasing schedule (fractions of the batch,
+// RADB_CHUNK_SCHED="0.5,0.3,0.2" or the built-in one for large batches) keeps the early chunks large -- the
+// thread-level reduction kernels want several waves -- and the LAST chunk small: its reductions are the only ones
+// that do not run under a later chunk's build kernel.  Only when the caller has not fixed the chunk size
+// (radb_set_chunk: equal chunks, which radb_chunk_rows / radb_set_chunk_events describe).  Returns the largest chunk.
+static int64_t chunk_plan(const radb_handle* h, const RadbParams& p, int64_t B, std::vector<int64_t>& sizes)
+{
+    sizes.clear();
+    const int64_t cap = chunk_for(h, p, B > 0 ? (int64_t)1 << 40 : 0);  // the cap itself (a huge batch is cut at the cap)
+    static const char* env = getenv("RADB_CHUNK_SCHED");
+    std::vector<double> fr;
+    if (h->chunk <= 0 && B >= 32768 && !p.rows) {
+        if (env && *env) {
+            for (const char* q = env; *q;) {
+                char* e;
+                double f = strtod(q, &e);
+                if (e == q) break;
+                if (f > 0) fr.push_back(f);
+                q = (*e == ',') ? e + 1 : e;
+                if (*e && *e != ',') break;
+            }
+        }
+    }
+    if (fr.size() >= 2) {
+        int64_t left = B;
+        for (size_t i = 0; i < fr.size() && left > 0; i++) {
+            int64_t n = (i + 1 == fr.size()) ? left : (int64_t)(B * fr[i] + 0.5);
+            n = (n + 3) / 4 * 4;
+            while (n > cap) { sizes.push_back(cap); left -= cap; n -= cap; }
+            if (n > left) n = left;
+            if (n > 0) { sizes.push_back(n); left -= n; }
+        }
+        while (left > 0) { int64_t n = left < cap ? left : cap; sizes.push_back(n); left -= n; }
+    } else {
+        const int64_t n = chunk_for(h, p, B);
+        for (int64_t done = 0; done < B; done += n) sizes.push_back(B - done < n ? B - done : n);
+    }
+    int64_t mx = 0;
+    for (int64_t n : sizes) mx = n > mx ? n : mx;
+    return mx;
+}
+
 // Grow-only workspace: one record (+ scratch) per patch of a chunk, keyed by the stream the kernels run on.
 // Batches of several chunks get two such slots: chunk i+1 is built while chunk i is being reduced.
 static int ensure_ws(radb_handle* h, const RadbParams& p, int64_t B, void* stream, unsigned char** out)
 {
-    const int64_t n = chunk_for(h, p, B);
+    std::vector<int64_t> sizes;
+    const int64_t n = chunk_plan(h, p, B, sizes);
     const size_t slots = B > n ? 2 : 1;
     const size_t need = slots * (size_t)n * ((size_t)p.rec_bytes + (size_t)p.scr_bytes);
     radb_handle::Ws* w = nullptr;
@@ -291,7 +334,8 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     unsigned char* wsp = nullptr;
     if (!rc) rc = ensure_ws(h, p, p.B, stream, &wsp);
     if (rc) return rc;
-    const long long chunk = chunk_for(h, p, p.B);
+    std::vector<int64_t> sizes;
+    const long long chunk = chunk_plan(h, p, p.B, sizes);  // largest chunk = slot size
     const size_t slot_bytes = (size_t)chunk * ((size_t)p.rec_bytes + (size_t)p.scr_bytes);
     p.g_inv2 = h->d_inv2;
     p.g_tlog = h->d_tlog;
@@ -304,7 +348,7 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     // waits for the last reduction, so the call stays stream-ordered for the caller.  Per-kernel timing
     // (radb_set_profiling) needs the kernels back to back: profiling runs serialise on the caller's stream.
     static const bool no_overlap = getenv("RADB_NO_OVERLAP") != nullptr;
-    const long long nchunks = (p.B + chunk - 1) / chunk;
+    const long long nchunks = (long long)sizes.size();
     // (single-chunk calls of at least 4096 patches fork too: the two reduction families are latency-bound kernels with
     // few resident warps and run side by side)
     const bool piped = (nchunks > 1 || p.B >= 4096) && !h->profiling && !no_overlap;
@@ -329,7 +373,7 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     cudaStream_t as = (piped && p.use_lanczos) ? h->red_stream3 : rs;  // warp-per-angle kernel beside the Lanczos kernel
     long long done = 0;
     for (long long c = 0; done < p.B; c++) {
-        const long long n = p.B - done < chunk ? p.B - done : chunk;
+        const long long n = sizes[(size_t)c];
         RadbParams q = p;
         q.ws = wsp + (size_t)(c & 1) * (nchunks > 1 ? slot_bytes : 0);
         q.ws_scr = q.ws + (size_t)chunk * (size_t)p.rec_bytes;
