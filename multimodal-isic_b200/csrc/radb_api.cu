@@ -421,7 +421,9 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         }
         const bool angle_classes = p.off_glcm >= 0 || p.off_glrlm >= 0;  // nothing to reduce per angle otherwise
         if (p.use_lane == 2 && p.off_glcm >= 0) {
-            radb_mcc_g8_kernel<<<(unsigned)((n + RADB_NTM / 32 - 1) / (RADB_NTM / 32)), RADB_NTM, p.g8_smem_total, rs>>>(q);
+            const int na = p.n_angles;
+            const long long g8_warps = (na == 1 || na == 2 || na == 4) ? (n * na + 3) / 4 : n;  // 4 (patch, angle) tasks per warp
+            radb_mcc_g8_kernel<<<(unsigned)((g8_warps + RADB_NTM / 32 - 1) / (RADB_NTM / 32)), RADB_NTM, p.g8_smem_total, rs>>>(q);
             RADB_CHECK_LAUNCH("radb_mcc_g8_kernel");
             h->launches += 1;
         }

@@ -854,22 +854,28 @@ __device__ void radb_misc_lane_cta(const RadbParams& p, long long cta, unsigned 
                    out + p.off_glszm);
 }
 
-// ==================================================================== MCC kernel: one warp per patch
-// The aligned 8-lane group g of the warp owns angle g: row sums of its matrix (p_x), then mcc_task_g8.  The
+// ==================================================================== MCC kernel: 8 lanes per (patch, angle)
+// The aligned 8-lane group g of a warp owns one (patch, angle) task: row sums of its matrix (p_x), then mcc_task_g8.  The
 // four values go to the record header (RADB_REC_MCC_INT) for the thread-per-angle kernel's nanmean.
 __device__ void radb_mcc_g8_cta(const RadbParams& p, long long cta, unsigned char* smem)
 {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const long long patch = cta * (RADB_NTM / 32) + warp;
-    if (patch >= p.B || p.off_glcm < 0) return;
+    if (p.off_glcm < 0) return;
+    const int g = lane >> 3, gl = lane & 7, NA = p.n_angles;
+    // 1, 2 or 4 angles: the four groups of a warp take consecutive (patch, angle) tasks, so a one-angle extractor (the
+    // literal force2D reading of /root/reference/params.yml:100) solves four patches per warp instead of leaving 24
+    // lanes idle; 3 angles: one patch per warp, group <-> angle
+    const bool packed = NA == 1 || NA == 2 || NA == 4;
+    const long long wi = cta * (RADB_NTM / 32) + warp, t = wi * 4 + g;
+    const long long patch = packed ? t / NA : wi;
+    const int ang = packed ? (int)(t - patch * NA) : g;
+    if (patch >= p.B || ang >= NA) return;  // every collective below runs on the group's own mask
     if (p.status[radb_row(p, patch)] != 0) return;
-    const int g = lane >> 3, gl = lane & 7;
-    if (g >= p.n_angles) return;  // every collective below runs on the group's own mask
     const unsigned gm = 0xffu << (8 * g);
     unsigned char* rec = p.ws + patch * (long long)p.rec_bytes;
     int* misc = (int*)(rec + (p.o_misc - p.o_rec));
     const int n = misc[8];
-    const int* P = (const int*)(rec + (p.o_glcm - p.o_rec)) + g * n * n;
+    const int* P = (const int*)(rec + (p.o_glcm - p.o_rec)) + ang * n * n;
     unsigned char* ws = smem + (warp * 4 + g) * p.g8_group_bytes;
     int* px = (int*)(ws + p.g8_px);
     for (int i = gl; i < n; i += 8) {
@@ -879,5 +885,5 @@ __device__ void radb_mcc_g8_cta(const RadbParams& p, long long cta, unsigned cha
     }
     __syncwarp(gm);
     const double mcc = mcc_task_g8(P, px, px, n, 1, (double*)(ws + p.g8_mcc), ws + p.g8_idx, gl, gm, 8 * g);
-    if (gl == 0) ((double*)(misc + RADB_REC_MCC_INT))[g] = mcc;
+    if (gl == 0) ((double*)(misc + RADB_REC_MCC_INT))[ang] = mcc;
 }

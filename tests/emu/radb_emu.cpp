@@ -75,7 +75,11 @@ static int emu_launch(RadbParams& p, int dtype, int64_t B)
     if (p.use_lanczos && p.off_glcm >= 0)
         emu::launch((unsigned)(B * p.n_angles), RADB_NTZ, [&]() { radb_mcc_lanczos_cta(p, (long long)blockIdx.x, sm); });
     if (p.use_lane == 2 && p.off_glcm >= 0)
-        emu::launch((unsigned)((B + RADB_NTM / 32 - 1) / (RADB_NTM / 32)), RADB_NTM, [&]() { radb_mcc_g8_cta(p, (long long)blockIdx.x, sm); });
+    {
+        const int na = p.n_angles;
+        const long long g8_warps = (na == 1 || na == 2 || na == 4) ? (B * na + 3) / 4 : B;  // as radb_api.cu: launch
+        emu::launch((unsigned)((g8_warps + RADB_NTM / 32 - 1) / (RADB_NTM / 32)), RADB_NTM, [&]() { radb_mcc_g8_cta(p, (long long)blockIdx.x, sm); });
+    }
     if (p.use_lane)
         emu::launch((unsigned)((B * p.l_nap + RADB_NTL - 1) / RADB_NTL), RADB_NTL, [&]() { radb_angle_lane_cta(p, (long long)blockIdx.x, sm); });
     else

@@ -407,3 +407,11 @@ def test_emu_word_pass_stress_patterns(emu, bw):
     imgs, masks = word_pass_stress_batch(32, 32)
     r = emu.run(imgs, masks, bw, 255, INPLANE)
     assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=bw, force2D=False)) == len(imgs)
+
+
+def test_emu_one_angle_mid_levels_packs_four_patches_per_mcc_warp(emu):
+    """Literal force2D (one angle) at binWidth 10 (15-40 gray levels): radb_mcc_g8_kernel packs four (patch, angle)
+    tasks per warp; 6 patches cross a warp boundary."""
+    imgs, masks = synth.make_patches(6, 32, seed=5)
+    r = emu.run(imgs, masks, 10, 255, LITERAL)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=True)) == 6

@@ -46,6 +46,13 @@ def test_literal_force2d_bw25(gpu_pkg):
     assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=25, force2D=True)) == 12
 
 
+def test_literal_force2d_bw10_mid_levels(gpu_pkg):
+    """One angle at 15-40 gray levels: the MCC kernel packs four (patch, angle) tasks per warp (37 patches: ragged tail)."""
+    imgs, masks = gpu_pkg.synth.make_patches(37, 64, seed=3)
+    r = _dbg(_engine(gpu_pkg, 10, LITERAL), imgs, masks)
+    assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=10, force2D=True)) == 37
+
+
 def test_nonsymmetric_glcm_alpha1(gpu_pkg):
     imgs, masks = gpu_pkg.synth.make_patches(8, 32, seed=2)
     r = _dbg(_engine(gpu_pkg, 16, INPLANE, False, 1), imgs, masks)
