@@ -579,7 +579,14 @@ template <bool L16> struct LevT { typedef unsigned char T; };
 template <> struct LevT<true> { typedef unsigned short T; };
 
 // ------------------------------------------------------------------ build kernel: one CTA per patch
-template <typename PT, bool DBG, bool WIDE, bool L16 = false>
+// FAST: the headline configuration as a compile-time specialisation -- uint8 pixels staged by TMA, narrow mode with the
+// 4-pixel-word level image and the run list, integer binWidth, the four in-plane angles in canonical order, symmetric
+// GLCM, alpha = 0, every texture class wanted, no debug output (radb_host.h: radb_fast_config).  The generic instance
+// carries all the other paths (one pixel per thread, bbox scans, binCount, generic angle sets ...) as run-time
+// branches: 7 000 SASS instructions, of which a CTA executes about half, against an instruction cache of 32 KB shared
+// by five CTAs in five different phases (14 % of the warp stalls were "no instruction").  The specialisation drops
+// them at compile time.
+template <typename PT, bool DBG, bool WIDE, bool L16 = false, bool FAST = false>
 __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned char* smem)
 {
     typedef typename LevT<L16>::T LT;
@@ -587,7 +594,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     const int US = UF<WIDE>::S;
     const UW ULO = (((UW)1) << US) - 1;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int H = p.H, W = p.W, HW = p.HW, WP = p.WP, XO = p.xo, NA = p.n_angles, NB = 2 * p.n_angles;
+    const int H = p.H, W = p.W, HW = p.HW, WP = p.WP, XO = FAST ? 4 : p.xo, NA = FAST ? 4 : p.n_angles, NB = 2 * NA;
+    const bool use_tma = FAST || p.use_tma, vec4 = FAST || p.vec4;
     const int LP = p.lp;  // pitch of the union-find array (pixel (y, x) <-> word y * LP + x)
     const PT* g_img = (const PT*)((const unsigned char*)p.img + (p.img_off ? p.img_off[patch] : patch * p.img_stride));
     const unsigned char* g_msk = radb_mask_ptr(p, patch);
@@ -612,12 +620,12 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     unsigned char* glrlm_base = WIDE ? g_rec + (p.o_glrlm - p.o_rec) : smem + p.o_glrlm;
     int* misc = (int*)(smem + p.o_misc);
     unsigned short* runs = (unsigned short*)(smem + (p.o_runs >= 0 ? p.o_runs : 0));  // row-run start pixels (narrow)
-    const bool keep_runs = !WIDE && p.o_runs >= 0;
+    const bool keep_runs = FAST || (!WIDE && p.o_runs >= 0);
     double* out = p.out + row * (long long)p.F;
 
     // ---- phase 0: stage the patch, zero the counters
 #ifndef RADB_EMU
-    if (!WIDE && p.use_tma) {
+    if (!WIDE && use_tma) {
         void* bar = smem + p.o_mbar;
         if (tid == 0) mbar_init(bar, 1);
         __syncthreads();
@@ -650,7 +658,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     }
     if (!WIDE) {
 #ifndef RADB_EMU
-        if (p.use_tma) {
+        if (use_tma) {
             mbar_wait(smem + p.o_mbar, 0);
         } else
 #endif
@@ -672,7 +680,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     {
         int np = 0, ymin = H, ymax = -1, xmin = W, xmax = -1;
         double vmn = 1e308, vmx = -1e308;
-        if (U8 && p.vec4) {
+        if (U8 && vec4) {
             // uint8 patches whose width is a multiple of 4: four pixels per 32-bit shared-memory load
             const int WQ = W >> 2, NQ = HW >> 2;
             const float inv_wq = 1.0f / (float)WQ;
@@ -774,7 +782,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         int ng = 0;
         if (!st) {
             const double bw = p.bin_width;
-            if (U8 && p.bw_int && p.bin_count <= 0) {
+            if (FAST || (U8 && p.bw_int && p.bin_count <= 0)) {
                 // uint8 pixels and an integer binWidth (25, 10: the reference's settings): the fp64 edges low + k*bw
                 // are exact integers, so the level is an integer quotient (float reciprocal, exact below 2^16)
                 const int ibw = p.bw_int, ivmin = (int)vmin, ivmax = (int)vmax, ilow = ivmin - ivmin % ibw;
@@ -827,8 +835,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     // Only first-order features enabled (the discretise / histogram stage on its own: the HBM-bound part of the
     // path): uint8 pixels need neither the level image nor any texture matrix -- level histogram from the raw
     // histogram through the LUT, publish the head of the record, done.
-    const bool dbg_on = DBG && (p.dbg_levels || p.dbg_glcm || p.dbg_glrlm || p.dbg_glszm || p.dbg_gldm || p.dbg_ngn);
-    const bool tex = dbg_on || p.off_glcm >= 0 || p.off_gldm >= 0 || p.off_glrlm >= 0 || p.off_glszm >= 0 || p.off_ngtdm >= 0;
+    const bool dbg_on = !FAST && DBG && (p.dbg_levels || p.dbg_glcm || p.dbg_glrlm || p.dbg_glszm || p.dbg_gldm || p.dbg_ngn);
+    const bool tex = FAST || dbg_on || p.off_glcm >= 0 || p.off_gldm >= 0 || p.off_glrlm >= 0 || p.off_glszm >= 0 || p.off_ngtdm >= 0;
     if (!tex && U8) {
         for (int v = tid; v < 256; v += RADB_NTB)
             if (hist[v]) atomicAdd(&lhist[lut[v] - 1], hist[v]);
@@ -841,7 +849,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     }
 
     // ---- phase 2: discretised level image (padded, 0 outside the ROI) + level histogram
-    if (U8 && p.vec4) {
+    if (U8 && vec4) {
         const int WQ = W >> 2, NQ = HW >> 2;
         const float inv_wq = 1.0f / (float)WQ;
         const unsigned l4 = (unsigned)(p.label & 0xff) * 0x01010101u;
@@ -889,9 +897,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     const float inv_bw = 1.0f / (float)bw;
     // which angle (if any) is the along-row offset (0, +-1): its line walk doubles as the
     // run-labelling pass of the zone finder
-    int a_row = -1;
-    for (int a = 0; a < NA; a++)
-        if (p.ang_y[a] == 0) a_row = a;
+    int a_row = FAST ? 1 : -1;
+    if (!FAST)
+        for (int a = 0; a < NA; a++)
+            if (p.ang_y[a] == 0) a_row = a;
     if (a_row < 0) {  // no along-row connectivity: every ROI pixel starts as its own run of length 1
         for (int i = tid; i < H * LP; i += RADB_NTB) lab[i] = (((UW)1) << US) | (UW)i;
     }
@@ -996,8 +1005,9 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     // ---- phase 3b: neighbourhood pass over the bbox -> GLCM, GLDM, NGTDM, zone unions
     // GLCM counters while they are built: row pitch gp, angle stride gas.  Padded (gp = ng + 1): level 0 -- a
     // neighbour or a centre outside the ROI -- has its own row and column, so the increments need no test.
-    const int gp = p.glcm_pad ? ng + 1 : ng, gas = gp * gp;
-    int* const glcm0 = p.glcm_pad ? glcm : glcm - (ng + 1);  // cell (level i, level j) of angle a: glcm0[a * gas + i * gp + j]
+    const bool glcm_pad = FAST || p.glcm_pad, symmetric = FAST || p.symmetric;
+    const int gp = glcm_pad ? ng + 1 : ng, gas = gp * gp;
+    int* const glcm0 = glcm_pad ? glcm : glcm - (ng + 1);  // cell (level i, level j) of angle a: glcm0[a * gas + i * gp + j]
     {
         int doff[RADB_MAX_ANGLES], loff[RADB_MAX_ANGLES];
         for (int a = 0; a < RADB_MAX_ANGLES; a++) {
@@ -1027,7 +1037,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             __syncwarp();
             if (qn >= 32) drain(32);
         };
-        if (!WIDE && !L16 && p.lev4 && p.glcm_pad && inplane && p.alpha == 0 && a_row == 1) {
+        if (FAST || (!WIDE && !L16 && p.lev4 && glcm_pad && inplane && p.alpha == 0 && a_row == 1)) {
             // Four pixels per thread: the level image is read as aligned 32-bit words (3 rows x 3 words), the eight
             // neighbours of the four pixels of the centre word are byte permutes of those, and the neighbour
             // counts (NGTDM), equal-level counts (GLDM, alpha = 0) and the run-adjacency / run-end tests are
@@ -1286,7 +1296,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int c = lev[ctr];
         if (c && (a_row < 0 || lev[ctr + 1] != c)) fold_run((unsigned)(y * LP + x));  // run end
     }
-    if (p.glcm_pad) {
+    if (glcm_pad) {
         // the padded counters become the record's compact [NA][ng][ng] matrix (symmetrised: P + P^T) in global
         // memory; (a, i, j) by float reciprocals (exact: indices < 2^18)
         const int ng2 = ng * ng, tot = NA * ng2;
@@ -1297,10 +1307,10 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             const int i = (int)(((float)cell + 0.5f) * r1), j = cell - i * ng;
             const int* P = glcm0 + a * gas;
             int v = P[(i + 1) * gp + j + 1];
-            if (p.symmetric) v += P[(j + 1) * gp + i + 1];
+            if (symmetric) v += P[(j + 1) * gp + i + 1];
             G[t] = v;
         }
-    } else if (p.symmetric) {  // big mode: in place in the global record, all angles in one flat loop
+    } else if (symmetric) {  // big mode: in place in the global record, all angles in one flat loop
         const int ng2 = ng * ng, tot = NA * ng2;
         for (int t = tid; t < tot; t += RADB_NTB) {
             const int a = t / ng2, cell = t - a * ng2;
@@ -1386,7 +1396,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         uint4* dst = (uint4*)g_rec;
         const int n16 = p.rec_copy_bytes / 16;  // wide: GLRLM and the overflow list are already in place
         // the GLCM region was written (compact) in phase 4; big mode keeps it out of the copied part altogether
-        const int g0 = p.glcm_pad ? (p.o_glcm - p.o_rec) / 16 : n16, g1 = p.glcm_pad ? (p.o_gldm - p.o_rec) / 16 : n16;
+        const int g0 = glcm_pad ? (p.o_glcm - p.o_rec) / 16 : n16, g1 = glcm_pad ? (p.o_gldm - p.o_rec) / 16 : n16;
         for (int i = tid; i < n16; i += RADB_NTB)
             if (i < g0 || i >= g1) dst[i] = src[i];
     }
@@ -1673,11 +1683,11 @@ __device__ void radb_shape_cta(const RadbParams& p, long long patch, unsigned ch
 }
 
 #ifndef RADB_EMU
-template <typename PT, bool DBG, bool WIDE, bool L16 = false>
+template <typename PT, bool DBG, bool WIDE, bool L16 = false, bool FAST = false>
 __global__ void __launch_bounds__(RADB_NTB, RADB_NTB_MINB) radb_build_kernel(const RadbParams p)
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
-    radb_build_cta<PT, DBG, WIDE, L16>(p, (long long)blockIdx.x, radb_smem);
+    radb_build_cta<PT, DBG, WIDE, L16, FAST>(p, (long long)blockIdx.x, radb_smem);
 }
 #ifndef RADB_ANGLE_MINB
 #define RADB_ANGLE_MINB 6

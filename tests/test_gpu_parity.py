@@ -133,8 +133,35 @@ def test_word_pass_stress_patterns(gpu_pkg, bw, hw):
     """The 4-pixels-per-thread neighbourhood pass (and its request-queue overflow path) on adversarial patterns:
     checkerboards, stripes, noise masks, bounding boxes at every column offset inside a word."""
     imgs, masks = word_pass_stress_batch(hw, hw)
-    r = _dbg(_engine(gpu_pkg, bw), imgs, masks)
+    eng = _engine(gpu_pkg, bw)
+    r = _dbg(eng, imgs, masks)
     assert compare_with_oracle(r, imgs, masks, dict(label=255, binWidth=bw, force2D=False)) == len(imgs)
+    # the production call (no debug buffers) runs the compile-time specialised build kernel where the configuration
+    # allows it (radb_kernels.cuh: FAST); the debug call above always runs the generic instance: identical rows
+    out, st = eng.extract_device(torch.as_tensor(imgs).cuda(), torch.as_tensor(masks).cuda())
+    assert np.array_equal(out.cpu().numpy().view(np.int64), r["features"].view(np.int64))
+    assert not st.cpu().numpy().any()
+
+
+@pytest.mark.parametrize("bw", [25, 10, 7.5])
+def test_specialised_build_kernel_equals_generic_instance(gpu_pkg, bw):
+    """2 048 synthetic patches + the edge cases: production rows (FAST instance when eligible: integer binWidth) equal the
+    rows of the generic instance (debug call) bit for bit; 64 of them are checked against the oracle."""
+    imgs, masks = gpu_pkg.synth.make_patches(2048, 64, seed=21)
+    eimg, emsk = edge_case_batch()
+    if eimg.shape[1:] == imgs.shape[1:]:
+        imgs, masks = np.concatenate([imgs, eimg]), np.concatenate([masks, emsk])
+    eng = _engine(gpu_pkg, bw)
+    d_img, d_msk = torch.as_tensor(imgs).cuda(), torch.as_tensor(masks).cuda()
+    out, st = eng.extract_device(d_img, d_msk)
+    r = eng.debug_matrices(d_img, d_msk)
+    got, ref = out.cpu().numpy(), r["features"]
+    assert np.array_equal(np.isnan(got), np.isnan(ref))
+    assert np.array_equal(np.nan_to_num(got).view(np.int64), np.nan_to_num(ref).view(np.int64))
+    assert np.array_equal(st.cpu().numpy(), r["status"])
+    sub = np.linspace(0, len(imgs) - 1, 64).astype(int)
+    rs = {k: v[sub] for k, v in r.items()}
+    compare_with_oracle(rs, imgs[sub], masks[sub], dict(label=255, binWidth=bw, force2D=False))
 
 
 def test_smooth_image_large_zones(gpu_pkg):
