@@ -641,6 +641,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         uint4* z = (uint4*)(smem + p.o_zero);
         const int nz = ((p.o_runs >= 0 ? p.o_runs : p.smem_total) - p.o_zero) / 16;  // (the run list is written before it is read)
         const uint4 zero = {0u, 0u, 0u, 0u};
+        RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
         for (int i = tid; i < nz; i += RADB_NTB) z[i] = zero;
         if (WIDE) {  // level image + GLRLM counters in global memory
             uint4* zl = (uint4*)lev;
@@ -687,6 +688,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             const unsigned l4 = (unsigned)(p.label & 0xff) * 0x01010101u;
             const unsigned* v4p = (const unsigned*)s_img;
             if (p.mask_bits || (p.label >= 0 && p.label <= 255))
+                RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
                 for (int q = tid; q < NQ; q += RADB_NTB) {
                     const unsigned eq = radb_roi4(s_msk, q, l4, p.mask_bits);
                     if (!eq) continue;
@@ -788,6 +790,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 const int ibw = p.bw_int, ivmin = (int)vmin, ivmax = (int)vmax, ilow = ivmin - ivmin % ibw;
                 const float rbw = 1.0f / (float)ibw;
                 low = (double)ilow;
+                RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
                 for (int v = tid; v < 256; v += RADB_NTB)
                     lut[v] = (v >= ivmin && v <= ivmax) ? (unsigned char)((int)(((float)(v - ilow) + 0.5f) * rbw) + 1) : 0;
                 ng = (int)(((float)(ivmax - ilow) + 0.5f) * rbw) + 1;
@@ -820,6 +823,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             if (ng > p.max_ng) st = 4;
         }
         if (st) {
+            RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
             for (int f = tid; f < p.F; f += RADB_NTB) out[f] = nan_f64();
             if (tid == 0) {
                 p.status[row] = st;
@@ -855,6 +859,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const unsigned l4 = (unsigned)(p.label & 0xff) * 0x01010101u;
         const unsigned* v4p = (const unsigned*)s_img;
         if (p.mask_bits || (p.label >= 0 && p.label <= 255))
+            RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
             for (int q = tid; q < NQ; q += RADB_NTB) {
                 const unsigned eq = radb_roi4(s_msk, q, l4, p.mask_bits);
                 if (!eq) continue;  // the level image is pre-zeroed
@@ -883,6 +888,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             lev[(y + 1) * WP + x + XO] = L;
         }
     if (U8)
+        RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
         for (int v = tid; v < 256; v += RADB_NTB)
             if (hist[v]) atomicAdd(&lhist[lut[v] - 1], hist[v]);
     __syncthreads();
@@ -1051,6 +1057,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             int* const ngc_p = ngc - NB - 1;        // cell (level c, count n >= 1) at ngc_p + c * NB + n
             int* const ngn_p = ngn - NB - 1;
             int* const trash = misc + 30;
+            RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
             for (int base = 0; base < nq; base += RADB_NTB) {  // uniform trip count (warp collectives below)
                 const int idx = base + tid;
                 const int yb = (int)(((float)idx + 0.5f) * inv_nqx);
@@ -1287,6 +1294,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         return own ? r : 0xffffu;
     };
     // the list entry of a root run becomes its start pixel, every other entry 0xffff: phase 5 then only touches roots
+    RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
     for (int k = tid; k < nruns; k += RADB_NTB) runs[k] = (unsigned short)fold_run(runs[k]);
     if (!by_list)
     for (int idx = tid; idx < nbox; idx += RADB_NTB) {
@@ -1302,6 +1310,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int ng2 = ng * ng, tot = NA * ng2;
         const float r2 = 1.0f / (float)ng2, r1 = 1.0f / (float)ng;
         int* const G = (int*)(g_rec + (p.o_glcm - p.o_rec));
+        RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
         for (int t = tid; t < tot; t += RADB_NTB) {
             const int a = (int)(((float)t + 0.5f) * r2), cell = t - a * ng2;
             const int i = (int)(((float)cell + 0.5f) * r1), j = cell - i * ng;
@@ -1353,6 +1362,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const UW ws = lab[s];
         if ((unsigned)(ws & ULO) == s) emit_zone(c, (int)(ws >> US));
     };
+    RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
     for (int k = tid; k < nruns; k += RADB_NTB) {
         const int r = runs[k];
         if (r == 0xffff) continue;
@@ -1397,6 +1407,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         const int n16 = p.rec_copy_bytes / 16;  // wide: GLRLM and the overflow list are already in place
         // the GLCM region was written (compact) in phase 4; big mode keeps it out of the copied part altogether
         const int g0 = glcm_pad ? (p.o_glcm - p.o_rec) / 16 : n16, g1 = glcm_pad ? (p.o_gldm - p.o_rec) / 16 : n16;
+        RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
         for (int i = tid; i < n16; i += RADB_NTB)
             if (i < g0 || i >= g1) dst[i] = src[i];
     }
