@@ -323,12 +323,12 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     // the headline configuration has a compile-time specialisation of the build kernel (radb_kernels.cuh: FAST)
     static const bool no_fast = getenv("RADB_NO_FAST") != nullptr;  // A/B switch
     const bool fast = !no_fast && dtype == RADB_DTYPE_U8 && !dbg && !p.wide && !p.big && !l16 && p.vec4 && p.lev4 && p.use_tma &&
-                      p.xo == 4 && p.o_runs >= 0 && p.bw_int != 0 && p.bin_count <= 0 && p.n_angles == 4 && p.symmetric &&
+                      p.xo == 4 && p.bw_int != 0 && p.bin_count <= 0 && p.n_angles == 4 && p.symmetric &&
                       p.alpha == 0 && p.glcm_pad && p.off_glcm >= 0 && p.off_gldm >= 0 && p.off_glrlm >= 0 &&
                       p.off_glszm >= 0 && p.off_ngtdm >= 0 && p.ang_y[0] == 1 && p.ang_x[0] == 1 && p.ang_y[1] == 0 &&
                       p.ang_x[1] == 1 && p.ang_y[2] == -1 && p.ang_x[2] == 1 && p.ang_y[3] == 1 && p.ang_x[3] == 0;
-    if (fast) build = radb_build_kernel<unsigned char, false, false, false, true>;
-    int rc = set_smem(h, build, fast ? 39 : (l16 ? 25 + dtype * 2 + (dbg ? 1 : 0) : 9 + dtype * 4 + (p.wide ? 2 : 0) + (dbg ? 1 : 0)), p.smem_total);
+    if (fast) build = p.o_runs >= 0 ? radb_build_kernel<unsigned char, false, false, false, 1> : radb_build_kernel<unsigned char, false, false, false, 2>;
+    int rc = set_smem(h, build, fast ? (p.o_runs >= 0 ? 39 : 38) : (l16 ? 25 + dtype * 2 + (dbg ? 1 : 0) : 9 + dtype * 4 + (p.wide ? 2 : 0) + (dbg ? 1 : 0)), p.smem_total);
     static const bool no_lane = getenv("RADB_NO_LANE") != nullptr;  // A/B switch: force the warp-per-angle kernel
     if (no_lane) p.use_lane = 0;
     if (!rc) rc = p.use_lane ? set_smem(h, radb_angle_lane_kernel, 3, p.l_smem_total) : set_smem(h, radb_angle_kernel, 1, p.a_smem_total);

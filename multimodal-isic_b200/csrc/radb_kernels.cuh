@@ -580,13 +580,13 @@ template <> struct LevT<true> { typedef unsigned short T; };
 
 // ------------------------------------------------------------------ build kernel: one CTA per patch
 // FAST: the headline configuration as a compile-time specialisation -- uint8 pixels staged by TMA, narrow mode with the
-// 4-pixel-word level image and the run list, integer binWidth, the four in-plane angles in canonical order, symmetric
+// 4-pixel-word level image (1: with the run list, 2: without -- more gray levels, no room for it), integer binWidth, the four in-plane angles in canonical order, symmetric
 // GLCM, alpha = 0, every texture class wanted, no debug output (radb_host.h: radb_fast_config).  The generic instance
 // carries all the other paths (one pixel per thread, bbox scans, binCount, generic angle sets ...) as run-time
 // branches: 7 000 SASS instructions, of which a CTA executes about half, against an instruction cache of 32 KB shared
 // by five CTAs in five different phases (14 % of the warp stalls were "no instruction").  The specialisation drops
 // them at compile time.
-template <typename PT, bool DBG, bool WIDE, bool L16 = false, bool FAST = false>
+template <typename PT, bool DBG, bool WIDE, bool L16 = false, int FAST = 0>  // FAST: 0 generic | 1 with run list | 2 without
 __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned char* smem)
 {
     typedef typename LevT<L16>::T LT;
@@ -620,7 +620,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     unsigned char* glrlm_base = WIDE ? g_rec + (p.o_glrlm - p.o_rec) : smem + p.o_glrlm;
     int* misc = (int*)(smem + p.o_misc);
     unsigned short* runs = (unsigned short*)(smem + (p.o_runs >= 0 ? p.o_runs : 0));  // row-run start pixels (narrow)
-    const bool keep_runs = FAST || (!WIDE && p.o_runs >= 0);
+    const bool keep_runs = FAST == 1 || (!FAST && !WIDE && p.o_runs >= 0);
     double* out = p.out + row * (long long)p.F;
 
     // ---- phase 0: stage the patch, zero the counters
@@ -1028,7 +1028,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         UW* uq = (UW*)(smem + p.o_uq) + warp * QCAP;
         int qn = 0;
         const unsigned lt_mask = (1u << lane) - 1u;
-        auto drain = [&](int count) {
+        auto drain = [&](int count) {  // (inlined at its four call sites: a non-inlined drain function measured 1.5 % slower)
             if (lane < count) {
                 const UW pr = uq[qn - count + lane];
                 uf_union<UW, UF<WIDE>::S>(lab, (unsigned)(pr >> US), (unsigned)(pr & ULO));
@@ -1694,7 +1694,7 @@ __device__ void radb_shape_cta(const RadbParams& p, long long patch, unsigned ch
 }
 
 #ifndef RADB_EMU
-template <typename PT, bool DBG, bool WIDE, bool L16 = false, bool FAST = false>
+template <typename PT, bool DBG, bool WIDE, bool L16 = false, int FAST = 0>
 __global__ void __launch_bounds__(RADB_NTB, RADB_NTB_MINB) radb_build_kernel(const RadbParams p)
 {
     extern __shared__ __align__(16) unsigned char radb_smem[];
