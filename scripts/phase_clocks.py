@@ -40,7 +40,7 @@ for i, l in enumerate(lines):
     if i in marks:
         out.append("    if (tid == 0 && p.clk) p.clk[patch * 16 + %d] = clock64();" % (marks.index(i) + 1))
 s = "\n".join(out)
-split = "    if (p.glcm_pad) {\n        // the padded counters become the record's compact"
+split = "    if (glcm_pad) {\n        // the padded counters become the record's compact"
 assert split in s
 s = s.replace(split, "    __syncthreads();\n    if (tid == 0 && p.clk) p.clk[patch * 16 + 12] = clock64();\n" + split, 1)
 s = s.replace("    // ---- phase 0: stage the patch, zero the counters",
@@ -59,7 +59,7 @@ s = s.replace(x3, "radb_red_add_if(endp && g && !(p.dbg_skip & 4), w, val);")   
 s = s.replace(x4, "if (!(p.dbg_skip & 8)) atomicAdd(has ? &ngn_p[c * NB + cnt] : trash, num);")  # 8 = no NGTDM numerator updates
 x5 = "    for (int k = tid; k < nruns; k += RADB_NTB) runs[k] = (unsigned short)fold_run(runs[k]);"
 assert x5 in s
-s = s.replace(x5, "    if (!(p.dbg_skip & 16))\n" + x5)   # 16 = no fold at all (timing floor of the phase)
+s = s.replace(x5, x5.replace("k < nruns", "k < ((p.dbg_skip & 16) ? 0 : nruns)"))   # 16 = no fold at all (timing floor of the phase)
 s = s.replace(x1, "        if (!(p.dbg_skip & 1)) atomicAdd(&lab[r], (UW)(len - own) << US);", 1)
 s = s.replace(x2, "        unsigned r = st;\n        while (!(p.dbg_skip & 2)) {\n            const unsigned pa = (unsigned)(ws & ULO);", 1)
 open(os.path.join(DST, "radb_kernels.cuh"), "w").write(s)

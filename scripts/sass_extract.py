@@ -11,7 +11,7 @@ import subprocess
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 LIB = os.path.join(ROOT, "multimodal-isic_b200", "csrc", "libradb_b200.so")
-FUN = "_Z17radb_build_kernelIhLb0ELb0ELb0EEv10RadbParams"
+FUN = "_Z17radb_build_kernelIhLb0ELb0ELb0ELi1EEv10RadbParams"  # the compile-time specialised (FAST = 1) instance
 out = subprocess.run(["cuobjdump", "-sass", LIB], capture_output=True, text=True).stdout
 lines, on = [], False
 for l in out.split("\n"):
@@ -25,7 +25,7 @@ for l in lines:
     t = l.split("*/", 1)[1].split()
     op = t[1] if t[0].startswith("@") else t[0]
     ops[op.split(".")[0]] += 1
-print("# SASS extract: radb_build_kernel<unsigned char, false, false, false> (sm_100a), round 2 (final)")
+print("# SASS extract: radb_build_kernel<unsigned char, false, false, false, 1> -- the specialised headline instance -- (sm_100a), round 2 (final)")
 print("# cuobjdump -sass multimodal-isic_b200/csrc/libradb_b200.so, function %s" % FUN)
 print("# %d SASS instructions in total.  Mnemonics that prove the design choices:" % len(lines))
 notes = [("UBLKCP", "TMA 1-D bulk copy (cp.async.bulk) of the raw patch and the mask into shared memory"),
