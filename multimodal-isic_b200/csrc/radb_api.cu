@@ -324,7 +324,7 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
     static const bool no_fast = getenv("RADB_NO_FAST") != nullptr;  // A/B switch
     const bool fast = !no_fast && dtype == RADB_DTYPE_U8 && !dbg && !p.wide && !p.big && !l16 && p.vec4 && p.lev4 && p.use_tma &&
                       p.xo == 4 && p.bw_int != 0 && p.bin_count <= 0 && p.n_angles == 4 && p.symmetric &&
-                      p.alpha == 0 && p.glcm_pad && p.off_glcm >= 0 && p.off_gldm >= 0 && p.off_glrlm >= 0 &&
+                      p.alpha == 0 && p.glcm_pad && p.glrlm_dense == 16 && p.off_glcm >= 0 && p.off_gldm >= 0 && p.off_glrlm >= 0 &&
                       p.off_glszm >= 0 && p.off_ngtdm >= 0 && p.ang_y[0] == 1 && p.ang_x[0] == 1 && p.ang_y[1] == 0 &&
                       p.ang_x[1] == 1 && p.ang_y[2] == -1 && p.ang_x[2] == 1 && p.ang_y[3] == 1 && p.ang_x[3] == 0;
     if (fast) build = p.o_runs >= 0 ? radb_build_kernel<unsigned char, false, false, false, 1> : radb_build_kernel<unsigned char, false, false, false, 2>;

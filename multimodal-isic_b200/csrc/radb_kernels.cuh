@@ -596,6 +596,8 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int H = p.H, W = p.W, HW = p.HW, WP = p.WP, XO = FAST ? 4 : p.xo, NA = FAST ? 4 : p.n_angles, NB = 2 * NA;
     const bool use_tma = FAST || p.use_tma, vec4 = FAST || p.vec4;
+    const bool dense = FAST || (!WIDE && p.glrlm_dense != 0);  // GLRLM built as u32 [NA][max_ng][16] + global overflow
+    const int DL = 16;                                         // (= p.glrlm_dense)
     const int LP = p.lp;  // pitch of the union-find array (pixel (y, x) <-> word y * LP + x)
     const PT* g_img = (const PT*)((const unsigned char*)p.img + (p.img_off ? p.img_off[patch] : patch * p.img_stride));
     const unsigned char* g_msk = radb_mask_ptr(p, patch);
@@ -891,6 +893,20 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
         for (int v = tid; v < 256; v += RADB_NTB)
             if (hist[v]) atomicAdd(&lhist[lut[v] - 1], hist[v]);
+    if (dense) {
+        // dense GLRLM: the record's cells for run lengths > 16 are only ever touched by the (rare) global atomics of the
+        // line walks: zero them for the rows that exist (the barrier below orders this before the walks)
+        const int per = p.nrp / 8 - DL / 8, tot = NA * ng * per;  // uint4 (8 packed cells) per (angle, level) row
+        const float rper = 1.0f / (float)(per > 0 ? per : 1), rng = 1.0f / (float)ng;
+        uint4* Z = (uint4*)(g_rec + (p.o_glrlm - p.o_rec));
+        const uint4 zero = {0u, 0u, 0u, 0u};
+        RADB_UNROLL(1)
+        for (int t = tid; t < tot; t += RADB_NTB) {
+            const int row = (int)(((float)t + 0.5f) * rper), k = t - row * per;
+            const int a = (int)(((float)row + 0.5f) * rng), g = row - a * ng;
+            Z[a * (p.glrlm_stride / 16) + g * (p.nrp / 8) + DL / 8 + k] = zero;
+        }
+    }
     __syncthreads();
     if (!U8 && p.off_fo >= 0)  // first-order features need the raw values: now, before the stage is re-used
         fo_dispatch<PT>::run(p, s_img, s_msk, HW, misc[0], roi_min, roi_max, lhist, ng, smem + p.o_fo, out + p.off_fo, tid);
@@ -946,11 +962,17 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                 l = u - k * bw;
             }
             unsigned* R = (unsigned*)(glrlm_base + a * p.glrlm_stride);
-            // narrow: kc = byte address of the u16 counter (level 0, current position) -- one level row below R
+            // narrow, packed: kc = byte address of the u16 counter (level 0, current position) -- one level row below R
             const radb_saddr kc0 = radb_to_saddr(R) - gpitch;
             radb_saddr kc = kc0, kmax = kc0 - 2;
             unsigned val = 1u;
             int rl = 0, mylen = 0;  // wide: position inside the current run, longest run
+            // narrow, dense: counter of (level g, run length k + 1 <= 16) at Dm[g * 16 + k]; longer runs (rare) go to the
+            // packed record in global memory (zeroed in phase 2)
+            int* const Dm = (int*)glrlm_base + (a * p.max_ng - 1) * DL;
+            unsigned* const Rg = (unsigned*)(g_rec + (p.o_glrlm - p.o_rec) + a * p.glrlm_stride);
+            int* const dtrash = misc + 30;
+            int ki = 0, kimax = -1;
             bool endp = true;       // "the previous pixel ended a run"
             if (is_row) {
                 const int base = (by0 + l + 1) * WP + bx0 + XO, lbase = (by0 + l) * LP + bx0;
@@ -965,6 +987,13 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                     if (WIDE) {
                         endp = (gn != g);
                         if (endp && g) { atomicAdd(&R[(g - 1) * nrp + rp - 1], 1u); mylen = rp > mylen ? rp : mylen; }
+                    } else if (dense) {
+                        ki = rp - 1;
+                        endp = (gn != g);
+                        const bool fin = endp && g;
+                        atomicAdd((fin && ki < DL) ? &Dm[g * DL + ki] : dtrash, 1);  // ATOMS.POPC.INC (same-address lanes merge)
+                        if (fin && ki >= DL) add_u16(Rg, (g - 1) * nrp + ki);
+                        if (g) kimax = ki > kimax ? ki : kimax;
                     } else {
                         kc = endp ? kc0 : kc + 2;
                         val = endp ? 1u : val ^ 0x10001u;
@@ -992,6 +1021,13 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                         rl = endp ? 1 : rl + 1;
                         endp = (gn != g) || brk;
                         if (endp && g) { atomicAdd(&R[(g - 1) * nrp + rl - 1], 1u); mylen = rl > mylen ? rl : mylen; }
+                    } else if (dense) {
+                        ki = endp ? 0 : ki + 1;
+                        endp = (gn != g) || brk;
+                        const bool fin = endp && g;
+                        atomicAdd((fin && ki < DL) ? &Dm[g * DL + ki] : dtrash, 1);
+                        if (fin && ki >= DL) add_u16(Rg, (g - 1) * nrp + ki);
+                        if (g) kimax = ki > kimax ? ki : kimax;
                     } else {
                         kc = endp ? kc0 : kc + 2;
                         val = endp ? 1u : val ^ 0x10001u;
@@ -1002,7 +1038,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
                     }
                 }
             }
-            if (!WIDE) mylen = (int)(kmax + 2 - kc0) >> 1;
+            if (!WIDE) mylen = dense ? kimax + 1 : (int)(kmax + 2 - kc0) >> 1;
             if (mylen) atomicMax(&misc[10 + a], mylen);  // record header: longest run of angle a
         }
     }
@@ -1391,7 +1427,7 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
             for (int t = tid; t < ng * ng; t += RADB_NTB)
                 p.dbg_glcm[((patch * NA + a) * p.max_ng + t / ng) * p.max_ng + t % ng] = G[a * ng * ng + t];
     }
-    if (DBG && p.dbg_glrlm)
+    if (DBG && p.dbg_glrlm && !dense)
         for (int a = 0; a < NA; a++)
             for (int t = tid; t < ng * p.nr; t += RADB_NTB)
                 p.dbg_glrlm[((patch * NA + a) * p.max_ng + t / p.nr) * p.nr + t % p.nr] =
@@ -1410,6 +1446,29 @@ __device__ void radb_build_cta(const RadbParams& p, long long patch, unsigned ch
         RADB_UNROLL(1)  // (code size: the kernel is instruction-fetch sensitive, profiles/)
         for (int i = tid; i < n16; i += RADB_NTB)
             if (i < g0 || i >= g1) dst[i] = src[i];
+    }
+    if (dense) {  // the dense counters (run lengths <= 16) packed into the record: 8 u32 -> one uint4 of u16
+        const int tot = NA * ng * (DL / 8);
+        const float r2 = 1.0f / (float)(ng * (DL / 8));
+        RADB_UNROLL(1)
+        for (int t = tid; t < tot; t += RADB_NTB) {
+            const int a = (int)(((float)t + 0.5f) * r2), r = t - a * ng * (DL / 8), g = r / (DL / 8), hh = r % (DL / 8);
+            const int4* sp = (const int4*)((const int*)glrlm_base + (a * p.max_ng + g) * DL + hh * 8);
+            const int4 c0 = sp[0], c1 = sp[1];
+            uint4 o;
+            o.x = (unsigned)c0.x | ((unsigned)c0.y << 16);
+            o.y = (unsigned)c0.z | ((unsigned)c0.w << 16);
+            o.z = (unsigned)c1.x | ((unsigned)c1.y << 16);
+            o.w = (unsigned)c1.z | ((unsigned)c1.w << 16);
+            *(uint4*)(g_rec + (p.o_glrlm - p.o_rec) + a * p.glrlm_stride + g * p.nrp * 2 + hh * 16) = o;
+        }
+        if (DBG && p.dbg_glrlm) {  // parity tests: the packed record, once it is complete
+            __syncthreads();
+            for (int a = 0; a < NA; a++)
+                for (int t = tid; t < ng * p.nr; t += RADB_NTB)
+                    p.dbg_glrlm[((patch * NA + a) * p.max_ng + t / p.nr) * p.nr + t % p.nr] =
+                        get_u16((const unsigned*)(g_rec + (p.o_glrlm - p.o_rec) + a * p.glrlm_stride), (t / p.nr) * p.nrp + t % p.nr);
+        }
     }
 }
 

@@ -87,6 +87,7 @@ struct RadbParams {
     long long scr_bytes; // wide mode: per-patch global scratch (level image + union-find words)
     long long g_lev, g_lab;  // offsets inside that scratch
     int glrlm_stride;  // bytes per angle of the packed-u16 GLRLM counters
+    int glrlm_dense;   // 16: narrow mode counts runs of length <= 16 in u32 [na][ng][16] shared-memory counters; 0: packed u16 in place
     int mcc_stride;    // doubles per angle in the MCC workspace
     int ninv;          // entries of the 1/k^2 table
     // ---- angle kernel (GLRLM + GLCM + MCC, one warp per angle): per-warp scratch + CTA scratch
@@ -125,7 +126,7 @@ static inline int radb_align(int v, int a) { return (v + a - 1) / a * a; }
 static inline int radb_no_lanczos(void) { return getenv("RADB_NO_LANCZOS") != 0; }
 
 // Fills WP/HW/nr/s0/ovf_cap and every shared-memory / record offset from H, W, max_ng, n_angles
-// and p->wide.  Record layout (both modes): header, hist, lhist, glcm, gldm, ngc, ngn, szm | glrlm, ovf.
+// and p->wide.  Record layout (both modes): header, hist, lhist, glcm, gldm, ngc, ngn, szm | ovf, glrlm.
 static inline void radb_layout(RadbParams* p, int pix_bytes)
 {
     const int H = p->H, W = p->W, ng = p->max_ng, na = p->n_angles, wide = p->wide, big = p->big;
@@ -217,12 +218,19 @@ static inline void radb_layout(RadbParams* p, int pix_bytes)
     p->o_szm = o; o += radb_align(ng * p->s0 * 4, 16);
     p->rec_copy_bytes = o - p->o_rec;
     p->glrlm_stride = radb_align(ng * p->nrp * (wide ? 4 : 2), 16);
-    p->o_glrlm = o; o += na * p->glrlm_stride;             // wide: lives in the global record only
     p->o_ovf = o; o += radb_align(p->ovf_cap * 4, 16);     // wide: lives in the global record only
+    // GLRLM, last in the record.  Record: packed u16 [na][ng][nrp] (u32 in wide mode).  Narrow mode builds it DENSE in
+    // shared memory when it can -- u32 [na][ng][16] for run lengths <= 16, incremented by 1 (ATOMS.POPC.INC: a fifth of
+    // the shared-memory wavefronts of an add of 1 << 16 to a packed pair) -- and sends the rare longer runs straight to
+    // the record with global atomics; the dense part is packed into the record at the end.
+    p->glrlm_dense = (!wide && p->nrp % 8 == 0 && p->nrp >= 16) ? 16 : 0;
+    p->o_glrlm = o;
+    const int smem_end = o + (p->glrlm_dense ? radb_align(na * ng * p->glrlm_dense * 4, 16) : na * p->glrlm_stride);
+    o += na * p->glrlm_stride;                             // wide: lives in the global record only
     if (big) { p->o_glcm = o; o += radb_align(na * ng * ng * 4, 16); }  // big: GLCM in the global record only
     p->rec_bytes = o - p->o_rec;
-    p->smem_total = wide ? p->o_rec + p->rec_copy_bytes : o;
-    if (!wide) p->rec_copy_bytes = p->rec_bytes;
+    p->smem_total = wide ? p->o_rec + p->rec_copy_bytes : smem_end;
+    if (!wide) p->rec_copy_bytes = p->glrlm_dense ? p->o_glrlm - p->o_rec : p->rec_bytes;
     // Run list: the along-row walk appends the start pixel of every run, and the zone phases (fold run lengths
     // into roots, emit roots) visit the ~HW/5 runs instead of scanning the bounding box twice.  Kept only when
     // its 2 * HW bytes do not cost a resident CTA (5 per SM at most: the register cap of the build kernel).
