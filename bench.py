@@ -46,6 +46,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true", help="device-resident measurement only (parameter sweeps)")
     ap.add_argument("--e2e-pack", default="auto", choices=["auto", "on", "off"], help="host-side mask packing of the e2e path")
     ap.add_argument("--pack-threads", type=int, default=0)
+    ap.add_argument("--e2e-ramp", default="off",
+                    help="graded chunk sizes at both ends of the host-to-host pipeline (HostPipeline.chunk_schedule)")
     ap.add_argument("--gather", default="slices", choices=["chunks", "slices"],
                     help="N > 1: all-gather per engine chunk of ONE extraction call (completion events), or per separately "
                          "extracted slice (--slices)")
@@ -222,6 +224,7 @@ def gpu_arm(args):
         ex.pipeline.pack_masks = args.e2e_pack == "on"
     if args.pack_threads:
         ex.pipeline.pack_threads = args.pack_threads
+    ex.pipeline.ramp = args.e2e_ramp if "/" in args.e2e_ramp else args.e2e_ramp == "on"
     F = ex.engine.F
     B, H = args.patches, args.size
     # every rank owns a different shard of the (virtual) global patch list

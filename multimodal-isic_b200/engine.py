@@ -356,17 +356,26 @@ class HostPipeline:
 
     The path is bound by the host-to-device link (pixels + masks, ~50 GB/s), and of a mask only
     ``mask == label`` matters, so with ``pack_masks`` the masks cross the link at 1 bit per pixel: packed on
-    the host by ``pack_threads`` threads (AVX2, memory bound: ~100 GB/s on 16 cores) while the device works on
+    the host by ``pack_threads`` persistent threads (AVX2, memory bound: ~100 GB/s on 16 cores) while the device works on
     the previous chunks (a helper thread runs one chunk ahead of the enqueue loop, ``slots`` chunks are in
-    flight), expanded on the device by ``radb_unpack_mask``: 16.0 -> 10.9 ms per 100 k 64x64 patches.  ``pack_masks=None`` (default)
+    flight) and read packed by the kernels (``radb_extract_packed``): 15.9 -> 9.7-10.1 ms per 100 k 64x64 patches
+    (the raw link needs 8.5 ms for the same bytes; caller-packed masks: 9.4 ms).  ``pack_masks=None`` (default)
     enables it when this process has at least 8 host cores to itself (``os.cpu_count() // LOCAL_WORLD_SIZE``):
     with eight ranks on one host the packing threads would only compete for the same memory bandwidth."""
 
-    def __init__(self, engine, chunk=8192, pack_masks=None, pack_threads=None, slots=6, slot_bytes=128 << 20, adaptive=False):
+    def __init__(self, engine, chunk=4096, pack_masks=None, pack_threads=None, slots=6, slot_bytes=128 << 20, adaptive=False,
+                 ramp=None):
         import os
 
         self.engine = engine
         self.chunk = int(chunk)
+        # graded chunk sizes (see chunk_schedule): small chunks first and last, so the pipeline's fill (pack + H2D of the
+        # first chunk before any kernel runs) and drain (kernels + D2H of the last chunk after the link went idle) shrink.
+        # Measured (scripts/e2e_ramp_ab.py, profiles/r2_e2e_chunking.jsonl): worth ~3 % with 8192-patch chunks, nothing
+        # with the 4096-patch chunks that are the default now (uniformly smaller chunks shorten both ends as well) -> off
+        # True / False, or "4,2/2,4,8": the divisors of ``chunk`` at the head / tail (tuning knob, env RADB_E2E_RAMP)
+        env = os.environ.get("RADB_E2E_RAMP", "0")
+        self.ramp = ramp if ramp is not None else (env if "/" in env else env == "1")
         self.slot_bytes = int(slot_bytes)  # pinned / device bytes of one image buffer of one slot, at most
         self.slots = max(2, int(slots))  # chunks in flight: the host packs / enqueues ahead of the device
         self._bufs = None
@@ -375,7 +384,8 @@ class HostPipeline:
         self._n = 0  # patches per slot of the current buffers
         ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
         cores = max(1, (os.cpu_count() or 1) // ranks)
-        self.pack_threads = int(pack_threads) if pack_threads else max(2, min(cores, 8))  # memory bound beyond ~8 threads
+        # 3/4 of the cores, 12 at most (measured on 16 cores: 6 / 8 / 12 / 16 threads -> 10.3 / 10.5 / 9.95 / 10.0 ms per step)
+        self.pack_threads = int(pack_threads) if pack_threads else max(2, min(cores * 3 // 4, 12))
         # Default policy (measured, scripts/e2e_modes.py -> profiles/r2_e2e_modes.jsonl): one rank per host with >= 8
         # cores packs (9.2 vs 6.7 M patches/s: the link is the bound and packing takes 7/16 of its bytes away); several
         # ranks per host do not -- their aggregate host-to-device rate is bound by the HOST (76 GB/s at 2 ranks, 165 GB/s
@@ -392,6 +402,29 @@ class HostPipeline:
         ten-image call at the reference's 600x450 size pins ~10 images, not 8192 of them."""
         n = min(self.chunk, max(1, int(B)), max(1, self.slot_bytes // (H * W * itemsize)))
         return max(1, n)
+
+    @staticmethod
+    def chunk_schedule(B, chunk, ramp=True):
+        """Chunk sizes of one run() over B patches, in order; they sum to B and none exceeds ``chunk``.  With ``ramp``
+        and enough patches the run starts with chunk/4 and chunk/2 and ends with chunk/2, chunk/4, chunk/8 (the
+        remainder sorted in among them): the link is the bottleneck of the host-to-host path, and what it cannot hide
+        is the time before the first kernel starts and after the last copy ends -- both proportional to the size of
+        the chunk at that end."""
+        B, chunk = int(B), max(1, int(chunk))
+        if B <= 0:
+            return []
+        head = [chunk // 4, chunk // 2]
+        tail = [chunk // 2, chunk // 4, chunk // 8]
+        if isinstance(ramp, str):  # "h1,h2/t1,t2,t3": divisors of chunk
+            hs, ts = ramp.split("/")
+            head = [max(1, chunk // int(d)) for d in hs.split(",") if d]
+            tail = [max(1, chunk // int(d)) for d in ts.split(",") if d]
+        if not ramp or chunk < 64 or B < sum(head) + sum(tail) + 2 * chunk:
+            return [min(chunk, B - s) for s in range(0, B, chunk)]
+        rest = B - sum(head) - sum(tail)
+        full, rem = divmod(rest, chunk)
+        last = sorted(tail + ([rem] if rem else []), reverse=True)
+        return head + [chunk] * full + last
 
     def _ensure(self, n, H, W, dtype=torch.uint8):
         key = (H, W, dtype)
@@ -444,7 +477,10 @@ class HostPipeline:
         pack = (not masks_packed) and self.pack_masks and masks.dtype == torch.uint8 and masks.is_contiguous() and self.engine.has_packed
         self.h2d_bytes = 0
         self.packed_chunks = 0
-        starts = list(range(0, B, chunk))
+        sizes = self.chunk_schedule(B, chunk, self.ramp)
+        starts = [0] * len(sizes)
+        for k in range(1, len(sizes)):
+            starts[k] = starts[k - 1] + sizes[k - 1]
         self.total_chunks = len(starts)
         dev = torch.device("cuda", self.engine.device)
 
@@ -457,12 +493,13 @@ class HostPipeline:
             If the slot had to be waited for, the link / device is the bottleneck -> pack; if it was already free the
             host is the bottleneck (few cores per rank) -> hand this chunk's masks over as bytes.  Returns whether
             the chunk was packed."""
-            s0 = starts[k]
-            n0 = min(chunk, B - s0)
+            s0, n0 = starts[k], sizes[k]
             bk = self._bufs[k % self.slots]
             t0 = time.perf_counter()
             bk["done"].synchronize()
-            waited = time.perf_counter() - t0 > 30e-6
+            t1 = time.perf_counter()
+            waited = t1 - t0 > 30e-6
+            self.stats["slot_wait_s"] += t1 - t0
             if not pack:
                 return False
             do = (not self.adaptive) or waited or (k < self.slots and self._host_ahead)
@@ -471,17 +508,23 @@ class HostPipeline:
             if do:
                 self.engine.pack_masks_host(masks[s0:s0 + n0], bk["h_pk"], self.pack_threads)
                 self.packed_chunks += 1
+                self.stats["pack_s"] += time.perf_counter() - t1
             return do
 
         if self._pool is None:
             from concurrent.futures import ThreadPoolExecutor
 
             self._pool = ThreadPoolExecutor(1)
+        # where the host side of the last run() spent its time: helper thread waiting for a slot to drain (the link /
+        # device is behind) and packing; enqueue loop waiting for the helper (the host is behind)
+        self.stats = {"slot_wait_s": 0.0, "pack_s": 0.0, "result_wait_s": 0.0}
         fut = self._pool.submit(prepare, 0) if starts else None
         for k, s in enumerate(starts):
-            n = min(chunk, B - s)
+            n = sizes[k]
             b = self._bufs[k % self.slots]
+            t_w = time.perf_counter()
             packed = fut.result()
+            self.stats["result_wait_s"] += time.perf_counter() - t_w
             if k + 1 < len(starts):
                 fut = self._pool.submit(prepare, k + 1)
             nb = n * pstride

@@ -39,7 +39,7 @@ class RadiomicsExtractor:
     ``NotImplementedError``; False: they are logged at ERROR level, skipped and listed in
     ``skipped_image_types``), ``chunk`` (patches per pipelined H2D chunk), ``max_ng``."""
 
-    def __init__(self, param_file, *, device=0, strict=True, chunk=8192, max_ng=0, **setting_overrides):
+    def __init__(self, param_file, *, device=0, strict=True, chunk=4096, max_ng=0, **setting_overrides):
         self.params = Settings(param_file, strict=strict, **setting_overrides)
         self.skipped_image_types = list(self.params.skipped_image_types)
         self.device = int(device)

@@ -178,6 +178,21 @@ def test_settings_derived_image_types():
         pkg.Settings(p)
 
 
+def test_host_pipeline_chunk_schedule():
+    """Graded chunk sizes of the host-to-host pipeline: every patch exactly once, in order, no chunk above the slot."""
+    from multimodal_isic_b200.engine import HostPipeline
+
+    for B in (0, 1, 100, 8191, 8192, 8193, 29695, 29696, 50000, 100000, 65543, 1000003):
+        for chunk in (1, 63, 64, 1000, 8192):
+            for ramp in (False, True):
+                s = HostPipeline.chunk_schedule(B, chunk, ramp)
+                assert sum(s) == B and all(0 < x <= chunk for x in s), (B, chunk, ramp)
+    s = HostPipeline.chunk_schedule(100000, 8192, True)
+    assert s[:3] == [2048, 4096, 8192] and s[-3:] == [4096, 2048, 1024]
+    assert HostPipeline.chunk_schedule(100000, 8192, ramp=False) == [8192] * 12 + [1696]
+    assert HostPipeline.chunk_schedule(100000, 8192, "4/4") == [2048] + [8192] * 11 + [5792, 2048]
+
+
 def test_pack_ragged_layout():
     """Host packing for radb_extract_ragged: 16-byte aligned patch starts, (H, W) table, lossless pools."""
     from multimodal_isic_b200 import pack_ragged

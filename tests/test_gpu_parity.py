@@ -211,6 +211,10 @@ def test_host_pipeline_overlapping_streams(gpu_pkg):
     host, st = ex.extract_batch(imgs.cpu().numpy(), masks.cpu().numpy())
     assert not st.any()
     np.testing.assert_array_equal(host, dev.cpu().numpy())
+    ex.pipeline.ramp = True  # graded chunk sizes (HostPipeline.chunk_schedule): same rows
+    assert len(set(ex.pipeline.chunk_schedule(B, 4096, True))) > 3
+    host2, st = ex.extract_batch(imgs.cpu().numpy(), masks.cpu().numpy())
+    np.testing.assert_array_equal(host2, dev.cpu().numpy())
 
 
 def test_record_path_matches_reference_call_pattern(gpu_pkg, tmp_path):
