@@ -138,6 +138,12 @@ int radb_extract_ragged(radb_handle* h, const void* img_pool, int dtype, const u
 int radb_extract_bgr(radb_handle* h, const uint8_t* bgr, const uint8_t* mask, int64_t n_images, int H, int W,
                      uint8_t* planes, double* out, int32_t* status, void* cuda_stream);
 
+/* RadiomicExtractor.py:34-35: when the mask's size differs from the image's, the reference nearest-resizes it with
+ * cv2.resize(mask, (W, H), interpolation=cv2.INTER_NEAREST).  Device twin, bit-exact with cv2 4.x: n masks
+ * src [n][sH][sW] -> dst [n][dH][dW] (DEVICE pointers, stream-ordered). */
+int radb_resize_mask(radb_handle* h, const uint8_t* src, int64_t n, int sH, int sW, uint8_t* dst, int dH, int dW,
+                     void* cuda_stream);
+
 /* Packed-mask transfer path.  The reference hands over uint8 masks (RadiomicExtractor.py:33-36) of which only
  * `mask == label` matters (params.yml:93): one bit per pixel.  End to end the extraction is bound by the
  * host-to-device link, so the host may pack a mask buffer to 1 bit per pixel (bit i of the byte stream <->

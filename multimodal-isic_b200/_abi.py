@@ -98,6 +98,8 @@ def load_library(path=None):
     lib.radb_pack_mask_host.restype = i32
     lib.radb_pack_masks_host.argtypes = [vp, i64, i64, i32, vp, i64, i32]
     lib.radb_pack_masks_host.restype = i32
+    lib.radb_resize_mask.argtypes = [vp, vp, i64, i32, i32, vp, i32, i32, vp]
+    lib.radb_resize_mask.restype = i32
     lib.radb_unpack_mask.argtypes = [vp, vp, i64, vp, vp]
     lib.radb_unpack_mask.restype = i32
     lib.radb_derive_image.argtypes = [vp, vp, i64, i64, i32, vp, vp, vp]
@@ -131,7 +133,7 @@ def load_library(path=None):
 
 EXPORTED_SYMBOLS = (
     "radb_create", "radb_destroy", "radb_feature_count", "radb_feature_name", "radb_reserve", "radb_smem_bytes",
-    "radb_extract", "radb_extract_packed", "radb_extract_ragged", "radb_extract_bgr", "radb_pack_mask_host", "radb_pack_masks_host", "radb_unpack_mask", "radb_derive_image", "radb_filter_image", "radb_debug_matrices", "radb_max_ng", "radb_launch_count", "radb_set_chunk", "radb_chunk_rows", "radb_set_chunk_events", "radb_set_profiling",
+    "radb_extract", "radb_extract_packed", "radb_extract_ragged", "radb_extract_bgr", "radb_pack_mask_host", "radb_pack_masks_host", "radb_unpack_mask", "radb_resize_mask", "radb_derive_image", "radb_filter_image", "radb_debug_matrices", "radb_max_ng", "radb_launch_count", "radb_set_chunk", "radb_chunk_rows", "radb_set_chunk_events", "radb_set_profiling",
     "radb_kernel_ms", "radb_last_error",
     "radb_version",
 )

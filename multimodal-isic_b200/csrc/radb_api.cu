@@ -692,6 +692,24 @@ extern "C" int radb_extract_bgr(radb_handle* h, const uint8_t* bgr, const uint8_
     return launch(h, p, RADB_DTYPE_U8, cuda_stream);
 }
 
+// RadiomicExtractor.py:34-35 on the device: n masks [sH][sW] -> [dH][dW], bit-exact with cv2.resize(INTER_NEAREST).
+extern "C" int radb_resize_mask(radb_handle* h, const uint8_t* src, int64_t n, int sH, int sW, uint8_t* dst, int dH, int dW,
+                                void* cuda_stream)
+{
+    if (!h || !src || !dst || n < 0) return fail(RADB_E_INVALID, "bad argument");
+    if (sH < 1 || sW < 1 || dH < 1 || dW < 1) return fail(RADB_E_INVALID, "mask sizes must be positive");
+    if (n == 0) return RADB_OK;
+    DeviceGuard guard(h->device);
+    // cv2 (resize -> resizeNN): inv_scale = (double)dsize / ssize, source index = floor(dst * (1. / inv_scale))
+    const double ify = 1.0 / ((double)dH / (double)sH), ifx = 1.0 / ((double)dW / (double)sW);
+    const long long threads = n * (long long)dH * dW;
+    radb_resize_mask_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, (cudaStream_t)cuda_stream>>>(src, sH, sW, dst, dH, dW, n, ify, ifx);
+    h->launches += 1;
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return cuda_fail(e, "radb_resize_mask launch");
+    return RADB_OK;
+}
+
 // Device half of the packed-mask transfer path (host half: radb_hostpack.cpp).
 extern "C" int radb_unpack_mask(radb_handle* h, const uint8_t* packed, int64_t n_bytes, uint8_t* mask, void* cuda_stream)
 {

@@ -1578,6 +1578,22 @@ __device__ void radb_misc_cta(const RadbParams& p, long long patch, unsigned cha
     }
 }
 
+// Nearest-neighbour mask resize (RadiomicExtractor.py:34-35: cv2.resize(mask, (W, H), INTER_NEAREST) when the mask's size
+// differs from the image's).  cv2 4.x (resizeNN): source index = min(floor(dst_index * (1 / (dst_size / src_size))),
+// src_size - 1) per axis, in double precision; `ify` / `ifx` are those reciprocal scales, computed by the caller.
+// One thread per destination pixel, q = linear index over [n][dH][dW].
+__device__ __forceinline__ void radb_resize_mask_thread(const unsigned char* src, int sH, int sW, unsigned char* dst,
+                                                        int dH, int dW, long long n, double ify, double ifx, long long q)
+{
+    const long long per = (long long)dH * dW;
+    if (q >= n * per) return;
+    const long long b = q / per;
+    const int r = (int)(q - b * per), y = r / dW, x = r - y * dW;
+    int sy = (int)floor((double)y * ify), sx = (int)floor((double)x * ifx);
+    sy = sy < sH - 1 ? sy : sH - 1;
+    sx = sx < sW - 1 ? sx : sW - 1;
+    dst[q] = src[(b * sH + sy) * (long long)sW + sx];
+}
 // ------------------------------------------------------------------ channel front-end
 // RadiomicExtractor.py:29-30,41-47: cv2.imread gives interleaved BGR uint8; the reference then runs
 // execute() on cvtColor(BGR2GRAY), R = im[:,:,2], G = im[:,:,1], B = im[:,:,0].  This kernel reads the
@@ -1844,6 +1860,11 @@ __global__ void radb_unpack_mask_kernel(const unsigned char* packed, long long n
     } else {
         for (int k = 0; k < 16 && p0 + k < n_bytes; k++) mask[p0 + k] = (unsigned char)(((bits >> k) & 1u) ? on : off);
     }
+}
+__global__ void radb_resize_mask_kernel(const unsigned char* src, int sH, int sW, unsigned char* dst, int dH, int dW,
+                                        long long n, double ify, double ifx)
+{
+    radb_resize_mask_thread(src, sH, sW, dst, dH, dW, n, ify, ifx, (long long)blockIdx.x * blockDim.x + threadIdx.x);
 }
 __global__ void radb_bgr_planes_kernel(const unsigned char* bgr, unsigned char* planes, long long n_images, long long HW)
 {

@@ -117,41 +117,58 @@ __device__ int glrlm_lane(const RadbTabs& tb, const unsigned* R, int wide, int n
 }
 
 // ------------------------------------------------------------------ MCC, one thread
-// #eigenvalues of the tridiagonal (d, e2) below x (same recurrence as sturm_count, slot-major operands)
-__device__ __forceinline__ int sturm_lane(LaneMem lm, int oD, int oE, int m, double x)
+// #eigenvalues of the tridiagonal (d, e2) below x (same recurrence and sign convention as sturm_count, slot-major
+// operands) and the last term of the sequence, p_m(x) = det(T - x I), in `pm`.  No rescaling: this kernel only takes
+// matrices of at most 14 levels (use_lane == 1), T = Q^T A Q has its spectrum, diagonal and x inside [-1, 1] and
+// e^2 <= 1, so |p_i| <= 3^i and a product of m <= 14 distances to eigenvalues cannot underflow either.  (The rescaling
+// was a quarter of this kernel's Sturm instructions and sat on the recurrence's dependency chain.)
+__device__ __forceinline__ int sturm_lane(LaneMem lm, int oD, int oE, int m, double x, double& pm)
 {
     double p0 = 1.0, p1 = LMD(lm, oD) - x;
     bool neg = p1 < 0.0;
     int cnt = neg ? 1 : 0;
-    int i = 1;
 #pragma unroll 1
-    for (; i + 1 < m; i += 2) {
-        const double pa = (LMD(lm, oD + i) - x) * p1 - LMD(lm, oE + i - 1) * p0;
-        const bool na = (pa < 0.0) || (pa == 0.0 && neg);
-        const double pb = (LMD(lm, oD + i + 1) - x) * pa - LMD(lm, oE + i) * p1;
-        const bool nb = (pb < 0.0) || (pb == 0.0 && na);
-        cnt += (na != neg) + (nb != na);
-        neg = nb;
-        const double ap = fabs(pb);
-        const double sc = ap > 1e100 ? 1e-100 : (ap < 1e-100 ? 1e100 : 1.0);
-        p0 = pa * sc;
-        p1 = pb * sc;
-    }
-    if (i < m) {
+    for (int i = 1; i < m; i++) {
         const double pn = (LMD(lm, oD + i) - x) * p1 - LMD(lm, oE + i - 1) * p0;
-        const bool nneg = (pn < 0.0) || (pn == 0.0 && neg);
-        cnt += (nneg != neg) ? 1 : 0;
+        const bool nn = (pn < 0.0) || (pn == 0.0 && neg);
+        cnt += (nn != neg) ? 1 : 0;
+        neg = nn;
+        p0 = p1;
+        p1 = pn;
     }
+    pm = p1;
     return cnt;
 }
-// k-th smallest eigenvalue by bisection; the spectrum of A = Dx^-1/2 P Dx^-1/2 lies in [-1, 1]
+// k-th smallest eigenvalue; the spectrum of A = Dx^-1/2 P Dx^-1/2 lies in [-1, 1].  Bisection on the Sturm count until
+// the bracket holds lambda_k alone (count(lo) == k, count(hi) == k + 1: p_m changes sign across it), then regula falsi
+// (Illinois) on p_m inside the bracket -- every evaluation still moves a bracket end by its COUNT, so a wrong secant
+// step costs an iteration, never the eigenvalue; every eighth step is a bisection.  ~12 evaluations instead of ~35.
 __device__ double tridiag_kth_lane(LaneMem lm, int oD, int oE, int m, int k)
 {
-    double lo = -1.000001, hi = 1.000001;
+    double lo = -1.000001, hi = 1.000001, flo = 0.0, fhi = 0.0, prev = 2.0;
+    int cl = 0, ch = m, side = 0;
+    bool klo = false, khi = false;
 #pragma unroll 1
-    for (int it = 0; it < 40 && hi - lo > 1e-10; it++) {
-        const double mid = 0.5 * (lo + hi);
-        if (sturm_lane(lm, oD, oE, m, mid) <= k) lo = mid; else hi = mid;  // count(x) <= k  <=>  x <= lambda_k
+    for (int it = 0; it < 44 && hi - lo > 1e-10; it++) {
+        double mid = 0.5 * (lo + hi);
+        const bool secant = cl == k && ch == k + 1 && klo && khi && ((flo < 0.0) != (fhi < 0.0)) && (it & 7) != 7;
+        if (secant) {
+            const double w = hi - lo, s = lo - flo * radb_div(w, fhi - flo);
+            mid = fmin(fmax(s, lo + 1e-4 * w), hi - 1e-4 * w);
+            if (fabs(mid - prev) <= 2e-11) return mid;  // superlinear: the error is far below the last step
+            prev = mid;
+        }
+        double f;
+        const int c = sturm_lane(lm, oD, oE, m, mid, f);
+        if (c <= k) {  // count(x) <= k  <=>  x <= lambda_k
+            lo = mid; cl = c; flo = f; klo = true;
+            if (side < 0) fhi *= 0.5;
+            side = -1;
+        } else {
+            hi = mid; ch = c; fhi = f; khi = true;
+            if (side > 0) flo *= 0.5;
+            side = 1;
+        }
     }
     return 0.5 * (lo + hi);
 }
@@ -244,7 +261,8 @@ __device__ double mcc_lane(LaneMem lm, int n, double rN)
     }
     const double t = fabs(tridiag_kth_lane(lm, oD, oE, m, m - 2));
     // second largest |lambda(A)|: lambda_min matters only if it lies below -|lambda_2|
-    if (sturm_lane(lm, oD, oE, m, -t * (1.0 + 1e-9) - 1e-12) == 0) return t;
+    double pm;
+    if (sturm_lane(lm, oD, oE, m, -t * (1.0 + 1e-9) - 1e-12, pm) == 0) return t;
     return fmax(t, fabs(tridiag_kth_lane(lm, oD, oE, m, 0)));
 }
 

@@ -244,6 +244,20 @@ class Engine:
         if rc != 0:
             raise RadbError("radb_unpack_mask failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
 
+    def resize_mask(self, masks, size, stream=None):
+        """``cv2.resize(mask, (W, H), interpolation=cv2.INTER_NEAREST)`` (RadiomicExtractor.py:34-35) on the device, bit-exact
+        with cv2 4.x: ``masks`` uint8 CUDA [n, h, w] -> uint8 CUDA [n, H, W] for ``size = (H, W)``."""
+        if masks.dtype != torch.uint8 or not masks.is_cuda or not masks.is_contiguous() or masks.dim() != 3:
+            raise ValueError("resize_mask takes a contiguous uint8 CUDA tensor [n, h, w]")
+        n, sh, sw = masks.shape
+        H, W = int(size[0]), int(size[1])
+        out = torch.empty((n, H, W), dtype=torch.uint8, device=masks.device)
+        st = stream if stream is not None else torch.cuda.current_stream(masks.device)
+        rc = self.lib.radb_resize_mask(self._h, masks.data_ptr(), n, sh, sw, out.data_ptr(), H, W, st.cuda_stream)
+        if rc != 0:
+            raise RadbError("radb_resize_mask failed (%d): %s" % (rc, self.lib.radb_last_error().decode()))
+        return out
+
     def derive_image(self, images, type_code, stream=None):
         """Point-wise derived image type (1 Square, 2 SquareRoot, 3 Logarithm, 4 Exponential) of uint8
         device images [B, H, W] -> float64 [B, H, W] (pyradiomics imageoperations.get*Image)."""

@@ -81,9 +81,10 @@ class RadiomicsExtractor:
 
     @staticmethod
     def _load_record(record):
-        """cv2 decode exactly as RadiomicExtractor.py:29,33-35 (host side): interleaved BGR image and
-        the mask, nearest-resized to the image if needed.  The gray / R / G / B planes of :30,41-47
-        are produced on the GPU by the front-end kernel (bit-exact with cv2.cvtColor)."""
+        """cv2 decode exactly as RadiomicExtractor.py:29,33 (host side): interleaved BGR image and the mask as
+        stored.  The nearest-neighbour resize of a mask whose size differs from the image's (:34-35) and the gray /
+        R / G / B planes of :30,41-47 are produced on the GPU (``radb_resize_mask``, the front-end kernel: both
+        bit-exact with cv2)."""
         import cv2
 
         im = cv2.imread(record["image_path"], cv2.IMREAD_COLOR)
@@ -92,23 +93,23 @@ class RadiomicsExtractor:
         sg = cv2.imread(record["segmentation_path"], cv2.IMREAD_GRAYSCALE)
         if sg is None:
             raise FileNotFoundError(record["segmentation_path"])
-        if im.shape[:2] != sg.shape[:2]:
-            sg = cv2.resize(sg, (im.shape[1], im.shape[0]), interpolation=cv2.INTER_NEAREST)
         return np.ascontiguousarray(im), np.ascontiguousarray(sg)
 
     def _extract_records(self, loaded, max_bytes=256 << 20):
         """loaded: list of (bgr [H,W,3], mask [H,W]) -> list of per-record channel dicts (input order)."""
         results = [None] * len(loaded)
         groups = {}
-        for i, (im, _) in enumerate(loaded):
-            groups.setdefault(im.shape[:2], []).append(i)
+        for i, (im, sg) in enumerate(loaded):  # one launch per (image size, stored mask size)
+            groups.setdefault(im.shape[:2] + sg.shape[:2], []).append(i)
         dev = torch.device("cuda", self.device)
-        for (H, W), idxs in groups.items():
+        for (H, W, mh, mw), idxs in groups.items():
             per = max(1, max_bytes // (H * W * 3))
             for s0 in range(0, len(idxs), per):
                 part = idxs[s0:s0 + per]
                 bgr = torch.as_tensor(np.stack([loaded[i][0] for i in part])).to(dev, non_blocking=True)
                 msk = torch.as_tensor(np.stack([loaded[i][1] for i in part])).to(dev, non_blocking=True)
+                if (mh, mw) != (H, W):  # RadiomicExtractor.py:34-35
+                    msk = self.engine.resize_mask(msk, (H, W))
                 if self.derived_types or not self._has_original:
                     out, status, planes = self.engine.extract_bgr(bgr, msk, return_planes=True)
                     out, status = self._device_blocks(planes.view(-1, H, W), msk.repeat_interleave(4, dim=0),

@@ -135,6 +135,14 @@ extern "C" void radb_emu_bgr_planes(const uint8_t* bgr, uint8_t* planes, int64_t
     for (long long q = 0; q < threads; q++) radb_bgr_planes_thread(bgr, planes, n_images, HW, q);
 }
 
+// Host twin of radb_resize_mask (same reciprocal scales as radb_api.cu, same per-pixel function).
+extern "C" void radb_emu_resize_mask(const uint8_t* src, int64_t n, int sH, int sW, uint8_t* dst, int dH, int dW)
+{
+    const double ify = 1.0 / ((double)dH / (double)sH), ifx = 1.0 / ((double)dW / (double)sW);
+    const long long threads = n * (long long)dH * dW;
+    for (long long q = 0; q < threads; q++) radb_resize_mask_thread(src, sH, sW, dst, dH, dW, n, ify, ifx, q);
+}
+
 // Host twin of radb_image_max_kernel + radb_derive_kernel.
 extern "C" void radb_emu_derive(const uint8_t* img, int64_t n_images, int64_t HW, int type, double* out)
 {

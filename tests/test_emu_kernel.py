@@ -233,6 +233,26 @@ def test_emu_bgr_front_end_matches_cv2(emu):
             np.testing.assert_array_equal(planes[i, k], bgr[i, :, :, ch])
 
 
+def test_emu_mask_resize_matches_cv2(emu):
+    # RadiomicExtractor.py:34-35: cv2.resize(mask, (W, H), interpolation=cv2.INTER_NEAREST)
+    import ctypes
+
+    import cv2
+
+    rng = np.random.default_rng(3)
+    emu.lib.radb_emu_resize_mask.argtypes = [ctypes.c_void_p, ctypes.c_int64, ctypes.c_int, ctypes.c_int, ctypes.c_void_p,
+                                             ctypes.c_int, ctypes.c_int]
+    sizes = [((450, 600), (450, 600)), ((24, 32), (48, 64)), ((450, 600), (768, 1024)), ((1, 1), (5, 7)), ((7, 5), (1, 1)),
+             ((333, 500), (450, 600)), ((1000, 1500), (450, 600))]
+    sizes += [(tuple(rng.integers(1, 300, 2)), tuple(rng.integers(1, 300, 2))) for _ in range(40)]
+    for (sh, sw), (dh, dw) in sizes:
+        src = rng.integers(0, 256, (2, int(sh), int(sw))).astype(np.uint8)
+        dst = np.zeros((2, int(dh), int(dw)), np.uint8)
+        emu.lib.radb_emu_resize_mask(src.ctypes.data, 2, int(sh), int(sw), dst.ctypes.data, int(dh), int(dw))
+        for i in range(2):
+            np.testing.assert_array_equal(dst[i], cv2.resize(src[i], (int(dw), int(dh)), interpolation=cv2.INTER_NEAREST))
+
+
 @pytest.mark.parametrize("dt", [np.uint16, np.float32, np.float64])
 def test_emu_other_pixel_types(emu, dt):
     """uint16 / float pixels (derived image types, BASELINE.json configs[4]): per-pixel fp64 binning,

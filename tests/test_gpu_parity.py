@@ -258,6 +258,20 @@ def test_record_path_matches_reference_call_pattern(gpu_pkg, tmp_path):
     assert len(win) == 9 and all(win[i] == res[i % 3] for i in range(9))
 
 
+def test_mask_resize_on_device_matches_cv2(gpu_pkg):
+    """RadiomicExtractor.py:34-35 (cv2.resize INTER_NEAREST of the mask) on the device: bit-exact."""
+    import cv2
+
+    rng = np.random.default_rng(5)
+    eng = gpu_pkg.Engine(25, 255, INPLANE)
+    for (sh, sw), (dh, dw) in [((450, 600), (768, 1024)), ((24, 32), (48, 64)), ((333, 500), (450, 600)), ((1000, 1500), (450, 600)),
+                               ((1, 1), (5, 7)), ((97, 13), (31, 211))]:
+        src = rng.integers(0, 256, (3, sh, sw)).astype(np.uint8)
+        got = eng.resize_mask(torch.as_tensor(src).cuda(), (dh, dw)).cpu().numpy()
+        for i in range(3):
+            np.testing.assert_array_equal(got[i], cv2.resize(src[i], (dw, dh), interpolation=cv2.INTER_NEAREST))
+
+
 def test_full_size_properties(gpu_pkg):
     """BASELINE.json configs[1] size (100k 64x64 patches): size-independent properties."""
     B = 100000
