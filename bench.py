@@ -324,7 +324,7 @@ def gpu_arm(args):
         sampler.join(2)
     same = bool(torch.equal(h_out, out.cpu()))
     e2e_stats = dict(h2d=ex.pipeline.h2d_bytes, packed=ex.pipeline.packed_chunks, chunks=ex.pipeline.total_chunks,
-                     pack_on=ex.pipeline.pack_masks, threads=ex.pipeline.pack_threads)
+                     pack_on=ex.pipeline.pack_masks, threads=ex.pipeline.pack_threads, adaptive=ex.pipeline.adaptive)
     # ---- N > 1: one step outside the timed region, checked end to end -- rank 0 receives every rank's input
     # shard (broadcast), recomputes it on its own GPU and compares the gathered blocks bit for bit
     # (/root/reference/RadiomicExtractor.py:63-65: the fan-out is order-preserving)
@@ -474,8 +474,9 @@ def gpu_arm(args):
                     "d2h_bytes_per_step": int(world * B * (F * 8 + 4)), "matches_device_path": same,
                     "h2d_gbs_per_rank": e2e_stats["h2d"] * args.steps / e2e_s / 1e9,
                     "masks": "uint8 masks handed over (as the reference does); %d of %d chunks per step packed to 1 bit per "
-                             "pixel by %d host threads and read packed by the kernels (radb_extract_packed)"
-                             % (e2e_stats["packed"], e2e_stats["chunks"], e2e_stats["threads"]),
+                             "pixel by %d host threads%s and read packed by the kernels (radb_extract_packed)"
+                             % (e2e_stats["packed"], e2e_stats["chunks"], e2e_stats["threads"],
+                                " (adaptive: only while the host keeps ahead of the link)" if e2e_stats["adaptive"] else ""),
                     "numa": numa},
             "gpu_launches": int(launches),
             "multi_gpu": None if world == 1 else {

@@ -374,10 +374,11 @@ class HostPipeline:
     the previous chunks (a helper thread runs one chunk ahead of the enqueue loop, ``slots`` chunks are in
     flight) and read packed by the kernels (``radb_extract_packed``): 15.9 -> 9.7-10.1 ms per 100 k 64x64 patches
     (the raw link needs 8.5 ms for the same bytes; caller-packed masks: 9.4 ms).  ``pack_masks=None`` (default)
-    enables it when this process has at least 8 host cores to itself (``os.cpu_count() // LOCAL_WORLD_SIZE``):
-    with eight ranks on one host the packing threads would only compete for the same memory bandwidth."""
+    enables it when this process has at least 3 host cores to itself (``os.cpu_count() // LOCAL_WORLD_SIZE``), and
+    ``adaptive=None`` makes it per-chunk adaptive below 6 cores per rank (eight ranks on a 32-core host are bound by
+    the host's memory system, not the link: see the policy note in ``__init__``)."""
 
-    def __init__(self, engine, chunk=4096, pack_masks=None, pack_threads=None, slots=6, slot_bytes=128 << 20, adaptive=False,
+    def __init__(self, engine, chunk=4096, pack_masks=None, pack_threads=None, slots=6, slot_bytes=128 << 20, adaptive=None,
                  ramp=None):
         import os
 
@@ -398,16 +399,21 @@ class HostPipeline:
         self._n = 0  # patches per slot of the current buffers
         ranks = max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
         cores = max(1, (os.cpu_count() or 1) // ranks)
-        # 3/4 of the cores, 12 at most (measured on 16 cores: 6 / 8 / 12 / 16 threads -> 10.3 / 10.5 / 9.95 / 10.0 ms per step)
-        self.pack_threads = int(pack_threads) if pack_threads else max(2, min(cores * 3 // 4, 12))
-        # Default policy (measured, scripts/e2e_modes.py -> profiles/r2_e2e_modes.jsonl): one rank per host with >= 8
-        # cores packs (9.2 vs 6.7 M patches/s: the link is the bound and packing takes 7/16 of its bytes away); several
-        # ranks per host do not -- their aggregate host-to-device rate is bound by the HOST (76 GB/s at 2 ranks, 165 GB/s
-        # at 8, well below ranks x 55 GB/s), and the packing threads read the same mask bytes the DMA engines would.
-        self.pack_masks = bool(pack_masks) if pack_masks is not None else (ranks == 1 and cores >= 8)
+        # Packing threads: all of a rank's cores up to 4, then 3/4 of them, 12 at most (measured on 16 cores, one rank:
+        # 6 / 8 / 12 / 16 threads -> 10.3 / 10.5 / 9.95 / 10.0 ms per step)
+        self.pack_threads = int(pack_threads) if pack_threads else (cores if cores <= 4 else max(4, min(cores * 3 // 4, 12)))
+        # Default policy (measured with the persistent packing threads, scripts/e2e_modes.py ->
+        # profiles/r2_e2e_modes_{2,8}gpu_pool.jsonl).  Packing trades host memory traffic (the packer reads the 4 KB the
+        # DMA engine would have read) for link bytes, so it pays while the LINK is the bound: one rank on 16 cores 6.3 ->
+        # 10.3 M patches/s, two ranks on 24 cores 12.5 -> 17.1 M (8 threads each; break-even at 3 threads per rank).  Eight
+        # ranks on 32 cores are bound by the host's memory system either way (19.9 M raw, 19.7 M packed): there the
+        # adaptive mode -- pack a chunk only while the host keeps ahead of the link -- is best (20.5 M), and it is the
+        # default whenever a rank has fewer than 6 cores to itself.
+        self.pack_masks = bool(pack_masks) if pack_masks is not None else cores >= 3
         self.h2d_bytes = 0  # bytes copied host -> device by the last run()
         self.timeline = None  # set to [] to record per-chunk CUDA-event marks of the next run() (scripts/e2e_timeline.py)
-        self.adaptive = bool(adaptive)  # pack a chunk's masks only while the host keeps ahead of the link (see run())
+        # pack a chunk's masks only while the host keeps ahead of the link (see run())
+        self.adaptive = bool(adaptive) if adaptive is not None else (ranks > 1 and cores < 6)
         self._host_ahead = True
         self.packed_chunks = self.total_chunks = 0
 

@@ -62,14 +62,15 @@ def main():
     ex.pipeline.pack_masks = False
     measure("raw uint8 masks (8192 B/patch over the link)", lambda: ex.pipeline.run(h_img, h_msk, h_out, h_st))
     ex.pipeline.pack_masks = True
-    for t in (1, 2, 4, 8):
+    for t in (1, 2, 3, 4, 6, 8):
         if t * world > 2 * (os.cpu_count() or 1):
             continue
         ex.pipeline.pack_threads = t
         measure("host-packed, %d threads per rank" % t, lambda: ex.pipeline.run(h_img, h_msk, h_out, h_st))
     ex.pipeline.adaptive = True
-    ex.pipeline.pack_threads = 2
-    measure("adaptive packing, 2 threads per rank", lambda: ex.pipeline.run(h_img, h_msk, h_out, h_st))
+    for t in (2, 4):
+        ex.pipeline.pack_threads = t
+        measure("adaptive packing, %d threads per rank" % t, lambda: ex.pipeline.run(h_img, h_msk, h_out, h_st))
     ex.pipeline.adaptive = False
     measure("masks already packed by the caller (4608 B/patch)", lambda: ex.pipeline.run(h_img, h_pk, h_out, h_st, masks_packed=True))
     if world > 1:
