@@ -14,17 +14,14 @@ static thread_local std::string g_err;
 
 #define RADB_TAB_NINV 4096   // entries of the device 1/k^2 table (beyond it the kernels divide)
 #define RADB_CHUNK_DEFAULT 65536  // patches per pass through the kernels (bounds the workspace; the thread-level reduction kernels want >= 5 waves)
-static int64_t g_chunk = 0;
-static int64_t radb_chunk()
+// Default chunk of a handle, fixed when the handle is created (no process-global state): RADB_CHUNK (tuning knob,
+// multiples of 4) or RADB_CHUNK_DEFAULT; radb_set_chunk overrides it per handle.
+static int64_t radb_chunk_from_env()
 {
-    if (!g_chunk) {
-        const char* e = getenv("RADB_CHUNK");  // tuning knob, multiples of 4
-        long v = e ? atol(e) : 0;
-        g_chunk = (v >= 4) ? (v - v % 4) : RADB_CHUNK_DEFAULT;
-    }
-    return g_chunk;
+    const char* e = getenv("RADB_CHUNK");
+    const long v = e ? atol(e) : 0;
+    return (v >= 4) ? (v - v % 4) : RADB_CHUNK_DEFAULT;
 }
-#define RADB_CHUNK radb_chunk()
 
 struct radb_handle {
     radb::Plan plan;
@@ -37,14 +34,16 @@ struct radb_handle {
                                  // (launches on different streams may overlap; each owns its records)
     double* d_inv2;
     double* d_tlog;
-    int64_t chunk;               // patches per chunk (0: RADB_CHUNK env / default); radb_set_chunk
+    int64_t chunk;               // patches per chunk set by radb_set_chunk (0: chunk_default)
+    int64_t chunk_default;       // RADB_CHUNK env / RADB_CHUNK_DEFAULT, read once at radb_create
     cudaStream_t red_stream;     // high-priority side stream of the GLCM / GLRLM reduction kernels
     cudaStream_t red_stream3;    // third side stream: the warp-per-angle kernel next to the Lanczos MCC kernel (many gray levels)
     cudaStream_t red_stream2;    // second side stream: first-order / GLDM / NGTDM / GLSZM / shape reductions (concurrent with the first)
     std::vector<cudaEvent_t> sync_events;  // build-done / reduce-done events of the two-stream pipeline (re-used)
     std::vector<cudaEvent_t> chunk_events;  // caller's completion events for the chunks of the next call (radb_set_chunk_events)
     bool profiling;              // record CUDA events around every kernel (radb_set_profiling)
-    std::vector<cudaEvent_t> events;  // 4 per chunk: start, after build, after angle, after misc
+    std::vector<cudaEvent_t> events;  // 4 per chunk: start, after build, after angle, after misc (pool, re-used across calls)
+    size_t events_used;               // marks recorded since the last radb_kernel_ms
 };
 
 // Every entry point that launches work selects the handle's device and restores the caller's on return
@@ -95,6 +94,8 @@ extern "C" int radb_create(const radb_settings* s, radb_handle** out)
     h->red_stream2 = nullptr;
     h->red_stream3 = nullptr;
     h->chunk = 0;
+    h->chunk_default = radb_chunk_from_env();
+    h->events_used = 0;
     int ndev = 0;
     cudaError_t e = cudaGetDeviceCount(&ndev);
     if (e != cudaSuccess || ndev == 0) {
@@ -146,7 +147,7 @@ static int64_t chunk_for(const radb_handle* h, const RadbParams& p, int64_t B)
     // <= 1 GiB of records per slot; 4 GiB when a record is large (many gray levels: 1 MB per patch at 256 levels),
     // so that a chunk still fills the 148 SMs several times over
     int64_t n = (int64_t)(((size_t)(per > (256u << 10) ? 4 : 1) << 30) / per);
-    const int64_t want = h->chunk > 0 ? h->chunk : RADB_CHUNK;
+    const int64_t want = h->chunk > 0 ? h->chunk : h->chunk_default;
     if (n > want) n = want;
     n -= n % 4;  // keeps the 4 planes of an image (shared mask) in one chunk
     if (n < 4) n = 4;
@@ -409,10 +410,12 @@ static int launch(radb_handle* h, RadbParams& p, int dtype, void* stream)
         }
         auto mark = [&]() {
             if (!h->profiling) return;
-            cudaEvent_t ev;
-            cudaEventCreate(&ev);
-            cudaEventRecord(ev, st);
-            h->events.push_back(ev);
+            if (h->events_used == h->events.size()) {  // grow the pool; events are re-used by later calls
+                cudaEvent_t ev;
+                if (cudaEventCreate(&ev) != cudaSuccess) return;
+                h->events.push_back(ev);
+            }
+            cudaEventRecord(h->events[h->events_used++], st);
         };
         if (piped && c >= 2) {  // slot free again: both reduction families of chunk c - 2 are done
             cudaStreamWaitEvent(st, h->sync_events[4 * (c - 2) + 1], 0);
@@ -647,8 +650,7 @@ extern "C" int radb_set_chunk(radb_handle* h, int64_t patches)
 extern "C" int radb_set_profiling(radb_handle* h, int on)
 {
     if (!h) return fail(RADB_E_INVALID, "null handle");
-    for (auto ev : h->events) cudaEventDestroy(ev);
-    h->events.clear();
+    h->events_used = 0;
     h->profiling = on != 0;
     return RADB_OK;
 }
@@ -657,7 +659,7 @@ extern "C" int radb_kernel_ms(radb_handle* h, double* ms3)
 {
     if (!h || !ms3) return fail(RADB_E_INVALID, "null argument");
     ms3[0] = ms3[1] = ms3[2] = 0.0;
-    for (size_t i = 0; i + 3 < h->events.size(); i += 4) {
+    for (size_t i = 0; i + 3 < h->events_used; i += 4) {
         cudaError_t e = cudaEventSynchronize(h->events[i + 3]);
         if (e != cudaSuccess) return cuda_fail(e, "cudaEventSynchronize");
         for (int k = 0; k < 3; k++) {
@@ -666,8 +668,7 @@ extern "C" int radb_kernel_ms(radb_handle* h, double* ms3)
             ms3[k] += ms;
         }
     }
-    for (auto ev : h->events) cudaEventDestroy(ev);
-    h->events.clear();
+    h->events_used = 0;
     return RADB_OK;
 }
 
