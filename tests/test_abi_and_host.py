@@ -193,6 +193,30 @@ def test_host_pipeline_chunk_schedule():
     assert HostPipeline.chunk_schedule(100000, 8192, "4/4") == [2048] + [8192] * 11 + [5792, 2048]
 
 
+def test_host_pipeline_packing_policy(monkeypatch):
+    """Default hand-over policy per cores-per-rank (measured: profiles/r2_e2e_modes_{2,8}gpu_pool.jsonl): pack from 3 cores
+    per rank, per-chunk adaptive below 6 on several ranks; explicit arguments win."""
+    import os
+
+    from multimodal_isic_b200.engine import HostPipeline
+
+    def make(cpus, ranks, **kw):
+        monkeypatch.setattr(os, "cpu_count", lambda: cpus)
+        monkeypatch.setenv("LOCAL_WORLD_SIZE", str(ranks))
+        return HostPipeline(None, **kw)
+
+    p = make(16, 1)
+    assert (p.pack_masks, p.adaptive, p.pack_threads, p.chunk, p.ramp) == (True, False, 12, 4096, False)
+    p = make(24, 2)
+    assert (p.pack_masks, p.adaptive, p.pack_threads) == (True, False, 9)
+    p = make(32, 8)
+    assert (p.pack_masks, p.adaptive, p.pack_threads) == (True, True, 4)
+    p = make(8, 8)
+    assert (p.pack_masks, p.pack_threads) == (False, 1)
+    p = make(32, 8, pack_masks=False, adaptive=False, pack_threads=2, ramp="4/4")
+    assert (p.pack_masks, p.adaptive, p.pack_threads, p.ramp) == (False, False, 2, "4/4")
+
+
 def test_pack_ragged_layout():
     """Host packing for radb_extract_ragged: 16-byte aligned patch starts, (H, W) table, lossless pools."""
     from multimodal_isic_b200 import pack_ragged
